@@ -1,0 +1,113 @@
+/*
+ * comm.c -- communicator wrapper: NCCL over NVLink 5 / NVSwitch.
+ *
+ * Own implementation of the acgcomm_* entry points the solver path uses
+ * (reference: acg/comm.c:76-398).  The communicator is borrowed, never
+ * destroyed here (acg/comm.c:139-141).
+ */
+#include "acgb200/comm.h"
+#include "acgb200/error.h"
+
+#include <stddef.h>
+
+const char *acgcommtypestr(enum acgcommtype t)
+{
+    switch (t) {
+    case acgcomm_null: return "null";
+    case acgcomm_mpi: return "mpi";
+    case acgcomm_nccl: return "nccl";
+    case acgcomm_rccl: return "rccl";
+    case acgcomm_nvshmem: return "nvshmem";
+    case acgcomm_rocshmem: return "rocshmem";
+    default: return "unknown";
+    }
+}
+
+int acgcomm_init_nccl(struct acgcomm *comm, ncclComm_t ncclcomm, int *ncclerrcode)
+{
+    (void) ncclerrcode;
+    comm->type = acgcomm_nccl;
+#if defined(ACG_HAVE_MPI)
+    comm->mpicomm = MPI_COMM_NULL;
+#endif
+    comm->ncclcomm = ncclcomm;
+    return ACG_SUCCESS;
+}
+
+#if defined(ACG_HAVE_MPI)
+int acgcomm_init_mpi(struct acgcomm *comm, MPI_Comm mpicomm, int *mpierrcode)
+{
+    (void) mpierrcode;
+    comm->type = acgcomm_mpi;
+    comm->mpicomm = mpicomm;
+    comm->ncclcomm = NULL;
+    return ACG_SUCCESS;
+}
+#endif
+
+void acgcomm_free(struct acgcomm *comm)
+{
+    comm->type = acgcomm_null;
+    comm->ncclcomm = NULL;
+}
+
+int acgcomm_size(const struct acgcomm *comm, int *commsize)
+{
+    if (!comm || comm->type == acgcomm_null) { *commsize = 1; return ACG_SUCCESS; }
+    if (comm->type == acgcomm_nccl) {
+        ncclResult_t r = ncclCommCount(comm->ncclcomm, commsize);
+        return r == ncclSuccess ? ACG_SUCCESS : ACG_ERR_NCCL;
+    }
+#if defined(ACG_HAVE_MPI)
+    if (comm->type == acgcomm_mpi) return MPI_Comm_size(comm->mpicomm, commsize) ? ACG_ERR_MPI : ACG_SUCCESS;
+#endif
+    return ACG_ERR_INVALID_VALUE;
+}
+
+int acgcomm_rank(const struct acgcomm *comm, int *rank)
+{
+    if (!comm || comm->type == acgcomm_null) { *rank = 0; return ACG_SUCCESS; }
+    if (comm->type == acgcomm_nccl) {
+        ncclResult_t r = ncclCommUserRank(comm->ncclcomm, rank);
+        return r == ncclSuccess ? ACG_SUCCESS : ACG_ERR_NCCL;
+    }
+#if defined(ACG_HAVE_MPI)
+    if (comm->type == acgcomm_mpi) return MPI_Comm_rank(comm->mpicomm, rank) ? ACG_ERR_MPI : ACG_SUCCESS;
+#endif
+    return ACG_ERR_INVALID_VALUE;
+}
+
+int acgcomm_allreduce(const void *src, void *dst, int count, enum acgdatatype datatype,
+                      enum acgop op, cudaStream_t stream, const struct acgcomm *comm, int *errcode)
+{
+    if (datatype != ACG_DOUBLE || op != ACG_SUM) return ACG_ERR_INVALID_VALUE;
+    if (!comm || comm->type == acgcomm_null) {
+        if (src != ACG_IN_PLACE && src != dst) {
+            cudaError_t e = cudaMemcpyAsync(dst, src, (size_t) count * sizeof(double), cudaMemcpyDeviceToDevice, stream);
+            if (e) { if (errcode) *errcode = (int) e; return ACG_ERR_CUDA; }
+        }
+        return ACG_SUCCESS;
+    }
+    if (comm->type == acgcomm_nccl) {
+        if (src == ACG_IN_PLACE) src = dst;
+        ncclResult_t r = ncclAllReduce(src, dst, (size_t) count, ncclDouble, ncclSum, comm->ncclcomm, stream);
+        if (r != ncclSuccess) { if (errcode) *errcode = (int) r; return ACG_ERR_NCCL; }
+        return ACG_SUCCESS;
+    }
+    if (comm->type == acgcomm_mpi) return ACG_ERR_MPI_NOT_SUPPORTED;
+    if (comm->type == acgcomm_nvshmem) return ACG_ERR_NVSHMEM_NOT_SUPPORTED;
+    return ACG_ERR_INVALID_VALUE;
+}
+
+int acgcomm_barrier(cudaStream_t stream, const struct acgcomm *comm, int *errcode)
+{
+    if (!comm || comm->type == acgcomm_null) return ACG_SUCCESS;
+    if (comm->type == acgcomm_nccl) {
+        /* acg/comm.c:331: a zero-length allreduce orders the stream behind every rank */
+        ncclResult_t r = ncclAllReduce(NULL, NULL, 0, ncclDouble, ncclSum, comm->ncclcomm, stream);
+        if (r != ncclSuccess) { if (errcode) *errcode = (int) r; return ACG_ERR_NCCL; }
+        return ACG_SUCCESS;
+    }
+    if (comm->type == acgcomm_mpi) return ACG_ERR_MPI_NOT_SUPPORTED;
+    return ACG_ERR_INVALID_VALUE;
+}

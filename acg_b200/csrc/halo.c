@@ -1,0 +1,181 @@
+/*
+ * halo.c -- halo exchange of vector ghost entries on the device over NCCL.
+ *
+ * Own implementation of the acghalo_* / acghaloexchange_* CUDA+NCCL entry
+ * points (reference: acg/halo.c:860-1627, acg/halo.cu:41-146).  Differences
+ * behind the same interface:
+ *   - when the receive indices are one contiguous run (always true for
+ *     patterns built from graph neighbours: recvbufidx[k] = ghostrowoffset+k,
+ *     acg/graph.c:1964-1971) ncclRecv writes straight into the ghost tail of
+ *     the destination vector and the unpack kernel is skipped;
+ *   - the MPI and NVSHMEM transports are not built (north-star: NCCL only).
+ */
+#include "acgb200/error.h"
+#include "acgb200/halo.h"
+#include "internal.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+void acghalo_free(struct acghalo *halo)
+{
+    free(halo->recipients); free(halo->sendcounts); free(halo->sdispls); free(halo->sendbufidx);
+    free(halo->senders); free(halo->recvcounts); free(halo->rdispls); free(halo->recvbufidx);
+    free(halo->thaloexchangestats);
+    memset(halo, 0, sizeof(*halo));
+}
+
+/* private per-exchange facts, kept in fields the CUDA+NCCL path does not
+ * otherwise use: putdispls[0] = 1 if the receive side is contiguous,
+ * putdispls[1] = first destination index of that run */
+static int recv_is_contiguous(const struct acghalo *halo)
+{
+    for (int k = 1; k < halo->recvsize; k++)
+        if (halo->recvbufidx[k] != halo->recvbufidx[0] + k) return 0;
+    return 1;
+}
+
+int acghaloexchange_init_cuda(
+    struct acghaloexchange *hx, const struct acghalo *halo,
+    enum acgdatatype sendtype, enum acgdatatype recvtype,
+    const struct acgcomm *comm, cudaStream_t stream)
+{
+    (void) comm;
+    memset(hx, 0, sizeof(*hx));
+    hx->sendtype = sendtype; hx->recvtype = recvtype;
+    hx->cudastream = stream;
+    hx->maxevents = 0; hx->nevents = 0;
+    hx->putdispls = calloc(2, sizeof(int));
+    if (!hx->putdispls) return ACG_ERR_ERRNO;
+    hx->putdispls[0] = recv_is_contiguous(halo);
+    hx->putdispls[1] = halo->recvsize > 0 ? halo->recvbufidx[0] : 0;
+    const size_t ns = (size_t) (halo->sendsize > 0 ? halo->sendsize : 1);
+    const size_t nr = (size_t) (halo->recvsize > 0 ? halo->recvsize : 1);
+    if (cudaMalloc(&hx->d_sendbuf, ns * sizeof(double))) return ACG_ERR_CUDA;
+    if (cudaMalloc(&hx->d_recvbuf, nr * sizeof(double))) return ACG_ERR_CUDA;
+    if (cudaMalloc(&hx->d_sendbufidx, ns * sizeof(int))) return ACG_ERR_CUDA;
+    if (cudaMalloc(&hx->d_recvbufidx, nr * sizeof(int))) return ACG_ERR_CUDA;
+    if (cudaMemcpy(hx->d_sendbufidx, halo->sendbufidx, (size_t) halo->sendsize * sizeof(int), cudaMemcpyHostToDevice)) return ACG_ERR_CUDA;
+    if (cudaMemcpy(hx->d_recvbufidx, halo->recvbufidx, (size_t) halo->recvsize * sizeof(int), cudaMemcpyHostToDevice)) return ACG_ERR_CUDA;
+    if (cudaMemset(hx->d_sendbuf, 0, ns * sizeof(double))) return ACG_ERR_CUDA;
+    if (cudaMemset(hx->d_recvbuf, 0, nr * sizeof(double))) return ACG_ERR_CUDA;
+    return ACG_SUCCESS;
+}
+
+void acghaloexchange_free(struct acghaloexchange *hx)
+{
+    cudaFree(hx->d_sendbuf); cudaFree(hx->d_recvbuf);
+    cudaFree(hx->d_sendbufidx); cudaFree(hx->d_recvbufidx);
+    free(hx->putdispls);
+    memset(hx, 0, sizeof(*hx));
+}
+
+int acghaloexchange_profile(
+    const struct acghaloexchange *hx, int maxevents, int *nevents,
+    double *texchange, double *tpack, double *tsendrecv, double *tunpack)
+{
+    /* per-exchange event timing is not recorded (it is commented out in the
+     * reference as well: acg/halo.c:1371,:1489) */
+    (void) hx; (void) maxevents; (void) texchange; (void) tpack; (void) tsendrecv; (void) tunpack;
+    if (nevents) *nevents = 0;
+    return ACG_SUCCESS;
+}
+
+int acghalo_pack_cuda(
+    int sendbufsize, void *d_sendbuf, enum acgdatatype datatype,
+    int srcbufsize, const void *d_srcbuf, const int *d_srcbufidx,
+    cudaStream_t stream, int64_t *nbytes, int *errcode)
+{
+    (void) srcbufsize;
+    if (datatype != ACG_DOUBLE) return ACG_ERR_NOT_SUPPORTED;
+    int e = acgb200_gather(sendbufsize, (double *) d_sendbuf, (const double *) d_srcbuf, d_srcbufidx, stream);
+    if (e) { if (errcode) *errcode = e; return ACG_ERR_CUDA; }
+    if (nbytes) *nbytes += (int64_t) sendbufsize * (int64_t) sizeof(double);
+    return ACG_SUCCESS;
+}
+
+int acghalo_unpack_cuda(
+    int recvbufsize, const void *d_recvbuf, enum acgdatatype datatype,
+    int dstbufsize, void *d_dstbuf, const int *d_dstbufidx,
+    cudaStream_t stream, int64_t *nbytes, int *errcode)
+{
+    (void) dstbufsize;
+    if (datatype != ACG_DOUBLE) return ACG_ERR_NOT_SUPPORTED;
+    int e = acgb200_scatter(recvbufsize, (const double *) d_recvbuf, (double *) d_dstbuf, d_dstbufidx, stream);
+    if (e) { if (errcode) *errcode = e; return ACG_ERR_CUDA; }
+    if (nbytes) *nbytes += (int64_t) recvbufsize * (int64_t) sizeof(double);
+    return ACG_SUCCESS;
+}
+
+int acghalo_exchange_cuda_begin(
+    struct acghalo *halo, struct acghaloexchange *hx,
+    int srcbufsize, const void *d_srcbuf, enum acgdatatype sendtype,
+    int dstbufsize, void *d_dstbuf, enum acgdatatype recvtype,
+    const struct acgcomm *comm, int tag, int *errcode, int warmup, cudaStream_t stream)
+{
+    (void) tag;
+    if (sendtype != hx->sendtype || recvtype != hx->recvtype) return ACG_ERR_INVALID_VALUE;
+    if (comm->type == acgcomm_mpi) return ACG_ERR_MPI_NOT_SUPPORTED;
+    if (comm->type == acgcomm_nvshmem) return ACG_ERR_NVSHMEM_NOT_SUPPORTED;
+    if (comm->type != acgcomm_nccl) return ACG_ERR_INVALID_VALUE;
+    int err = acghalo_pack_cuda(halo->sendsize, hx->d_sendbuf, sendtype, srcbufsize, d_srcbuf,
+                                (const int *) hx->d_sendbufidx, stream, warmup ? NULL : &halo->Bpack, errcode);
+    if (err) return err;
+    if (!warmup) halo->npack++;
+    const int inplace = hx->putdispls && hx->putdispls[0] && halo->recvsize > 0 &&
+        hx->putdispls[1] + halo->recvsize <= dstbufsize;
+    double *rbase = inplace ? (double *) d_dstbuf + hx->putdispls[1] : (double *) hx->d_recvbuf;
+    ncclResult_t r = ncclGroupStart();
+    if (r != ncclSuccess) { if (errcode) *errcode = (int) r; return ACG_ERR_NCCL; }
+    for (int p = 0; p < halo->nsenders; p++) {
+        r = ncclRecv(rbase + halo->rdispls[p], (size_t) halo->recvcounts[p], ncclDouble, halo->senders[p], comm->ncclcomm, stream);
+        if (r != ncclSuccess) { if (errcode) *errcode = (int) r; return ACG_ERR_NCCL; }
+    }
+    for (int p = 0; p < halo->nrecipients; p++) {
+        r = ncclSend((const double *) hx->d_sendbuf + halo->sdispls[p], (size_t) halo->sendcounts[p], ncclDouble, halo->recipients[p], comm->ncclcomm, stream);
+        if (r != ncclSuccess) { if (errcode) *errcode = (int) r; return ACG_ERR_NCCL; }
+    }
+    r = ncclGroupEnd();
+    if (r != ncclSuccess) { if (errcode) *errcode = (int) r; return ACG_ERR_NCCL; }
+    if (!warmup) {
+        halo->nmpisend += halo->nrecipients; halo->Bmpisend += (int64_t) halo->sendsize * (int64_t) sizeof(double);
+        halo->nmpiirecv += halo->nsenders; halo->Bmpiirecv += (int64_t) halo->recvsize * (int64_t) sizeof(double);
+    }
+    return ACG_SUCCESS;
+}
+
+int acghalo_exchange_cuda_end(
+    struct acghalo *halo, struct acghaloexchange *hx,
+    int srcbufsize, const void *d_srcbuf, enum acgdatatype sendtype,
+    int dstbufsize, void *d_dstbuf, enum acgdatatype recvtype,
+    const struct acgcomm *comm, int tag, int *errcode, int warmup, cudaStream_t stream)
+{
+    (void) srcbufsize; (void) d_srcbuf; (void) tag;
+    if (sendtype != hx->sendtype || recvtype != hx->recvtype) return ACG_ERR_INVALID_VALUE;
+    if (comm->type != acgcomm_nccl) return comm->type == acgcomm_mpi ? ACG_ERR_MPI_NOT_SUPPORTED : ACG_ERR_INVALID_VALUE;
+    const int inplace = hx->putdispls && hx->putdispls[0] && halo->recvsize > 0 &&
+        hx->putdispls[1] + halo->recvsize <= dstbufsize;
+    if (!inplace) {
+        int err = acghalo_unpack_cuda(halo->recvsize, hx->d_recvbuf, recvtype, dstbufsize, d_dstbuf,
+                                      (const int *) hx->d_recvbufidx, stream, warmup ? NULL : &halo->Bunpack, errcode);
+        if (err) return err;
+    }
+    if (!warmup) { halo->nunpack++; halo->nexchanges++; }
+    return ACG_SUCCESS;
+}
+
+int acghalo_exchange_cuda(
+    struct acghalo *halo, struct acghaloexchange *hx,
+    int srcbufsize, const void *d_srcbuf, enum acgdatatype sendtype,
+    int dstbufsize, void *d_dstbuf, enum acgdatatype recvtype,
+    const struct acgcomm *comm, int tag, int *errcode, int warmup)
+{
+    int err = acghalo_exchange_cuda_begin(halo, hx, srcbufsize, d_srcbuf, sendtype, dstbufsize, d_dstbuf, recvtype,
+                                          comm, tag, errcode, warmup, hx->cudastream);
+    if (err) return err;
+    err = acghalo_exchange_cuda_end(halo, hx, srcbufsize, d_srcbuf, sendtype, dstbufsize, d_dstbuf, recvtype,
+                                    comm, tag, errcode, warmup, hx->cudastream);
+    if (err) return err;
+    if (cudaStreamSynchronize(hx->cudastream)) return ACG_ERR_CUDA;
+    return ACG_SUCCESS;
+}

@@ -1,0 +1,147 @@
+/*
+ * internal.h -- private interfaces between the C host layer and the CUDA
+ * kernels of libacgb200.  Not installed; the public C-ABI is include/acgb200/.
+ */
+#ifndef ACGB200_INTERNAL_H
+#define ACGB200_INTERNAL_H
+
+#include <cuda_runtime_api.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------
+ * SpMV tile plan
+ *
+ * The local CSR block is cut, once at init, into row-aligned tiles of at most
+ * `rows_cap` rows and `nnz_cap` nonzeros.  A tile is one unit of TMA staging:
+ * its slice of values / column indices / row pointers is fetched with three
+ * cp.async.bulk copies into one shared-memory stage.  Bulk copies need
+ * 16-byte aligned addresses and sizes, so every slice start is rounded down to
+ * a multiple of 4 elements and every length rounded up; the device arrays are
+ * allocated with padding so the over-read stays in bounds.
+ *
+ * Rows longer than nnz_cap ("long rows", power-law matrices) are left out of
+ * the tiles and listed separately; a second kernel streams each of them with
+ * several CTAs and combines partial sums with atomics.
+ * ------------------------------------------------------------------------ */
+struct acgb200_tile {        /* 16 bytes, read as one int4 */
+    int row_begin;           /* first row of the tile */
+    int nrows;               /* number of rows */
+    int k_al;                /* rowptr[row_begin] rounded down to a multiple of 4 */
+    int nnz_al;              /* padded slice length: multiple of 4, covers the tile's nonzeros */
+};
+
+struct acgb200_spmvplan {
+    int nrows;                       /* rows covered (owned rows) */
+    int64_t nnz;
+    int lanes_per_row;               /* G: 1,2,4,8,16,32 */
+    int rows_cap, nnz_cap;           /* tile limits */
+    int nstages;                     /* smem ring depth */
+    int threads;                     /* CTA size */
+    int ntiles;
+    struct acgb200_tile *d_tiles;    /* [ntiles] */
+    int nlong;                       /* rows with more than nnz_cap nonzeros */
+    int *d_longrows;                 /* [nlong] */
+    int grid;                        /* persistent grid size */
+    int smem_bytes;                  /* dynamic shared memory per CTA */
+    int long_chunks;                 /* CTAs per long row */
+};
+
+/* epilogue of the SpMV kernels */
+enum acgb200_spmvmode {
+    SPMV_Y_AX = 0,        /* y = A x                                            */
+    SPMV_Y_AX_DOT = 1,    /* y = A x ; acc += sum_{row<dotrows} x[row]*y[row]   */
+    SPMV_R_B_AX = 2,      /* y = b - A x ; acc += sum_{row<dotrows} y[row]^2    */
+    SPMV_Y_PLUS_AX = 3,   /* y += A x  (off-diagonal block)                     */
+};
+
+/* ------------------------------------------------------------------------
+ * Device-resident CG state: iteration control and all scalars.  One
+ * allocation; kernels never read a control word that the same kernel writes
+ * (see DESIGN.md "control ring").
+ * ------------------------------------------------------------------------ */
+struct acgb200_ctrl { int iter; int done; int pad0, pad1; };
+
+struct acgb200_devstate {
+    struct acgb200_ctrl ctrl[4];     /* ring: kernel i of an iteration reads ctrl[i], writes ctrl[i+1 mod nk] */
+    int maxits;
+    int pad[3];
+    double tol;                      /* stop when ||r|| < tol (0: never) */
+    double final_rr;                 /* (r,r) at the iteration that set done */
+    /* classic CG: slot = iteration parity */
+    double pap_loc[2], pap[2];       /* local partial / global (p,Ap) */
+    double rr_loc[2], rr[2];         /* (r_k,r_k) lives in slot k&1 */
+    /* pipelined CG */
+    double gd_loc[2][2], gd[2][2];   /* {gamma,delta} = {(r,r),(w,r)} */
+    double prev[2][2];               /* {gamma_{k-1}, alpha_{k-1}} read by update k from slot k&1 */
+    /* setup-time reductions */
+    double tmp_loc[2], tmp[2];
+};
+
+/* kernels.cu ------------------------------------------------------------- */
+
+/* choose tile parameters for a matrix with the given shape; fills everything
+ * in *plan except the device arrays */
+void acgb200_spmv_choose(struct acgb200_spmvplan *plan, int nrows, int64_t nnz, int64_t maxrowlen);
+int acgb200_spmv_configure(struct acgb200_spmvplan *plan);   /* occupancy -> grid; returns cudaError */
+
+struct acgb200_spmvargs {
+    const struct acgb200_spmvplan *plan;
+    const int *rowptr;        /* [nrows+1] (+pad) */
+    const int *colidx;        /* [nnz] (+pad) */
+    const double *a;          /* [nnz] (+pad) */
+    const double *x;
+    double *y;
+    const double *b;          /* SPMV_R_B_AX */
+    double *acc;              /* device accumulator for the fused dot */
+    int dotrows;              /* rows [0,dotrows) contribute to acc */
+    int mode;
+    const struct acgb200_ctrl *ctrl_in;   /* may be NULL: unconditional */
+    struct acgb200_ctrl *ctrl_out;
+    struct acgb200_devstate *st;          /* for per-iteration scalar housekeeping; may be NULL */
+    int housekeeping;                     /* 0 none, 1 classic, 2 pipelined */
+};
+int acgb200_spmv_launch(const struct acgb200_spmvargs *args, cudaStream_t stream);
+
+/* y[rowoffset+i] (+)= sum_k oa[k]*x[xoffset + ocolidx[k]], i in [0,nrows): the
+ * border x ghost block (acg/cgcuda.c:878); epilogue per `mode` */
+struct acgb200_offdiagargs {
+    int nrows;                /* border rows */
+    int rowoffset;            /* borderrowoffset */
+    const int *orowptr; const int *ocolidx; const double *oa;
+    const double *x; double *y;
+    double *acc; int mode;    /* SPMV_Y_PLUS_AX (+ dot with x over these rows if acc) or SPMV_R_B_AX-style minus */
+    int minus;                /* y -= instead of += (residual) */
+    int dotkind;              /* 0 none, 1 x[row]*y[row], 2 y[row]^2 */
+    const struct acgb200_ctrl *ctrl_in;
+    struct acgb200_ctrl *ctrl_out;
+    struct acgb200_devstate *st;
+};
+int acgb200_offdiag_launch(const struct acgb200_offdiagargs *args, cudaStream_t stream);
+
+/* classic CG fused BLAS-1 (replace acg/cg-kernels-cuda.cu:119-303 and the two
+ * cublasDdot calls at acg/cgcuda.c:894,933) */
+int acgb200_cg_update_r(int n, struct acgb200_devstate *st, int cin, int cout, int multi,
+                        const double *t, double *r, cudaStream_t stream);
+int acgb200_cg_update_xp(int n, struct acgb200_devstate *st, int cin, int cout, int multi,
+                         const double *r, double *p, double *x, cudaStream_t stream);
+/* pipelined CG fused update + next dots (replaces acg/cg-kernels-cuda.cu:187-269
+ * and the cublasDdot calls at acg/cgcuda.c:1680,1688) */
+int acgb200_pcg_update(int n, struct acgb200_devstate *st, int cin, int cout, int multi,
+                       const double *q, double *z, double *w, double *t, double *p,
+                       double *r, double *x, cudaStream_t stream);
+
+/* setup-time helpers */
+int acgb200_dot(int n, const double *x, const double *y, double *acc, cudaStream_t stream); /* acc += x.y */
+int acgb200_dot2(int n, const double *r, const double *w, double *acc2, cudaStream_t stream); /* acc2[0]+=r.r, acc2[1]+=w.r */
+int acgb200_gather(int n, double *dst, const double *src, const int *idx, cudaStream_t stream);  /* dst[i]=src[idx[i]] */
+int acgb200_scatter(int n, const double *src, double *dst, const int *idx, cudaStream_t stream); /* dst[idx[i]]=src[i] */
+int acgb200_num_sms(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

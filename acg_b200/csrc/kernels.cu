@@ -1,0 +1,708 @@
+/*
+ * kernels.cu -- hand-written sm_100a kernels of the CG hot path.
+ *
+ * What each kernel replaces in the reference (paths relative to the aCG tree):
+ *
+ *   spmv_tiles_kernel     cusparseSpMV(matA)  acg/cgcuda.c:858,:1724 (+:775,:1639)
+ *                         + cublasDdot(p,t)   acg/cgcuda.c:894  (fused epilogue)
+ *   spmv_long_*           same, rows longer than one tile (power-law inputs);
+ *                         the role csrgemv_merge plays in acg/cg-kernels-cuda.cu:340
+ *   offdiag_kernel        cusparseSpMV(matO)  acg/cgcuda.c:878,:1744; csrgemv :443
+ *   cg_update_r_kernel    daxpy_minus_alpha   acg/cg-kernels-cuda.cu:153 + cublasDdot(r,r) acg/cgcuda.c:933
+ *   cg_update_xp_kernel   daxpy_alpha :119 + daypx_beta :271 (one pass instead of two)
+ *   pcg_update_kernel     pipelined_daxpy_fused :187 + cublasDdot x2 acg/cgcuda.c:1680,:1688
+ *   gather/scatter        acghalo_pack/unpack_cuda_double acg/halo.cu:41,:94
+ *
+ * Design (details in DESIGN.md): FP64 SIMT, HBM-bound, tensor cores unused.
+ * The CSR streams (values, column indices, row pointers) are moved by the TMA
+ * engine -- 1-D cp.async.bulk global->shared copies completing on an mbarrier
+ * -- into a multi-stage shared-memory ring, so the SMs' load/store units only
+ * issue the x gathers and the y stores.  Rows are processed from shared memory
+ * by G-lane groups (G=1: one thread per row, the warp's gathers of 32
+ * consecutive rows then coalesce for banded/stencil matrices).  Dot products
+ * are folded into the kernels that produce their operands: warp shuffle ->
+ * per-CTA shared reduce -> one atomicAdd(double) per CTA into a device scalar.
+ */
+#include "internal.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SPMV_THREADS 128
+#define SPMV_MAX_STAGES 8
+#define BLAS1_THREADS 512
+
+/* ------------------------------------------------------------------------ */
+/* PTX wrappers: mbarrier + bulk async copy (TMA, 1-D)                       */
+/* ------------------------------------------------------------------------ */
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p)
+{
+    return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init_fence()
+{
+    /* make the initialised barriers visible to the async (TMA) proxy */
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" :: "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+/* global -> shared bulk copy; bytes and both addresses are multiples of 16.
+ * The matrix streams are read exactly once per SpMV: evict-first keeps them
+ * from displacing the x vector in L2. */
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(pol) : "memory");
+}
+
+/* ------------------------------------------------------------------------ */
+/* reductions                                                                */
+/* ------------------------------------------------------------------------ */
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+/* sum over the CTA, result valid in thread 0; `red` holds blockDim/32 doubles */
+__device__ __forceinline__ double block_sum(double v, double *red)
+{
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+    if (w == 0) v = warp_sum(v);
+    __syncthreads();
+    return v;
+}
+
+/* ------------------------------------------------------------------------ */
+/* iteration control                                                         */
+/* ------------------------------------------------------------------------ */
+
+struct Gate { int iter; bool active; };
+
+/* Read the incoming control word.  The word a kernel reads is never written
+ * by that same kernel, so every thread sees the same value. */
+__device__ __forceinline__ Gate gate_read(const acgb200_ctrl *cin, const acgb200_devstate *st)
+{
+    Gate g; g.iter = 0; g.active = true;
+    if (cin) {
+        const int4 c = *reinterpret_cast<const int4 *>(cin);
+        g.iter = c.x;
+        g.active = (c.y == 0) && (c.x < st->maxits);
+    }
+    return g;
+}
+
+/* ------------------------------------------------------------------------ */
+/* SpMV over TMA-staged row tiles                                            */
+/* ------------------------------------------------------------------------ */
+
+struct SpmvParams {
+    const acgb200_tile *tiles;
+    int ntiles;
+    int sc;                 /* slots per stage for values/indices (multiple of 4) */
+    int stage_bytes;
+    int nstages;
+    const int *rowptr;
+    const int *colidx;
+    const double *a;
+    const double *x;
+    double *y;
+    const double *b;
+    double *acc;
+    int dotrows;
+    int mode;
+    const acgb200_ctrl *ctrl_in;
+    acgb200_ctrl *ctrl_out;
+    acgb200_devstate *st;
+    int housekeeping;
+};
+
+__device__ __forceinline__ void spmv_issue(
+    const SpmvParams &P, const acgb200_tile &tl, unsigned char *stage, uint64_t *bar, uint64_t pol)
+{
+    const int row_al = tl.row_begin & ~3;
+    const int nrp = (tl.row_begin + tl.nrows + 1 - row_al + 3) & ~3;
+    double *vals = reinterpret_cast<double *>(stage);
+    int *cols = reinterpret_cast<int *>(stage + (size_t) P.sc * 8);
+    int *rptr = reinterpret_cast<int *>(stage + (size_t) P.sc * 12);
+    mbar_arrive_expect_tx(bar, (uint32_t) tl.nnz_al * 12u + (uint32_t) nrp * 4u);
+    if (tl.nnz_al > 0) {
+        bulk_g2s(vals, P.a + tl.k_al, (uint32_t) tl.nnz_al * 8u, bar, pol);
+        bulk_g2s(cols, P.colidx + tl.k_al, (uint32_t) tl.nnz_al * 4u, bar, pol);
+    }
+    bulk_g2s(rptr, P.rowptr + row_al, (uint32_t) nrp * 4u, bar, pol);
+}
+
+template <int G>
+__global__ void __launch_bounds__(SPMV_THREADS)
+spmv_tiles_kernel(const SpmvParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[SPMV_MAX_STAGES];
+    __shared__ double red[SPMV_THREADS / 32];
+
+    const int tid = threadIdx.x;
+    const Gate gate = gate_read(P.ctrl_in, P.st);
+    if (blockIdx.x == 0 && tid == 0 && P.ctrl_in) {
+        *P.ctrl_out = *P.ctrl_in;
+        if (gate.active) {
+            /* zero the accumulator the *next* producer will add into; nothing
+             * reads that slot while this kernel runs (control ring) */
+            const int s = gate.iter & 1;
+            if (P.housekeeping == 1) P.st->rr_loc[s ^ 1] = 0.0;
+            if (P.housekeeping == 2) { P.st->gd_loc[s ^ 1][0] = 0.0; P.st->gd_loc[s ^ 1][1] = 0.0; }
+        }
+    }
+    if (!gate.active) return;
+
+    const int S = P.nstages;
+    uint64_t pol = 0;
+    if (tid == 0) {
+        pol = l2_policy_evict_first();
+        for (int s = 0; s < S; s++) mbar_init(&full_bar[s], 1);
+        mbar_init_fence();
+        for (int s = 0; s < S; s++) {
+            const int t = blockIdx.x + s * gridDim.x;
+            if (t < P.ntiles) spmv_issue(P, P.tiles[t], smem + (size_t) s * P.stage_bytes, &full_bar[s], pol);
+        }
+    }
+    __syncthreads();
+
+    constexpr int RPP = SPMV_THREADS / G;      /* rows per pass */
+    const int lane = tid % G;
+    const int grp = tid / G;
+    double dot = 0.0;
+
+    int i = 0;
+    for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, i++) {
+        const int s = i % S;
+        const acgb200_tile tl = P.tiles[t];
+        unsigned char *stage = smem + (size_t) s * P.stage_bytes;
+        const double *vals = reinterpret_cast<const double *>(stage);
+        const int *cols = reinterpret_cast<const int *>(stage + (size_t) P.sc * 8);
+        const int *rp = reinterpret_cast<const int *>(stage + (size_t) P.sc * 12) + (tl.row_begin & 3);
+
+        mbar_wait(&full_bar[s], (uint32_t) ((i / S) & 1));
+
+        for (int base = 0; base < tl.nrows; base += RPP) {
+            const int lr = base + grp;
+            double sum = 0.0;
+            if (lr < tl.nrows) {
+                const int kb = rp[lr] - tl.k_al;
+                const int ke = rp[lr + 1] - tl.k_al;
+                int k = kb + lane;
+                for (; k + 3 * G < ke; k += 4 * G) {
+                    const int c0 = cols[k], c1 = cols[k + G], c2 = cols[k + 2 * G], c3 = cols[k + 3 * G];
+                    const double x0 = __ldg(P.x + c0), x1 = __ldg(P.x + c1);
+                    const double x2 = __ldg(P.x + c2), x3 = __ldg(P.x + c3);
+                    sum = fma(vals[k], x0, sum);
+                    sum = fma(vals[k + G], x1, sum);
+                    sum = fma(vals[k + 2 * G], x2, sum);
+                    sum = fma(vals[k + 3 * G], x3, sum);
+                }
+                for (; k < ke; k += G) sum = fma(vals[k], __ldg(P.x + cols[k]), sum);
+            }
+            if (G > 1) sum = group_sum<G>(sum);
+            if (lr < tl.nrows && lane == 0) {
+                const int row = tl.row_begin + lr;
+                if (P.mode == SPMV_R_B_AX) {
+                    const double v = P.b[row] - sum;
+                    P.y[row] = v;
+                    if (row < P.dotrows) dot = fma(v, v, dot);
+                } else {
+                    P.y[row] = sum;
+                    if (P.mode == SPMV_Y_AX_DOT && row < P.dotrows) dot = fma(__ldg(P.x + row), sum, dot);
+                }
+            }
+        }
+
+        __syncthreads();        /* every thread is done reading stage s */
+        if (tid == 0) {
+            const int tn = t + S * gridDim.x;
+            if (tn < P.ntiles) spmv_issue(P, P.tiles[tn], stage, &full_bar[s], pol);
+        }
+    }
+
+    if (P.acc) {
+        const double v = block_sum(dot, red);
+        if (tid == 0 && v != 0.0) atomicAdd(P.acc, v);
+    }
+}
+
+/* ---- long rows: several CTAs per row, partials to scratch, then a finisher -- */
+
+__global__ void __launch_bounds__(256)
+spmv_long_partial_kernel(int nlong, const int *longrows, int chunks,
+                         const int *rowptr, const int *colidx, const double *a, const double *x,
+                         double *scratch, const acgb200_ctrl *cin, const acgb200_devstate *st)
+{
+    __shared__ double red[8];
+    if (!gate_read(cin, st).active) return;
+    const int lrow = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    const int row = longrows[lrow];
+    const long long kb = rowptr[row], ke = rowptr[row + 1];
+    const long long len = ke - kb;
+    const long long c0 = kb + len * chunk / chunks, c1 = kb + len * (chunk + 1) / chunks;
+    double sum = 0.0;
+    for (long long k = c0 + threadIdx.x; k < c1; k += blockDim.x)
+        sum = fma(a[k], __ldg(x + colidx[k]), sum);
+    sum = block_sum(sum, red);
+    if (threadIdx.x == 0) scratch[blockIdx.x] = sum;
+}
+
+__global__ void spmv_long_finish_kernel(int nlong, const int *longrows, int chunks, const double *scratch,
+                                        const double *x, double *y, const double *b, double *acc,
+                                        int dotrows, int mode, const acgb200_ctrl *cin, const acgb200_devstate *st)
+{
+    if (!gate_read(cin, st).active) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double dot = 0.0;
+    if (i < nlong) {
+        const int row = longrows[i];
+        double sum = 0.0;
+        for (int c = 0; c < chunks; c++) sum += scratch[(size_t) i * chunks + c];
+        if (mode == SPMV_R_B_AX) {
+            const double v = b[row] - sum; y[row] = v;
+            if (row < dotrows) dot = v * v;
+        } else {
+            y[row] = sum;
+            if (mode == SPMV_Y_AX_DOT && row < dotrows) dot = x[row] * sum;
+        }
+    }
+    dot = warp_sum(dot);
+    if (acc && (threadIdx.x & 31) == 0 && dot != 0.0) atomicAdd(acc, dot);
+}
+
+/* ---- border x ghost block: thread per border row, direct from global -------- */
+
+__global__ void __launch_bounds__(256)
+offdiag_kernel(const acgb200_offdiagargs A)
+{
+    __shared__ double red[8];
+    if (!gate_read(A.ctrl_in, A.st).active) return;
+    double dot = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.nrows; i += gridDim.x * blockDim.x) {
+        const int kb = A.orowptr[i], ke = A.orowptr[i + 1];
+        const int row = A.rowoffset + i;
+        double sum = 0.0;
+        /* ocolidx is rebased by -borderrowoffset (acg/symcsrmatrix.c:838) */
+        for (int k = kb; k < ke; k++) sum = fma(A.oa[k], __ldg(A.x + A.rowoffset + A.ocolidx[k]), sum);
+        double v = A.y[row];
+        if (kb != ke) { v = A.minus ? v - sum : v + sum; A.y[row] = v; }
+        if (A.dotkind == 1) dot = fma(__ldg(A.x + row), v, dot);
+        else if (A.dotkind == 2) dot = fma(v, v, dot);
+    }
+    if (A.acc) {
+        dot = block_sum(dot, red);
+        if (threadIdx.x == 0 && dot != 0.0) atomicAdd(A.acc, dot);
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* fused BLAS-1                                                              */
+/* ------------------------------------------------------------------------ */
+
+/* r -= alpha t with alpha = (r,r)/(p,Ap), and the new (r,r) in the same pass */
+__global__ void __launch_bounds__(BLAS1_THREADS)
+cg_update_r_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi,
+                   const double *__restrict__ t, double *__restrict__ r)
+{
+    __shared__ double red[BLAS1_THREADS / 32];
+    const Gate g = gate_read(&st->ctrl[cin], st);
+    if (cin != cout && blockIdx.x == 0 && threadIdx.x == 0) st->ctrl[cout] = st->ctrl[cin];
+    if (!g.active) return;
+    const int s = g.iter & 1;
+    const double rr = multi ? st->rr[s] : st->rr_loc[s];
+    const double pap = multi ? st->pap[s] : st->pap_loc[s];
+    const double alpha = rr / pap;
+    double acc = 0.0;
+    const int n2 = n >> 1;
+    const double2 *t2 = reinterpret_cast<const double2 *>(t);
+    double2 *r2 = reinterpret_cast<double2 *>(r);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+        const double2 tv = t2[i];
+        double2 rv = r2[i];
+        rv.x = fma(-alpha, tv.x, rv.x);
+        rv.y = fma(-alpha, tv.y, rv.y);
+        r2[i] = rv;
+        acc = fma(rv.x, rv.x, acc);
+        acc = fma(rv.y, rv.y, acc);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const double rv = fma(-alpha, t[n - 1], r[n - 1]);
+        r[n - 1] = rv;
+        acc = fma(rv, rv, acc);
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(&st->rr_loc[s ^ 1], acc);
+}
+
+/* x += alpha p ; p = r + beta p ; decides convergence for the next iteration */
+__global__ void __launch_bounds__(BLAS1_THREADS)
+cg_update_xp_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi,
+                    const double *__restrict__ r, double *__restrict__ p, double *__restrict__ x)
+{
+    const Gate g = gate_read(&st->ctrl[cin], st);
+    const int s = g.iter & 1;
+    const double rr = multi ? st->rr[s] : st->rr_loc[s];
+    const double rrn = multi ? st->rr[s ^ 1] : st->rr_loc[s ^ 1];
+    const double pap = multi ? st->pap[s] : st->pap_loc[s];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        acgb200_ctrl c = st->ctrl[cin];
+        if (g.active) {
+            c.iter = g.iter + 1;
+            /* acg/cgcuda.c:1008-1012: test ||r|| < tol with the norm, strictly */
+            if (st->tol > 0.0 && sqrt(rrn) < st->tol) { c.done = 1; st->final_rr = rrn; }
+            st->pap_loc[s ^ 1] = 0.0;      /* accumulator of the next SpMV */
+        }
+        st->ctrl[cout] = c;
+    }
+    if (!g.active) return;
+    const double alpha = rr / pap;
+    const double beta = rrn / rr;
+    const int n2 = n >> 1;
+    const double2 *r2 = reinterpret_cast<const double2 *>(r);
+    double2 *p2 = reinterpret_cast<double2 *>(p);
+    double2 *x2 = reinterpret_cast<double2 *>(x);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+        const double2 rv = r2[i];
+        double2 pv = p2[i];
+        double2 xv = x2[i];
+        xv.x = fma(alpha, pv.x, xv.x);
+        xv.y = fma(alpha, pv.y, xv.y);
+        pv.x = fma(beta, pv.x, rv.x);
+        pv.y = fma(beta, pv.y, rv.y);
+        x2[i] = xv;
+        p2[i] = pv;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const double pv = p[n - 1];
+        x[n - 1] = fma(alpha, pv, x[n - 1]);
+        p[n - 1] = fma(beta, pv, r[n - 1]);
+    }
+}
+
+/* Pipelined CG: z=q+beta z; t=w+beta t; p=r+beta p; x+=alpha p; r-=alpha t;
+ * w-=alpha z (acg/cg-kernels-cuda.cu:201-214), plus gamma'=(r,r), delta'=(w,r)
+ * of the updated vectors for the next iteration. */
+__global__ void __launch_bounds__(BLAS1_THREADS)
+pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi,
+                  const double *__restrict__ q, double *__restrict__ z, double *__restrict__ w,
+                  double *__restrict__ t, double *__restrict__ p, double *__restrict__ r,
+                  double *__restrict__ x)
+{
+    __shared__ double red[BLAS1_THREADS / 32];
+    const Gate g = gate_read(&st->ctrl[cin], st);
+    const int s = g.iter & 1;
+    const double gamma = multi ? st->gd[s][0] : st->gd_loc[s][0];
+    const double delta = multi ? st->gd[s][1] : st->gd_loc[s][1];
+    const double gamma_prev = st->prev[s][0], alpha_prev = st->prev[s][1];
+    /* acg/cgcuda.c:1764-1772: the test precedes the update */
+    const bool conv = st->tol > 0.0 && sqrt(gamma) < st->tol;
+    const double beta = gamma / gamma_prev;
+    const double alpha = gamma / (delta - beta * gamma / alpha_prev);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        acgb200_ctrl c = st->ctrl[cin];
+        if (g.active) {
+            if (conv) { c.done = 1; st->final_rr = gamma; }
+            else { c.iter = g.iter + 1; st->prev[s ^ 1][0] = gamma; st->prev[s ^ 1][1] = alpha; }
+        }
+        st->ctrl[cout] = c;
+    }
+    if (!g.active || conv) return;
+    double g2 = 0.0, d2 = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double zv = fma(beta, z[i], q[i]);
+        const double tv = fma(beta, t[i], w[i]);
+        const double pv = fma(beta, p[i], r[i]);
+        const double rv = fma(-alpha, tv, r[i]);
+        const double wv = fma(-alpha, zv, w[i]);
+        z[i] = zv; t[i] = tv; p[i] = pv;
+        x[i] = fma(alpha, pv, x[i]);
+        r[i] = rv; w[i] = wv;
+        g2 = fma(rv, rv, g2);
+        d2 = fma(wv, rv, d2);
+    }
+    g2 = block_sum(g2, red);
+    d2 = block_sum(d2, red);
+    if (threadIdx.x == 0) {
+        atomicAdd(&st->gd_loc[s ^ 1][0], g2);
+        atomicAdd(&st->gd_loc[s ^ 1][1], d2);
+    }
+}
+
+__global__ void __launch_bounds__(BLAS1_THREADS)
+dot_kernel(int n, const double *__restrict__ x, const double *__restrict__ y, double *acc)
+{
+    __shared__ double red[BLAS1_THREADS / 32];
+    double v = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v = fma(x[i], y[i], v);
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) atomicAdd(acc, v);
+}
+
+__global__ void __launch_bounds__(BLAS1_THREADS)
+dot2_kernel(int n, const double *__restrict__ r, const double *__restrict__ w, double *acc2)
+{
+    __shared__ double red[BLAS1_THREADS / 32];
+    double g = 0.0, d = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double rv = r[i];
+        g = fma(rv, rv, g);
+        d = fma(w[i], rv, d);
+    }
+    g = block_sum(g, red);
+    d = block_sum(d, red);
+    if (threadIdx.x == 0) { atomicAdd(&acc2[0], g); atomicAdd(&acc2[1], d); }
+}
+
+__global__ void gather_kernel(int n, double *__restrict__ dst, const double *__restrict__ src, const int *__restrict__ idx)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[idx[i]];
+}
+
+__global__ void scatter_kernel(int n, const double *__restrict__ src, double *__restrict__ dst, const int *__restrict__ idx)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[idx[i]] = src[i];
+}
+
+/* ------------------------------------------------------------------------ */
+/* host-side launchers (C linkage)                                           */
+/* ------------------------------------------------------------------------ */
+
+static int g_num_sms = 0;
+
+extern "C" int acgb200_num_sms(void)
+{
+    if (g_num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0)
+            g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+static int blas1_grid(int n)
+{
+    const int per = BLAS1_THREADS * 2;
+    long long want = ((long long) n + per - 1) / per;
+    const long long cap = (long long) acgb200_num_sms() * 4;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return (int) want;
+}
+
+typedef void (*spmv_fn)(const SpmvParams);
+
+static spmv_fn spmv_variant(int G)
+{
+    switch (G) {
+    case 1: return spmv_tiles_kernel<1>;
+    case 2: return spmv_tiles_kernel<2>;
+    case 4: return spmv_tiles_kernel<4>;
+    case 8: return spmv_tiles_kernel<8>;
+    case 16: return spmv_tiles_kernel<16>;
+    default: return spmv_tiles_kernel<32>;
+    }
+}
+
+static inline int stage_slots(const acgb200_spmvplan *pl) { return (pl->nnz_cap + 8 + 3) & ~3; }
+static inline int stage_bytes(const acgb200_spmvplan *pl)
+{
+    const int sc = stage_slots(pl);
+    const int rc = (pl->rows_cap + 1 + 8 + 3) & ~3;
+    return (sc * 12 + rc * 4 + 127) & ~127;
+}
+
+extern "C" void acgb200_spmv_choose(acgb200_spmvplan *pl, int nrows, int64_t nnz, int64_t maxrowlen)
+{
+    const double avg = nrows > 0 ? (double) nnz / nrows : 0.0;
+    /* lanes per row: one thread per row up to ~48 nonzeros (gathers of
+     * neighbouring rows coalesce), then widen with the mean row length */
+    int G = 1;
+    if (avg > 48) G = 2;
+    if (avg > 96) G = 4;
+    if (avg > 192) G = 8;
+    if (avg > 384) G = 16;
+    if (avg > 768) G = 32;
+    /* one stage holds ~4k nonzeros (48 KiB) or 4 passes of rows, whichever is smaller */
+    int nnz_cap = 4096;
+    const int rpp = SPMV_THREADS / G;
+    int rows_cap = rpp;
+    if (avg > 0) {
+        int want = (int) (nnz_cap / avg);
+        want = (want / rpp) * rpp;
+        if (want < rpp) want = rpp;
+        if (want > 8 * rpp) want = 8 * rpp;
+        rows_cap = want;
+    }
+    /* a stencil row block should fit exactly: rows_cap full rows of the longest row */
+    if (maxrowlen > 0 && maxrowlen * rows_cap < 2 * (int64_t) nnz_cap && maxrowlen * rows_cap > nnz_cap)
+        nnz_cap = (int) (maxrowlen * rows_cap);
+    pl->nrows = nrows; pl->nnz = nnz;
+    pl->lanes_per_row = G; pl->rows_cap = rows_cap; pl->nnz_cap = nnz_cap;
+    pl->nstages = 2; pl->threads = SPMV_THREADS;
+    pl->long_chunks = 8;
+}
+
+extern "C" int acgb200_spmv_configure(acgb200_spmvplan *pl)
+{
+    spmv_fn fn = spmv_variant(pl->lanes_per_row);
+    pl->smem_bytes = stage_bytes(pl) * pl->nstages;
+    cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes);
+    if (err) return (int) err;
+    int per_sm = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SPMV_THREADS, pl->smem_bytes);
+    if (err) return (int) err;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long) acgb200_num_sms() * per_sm;
+    if (grid > pl->ntiles) grid = pl->ntiles;
+    if (grid < 1) grid = 1;
+    pl->grid = (int) grid;
+    return 0;
+}
+
+static double *g_long_scratch = NULL;
+static size_t g_long_scratch_len = 0;
+
+extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t stream)
+{
+    const acgb200_spmvplan *pl = a->plan;
+    if (pl->ntiles > 0 || a->ctrl_in) {   /* with no tiles the kernel still forwards the control word */
+        SpmvParams P;
+        P.tiles = pl->d_tiles; P.ntiles = pl->ntiles;
+        P.sc = stage_slots(pl); P.stage_bytes = stage_bytes(pl); P.nstages = pl->nstages;
+        P.rowptr = a->rowptr; P.colidx = a->colidx; P.a = a->a; P.x = a->x; P.y = a->y; P.b = a->b;
+        P.acc = a->acc; P.dotrows = a->dotrows; P.mode = a->mode;
+        P.ctrl_in = a->ctrl_in; P.ctrl_out = a->ctrl_out; P.st = a->st; P.housekeeping = a->housekeeping;
+        spmv_variant(pl->lanes_per_row)<<<pl->grid, SPMV_THREADS, pl->smem_bytes, stream>>>(P);
+        cudaError_t err = cudaGetLastError();
+        if (err) return (int) err;
+    }
+    if (pl->nlong > 0) {
+        const size_t need = (size_t) pl->nlong * pl->long_chunks;
+        if (need > g_long_scratch_len) {
+            cudaFree(g_long_scratch);
+            cudaError_t err = cudaMalloc((void **) &g_long_scratch, need * sizeof(double));
+            if (err) return (int) err;
+            g_long_scratch_len = need;
+        }
+        spmv_long_partial_kernel<<<pl->nlong * pl->long_chunks, 256, 0, stream>>>(
+            pl->nlong, pl->d_longrows, pl->long_chunks, a->rowptr, a->colidx, a->a, a->x, g_long_scratch,
+            a->ctrl_in, a->st);
+        spmv_long_finish_kernel<<<(pl->nlong + 127) / 128, 128, 0, stream>>>(
+            pl->nlong, pl->d_longrows, pl->long_chunks, g_long_scratch, a->x, a->y, a->b, a->acc,
+            a->dotrows, a->mode, a->ctrl_in, a->st);
+        cudaError_t err = cudaGetLastError();
+        if (err) return (int) err;
+    }
+    return 0;
+}
+
+extern "C" int acgb200_offdiag_launch(const acgb200_offdiagargs *a, cudaStream_t stream)
+{
+    if (a->nrows <= 0) return 0;
+    int grid = (a->nrows + 255) / 256;
+    const int cap = acgb200_num_sms() * 8;
+    if (grid > cap) grid = cap;
+    offdiag_kernel<<<grid, 256, 0, stream>>>(*a);
+    return (int) cudaGetLastError();
+}
+
+extern "C" int acgb200_cg_update_r(int n, acgb200_devstate *st, int cin, int cout, int multi,
+                                   const double *t, double *r, cudaStream_t stream)
+{
+    cg_update_r_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, st, cin, cout, multi, t, r);
+    return (int) cudaGetLastError();
+}
+
+extern "C" int acgb200_cg_update_xp(int n, acgb200_devstate *st, int cin, int cout, int multi,
+                                    const double *r, double *p, double *x, cudaStream_t stream)
+{
+    cg_update_xp_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, st, cin, cout, multi, r, p, x);
+    return (int) cudaGetLastError();
+}
+
+extern "C" int acgb200_pcg_update(int n, acgb200_devstate *st, int cin, int cout, int multi,
+                                  const double *q, double *z, double *w, double *t, double *p,
+                                  double *r, double *x, cudaStream_t stream)
+{
+    pcg_update_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, st, cin, cout, multi, q, z, w, t, p, r, x);
+    return (int) cudaGetLastError();
+}
+
+extern "C" int acgb200_dot(int n, const double *x, const double *y, double *acc, cudaStream_t stream)
+{
+    dot_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, x, y, acc);
+    return (int) cudaGetLastError();
+}
+
+extern "C" int acgb200_dot2(int n, const double *r, const double *w, double *acc2, cudaStream_t stream)
+{
+    dot2_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, r, w, acc2);
+    return (int) cudaGetLastError();
+}
+
+extern "C" int acgb200_gather(int n, double *dst, const double *src, const int *idx, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    gather_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, dst, src, idx);
+    return (int) cudaGetLastError();
+}
+
+extern "C" int acgb200_scatter(int n, const double *src, double *dst, const int *idx, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    scatter_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, src, dst, idx);
+    return (int) cudaGetLastError();
+}

@@ -1,0 +1,57 @@
+/*
+ * acgb200/ext.h -- entry points that have no counterpart in the reference's
+ * headers.  They exist for tests, bench.py and bindings (ctypes cannot size
+ * the ABI structs by itself); nothing in the reference driver needs them.
+ */
+#ifndef ACGB200_EXT_H
+#define ACGB200_EXT_H
+
+#include "acgb200/cgcuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* tunables: "profile" (0/1: CUDA-event timing of each kernel class, fills
+ * tgemv/taxpy like the reference's -DACG_ENABLE_PROFILING, acg/cgcuda.c:69-73),
+ * "check_every" (iterations between convergence polls), "spmv_lanes",
+ * "spmv_nnz_cap", "spmv_rows_cap", "spmv_stages" (SpMV tile plan overrides,
+ * read at acgsolvercuda_init).  Environment variables ACGB200_<KEY> set the
+ * same values at first use. */
+ACG_API int acgb200_set_option(const char *key, int value);
+
+/* y = A*x through the solver's device matrix: the standalone form of the
+ * kernel that replaces cusparseSpMV (acg/cgcuda.c:858).  x, y are HOST arrays
+ * of nownedrows doubles (unpartitioned matrices only).  If nrep > 0 the kernel
+ * is additionally launched nrep times between two CUDA events on its own
+ * stream and the mean duration is returned in milliseconds. */
+ACG_API int acgsolvercuda_spmv(struct acgsolvercuda *cg, const double *x, double *y, int nrep, double *ms_per_spmv);
+
+struct acgb200_info {
+    int spmv_lanes_per_row, spmv_rows_cap, spmv_nnz_cap, spmv_stages;
+    int spmv_ntiles, spmv_nlong, spmv_grid, spmv_smem_bytes;
+    int num_sms;
+    int last_launches;          /* kernels + NCCL launches enqueued by the last solve's timed region */
+    int last_spmv_count;        /* SpMV applications timed in the last solve (profile=1) */
+    double last_spmv_ms;        /* their total device time, CUDA events on the launching stream */
+};
+ACG_API int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info);
+
+/* struct sizes, for bindings: "acgsolvercuda", "acgsymcsrmatrix", "acgvector",
+ * "acgcomm", "acghalo"; returns 0 for unknown names */
+ACG_API size_t acgb200_sizeof(const char *name);
+/* 1 if this build was compiled with ACG_HAVE_MPI (struct acgcomm then has the
+ * MPI member), else 0 */
+ACG_API int acgb200_have_mpi(void);
+
+/* NCCL bootstrap for hosts without MPI (the reference driver broadcasts the
+ * unique id over MPI, cuda/acg-cuda.c:1104-1122; bench.py / tests broadcast
+ * these 128 bytes over torch.distributed instead) */
+ACG_API int acgb200_nccl_unique_id(void *id128);
+ACG_API int acgb200_comm_init_rank(struct acgcomm *comm, int nranks, const void *id128, int rank, int *ncclerrcode);
+ACG_API int acgb200_comm_destroy(struct acgcomm *comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
