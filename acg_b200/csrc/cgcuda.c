@@ -43,9 +43,9 @@ static struct {
     int profile;        /* record CUDA events around each kernel class */
     int check_every;    /* iterations between convergence polls */
     int spmv_lanes;     /* 0 = heuristic */
-    int spmv_nnz_cap, spmv_rows_cap, spmv_stages;
+    int spmv_nnz_cap, spmv_rows_cap, spmv_stages, spmv_threads, spmv_unroll;
     int loaded;
-} cfg = { 0, 8, 0, 0, 0, 0, 0 };
+} cfg = { 0, 8, 0, 0, 0, 0, 0, 0, 0 };
 
 static void cfg_load(void)
 {
@@ -58,6 +58,8 @@ static void cfg_load(void)
     if ((s = getenv("ACGB200_SPMV_NNZ_CAP"))) cfg.spmv_nnz_cap = atoi(s);
     if ((s = getenv("ACGB200_SPMV_ROWS_CAP"))) cfg.spmv_rows_cap = atoi(s);
     if ((s = getenv("ACGB200_SPMV_STAGES"))) cfg.spmv_stages = atoi(s);
+    if ((s = getenv("ACGB200_SPMV_THREADS"))) cfg.spmv_threads = atoi(s);
+    if ((s = getenv("ACGB200_SPMV_UNROLL"))) cfg.spmv_unroll = atoi(s);
     if (cfg.check_every < 1) cfg.check_every = 1;
 }
 
@@ -70,6 +72,8 @@ int acgb200_set_option(const char *key, int value)
     else if (!strcmp(key, "spmv_nnz_cap")) cfg.spmv_nnz_cap = value;
     else if (!strcmp(key, "spmv_rows_cap")) cfg.spmv_rows_cap = value;
     else if (!strcmp(key, "spmv_stages")) cfg.spmv_stages = value;
+    else if (!strcmp(key, "spmv_threads")) cfg.spmv_threads = value;
+    else if (!strcmp(key, "spmv_unroll")) cfg.spmv_unroll = value;
     else return ACG_ERR_INVALID_VALUE;
     return ACG_SUCCESS;
 }
@@ -312,6 +316,8 @@ int acgsolvercuda_init(
     if (cfg.spmv_nnz_cap > 0) pv->plan.nnz_cap = cfg.spmv_nnz_cap;
     if (cfg.spmv_rows_cap > 0) pv->plan.rows_cap = cfg.spmv_rows_cap;
     if (cfg.spmv_stages > 0) pv->plan.nstages = cfg.spmv_stages > 8 ? 8 : cfg.spmv_stages;
+    if (cfg.spmv_threads > 0) pv->plan.threads = cfg.spmv_threads;
+    if (cfg.spmv_unroll > 0) pv->plan.unroll = cfg.spmv_unroll;
     OK(build_tiles(&pv->plan, A->frowptr, errcode));
     KL(acgb200_spmv_configure(&pv->plan));
     return ACG_SUCCESS;

@@ -41,6 +41,7 @@ struct acgb200_spmvplan {
     int rows_cap, nnz_cap;           /* tile limits */
     int nstages;                     /* smem ring depth */
     int threads;                     /* CTA size */
+    int unroll;                      /* gathers in flight per lane */
     int ntiles;
     struct acgb200_tile *d_tiles;    /* [ntiles] */
     int nlong;                       /* rows with more than nnz_cap nonzeros */

@@ -89,6 +89,16 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
         :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(pol) : "memory");
 }
 
+/* gather of a vector entry through the read-only path.  volatile: the batch of
+ * gathers of one row stays a batch (the compiler may not sink individual loads
+ * down to their uses, which would serialise their latencies). */
+__device__ __forceinline__ double ld_x(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 /* ------------------------------------------------------------------------ */
 /* reductions                                                                */
 /* ------------------------------------------------------------------------ */
@@ -182,13 +192,23 @@ __device__ __forceinline__ void spmv_issue(
     bulk_g2s(rptr, P.rowptr + row_al, (uint32_t) nrp * 4u, bar, pol);
 }
 
-template <int G>
-__global__ void __launch_bounds__(SPMV_THREADS)
+/*
+ * G lanes per row, T threads per CTA, U gathers in flight per lane.  A tile of
+ * R rows is processed in ceil(R / (T/G)) passes; in a pass every G-lane group
+ * owns one row and walks it in batches of U*G nonzeros: all U column indices
+ * and values are read from shared memory first, then the U x-gathers are
+ * issued back to back, then the FMAs -- the only long-latency operation (the
+ * gather, an L1/L2 access) is thus U-deep per lane.  Slots past the end of the
+ * row multiply a zero value with x[row's first column], which is always a
+ * valid address.
+ */
+template <int G, int T, int U>
+__global__ void __launch_bounds__(T)
 spmv_tiles_kernel(const SpmvParams P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[SPMV_MAX_STAGES];
-    __shared__ double red[SPMV_THREADS / 32];
+    __shared__ double red[T / 32];
 
     const int tid = threadIdx.x;
     const Gate gate = gate_read(P.ctrl_in, P.st);
@@ -217,7 +237,7 @@ spmv_tiles_kernel(const SpmvParams P)
     }
     __syncthreads();
 
-    constexpr int RPP = SPMV_THREADS / G;      /* rows per pass */
+    constexpr int RPP = T / G;                 /* rows per pass */
     const int lane = tid % G;
     const int grp = tid / G;
     double dot = 0.0;
@@ -239,17 +259,23 @@ spmv_tiles_kernel(const SpmvParams P)
             if (lr < tl.nrows) {
                 const int kb = rp[lr] - tl.k_al;
                 const int ke = rp[lr + 1] - tl.k_al;
-                int k = kb + lane;
-                for (; k + 3 * G < ke; k += 4 * G) {
-                    const int c0 = cols[k], c1 = cols[k + G], c2 = cols[k + 2 * G], c3 = cols[k + 3 * G];
-                    const double x0 = __ldg(P.x + c0), x1 = __ldg(P.x + c1);
-                    const double x2 = __ldg(P.x + c2), x3 = __ldg(P.x + c3);
-                    sum = fma(vals[k], x0, sum);
-                    sum = fma(vals[k + G], x1, sum);
-                    sum = fma(vals[k + 2 * G], x2, sum);
-                    sum = fma(vals[k + 3 * G], x3, sum);
+                for (int k = kb + lane; k < ke; k += U * G) {
+                    int c[U];
+                    double v[U], xv[U];
+                    /* slots past the row end re-read its last entry and are
+                     * zeroed after the load: straight-line code, no predicated
+                     * loads, so all U gathers are issued before the first FMA */
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int kk = min(k + u * G, ke - 1);
+                        c[u] = cols[kk];
+                        v[u] = vals[kk];
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; u++) xv[u] = ld_x(P.x + c[u]);
+#pragma unroll
+                    for (int u = 0; u < U; u++) sum = fma((k + u * G < ke) ? v[u] : 0.0, xv[u], sum);
                 }
-                for (; k < ke; k += G) sum = fma(vals[k], __ldg(P.x + cols[k]), sum);
             }
             if (G > 1) sum = group_sum<G>(sum);
             if (lr < tl.nrows && lane == 0) {
@@ -544,16 +570,25 @@ static int blas1_grid(int n)
 
 typedef void (*spmv_fn)(const SpmvParams);
 
-static spmv_fn spmv_variant(int G)
+/* instantiated (lanes per row, threads per CTA) pairs; gathers in flight U=8 */
+#define SPMV_VARIANTS(X) \
+    X(1, 64) X(2, 64) X(4, 64) X(8, 128) X(1, 128) X(1, 256) X(2, 128) X(2, 256) X(2, 512) X(4, 128) X(4, 256) X(4, 512) \
+    X(8, 256) X(8, 512) X(16, 256) X(16, 512) X(32, 256) X(32, 512)
+
+static spmv_fn spmv_variant(int G, int T, int U)
 {
-    switch (G) {
-    case 1: return spmv_tiles_kernel<1>;
-    case 2: return spmv_tiles_kernel<2>;
-    case 4: return spmv_tiles_kernel<4>;
-    case 8: return spmv_tiles_kernel<8>;
-    case 16: return spmv_tiles_kernel<16>;
-    default: return spmv_tiles_kernel<32>;
-    }
+    if (U == 4 && G == 1 && T == 128) return spmv_tiles_kernel<1, 128, 4>;
+    if (U == 16 && G == 1 && T == 128) return spmv_tiles_kernel<1, 128, 16>;
+    if (U == 16 && G == 1 && T == 256) return spmv_tiles_kernel<1, 256, 16>;
+    if (U == 4 && G == 2 && T == 256) return spmv_tiles_kernel<2, 256, 4>;
+    if (U == 16 && G == 2 && T == 256) return spmv_tiles_kernel<2, 256, 16>;
+    if (U == 4 && G == 4 && T == 512) return spmv_tiles_kernel<4, 512, 4>;
+    if (U == 4 && G == 4 && T == 128) return spmv_tiles_kernel<4, 128, 4>;
+    if (U == 4 && G == 4 && T == 256) return spmv_tiles_kernel<4, 256, 4>;
+#define X(g, t) if (G == g && T == t) return spmv_tiles_kernel<g, t, 8>;
+    SPMV_VARIANTS(X)
+#undef X
+    return NULL;
 }
 
 static inline int stage_slots(const acgb200_spmvplan *pl) { return (pl->nnz_cap + 8 + 3) & ~3; }
@@ -564,45 +599,44 @@ static inline int stage_bytes(const acgb200_spmvplan *pl)
     return (sc * 12 + rc * 4 + 127) & ~127;
 }
 
+/*
+ * Tile-plan heuristic, from sweeps on B200 (profiles/r01_spmv_sweep.md).  The
+ * compute phase of a tile is a chain LDS(col) -> LDG(x) -> DFMA per nonzero and
+ * ptxas keeps only ~2 gathers in flight per thread, so throughput comes from
+ * resident warps: small stages (0.5-1k nonzeros, 6-11 KiB) let 10-18 CTAs of 128
+ * threads share an SM.  Deeper TMA rings lower the CTA count and lose.
+ *   lanes per row G : largest power of two with mean row length / G >= 4
+ *   rows per tile   : T / G   (one pass per tile)
+ *   nonzeros/tile   : rows * longest row for near-uniform rows (stencils),
+ *                     else twice the mean -- rows longer than that take the
+ *                     long-row path
+ */
 extern "C" void acgb200_spmv_choose(acgb200_spmvplan *pl, int nrows, int64_t nnz, int64_t maxrowlen)
 {
     const double avg = nrows > 0 ? (double) nnz / nrows : 0.0;
-    /* lanes per row: one thread per row up to ~48 nonzeros (gathers of
-     * neighbouring rows coalesce), then widen with the mean row length */
     int G = 1;
-    if (avg > 48) G = 2;
-    if (avg > 96) G = 4;
-    if (avg > 192) G = 8;
-    if (avg > 384) G = 16;
-    if (avg > 768) G = 32;
-    /* one stage holds ~4k nonzeros (48 KiB) or 4 passes of rows, whichever is smaller */
-    int nnz_cap = 4096;
-    const int rpp = SPMV_THREADS / G;
-    int rows_cap = rpp;
-    if (avg > 0) {
-        int want = (int) (nnz_cap / avg);
-        want = (want / rpp) * rpp;
-        if (want < rpp) want = rpp;
-        if (want > 8 * rpp) want = 8 * rpp;
-        rows_cap = want;
-    }
-    /* a stencil row block should fit exactly: rows_cap full rows of the longest row */
-    if (maxrowlen > 0 && maxrowlen * rows_cap < 2 * (int64_t) nnz_cap && maxrowlen * rows_cap > nnz_cap)
-        nnz_cap = (int) (maxrowlen * rows_cap);
+    while (G < 32 && avg / (2 * G) >= 4.0) G *= 2;
+    const int T = SPMV_THREADS;
+    const int rows_cap = T / G;
+    int64_t cap = (int64_t) (2.0 * avg * rows_cap) + 8;
+    if (maxrowlen > 0 && (double) maxrowlen <= 2.0 * avg + 8.0) cap = maxrowlen * rows_cap;
+    if (cap < 256) cap = 256;
+    if (cap > 6144) cap = 6144;
     pl->nrows = nrows; pl->nnz = nnz;
-    pl->lanes_per_row = G; pl->rows_cap = rows_cap; pl->nnz_cap = nnz_cap;
-    pl->nstages = 2; pl->threads = SPMV_THREADS;
+    pl->lanes_per_row = G; pl->rows_cap = rows_cap; pl->nnz_cap = (int) ((cap + 3) & ~(int64_t) 3);
+    pl->nstages = 2; pl->threads = T; pl->unroll = 8;
     pl->long_chunks = 8;
 }
 
 extern "C" int acgb200_spmv_configure(acgb200_spmvplan *pl)
 {
-    spmv_fn fn = spmv_variant(pl->lanes_per_row);
+    spmv_fn fn = spmv_variant(pl->lanes_per_row, pl->threads, pl->unroll);
+    if (!fn) return (int) cudaErrorInvalidConfiguration;
     pl->smem_bytes = stage_bytes(pl) * pl->nstages;
     cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes);
     if (err) return (int) err;
     int per_sm = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SPMV_THREADS, pl->smem_bytes);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, pl->threads, pl->smem_bytes);
     if (err) return (int) err;
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long) acgb200_num_sms() * per_sm;
@@ -625,7 +659,7 @@ extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t strea
         P.rowptr = a->rowptr; P.colidx = a->colidx; P.a = a->a; P.x = a->x; P.y = a->y; P.b = a->b;
         P.acc = a->acc; P.dotrows = a->dotrows; P.mode = a->mode;
         P.ctrl_in = a->ctrl_in; P.ctrl_out = a->ctrl_out; P.st = a->st; P.housekeeping = a->housekeeping;
-        spmv_variant(pl->lanes_per_row)<<<pl->grid, SPMV_THREADS, pl->smem_bytes, stream>>>(P);
+        spmv_variant(pl->lanes_per_row, pl->threads, pl->unroll)<<<pl->grid, pl->threads, pl->smem_bytes, stream>>>(P);
         cudaError_t err = cudaGetLastError();
         if (err) return (int) err;
     }
