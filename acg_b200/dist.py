@@ -1,0 +1,83 @@
+"""One-process-per-GPU plumbing for the distributed solve.
+
+The reference driver bootstraps NCCL over MPI (cuda/acg-cuda.c:1104-1122:
+rank 0 calls ncclGetUniqueId, MPI_Bcast, ncclCommInitRank) and lets rank 0
+partition the matrix and scatter the parts (:1516-1782).  This image has no
+MPI; the same steps run over ``torch.distributed`` (gloo for the CPU-side
+object broadcast, NCCL for the data path inside libacgb200):
+
+* ``init_process()``     -- rendezvous from the torchrun environment
+* ``nccl_comm()``        -- unique id from rank 0, broadcast, ``Comm.init_nccl``
+* ``local_part()``       -- every rank builds the (synthetic) matrix, partitions
+                            it with the same row->part map and keeps its part
+* ``block_partition()``  -- geometric px*py*pz row->part map for stencil grids
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def init_process(backend: str | None = None):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local % torch.cuda.device_count())
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group(backend or ("nccl" if torch.cuda.is_available() else "gloo"),
+                                rank=rank, world_size=world)
+    return rank, world, local
+
+
+def nccl_comm(rank: int, world: int):
+    """Communicator for libacgb200: a null comm for one process, else NCCL."""
+    from .api import Comm
+    if world == 1:
+        return Comm()
+    import torch.distributed as dist
+    box = [Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return Comm.init_nccl(world, rank, box[0])
+
+
+def block_partition(nx: int, ny: int, nz: int, px: int, py: int, pz: int) -> np.ndarray:
+    i = np.arange(nx * ny * nz, dtype=np.int64)
+    x, y, z = i % nx, (i // nx) % ny, i // (nx * ny)
+    return ((x * px // nx) + px * ((y * py // ny) + py * (z * pz // nz))).astype(np.int32)
+
+
+def grid_factors(nparts: int) -> tuple[int, int, int]:
+    """px*py*pz = nparts, as cubic as possible, larger factors on the slow axes."""
+    best = (1, 1, nparts)
+    for a in range(1, nparts + 1):
+        if nparts % a:
+            continue
+        for b in range(a, nparts // a + 1):
+            if (nparts // a) % b:
+                continue
+            c = nparts // a // b
+            if c >= b and (c - a) < (best[2] - best[0]):
+                best = (a, b, c)
+    return best
+
+
+def local_part(n, rows, cols, vals, rowparts, rank: int, world: int, eps: float = 0.0):
+    """This rank's submatrix (full storage initialised), as the reference's
+    rank 0 would have scattered it (acg/symcsrmatrix.c:685 + :1238)."""
+    from .api import SymCsrMatrix
+    A = SymCsrMatrix.init_real_double(n, rows, cols, vals)
+    if world == 1:
+        return A.dsymv_init(eps)
+    parts = A.partition(world, rowparts)
+    A.free()
+    mine = parts[rank]
+    for p, m in enumerate(parts):
+        if p != rank:
+            m.free()
+    return mine.dsymv_init(eps)

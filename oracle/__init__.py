@@ -130,6 +130,11 @@ class Ref:
         L.ref_cg.argtypes = [C.c_int, C.c_int64, _i32, _i32, _f64, C.c_double, _f64, _f64, C.c_int,
                              C.c_double, C.c_double, _f64]
         L.ref_num_threads.restype = C.c_int
+        L.ref_setup.restype = C.c_void_p
+        L.ref_setup.argtypes = [C.c_int, C.c_int64, _i32, _i32, _f64, C.c_double]
+        L.ref_solve.argtypes = [C.c_void_p, _f64, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, _f64]
+        L.ref_free.restype = None
+        L.ref_free.argtypes = [C.c_void_p]
         vp = C.c_void_p
         L.ref_partition_part.argtypes = [C.c_int, C.c_int64, _i32, _i32, _f64, C.c_int, _i32, C.c_int,
                                          _i64] + [vp] * 13
@@ -166,6 +171,23 @@ class Ref:
                                  maxits, atol, rtol, out)
         return dict(status=status, niterations=int(out[0]), bnrm2=out[1], r0nrm2=out[2], rnrm2=out[3],
                     tsolve=out[4], tgemv=out[5], x=x)
+
+    def setup(self, n, rows, cols, vals, eps=0.0):
+        """Persistent problem handle (reference setup path run once)."""
+        h = self.lib.ref_setup(n, len(vals), rows, cols, vals, eps)
+        assert h, "ref_setup failed"
+        return h
+
+    def solve(self, handle, b, maxits=100, atol=0.0, rtol=0.0, want_x=False):
+        out = np.zeros(6)
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.zeros(len(b)) if want_x else None
+        status = self.lib.ref_solve(handle, b, None, x.ctypes.data if want_x else None, maxits, atol, rtol, out)
+        return dict(status=status, niterations=int(out[0]), bnrm2=out[1], r0nrm2=out[2], rnrm2=out[3],
+                    tsolve=out[4], tgemv=out[5], x=x)
+
+    def free(self, handle):
+        self.lib.ref_free(handle)
 
     def partition_part(self, n, rows, cols, vals, nparts, rowparts, p):
         """Local structure of part p as the reference builds it (see ref_shim.c)."""

@@ -149,6 +149,53 @@ int ref_cg(int n, int64_t nnz, const int *row, const int *col, const double *a,
 }
 
 /*
+ * Persistent variant for benchmarking: set the problem up once (the
+ * reference's COO -> packed -> full-storage path, acg/symcsrmatrix.c:66,:760),
+ * then time acgsolver_solve alone as often as needed.
+ */
+struct ref_problem {
+    struct acgsymcsrmatrix A;
+    struct acgsolver cg;
+    struct acgvector b, x;
+};
+
+void *ref_setup(int n, int64_t nnz, const int *row, const int *col, const double *a, double eps)
+{
+    struct ref_problem *P = calloc(1, sizeof(*P));
+    if (!P) return NULL;
+    if (build(&P->A, n, nnz, row, col, a, eps)) { free(P); return NULL; }
+    if (wrapvec(&P->A, &P->b, NULL) || wrapvec(&P->A, &P->x, NULL)) return NULL;
+    if (acgsolver_init(&P->cg, &P->A)) return NULL;
+    return P;
+}
+
+/* out[0..5] as in ref_cg; x0 may be NULL (zero initial guess) */
+int ref_solve(void *handle, const double *b, const double *x0, double *xout, int maxits,
+              double residualatol, double residualrtol, double *out)
+{
+    struct ref_problem *P = handle;
+    const size_t n = (size_t) P->A.nrows;
+    memcpy(P->b.x, b, n * sizeof(double));
+    if (x0) memcpy(P->x.x, x0, n * sizeof(double)); else memset(P->x.x, 0, n * sizeof(double));
+    const double tsolve0 = P->cg.tsolve, tgemv0 = P->cg.tgemv;
+    int err = acgsolver_solve(&P->cg, &P->A, &P->b, &P->x, maxits, 0.0, 0.0, residualatol, residualrtol);
+    if (xout) memcpy(xout, P->x.x, n * sizeof(double));
+    out[0] = P->cg.niterations; out[1] = P->cg.bnrm2; out[2] = P->cg.r0nrm2;
+    out[3] = P->cg.rnrm2; out[4] = P->cg.tsolve - tsolve0; out[5] = P->cg.tgemv - tgemv0;
+    return err;
+}
+
+void ref_free(void *handle)
+{
+    struct ref_problem *P = handle;
+    if (!P) return;
+    acgsolver_free(&P->cg);
+    acgvector_free(&P->b); acgvector_free(&P->x);
+    acgsymcsrmatrix_free(&P->A);
+    free(P);
+}
+
+/*
  * Partition the matrix with the reference's acgsymcsrmatrix_partition
  * (acg/symcsrmatrix.c:685) for a given row->part map and report, for part
  * p, the sizes and index arrays that define the local ordering and the

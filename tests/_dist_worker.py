@@ -1,0 +1,166 @@
+"""Worker for the multi-process tests (launched by torch.distributed.run).
+
+mode cpu : gloo only.  Exercises the N>1 host logic end to end: every rank
+           partitions the same synthetic matrix, keeps its part, exchanges
+           ghost values with its neighbours following its acghalo pattern
+           (gloo send/recv) and runs a distributed CG whose local arithmetic is
+           numpy (test-only code); rank 0 compares with the single-rank oracle.
+mode gpu : the product path: NCCL communicator inside libacgb200, device SpMV /
+           halo / allreduce; rank 0 compares with the single-rank oracle.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import acg_b200 as ab                      # noqa: E402
+from acg_b200 import dist as abdist        # noqa: E402
+from acg_b200 import matgen as mg          # noqa: E402
+from oracle import Oracle                  # noqa: E402
+
+
+def halo_exchange_gloo(h, xl):
+    reqs = []
+    recvbufs = []
+    for j, q in enumerate(h["senders"]):
+        buf = torch.empty(int(h["recvcounts"][j]), dtype=torch.float64)
+        recvbufs.append(buf)
+        reqs.append(dist.irecv(buf, src=int(q)))
+    for i, q in enumerate(h["recipients"]):
+        seg = torch.from_numpy(xl[h["sendbufidx"][h["sdispls"][i]:h["sdispls"][i] + h["sendcounts"][i]]].copy())
+        reqs.append(dist.isend(seg, dst=int(q)))
+    for r in reqs:
+        r.wait()
+    for j in range(len(h["senders"])):
+        idx = h["recvbufidx"][h["rdispls"][j]:h["rdispls"][j] + h["recvcounts"][j]]
+        xl[idx] = recvbufs[j].numpy()
+
+
+def local_matvec(m, h, xl):
+    halo_exchange_gloo(h, xl)
+    no = m.c.nownedrows
+    y = np.zeros(no)
+    rp, ci, va = m.frowptr, m.fcolidx, m.fa
+    y[:] = np.add.reduceat(va * xl[ci], rp[:-1][:no])[:no] if len(va) else 0.0
+    empty = np.diff(rp[:no + 1]) == 0
+    y[empty] = 0.0
+    b0 = m.c.borderrowoffset
+    orp = m.orowptr
+    for i in range(m.c.nborderrows):
+        k0, k1 = orp[i], orp[i + 1]
+        if k1 > k0:
+            y[b0 + i] += m.oa[k0:k1] @ xl[b0 + m.ocolidx[k0:k1]]
+    return y
+
+
+def allsum(v):
+    t = torch.tensor([v], dtype=torch.float64)
+    dist.all_reduce(t)
+    return float(t[0])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="cpu")
+    ap.add_argument("--matrix", default="27pt")
+    ap.add_argument("--size", type=int, default=10)
+    ap.add_argument("--partition", default="block")
+    args = ap.parse_args()
+    rank, world, _ = abdist.init_process(backend="gloo")
+    N = args.size
+    if args.matrix == "27pt":
+        n, r, c, v = mg.stencil3d_27pt(N)
+    elif args.matrix == "7pt":
+        n, r, c, v = mg.laplace3d_7pt(N)
+    else:
+        n, r, c, v = mg.rmat_spd(N, 12 * N, seed=4)
+    if args.partition == "block" and args.matrix != "rmat":
+        rowparts = abdist.block_partition(N, N, N, *abdist.grid_factors(world))
+    elif args.partition == "random":
+        rowparts = np.random.default_rng(3).integers(0, world, n).astype(np.int32)
+    else:
+        rowparts = (np.arange(n) * world // n).astype(np.int32)
+    m = abdist.local_part(n, r, c, v, rowparts, rank, world)
+    no = m.c.nownedrows
+    rng = np.random.default_rng(11)
+    bglob = rng.standard_normal(n)
+    maxits, rtol = 200, 1e-9
+    failures = []
+
+    if args.mode == "cpu":
+        h = m.halo()
+        b = bglob[m.nzrows[:no]]
+        x = np.zeros(m.c.nprows)
+        rvec = b.copy()
+        p = np.zeros(m.c.nprows); p[:no] = rvec
+        rr = allsum(rvec @ rvec); r0 = np.sqrt(rr)
+        its = 0
+        for k in range(maxits):
+            t = local_matvec(m, h, p)
+            alpha = rr / allsum(p[:no] @ t)
+            x[:no] += alpha * p[:no]
+            rvec -= alpha * t
+            rr_new = allsum(rvec @ rvec)
+            its += 1
+            if np.sqrt(rr_new) < rtol * r0:
+                break
+            p[:no] = rvec + (rr_new / rr) * p[:no]
+            rr = rr_new
+        xloc, niter = x[:no], its
+        methods = [("cpu-classic", xloc, niter)]
+    else:
+        comm = abdist.nccl_comm(rank, world)
+        assert comm.size() == world and comm.rank() == rank
+        cg = ab.SolverCuda(m, comm)
+        b = m.vector(); b.x[:no] = bglob[m.nzrows[:no]]
+        methods = []
+        for meth in ("solvempi", "solve_pipelined"):
+            x = m.vector()
+            code = getattr(cg, meth)(b, x, maxits=maxits, residualrtol=rtol, warmup=2)
+            if code != 0:
+                failures.append(f"{meth}: status {code}")
+            methods.append((meth, x.x[:no].copy(), cg.c.niterations))
+        # fixed iteration count, tolerances off
+        x = m.vector()
+        code = cg.solvempi(b, x, maxits=7)
+        methods.append(("solvempi-7its", x.x[:no].copy(), cg.c.niterations))
+        cg.free(); comm.destroy()
+
+    # gather solutions on rank 0 and compare with the single-rank oracle
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (m.nzrows[:no].copy(), [(name, xl, it) for name, xl, it in methods]))
+    if rank == 0:
+        O = Oracle()
+        csr = O.full_csr(n, r, c, v)
+        for mi, (name, _, _) in enumerate(methods):
+            xg = np.zeros(n)
+            its = set()
+            for rows, ms in gathered:
+                xg[rows] = ms[mi][1]
+                its.add(ms[mi][2])
+            if name.endswith("7its"):
+                want = O.cg(csr, bglob, maxits=7)
+            elif name == "solve_pipelined":
+                want = O.cg_pipelined(csr, bglob, maxits=maxits, rtol=rtol)
+            else:
+                want = O.cg(csr, bglob, maxits=maxits, rtol=rtol)
+            err = np.abs(xg - want["x"]).max() / np.abs(want["x"]).max()
+            ok = its == {want["niterations"]} and err < 1e-9
+            print(f"[{args.mode} world={world} {args.matrix}-{N} {args.partition}] {name}: its {sorted(its)} oracle {want['niterations']} xerr {err:.2e} {'OK' if ok else 'FAIL'}", flush=True)
+            if not ok:
+                failures.append(name)
+    flag = torch.tensor([len(failures)], dtype=torch.int64)
+    dist.all_reduce(flag)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(1 if int(flag[0]) else 0)
+
+
+if __name__ == "__main__":
+    main()

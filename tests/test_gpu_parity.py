@@ -1,0 +1,192 @@
+"""Parity of the CUDA path with the oracle, through the C-ABI (B200, -m gpu)."""
+import os
+
+import numpy as np
+import pytest
+
+from acg_b200 import matgen as mg
+from conftest import GOLDEN, load_golden
+
+pytestmark = pytest.mark.gpu
+
+# FP64 tolerances.  The device sums each row and each dot product in a different
+# order than the CPU (and dot products through atomics, so not even run-to-run
+# bitwise): entries of A*x agree to a few ulp of sum|a_ij x_j|; CG iterates agree
+# with the oracle to 1e-10 relative in the residual norm (north-star) as long as
+# the iteration count is O(100) and the matrix is well conditioned.
+SPMV_RTOL = 1e-13
+RES_RTOL = 1e-10
+
+
+def _solver(ab, n, r, c, v):
+    A = ab.SymCsrMatrix.init_real_double(n, r, c, v).dsymv_init(0.0)
+    return A, ab.SolverCuda(A)
+
+
+CASES = [
+    ("27pt-12", lambda: mg.stencil3d_27pt(12)),
+    ("27pt-aniso", lambda: mg.stencil3d_27pt(9, 40, 17)),
+    ("7pt-31", lambda: mg.laplace3d_7pt(31, 17, 23)),
+    ("1d5pt", lambda: mg.poisson1d_5pt(20000)),
+    ("rand-dense-rows", lambda: mg.random_spd(400, 0.5, 2)),      # ~200 nnz/row: 16-lane groups
+    ("rmat-longrows", lambda: mg.rmat_spd(30000, 600000, seed=8)),  # power-law: long-row path
+    ("n1", lambda: mg.poisson1d_3pt(1)),
+    ("n3", lambda: mg.poisson1d_3pt(3)),
+]
+
+
+@pytest.mark.parametrize("name,gen", CASES, ids=[c[0] for c in CASES])
+def test_spmv_matches_oracle(name, gen, ab, oracle):
+    n, r, c, v = gen()
+    A, cg = _solver(ab, n, r, c, v)
+    csr = (A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy())
+    x = np.random.default_rng(1).standard_normal(n)
+    y, _ = cg.spmv(x)
+    want = oracle.dsymv(csr, 1.0, x, 0.0, np.zeros(n))
+    scale = oracle.dsymv((csr[0], csr[1], np.abs(csr[2])), 1.0, np.abs(x), 0.0, np.zeros(n))
+    assert np.all(np.abs(y - want) <= SPMV_RTOL * scale + 1e-300)
+    if name == "rmat-longrows":
+        assert cg.info()["spmv_nlong"] > 0
+    cg.free()
+
+
+@pytest.mark.parametrize("method", ["solvempi", "solve_pipelined"])
+@pytest.mark.parametrize("name,gen", CASES[:3] + CASES[4:], ids=[c[0] for c in CASES[:3] + CASES[4:]])
+def test_cg_matches_oracle(name, gen, method, ab, oracle):
+    n, r, c, v = gen()
+    A, cg = _solver(ab, n, r, c, v)
+    csr = (A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy())
+    b = A.vector()
+    b.x[:] = np.random.default_rng(5).standard_normal(n)
+    want = (oracle.cg if method == "solvempi" else oracle.cg_pipelined)(csr, b.x, maxits=300, rtol=1e-9, history=True)
+    x = A.vector()
+    code = getattr(cg, method)(b, x, maxits=300, residualrtol=1e-9, warmup=1)
+    assert code == want["status"] == 0
+    assert cg.c.niterations == want["niterations"]
+    assert cg.c.bnrm2 == pytest.approx(want["bnrm2"], rel=1e-14)
+    assert cg.c.r0nrm2 == pytest.approx(want["r0nrm2"], rel=1e-14)
+    assert cg.c.rnrm2 / cg.c.r0nrm2 == pytest.approx(want["rnrm2"] / want["r0nrm2"], rel=1e-6, abs=RES_RTOL)
+    assert np.abs(x.x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
+    cg.free()
+
+
+@pytest.mark.parametrize("method", ["solvempi", "solve_pipelined"])
+def test_residual_history_fixed_iterations(method, ab, oracle):
+    """Same residual after k iterations for every k (tolerances off)."""
+    n, r, c, v = mg.stencil3d_27pt(20)
+    A, cg = _solver(ab, n, r, c, v)
+    csr = (A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy())
+    b = A.vector(); b.x[:] = 1.0
+    orc = oracle.cg if method == "solvempi" else oracle.cg_pipelined
+    hist = orc(csr, b.x, maxits=40, history=True)["rnrm2hist"]
+    for k in (1, 2, 3, 8, 25, 40):
+        x = A.vector()
+        assert getattr(cg, method)(b, x, maxits=k) == 0
+        assert cg.c.niterations == k
+        # classic: ||r_k||; pipelined reports the last tested iterate, ||r_{k-1}||
+        want = hist[k] if method == "solvempi" else hist[k - 1]
+        assert cg.c.rnrm2 == pytest.approx(want, rel=1e-9)
+    cg.free()
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_vectors(path, ab):
+    """Fixtures produced by the reference's CPU solver alone (tools/make_golden.py)."""
+    g = load_golden(path)
+    n = int(g["n"])
+    A, cg = _solver(ab, n, g["rows"], g["cols"], g["vals"])
+    assert np.array_equal(A.frowptr, g["frowptr"]) and np.array_equal(A.fcolidx, g["fcolidx"]) and np.array_equal(A.fa, g["fa"])
+    y, _ = cg.spmv(g["xs"])
+    assert np.allclose(y, g["y"], rtol=1e-12, atol=1e-12 * np.abs(g["y"]).max())
+    b = A.vector(); b.x[:] = g["b"]
+    x = A.vector()
+    code = cg.solvempi(b, x, maxits=int(g["maxits"]), residualrtol=float(g["rtol"]))
+    assert code == int(g["status"])
+    assert cg.c.niterations == int(g["niterations"])
+    assert cg.c.bnrm2 == pytest.approx(float(g["bnrm2"]), rel=1e-14)
+    assert cg.c.r0nrm2 == pytest.approx(float(g["r0nrm2"]), rel=1e-13)
+    assert cg.c.rnrm2 == pytest.approx(float(g["rnrm2"]), rel=1e-6, abs=RES_RTOL * float(g["r0nrm2"]))
+    assert np.abs(x.x - g["x"]).max() <= 1e-9 * np.abs(g["x"]).max()
+    cg.free()
+
+
+def test_interface_behaviour(ab):
+    """Return codes of acg/cgcuda.c: :424 (diff tolerances), :1099-1107, and the
+    NVSHMEM-only entry points (acg/cg-kernels-cuda.cu:1012)."""
+    n, r, c, v = mg.stencil3d_27pt(8)
+    A, cg = _solver(ab, n, r, c, v)
+    b = A.vector(); b.x[:] = 1.0
+    x = A.vector()
+    assert cg.solvempi(b, x, maxits=0) == 0 and cg.c.niterations == 0 and np.all(x.x == 0)
+    assert cg.solvempi(b, x, maxits=2, residualrtol=1e-30) == 39          # ACG_ERR_NOT_CONVERGED
+    assert cg.c.niterations == 2
+    with pytest.raises(ab.AcgError) as e:
+        cg.solvempi(b, x, maxits=5, diffatol=1e-3)
+    assert e.value.code == 26                                             # ACG_ERR_NOT_SUPPORTED
+    with pytest.raises(ab.AcgError) as e:
+        cg.solve_device(b, x)
+    assert e.value.code == 16                                             # ACG_ERR_NVSHMEM_NOT_SUPPORTED
+    # already-converged initial guess: zero iterations, success
+    xs = A.vector(); xs.x[:] = np.random.default_rng(0).standard_normal(n)
+    bb = A.vector(); bb.x[:], _ = cg.spmv(xs.x)
+    assert cg.solvempi(bb, xs, maxits=10, residualatol=1e-6) == 0 and cg.c.niterations == 0
+    assert cg.c.nsolves == 4 and cg.c.ntotaliterations == 2
+    rep = cg.report()
+    assert "total solver time:" in rep and "iterations: 0" in rep and "gemv:" in rep
+    cg.free()
+
+
+def test_eps_shift_and_reuse(ab, oracle):
+    """--epsilon (acg/symcsrmatrix.c:796): diagonal shift; one solver, many solves."""
+    n, r, c, v = mg.laplace3d_7pt(12)
+    A = ab.SymCsrMatrix.init_real_double(n, r, c, v).dsymv_init(0.5)
+    csr = oracle.full_csr(n, r, c, v, eps=0.5)
+    cg = ab.SolverCuda(A)
+    for seed in range(3):
+        b = A.vector(); b.x[:] = np.random.default_rng(seed).standard_normal(n)
+        x = A.vector()
+        want = oracle.cg(csr, b.x, maxits=100, rtol=1e-10)
+        assert cg.solvempi(b, x, maxits=100, residualrtol=1e-10) == 0
+        assert cg.c.niterations == want["niterations"]
+        assert np.abs(x.x - want["x"]).max() <= 1e-10 * np.abs(want["x"]).max()
+    cg.free()
+
+
+@pytest.mark.parametrize("kind", ["27pt-224", "7pt-256"])
+def test_full_size_properties(kind, ab):
+    """BASELINE.json's full sizes, through size-independent properties: the
+    manufactured solution A*1 (row sums are known in closed form for the
+    stencils), linearity and symmetry of the product, and a CG residual check
+    recomputed from x."""
+    if kind == "27pt-224":
+        N = 224
+        n, r, c, v = mg.stencil3d_27pt(N)
+    else:
+        N = 256
+        n, r, c, v = mg.laplace3d_7pt(N)
+    A, cg = _solver(ab, n, r, c, v)
+    del r, c, v
+    nnz = A.c.fnpnzs
+    assert nnz == ((3 * N - 2) ** 3 if kind == "27pt-224" else 7 * N ** 3 - 6 * N ** 2)
+    ones = np.ones(n)
+    y1, _ = cg.spmv(ones)
+    # row sum = diag - (#neighbours): 26-(deg-1) resp. 6-(deg-1); deg from the row pointer
+    deg = np.diff(A.frowptr)
+    diag = 26.0 if kind == "27pt-224" else 6.0
+    assert np.array_equal(y1, diag - (deg - 1))
+    rng = np.random.default_rng(7)
+    u, w = rng.standard_normal(n), rng.standard_normal(n)
+    yu, _ = cg.spmv(u); yw, _ = cg.spmv(w); yuw, _ = cg.spmv(u + 2.0 * w)
+    assert np.abs(yuw - (yu + 2.0 * yw)).max() <= 1e-12 * np.abs(yuw).max()
+    assert abs(w @ yu - u @ yw) <= 1e-11 * abs(w @ yu)
+    b = A.vector(); b.x[:] = y1            # exact solution: all ones
+    for method in ("solvempi", "solve_pipelined"):
+        x = A.vector()
+        code = getattr(cg, method)(b, x, maxits=60, residualrtol=1e-8)
+        ax, _ = cg.spmv(x.x)
+        true_res = np.linalg.norm(b.x - ax)
+        assert code == 0 and cg.c.niterations < 60
+        assert true_res <= 1.5 * 1e-8 * cg.c.r0nrm2
+        assert true_res == pytest.approx(cg.c.rnrm2, rel=1e-3)
+        assert np.abs(x.x - 1.0).max() < 1e-6
+    cg.free()

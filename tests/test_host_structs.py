@@ -1,0 +1,144 @@
+"""Host-side data structures of libacgb200 (no GPU): packed/full storage,
+row partition, halo pattern.  Checked against the reference build where it is
+available and against the invariants of SURVEY.md §8(c) KAT-5 everywhere."""
+import numpy as np
+import pytest
+
+from acg_b200 import matgen as mg
+
+GENS = [
+    ("27pt", lambda: mg.stencil3d_27pt(7)),
+    ("7pt", lambda: mg.laplace3d_7pt(5, 6, 7)),
+    ("rand", lambda: mg.random_spd(120, 0.15, 1)),
+    ("rmat", lambda: mg.rmat_spd(500, 4000, seed=5)),
+    ("1d5", lambda: mg.poisson1d_5pt(300)),
+]
+
+
+def _parts(kind, n, nparts):
+    if kind == "slab":
+        return (np.arange(n) * nparts // n).astype(np.int32)
+    if kind == "cyclic":
+        return (np.arange(n) % nparts).astype(np.int32)
+    return np.random.default_rng(9).integers(0, nparts, n).astype(np.int32)
+
+
+@pytest.mark.parametrize("name,gen", GENS, ids=[g[0] for g in GENS])
+def test_full_storage_matches_reference(name, gen, ab, ref):
+    n, r, c, v = gen()
+    A = ab.SymCsrMatrix.init_real_double(n, r, c, v).dsymv_init(0.25)
+    rp, ci, va = ref.full_csr(n, r, c, v, eps=0.25)
+    assert np.array_equal(A.frowptr, rp) and np.array_equal(A.fcolidx, ci) and np.array_equal(A.fa, va)
+    assert A.c.nownedrows == n and A.c.nghostrows == 0 and A.c.onpnzs == 0
+
+
+def test_unsorted_and_one_based_input(ab, oracle):
+    n, r, c, v = mg.stencil3d_27pt(5)
+    perm = np.random.default_rng(3).permutation(len(v))
+    A = ab.SymCsrMatrix.init_real_double(n, r[perm] + 1, c[perm] + 1, v[perm], idxbase=1).dsymv_init(0.0)
+    rp, ci, va = oracle.full_csr(n, np.ascontiguousarray(r[perm]), np.ascontiguousarray(c[perm]), np.ascontiguousarray(v[perm]))
+    assert np.array_equal(A.frowptr, rp) and np.array_equal(A.fcolidx - 1, ci) and np.array_equal(A.fa, va)
+    with pytest.raises(ab.AcgError) as e:
+        ab.SymCsrMatrix.init_real_double(n, r, c + n, v)
+    assert e.value.code == 31   # ACG_ERR_INDEX_OUT_OF_BOUNDS
+
+
+@pytest.mark.parametrize("name,gen", GENS, ids=[g[0] for g in GENS])
+@pytest.mark.parametrize("kind,nparts", [("slab", 3), ("cyclic", 2), ("random", 5)])
+def test_partition_matches_reference(name, gen, kind, nparts, ab, ref):
+    n, r, c, v = gen()
+    A = ab.SymCsrMatrix.init_real_double(n, r, c, v)
+    rowparts = _parts(kind, n, nparts)
+    parts = A.partition(nparts, rowparts)
+    for p, m in enumerate(parts):
+        m.dsymv_init(0.0)
+        want = ref.partition_part(n, r, c, v, nparts, rowparts, p)
+        for k in ("nprows", "nownedrows", "ninnerrows", "nborderrows", "nghostrows"):
+            assert getattr(m.c, k) == want[k], k
+        assert np.array_equal(m.nzrows, want["nzrows"])
+        h = m.halo()
+        for k in ("recipients", "sendcounts", "sendbufidx", "senders", "recvcounts", "recvbufidx"):
+            assert np.array_equal(h[k], want[k]), k
+        for k in ("frowptr", "orowptr", "ocolidx", "oa"):
+            assert np.array_equal(getattr(m, k), want[k]), k
+        # order of entries inside a full row may legitimately differ; compare rows as sets
+        for i in range(m.c.nownedrows):
+            a = sorted(zip(m.fcolidx[m.frowptr[i]:m.frowptr[i + 1]], m.fa[m.frowptr[i]:m.frowptr[i + 1]]))
+            b = sorted(zip(want["fcolidx"][want["frowptr"][i]:want["frowptr"][i + 1]], want["fa"][want["frowptr"][i]:want["frowptr"][i + 1]]))
+            assert a == b
+
+
+@pytest.mark.parametrize("kind,nparts", [("slab", 4), ("random", 3)])
+def test_partition_invariants_and_distributed_product(kind, nparts, ab, oracle):
+    """KAT-5 plus an end-to-end check that the partitioned blocks and the halo
+    pattern reproduce y = A x (host arithmetic in numpy, test-only)."""
+    n, r, c, v = mg.stencil3d_27pt(6, 5, 7)
+    A = ab.SymCsrMatrix.init_real_double(n, r, c, v).dsymv_init(0.0)
+    csr = (A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy())
+    x = np.random.default_rng(0).standard_normal(n)
+    ywant = oracle.dsymv(csr, 1.0, x, 0.0, np.zeros(n))
+    rowparts = _parts(kind, n, nparts)
+    parts = A.partition(nparts, rowparts)
+    for m in parts:
+        m.dsymv_init(0.0)
+    assert sum(m.c.nownedrows for m in parts) == n
+    halos = [m.halo() for m in parts]
+    xloc = []
+    for p, m in enumerate(parts):
+        assert m.c.borderrowoffset == m.c.ninnerrows and m.c.ghostrowoffset == m.c.nownedrows
+        assert np.all(rowparts[m.nzrows[:m.c.nownedrows]] == p)
+        assert np.all(rowparts[m.nzrows[m.c.nownedrows:]] != p)
+        h = halos[p]
+        assert np.array_equal(h["recvbufidx"], m.c.ghostrowoffset + np.arange(m.c.nghostrows))
+        assert np.all((h["sendbufidx"] >= m.c.borderrowoffset) & (h["sendbufidx"] < m.c.ghostrowoffset))
+        assert np.all(m.fcolidx < m.c.ghostrowoffset)            # local block never touches ghosts
+        xl = np.zeros(m.c.nprows)
+        xl[:m.c.nownedrows] = x[m.nzrows[:m.c.nownedrows]]
+        xloc.append(xl)
+    # halo exchange "by hand": what p sends to q lands in q's segment for sender p
+    for p in range(nparts):
+        hp = halos[p]
+        for i, q in enumerate(hp["recipients"]):
+            seg = xloc[p][hp["sendbufidx"][hp["sdispls"][i]:hp["sdispls"][i] + hp["sendcounts"][i]]]
+            hq = halos[q]
+            j = list(hq["senders"]).index(p)
+            assert hq["recvcounts"][j] == len(seg)
+            xloc[q][hq["recvbufidx"][hq["rdispls"][j]:hq["rdispls"][j] + len(seg)]] = seg
+    y = np.zeros(n)
+    for p, m in enumerate(parts):
+        assert np.array_equal(xloc[p][m.c.nownedrows:], x[m.nzrows[m.c.nownedrows:]])
+        yl = np.zeros(m.c.nownedrows)
+        for i in range(m.c.nownedrows):
+            k0, k1 = m.frowptr[i], m.frowptr[i + 1]
+            yl[i] = m.fa[k0:k1] @ xloc[p][m.fcolidx[k0:k1]]
+        b0 = m.c.borderrowoffset
+        for i in range(m.c.nborderrows):
+            k0, k1 = m.orowptr[i], m.orowptr[i + 1]
+            yl[b0 + i] += m.oa[k0:k1] @ xloc[p][b0 + m.ocolidx[k0:k1]]
+        y[m.nzrows[:m.c.nownedrows]] = yl
+    assert np.allclose(y, ywant, rtol=1e-13, atol=1e-13)
+
+
+def test_vectors(ab):
+    n, r, c, v = mg.laplace3d_7pt(4)
+    A = ab.SymCsrMatrix.init_real_double(n, r, c, v)
+    parts = A.partition(2, _parts("slab", n, 2))
+    full = A.vector()
+    full.x[:] = np.arange(n)
+    for m in parts:
+        pv = m.vector()
+        assert pv.c.num_nonzeros == m.c.nprows and pv.c.num_ghost_nonzeros == m.c.nghostrows and pv.c.size == n
+        assert ab.lib().acgvector_usga(pv.c, full.c) == 0
+        assert np.array_equal(pv.x, m.nzrows.astype(float))
+
+
+def test_solver_refuses_without_device(ab):
+    """No CPU fallback: without a usable device init fails with ACG_ERR_CUDA."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    n, r, c, v = mg.poisson1d_3pt(10)
+    A = ab.SymCsrMatrix.init_real_double(n, r, c, v).dsymv_init(0.0)
+    with pytest.raises(ab.AcgError) as e:
+        ab.SolverCuda(A)
+    assert e.value.code == 4

@@ -1,0 +1,53 @@
+"""N>1 paths: world_size-2/3 gloo runs on CPU (host logic), NCCL runs on GPUs."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WORKER = os.path.join(ROOT, "tests", "_dist_worker.py")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _launch(nproc, extra, timeout=600):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), WORKER] + extra
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    sys.stdout.write(p.stdout[-4000:])
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "FAIL" not in p.stdout and "OK" in p.stdout
+
+
+@pytest.mark.parametrize("nproc,matrix,size,partition", [
+    (2, "27pt", 8, "block"),
+    (3, "7pt", 9, "slab"),
+    (2, "rmat", 600, "random"),
+])
+def test_gloo_host_logic(nproc, matrix, size, partition):
+    _launch(nproc, ["--mode", "cpu", "--matrix", matrix, "--size", str(size), "--partition", partition])
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("matrix,size,partition", [("27pt", 24, "block"), ("7pt", 20, "slab"), ("rmat", 5000, "random")])
+def test_nccl_multi_gpu(matrix, size, partition):
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs on the box (gpurun --gpus 2)")
+    _launch(min(n, 4) if n >= 4 and matrix == "27pt" else 2,
+            ["--mode", "gpu", "--matrix", matrix, "--size", str(size), "--partition", partition])
