@@ -572,7 +572,7 @@ typedef void (*spmv_fn)(const SpmvParams);
 
 /* instantiated (lanes per row, threads per CTA) pairs; gathers in flight U=8 */
 #define SPMV_VARIANTS(X) \
-    X(1, 64) X(2, 64) X(4, 64) X(8, 128) X(1, 128) X(1, 256) X(2, 128) X(2, 256) X(2, 512) X(4, 128) X(4, 256) X(4, 512) \
+    X(1, 64) X(2, 64) X(4, 64) X(8, 128) X(16, 128) X(32, 128) X(1, 128) X(1, 256) X(2, 128) X(2, 256) X(2, 512) X(4, 128) X(4, 256) X(4, 512) \
     X(8, 256) X(8, 512) X(16, 256) X(16, 512) X(32, 256) X(32, 512)
 
 static spmv_fn spmv_variant(int G, int T, int U)
