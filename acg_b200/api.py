@@ -107,7 +107,8 @@ class acgcomm(C.Structure):
 class acgb200_info(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("spmv_lanes_per_row", "spmv_rows_cap", "spmv_nnz_cap", "spmv_stages",
                                        "spmv_ntiles", "spmv_nlong", "spmv_grid", "spmv_smem_bytes", "num_sms",
-                                       "last_launches", "last_spmv_count")] + [("last_spmv_ms", C.c_double)]
+                                       "last_launches", "last_spmv_count")] + [("last_spmv_ms", C.c_double),
+                                                                                  ("last_solve_ms", C.c_double)]
 
 
 # every symbol include/acgb200/*.h declares (checked by tests/test_abi.py)
@@ -129,6 +130,7 @@ EXPORTS = [
     "acgsolvercuda_fwrite",
     "acgb200_set_option", "acgsolvercuda_spmv", "acgsolvercuda_info", "acgb200_sizeof", "acgb200_have_mpi",
     "acgb200_nccl_unique_id", "acgb200_comm_init_rank", "acgb200_comm_destroy",
+    "acgb200_host_register", "acgb200_host_unregister",
 ]
 
 
@@ -184,6 +186,8 @@ def lib() -> C.CDLL:
     L.acgsolvercuda_info.argtypes = [P(acgsolvercuda), P(acgb200_info)]
     L.acgb200_set_option.argtypes = [C.c_char_p, C.c_int]
     L.acgb200_nccl_unique_id.argtypes = [C.c_void_p]
+    L.acgb200_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    L.acgb200_host_unregister.argtypes = [C.c_void_p]
     L.acgb200_comm_init_rank.argtypes = [P(acgcomm), C.c_int, C.c_void_p, C.c_int, P(C.c_int)]
     L.acgb200_comm_destroy.argtypes = [P(acgcomm)]
     L.acgcomm_size.argtypes = [P(acgcomm), P(C.c_int)]
@@ -230,7 +234,16 @@ class Vector:
     def nowned(self) -> int:
         return self.c.num_nonzeros - self.c.num_ghost_nonzeros
 
+    def pin(self):
+        """Page-lock the storage (caller-side optimisation of the H2D/D2H copies)."""
+        _check(lib().acgb200_host_register(self.c.x, self.c.num_nonzeros * 8), "cudaHostRegister")
+        self._pinned = True
+        return self
+
     def free(self):
+        if getattr(self, "_pinned", False):
+            lib().acgb200_host_unregister(self.c.x)
+            self._pinned = False
         if self._owns:
             lib().acgvector_free(C.byref(self.c))
             self._owns = False

@@ -95,6 +95,8 @@ struct priv {
     int64_t fnnz, onnz;
     cudaStream_t stream, commstream;
     cudaEvent_t ev_ready, ev_halo, ev_poll[2];
+    cudaEvent_t ev_t0, ev_t1;           /* device-side bracket of the solve window */
+    double last_solve_ms;
     struct evpool gemv, blas;           /* profiling */
     int last_launches;                  /* kernels launched in the last solve's timed loop */
     double last_spmv_ms;                /* profiled SpMV time of the last solve */
@@ -159,6 +161,8 @@ void acgsolvercuda_free(struct acgsolvercuda *cg)
         if (pv->ev_ready) cudaEventDestroy(pv->ev_ready);
         if (pv->ev_halo) cudaEventDestroy(pv->ev_halo);
         for (int i = 0; i < 2; i++) if (pv->ev_poll[i]) cudaEventDestroy(pv->ev_poll[i]);
+        if (pv->ev_t0) cudaEventDestroy(pv->ev_t0);
+        if (pv->ev_t1) cudaEventDestroy(pv->ev_t1);
         for (int i = 0; i < pv->gemv.cap; i++) cudaEventDestroy(pv->gemv.ev[i]);
         for (int i = 0; i < pv->blas.cap; i++) cudaEventDestroy(pv->blas.ev[i]);
         free(pv->gemv.ev); free(pv->blas.ev);
@@ -277,6 +281,8 @@ int acgsolvercuda_init(
     CU(cudaEventCreateWithFlags(&pv->ev_ready, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&pv->ev_halo, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&pv->ev_poll[i], cudaEventDisableTiming));
+    CU(cudaEventCreate(&pv->ev_t0));
+    CU(cudaEventCreate(&pv->ev_t1));
     OK(acghaloexchange_init_cuda(cg->haloexchange, cg->halo, ACG_DOUBLE, ACG_DOUBLE, comm, pv->commstream));
     cg->use_nvshmem = 0;
     if (comm && comm->type == acgcomm_nvshmem) return ACG_ERR_NVSHMEM_NOT_SUPPORTED;
@@ -611,6 +617,7 @@ int acgsolvercuda_solvempi(
     OK(acgcomm_barrier(pv->stream, comm, errcode));
     CU(cudaStreamSynchronize(pv->stream));
     const double t0 = wall();
+    CU(cudaEventRecord(pv->ev_t0, pv->stream));
     c.launches = 0;
 
     /* ||b|| (acg/cgcuda.c:727-739) */
@@ -646,8 +653,11 @@ int acgsolvercuda_solvempi(
         cg->rnrm2 = sqrt(rr);
         cg->ntotaliterations += cg->niterations;
     }
+    CU(cudaEventRecord(pv->ev_t1, pv->stream));
+    CU(cudaEventSynchronize(pv->ev_t1));
     const double t1 = wall();
     cg->tsolve += t1 - t0;
+    { float ms = 0; if (cudaEventElapsedTime(&ms, pv->ev_t0, pv->ev_t1) == cudaSuccess) pv->last_solve_ms = ms; }
     account_classic(cg, pv, cg->niterations, c.multi);
     pv->last_launches = c.launches;
     if (cfg.profile) {
@@ -763,6 +773,7 @@ int acgsolvercuda_solve_pipelined(
     OK(acgcomm_barrier(pv->stream, comm, errcode));
     CU(cudaStreamSynchronize(pv->stream));
     const double t0 = wall();
+    CU(cudaEventRecord(pv->ev_t0, pv->stream));
     c.launches = 0;
 
     memset(&h, 0, sizeof(h));
@@ -803,8 +814,11 @@ int acgsolvercuda_solve_pipelined(
         cg->rnrm2 = sqrt(g);
         cg->ntotaliterations += cg->niterations;
     }
+    CU(cudaEventRecord(pv->ev_t1, pv->stream));
+    CU(cudaEventSynchronize(pv->ev_t1));
     const double t1 = wall();
     cg->tsolve += t1 - t0;
+    { float ms = 0; if (cudaEventElapsedTime(&ms, pv->ev_t0, pv->ev_t1) == cudaSuccess) pv->last_solve_ms = ms; }
     {
         const int64_t nits = cg->niterations, nnz = pv->fnnz + pv->onnz;
         const int64_t bgemv = nnz * 12 + (int64_t) n * 16 + (int64_t) (pv->nborder + pv->nghost) * 8 + (int64_t) pv->nvec * 8;
@@ -942,6 +956,7 @@ int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info
     info->spmv_nlong = pv->plan.nlong; info->spmv_grid = pv->plan.grid; info->spmv_smem_bytes = pv->plan.smem_bytes;
     info->last_launches = pv->last_launches;
     info->last_spmv_ms = pv->last_spmv_ms; info->last_spmv_count = pv->last_spmv_n;
+    info->last_solve_ms = pv->last_solve_ms;
     info->num_sms = acgb200_num_sms();
     return ACG_SUCCESS;
 }

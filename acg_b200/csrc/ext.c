@@ -5,6 +5,7 @@
 #include "acgb200/error.h"
 #include "acgb200/ext.h"
 
+#include <cuda_runtime_api.h>
 #include <string.h>
 
 size_t acgb200_sizeof(const char *name)
@@ -26,6 +27,16 @@ int acgb200_have_mpi(void)
 #else
     return 0;
 #endif
+}
+
+int acgb200_host_register(void *ptr, size_t bytes)
+{
+    return cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess ? ACG_SUCCESS : ACG_ERR_CUDA;
+}
+
+int acgb200_host_unregister(void *ptr)
+{
+    return cudaHostUnregister(ptr) == cudaSuccess ? ACG_SUCCESS : ACG_ERR_CUDA;
 }
 
 int acgb200_nccl_unique_id(void *id128)

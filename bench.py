@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py -- CG iterations/s and SpMV roofline of the B200 hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N=1)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N>1)
+    python bench.py --impl reference ...                     (the reference's CPU path)
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on):
+27-point stencil 224^3 (n = 11 239 424, nnz = 300 763 000), FP64, b = 1, x0 = 0,
+pipelined CG.  N>1 splits the same matrix into N geometric blocks (strong
+scaling), halo + allreduce over NCCL.
+
+A *step* is one call of the reference-facing solver entry point
+(acgsolvercuda_solve_pipelined / acgsolvercuda_solvempi) for ITERS iterations
+with all tolerances off -- one pass of the hot path over one right-hand side.
+
+  value   iterations/s from the device-side solve window (CUDA events inside the
+          library around the region the reference times as "total solver time",
+          acg/cgcuda.c:719-722,:1021): b and x are already in HBM.  Max over
+          ranks of the summed window, K*ITERS iterations.
+  e2e     iterations/s of the whole C-ABI call with HOST vectors: pinned b, x ->
+          H2D, solve, x -> D2H, inside the timed region (host clock, device
+          synchronised by the call itself; barrier before every step; max over
+          ranks).
+  roofline  the SpMV kernel (replaces cusparseSpMV): 16*nnz contract bytes
+          (2*nnz*8) per launch / mean launch duration, measured
+          with CUDA events on the launching stream inside the timed steps.
+  cpu_baseline  the reference's own CPU solver (acg/cg.c, oracle/_ref) -- or the
+          oracle port when that build is absent -- on the box's host cores, same
+          matrix, a bounded number of iterations.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "27pt-224": dict(kind="27pt", N=224, solver="pipelined"),     # BASELINE.json configs[2]  (metric config)
+    "7pt-256": dict(kind="7pt", N=256, solver="classic"),          # configs[1]
+    "27pt-128": dict(kind="27pt", N=128, solver="pipelined"),      # quick check
+    "27pt-64": dict(kind="27pt", N=64, solver="pipelined"),
+}
+
+
+def make_matrix(w):
+    from acg_b200 import matgen
+    N = w["N"]
+    return matgen.stencil3d_27pt(N) if w["kind"] == "27pt" else matgen.laplace3d_7pt(N)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [t.strip() for t in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc:
+            self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2 and len(r) >= 7] or [r for (_, r) in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in rows]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
+
+
+def cpu_reference(w, steps, warmup, iters, solver_note):
+    """Time the reference's CPU CG (acg/cg.c) on the host cores; falls back to the
+    oracle port when oracle/_ref was not built."""
+    from oracle import Oracle, Ref, ref_available
+    n, r, c, v = make_matrix(w)
+    b = np.ones(n)
+    out = []
+    if ref_available():
+        R = Ref()
+        kind, cores = "reference", R.num_threads()
+        h = R.setup(n, r, c, v)
+        for s in range(warmup + steps):
+            res = R.solve(h, b, maxits=iters)
+            if s >= warmup:
+                out.append(res["tsolve"])
+        R.free(h)
+    else:
+        O = Oracle()
+        kind, cores = "port", O.num_threads()
+        csr = O.full_csr(n, r, c, v)
+        for s in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.cg(csr, b, maxits=iters)
+            if s >= warmup:
+                out.append(time.perf_counter() - t0)
+    tot = sum(out)
+    return dict(value=len(out) * iters / tot, unit="iterations/s", cores=cores, kind=kind,
+                sample=f"{len(out)} x {iters} classic CG iterations (acgsolver_solve) on the full {w['kind']} "
+                       f"{w['N']}^3 matrix, b=1, x0=0; OpenMP dsymv on {cores} threads, BLAS-1 serial as in the reference"
+                       f"{solver_note}",
+                seconds=tot)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="acgb200", choices=["acgb200", "reference"])
+    ap.add_argument("--workload", default="27pt-224", choices=sorted(WORKLOADS))
+    ap.add_argument("--solver", default=None, choices=["pipelined", "classic"])
+    ap.add_argument("--iters", type=int, default=100, help="CG iterations per step (reference default --max-iterations 100)")
+    ap.add_argument("--cpu-iters", type=int, default=5, help="iterations per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    solver = args.solver or w["solver"]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    metric = "CG iterations/sec (27-pt stencil ~10M rows); SpMV achieved-HBM GB/s in roofline"
+    config = {"workload": f"{w['kind']} stencil {w['N']}^3, FP64, b=1, x0=0, {solver} CG, {args.iters} iterations/step, "
+                          f"tolerances off", "n": w["N"] ** 3, "solver": solver, "iters_per_step": args.iters,
+              "partition": f"{world} geometric block(s)" if world > 1 else "none",
+              "l2": "inputs larger than L2 (CSR 3.6 GB per SpMV vs 126 MB L2), no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        note = "" if solver == "classic" else "; the reference has no CPU pipelined CG, classic CG is its CPU path"
+        cb = cpu_reference(w, args.steps, args.warmup, args.cpu_iters, note)
+        line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "iterations/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * cb["seconds"] / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import acg_b200 as ab
+    from acg_b200 import dist as abdist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    rank, world, local = abdist.init_process(backend="gloo")
+    import torch.distributed as dist
+    comm = abdist.nccl_comm(rank, world)
+
+    n, r, c, v = make_matrix(w)
+    N = w["N"]
+    rowparts = abdist.block_partition(N, N, N, *abdist.grid_factors(world)) if world > 1 else None
+    A = abdist.local_part(n, r, c, v, rowparts, rank, world)
+    del r, c, v
+    nnz_local = int(A.c.fnpnzs + A.c.onpnzs)
+    cg = ab.SolverCuda(A, comm)
+    b = A.vector(); b.x[:] = 1.0
+    x = A.vector()
+    b.pin(); x.pin()
+    h2d = 2 * b.c.num_nonzeros * 8
+    d2h = x.c.num_nonzeros * 8
+    solve = cg.solve_pipelined if solver == "pipelined" else cg.solvempi
+
+    def step():
+        x.x[:] = 0.0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        code = solve(b, x, maxits=args.iters)
+        t1 = time.perf_counter()
+        assert code == 0 and cg.c.niterations == args.iters
+        return t1 - t0
+
+    for _ in range(max(args.warmup, 0)):
+        step()
+    ab.set_option("profile", 1)        # CUDA events around each SpMV, inside the timed region
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    tw0 = time.time()
+    host_s = dev_ms = spmv_ms = 0.0
+    spmv_n = launches = 0
+    for _ in range(args.steps):
+        host_s += step()
+        inf = cg.info()
+        dev_ms += inf["last_solve_ms"]
+        spmv_ms += inf["last_spmv_ms"]; spmv_n += inf["last_spmv_count"]
+        launches += inf["last_launches"]
+    torch.cuda.synchronize()
+    tw1 = time.time()
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
+    ab.set_option("profile", 0)
+    resid = cg.c.rnrm2 / cg.c.r0nrm2
+
+    t = torch.tensor([dev_ms, host_s], dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, host_s_max = float(t[0]), float(t[1])
+    total_iters = args.steps * args.iters
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        t_spmv = spmv_ms / max(spmv_n, 1) * 1e-3
+        achieved = 16.0 * nnz_local / t_spmv / 1e9
+        nloc = A.c.nownedrows
+        prof = os.path.join(ROOT, "profiles", "r01_ncu_spmv.json")
+        traffic = None
+        if os.path.exists(prof) and world == 1 and args.workload == "27pt-224":
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        line = {
+            "metric": metric, "value": total_iters / (dev_ms_max * 1e-3), "unit": "iterations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "e2e": {"value": total_iters / host_s_max, "unit": "iterations/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "whole acgsolvercuda_solve* call with pinned host b, x (cudaMalloc, H2D, solve, D2H, cudaFree)"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "spmv_tiles_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "bytes_per_launch": 16 * nnz_local, "ms_per_launch": t_spmv * 1e3, "launches_timed": spmv_n,
+                         "peak_source": peak_src,
+                         "achieved_min_traffic_gbs": (12.0 * nnz_local + 20.0 * nloc) / t_spmv / 1e9,
+                         "spmv_gflops": 2.0 * nnz_local / t_spmv / 1e9,
+                         "note": "16*nnz contract bytes (BASELINE.md); rank 0's local block"},
+            "clocks": clocks,
+            "residual_after_step": resid,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference(w, 1, 0, args.cpu_iters,
+                                                 "" if solver == "classic" else "; GPU arm runs pipelined CG")
+        print(json.dumps(line), flush=True)
+    cg.free(); b.free(); x.free()
+    comm.destroy()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

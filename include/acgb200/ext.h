@@ -34,6 +34,8 @@ struct acgb200_info {
     int last_launches;          /* kernels + NCCL launches enqueued by the last solve's timed region */
     int last_spmv_count;        /* SpMV applications timed in the last solve (profile=1) */
     double last_spmv_ms;        /* their total device time, CUDA events on the launching stream */
+    double last_solve_ms;       /* device time of the last solve window (after the H2D copies and warm-up, to the
+                                   end of the loop: the window of tsolve, acg/cgcuda.c:719-722,:1021), CUDA events */
 };
 ACG_API int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info);
 
@@ -43,6 +45,11 @@ ACG_API size_t acgb200_sizeof(const char *name);
 /* 1 if this build was compiled with ACG_HAVE_MPI (struct acgcomm then has the
  * MPI member), else 0 */
 ACG_API int acgb200_have_mpi(void);
+
+/* page-lock / unlock caller-owned host memory (b->x, x->x) so that the solver's
+ * H2D/D2H copies run at full PCIe speed; optional, the solve works on pageable memory */
+ACG_API int acgb200_host_register(void *ptr, size_t bytes);
+ACG_API int acgb200_host_unregister(void *ptr);
 
 /* NCCL bootstrap for hosts without MPI (the reference driver broadcasts the
  * unique id over MPI, cuda/acg-cuda.c:1104-1122; bench.py / tests broadcast

@@ -71,6 +71,8 @@ def main():
     ap.add_argument("--matrix", default="27pt")
     ap.add_argument("--size", type=int, default=10)
     ap.add_argument("--partition", default="block")
+    ap.add_argument("--maxits", type=int, default=200)
+    ap.add_argument("--rtol", type=float, default=1e-9)
     args = ap.parse_args()
     rank, world, _ = abdist.init_process(backend="gloo")
     N = args.size
@@ -90,7 +92,7 @@ def main():
     no = m.c.nownedrows
     rng = np.random.default_rng(11)
     bglob = rng.standard_normal(n)
-    maxits, rtol = 200, 1e-9
+    maxits, rtol = args.maxits, args.rtol
     failures = []
 
     if args.mode == "cpu":
@@ -108,7 +110,7 @@ def main():
             rvec -= alpha * t
             rr_new = allsum(rvec @ rvec)
             its += 1
-            if np.sqrt(rr_new) < rtol * r0:
+            if rtol > 0 and np.sqrt(rr_new) < rtol * r0:
                 break
             p[:no] = rvec + (rr_new / rr) * p[:no]
             rr = rr_new
