@@ -108,7 +108,9 @@ class acgb200_info(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("spmv_lanes_per_row", "spmv_rows_cap", "spmv_nnz_cap", "spmv_stages",
                                        "spmv_ntiles", "spmv_nlong", "spmv_grid", "spmv_smem_bytes", "num_sms",
                                        "last_launches", "last_spmv_count")] + [("last_spmv_ms", C.c_double),
-                                                                                  ("last_solve_ms", C.c_double)]
+                                                                                  ("last_solve_ms", C.c_double),
+                                                                                  ("last_h2d_ms", C.c_double),
+                                                                                  ("last_d2h_ms", C.c_double)]
 
 
 # every symbol include/acgb200/*.h declares (checked by tests/test_abi.py)
@@ -141,7 +143,7 @@ def lib() -> C.CDLL:
     if not os.path.exists(_LIBPATH):
         raise RuntimeError(f"{_LIBPATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(there is no fallback implementation)")
-    L = C.CDLL(_LIBPATH, mode=C.RTLD_GLOBAL)
+    L = C.CDLL(_LIBPATH, mode=C.RTLD_LOCAL)
     L.acgerrcodestr.restype = C.c_char_p
     L.acgerrcodestr.argtypes = [C.c_int, C.c_int]
     L.acgb200_sizeof.restype = C.c_size_t

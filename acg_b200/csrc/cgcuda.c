@@ -44,8 +44,11 @@ static struct {
     int check_every;    /* iterations between convergence polls */
     int spmv_lanes;     /* 0 = heuristic */
     int spmv_nnz_cap, spmv_rows_cap, spmv_stages, spmv_threads, spmv_unroll;
+    int spmv_max_ctas;  /* cap on resident SpMV CTAs per SM (0 = occupancy limit) */
+    int graph;          /* replay iteration pairs as CUDA graphs */
+    int redstream;      /* pipelined CG: allreduce on its own stream + communicator */
     int loaded;
-} cfg = { 0, 8, 0, 0, 0, 0, 0, 0, 0 };
+} cfg = { 0, 8, 0, 0, 0, 0, 0, 0, 0, 1, 1, 0 };
 
 static void cfg_load(void)
 {
@@ -60,6 +63,9 @@ static void cfg_load(void)
     if ((s = getenv("ACGB200_SPMV_STAGES"))) cfg.spmv_stages = atoi(s);
     if ((s = getenv("ACGB200_SPMV_THREADS"))) cfg.spmv_threads = atoi(s);
     if ((s = getenv("ACGB200_SPMV_UNROLL"))) cfg.spmv_unroll = atoi(s);
+    if ((s = getenv("ACGB200_SPMV_MAX_CTAS"))) cfg.spmv_max_ctas = atoi(s);
+    if ((s = getenv("ACGB200_GRAPH"))) cfg.graph = atoi(s);
+    if ((s = getenv("ACGB200_REDSTREAM"))) cfg.redstream = atoi(s);
     if (cfg.check_every < 1) cfg.check_every = 1;
 }
 
@@ -74,6 +80,9 @@ int acgb200_set_option(const char *key, int value)
     else if (!strcmp(key, "spmv_stages")) cfg.spmv_stages = value;
     else if (!strcmp(key, "spmv_threads")) cfg.spmv_threads = value;
     else if (!strcmp(key, "spmv_unroll")) cfg.spmv_unroll = value;
+    else if (!strcmp(key, "spmv_max_ctas")) cfg.spmv_max_ctas = value;
+    else if (!strcmp(key, "graph")) cfg.graph = value;
+    else if (!strcmp(key, "redstream")) cfg.redstream = value;
     else return ACG_ERR_INVALID_VALUE;
     return ACG_SUCCESS;
 }
@@ -93,8 +102,15 @@ struct priv {
     struct acgb200_devstate *h_st;      /* pinned scratch for state upload / readback */
     int nowned, ninner, nborder, nghost, borderoff, nvec;
     int64_t fnnz, onnz;
-    cudaStream_t stream, commstream;
-    cudaEvent_t ev_ready, ev_halo, ev_poll[2];
+    cudaStream_t stream, commstream, redstream;
+    cudaEvent_t ev_ready, ev_halo, ev_red, ev_poll[2];
+    struct acgcomm redcomm;             /* private duplicate of the caller's communicator for reductions */
+    int have_redcomm;
+    double *d_b, *d_x;                  /* right-hand side / solution on the device, kept between solves */
+    cudaGraphExec_t graph[2];           /* [0] classic, [1] pipelined: two iterations (parity 0 then 1) */
+    int graph_multi[2];
+    int graph_launches[2];              /* kernel/NCCL launches inside one replay */
+    double last_h2d_ms, last_d2h_ms;    /* host time spent before / after the solve window */
     cudaEvent_t ev_t0, ev_t1;           /* device-side bracket of the solve window */
     double last_solve_ms;
     struct evpool gemv, blas;           /* profiling */
@@ -158,6 +174,11 @@ void acgsolvercuda_free(struct acgsolvercuda *cg)
         cudaFreeHost(pv->h_ctrl); cudaFreeHost(pv->h_st);
         if (pv->stream) cudaStreamDestroy(pv->stream);
         if (pv->commstream) cudaStreamDestroy(pv->commstream);
+        if (pv->redstream) cudaStreamDestroy(pv->redstream);
+        if (pv->ev_red) cudaEventDestroy(pv->ev_red);
+        for (int i = 0; i < 2; i++) if (pv->graph[i]) cudaGraphExecDestroy(pv->graph[i]);
+        if (pv->have_redcomm && pv->redcomm.ncclcomm) ncclCommDestroy(pv->redcomm.ncclcomm);
+        cudaFree(pv->d_b); cudaFree(pv->d_x);
         if (pv->ev_ready) cudaEventDestroy(pv->ev_ready);
         if (pv->ev_halo) cudaEventDestroy(pv->ev_halo);
         for (int i = 0; i < 2; i++) if (pv->ev_poll[i]) cudaEventDestroy(pv->ev_poll[i]);
@@ -276,16 +297,40 @@ int acgsolvercuda_init(
     cg->haloexchange = malloc(sizeof(*cg->haloexchange));
     if (!cg->halo || !cg->haloexchange) return ACG_ERR_ERRNO;
     OK(acgsymcsrmatrix_halo(A, cg->halo));
-    CU(cudaStreamCreateWithFlags(&pv->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&pv->commstream, cudaStreamNonBlocking));
+    {
+        /* communication kernels are tiny and latency-critical: give their streams
+         * the highest priority so they are scheduled ahead of SpMV CTAs */
+        int plo = 0, phi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&plo, &phi));
+        CU(cudaStreamCreateWithPriority(&pv->stream, cudaStreamNonBlocking, plo));
+        CU(cudaStreamCreateWithPriority(&pv->commstream, cudaStreamNonBlocking, phi));
+        CU(cudaStreamCreateWithPriority(&pv->redstream, cudaStreamNonBlocking, phi));
+    }
     CU(cudaEventCreateWithFlags(&pv->ev_ready, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&pv->ev_halo, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&pv->ev_red, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&pv->ev_poll[i], cudaEventDisableTiming));
     CU(cudaEventCreate(&pv->ev_t0));
     CU(cudaEventCreate(&pv->ev_t1));
     OK(acghaloexchange_init_cuda(cg->haloexchange, cg->halo, ACG_DOUBLE, ACG_DOUBLE, comm, pv->commstream));
     cg->use_nvshmem = 0;
     if (comm && comm->type == acgcomm_nvshmem) return ACG_ERR_NVSHMEM_NOT_SUPPORTED;
+    {
+        /* a second communicator lets the pipelined allreduce run concurrently
+         * with the halo exchange (operations on one NCCL communicator are
+         * serialised).  Collective: every rank calls acgsolvercuda_init. */
+        int commsize = 1;
+        OK(acgcomm_size(comm, &commsize));
+        if (cfg.redstream && commsize > 1 && comm->type == acgcomm_nccl) {
+            int rank = 0;
+            OK(acgcomm_rank(comm, &rank));
+            ncclComm_t dup = NULL;
+            ncclResult_t r = ncclCommSplit(comm->ncclcomm, 0, rank, &dup, NULL);
+            if (r != ncclSuccess) { *errcode = (int) r; return ACG_ERR_NCCL; }
+            OK(acgcomm_init_nccl(&pv->redcomm, dup, errcode));
+            pv->have_redcomm = 1;
+        }
+    }
 
     pv->nowned = A->nownedrows; pv->ninner = A->ninnerrows; pv->nborder = A->nborderrows;
     pv->nghost = A->nghostrows; pv->borderoff = A->borderrowoffset;
@@ -325,6 +370,7 @@ int acgsolvercuda_init(
     if (cfg.spmv_threads > 0) pv->plan.threads = cfg.spmv_threads;
     if (cfg.spmv_unroll > 0) pv->plan.unroll = cfg.spmv_unroll;
     OK(build_tiles(&pv->plan, A->frowptr, errcode));
+    pv->plan.max_ctas_per_sm = cfg.spmv_max_ctas;
     KL(acgb200_spmv_configure(&pv->plan));
     return ACG_SUCCESS;
 }
@@ -341,6 +387,7 @@ struct solvectx {
     int *errcode;
     double *d_b, *d_x;
     int launches;
+    int capturing;            /* inside cudaStreamBeginCapture: no profiling marks */
 };
 
 static int evpool_reserve(struct evpool *p, int n)
@@ -356,7 +403,7 @@ static int evpool_reserve(struct evpool *p, int n)
 
 static void prof_mark(struct solvectx *c, struct evpool *p)
 {
-    if (!cfg.profile || p->n >= p->cap) return;
+    if (!cfg.profile || c->capturing || p->n >= p->cap) return;
     cudaEventRecord(p->ev[p->n++], c->pv->stream);
 }
 
@@ -452,24 +499,32 @@ static int solve_begin(struct solvectx *c, struct acgsolvercuda *cg, const struc
     c->cg = cg; c->pv = pv; c->comm = comm; c->multi = commsize > 1; c->tag = tag; c->errcode = errcode;
     if (c->multi && comm->type != acgcomm_nccl)
         return comm->type == acgcomm_mpi ? ACG_ERR_MPI_NOT_SUPPORTED : ACG_ERR_NVSHMEM_NOT_SUPPORTED;
-    /* b and x0 to the device (acg/cgcuda.c:484-493) */
+    /* b and x0 to the device (acg/cgcuda.c:484-493).  The reference allocates and
+     * frees the two device vectors in every solve; here they are kept with the
+     * solver (their addresses are baked into the replayed CUDA graphs). */
+    const double tb = wall();
     const size_t vbytes = ((size_t) pv->nvec + 2) * sizeof(double);
-    CU(cudaMalloc((void **) &c->d_b, vbytes));
-    CU(cudaMalloc((void **) &c->d_x, vbytes));
-    CU(cudaMemsetAsync(c->d_b, 0, vbytes, pv->stream));
-    CU(cudaMemsetAsync(c->d_x, 0, vbytes, pv->stream));
+    if (!pv->d_b) {
+        CU(cudaMalloc((void **) &pv->d_b, vbytes));
+        CU(cudaMalloc((void **) &pv->d_x, vbytes));
+        CU(cudaMemsetAsync(pv->d_b, 0, vbytes, pv->stream));
+        CU(cudaMemsetAsync(pv->d_x, 0, vbytes, pv->stream));
+    }
+    c->d_b = pv->d_b; c->d_x = pv->d_x;
     CU(cudaMemcpyAsync(c->d_b, b->x, (size_t) b->num_nonzeros * sizeof(double), cudaMemcpyHostToDevice, pv->stream));
     CU(cudaMemcpyAsync(c->d_x, x->x, (size_t) x->num_nonzeros * sizeof(double), cudaMemcpyHostToDevice, pv->stream));
+    CU(cudaStreamSynchronize(pv->stream));
+    pv->last_h2d_ms = 1e3 * (wall() - tb);
     return ACG_SUCCESS;
 }
 
 static int solve_end(struct solvectx *c, struct acgvector *x, int status)
 {
     int *errcode = c->errcode;
-    cudaError_t e = cudaMemcpy(x->x, c->d_x, (size_t) x->num_nonzeros * sizeof(double), cudaMemcpyDeviceToHost);
-    cudaFree(c->d_x); cudaFree(c->d_b);
-    c->d_x = c->d_b = NULL;
-    CU(e);
+    const double te = wall();
+    CU(cudaMemcpyAsync(x->x, c->d_x, (size_t) x->num_nonzeros * sizeof(double), cudaMemcpyDeviceToHost, c->pv->stream));
+    CU(cudaStreamSynchronize(c->pv->stream));
+    c->pv->last_d2h_ms = 1e3 * (wall() - te);
     CU(cudaGetLastError());
     return status;
 }
@@ -505,18 +560,56 @@ static double threshold(double atol, double rtol, double r0nrm2)
     return t;
 }
 
-/* run `issue(c,k)` for k < maxits, polling the device control word */
-static int iterate(struct solvectx *c, int maxits, int poll, int (*issue)(struct solvectx *, int))
+/* Capture iterations (parity 0, parity 1) of `issue` into a graph.  All
+ * pointers the kernels and NCCL calls use are fixed for the life of the solver
+ * and the iteration index only enters through its parity, so one two-iteration
+ * graph serves the whole solve (and later solves). */
+static int capture_pair(struct solvectx *c, int kind, int (*issue)(struct solvectx *, int))
 {
     struct priv *pv = c->pv;
     int *errcode = c->errcode;
-    int issued = 0, slot = 0, have_prev = 0;
+    if (pv->graph[kind] && pv->graph_multi[kind] == c->multi) return ACG_SUCCESS;
+    if (pv->graph[kind]) { cudaGraphExecDestroy(pv->graph[kind]); pv->graph[kind] = NULL; }
+    const int before = c->launches;
+    cudaGraph_t g = NULL;
+    c->capturing = 1;
+    CU(cudaStreamBeginCapture(pv->stream, cudaStreamCaptureModeThreadLocal));
+    int err = issue(c, 2);
+    if (!err) err = issue(c, 3);
+    cudaError_t e = cudaStreamEndCapture(pv->stream, &g);
+    c->capturing = 0;
+    pv->graph_launches[kind] = c->launches - before;
+    c->launches = before;
+    if (err) { if (g) cudaGraphDestroy(g); return err; }
+    CU(e);
+    e = cudaGraphInstantiate(&pv->graph[kind], g, 0);
+    cudaGraphDestroy(g);
+    CU(e);
+    pv->graph_multi[kind] = c->multi;
+    return ACG_SUCCESS;
+}
+
+/* Run `issue(c,k)` for k < maxits, polling the device control word.  The
+ * first two iterations are issued directly (they also serve as the un-captured
+ * first use of every NCCL path), the rest as replays of the two-iteration graph. */
+static int iterate(struct solvectx *c, int maxits, int poll, int kind, int (*issue)(struct solvectx *, int))
+{
+    struct priv *pv = c->pv;
+    int *errcode = c->errcode;
+    int issued = 0, slot = 0, have_prev = 0, since_poll = 0;
+    const int use_graph = cfg.graph && !cfg.profile && maxits >= 6;
     while (issued < maxits) {
-        int batch = cfg.check_every;
-        if (batch > maxits - issued) batch = maxits - issued;
-        for (int i = 0; i < batch; i++) OK(issue(c, issued + i));
-        issued += batch;
-        if (!poll) continue;
+        if (use_graph && issued >= 2 && maxits - issued >= 2) {
+            if (!pv->graph[kind] || pv->graph_multi[kind] != c->multi) OK(capture_pair(c, kind, issue));
+            CU(cudaGraphLaunch(pv->graph[kind], pv->stream));
+            c->launches += pv->graph_launches[kind];
+            issued += 2; since_poll += 2;
+        } else {
+            OK(issue(c, issued));
+            issued += 1; since_poll += 1;
+        }
+        if (!poll || (since_poll < cfg.check_every && issued < maxits)) continue;
+        since_poll = 0;
         CU(cudaMemcpyAsync(&pv->h_ctrl[slot], &pv->d_st->ctrl[0], sizeof(struct acgb200_ctrl),
                            cudaMemcpyDeviceToHost, pv->stream));
         CU(cudaEventRecord(pv->ev_poll[slot], pv->stream));
@@ -527,7 +620,7 @@ static int iterate(struct solvectx *c, int maxits, int poll, int (*issue)(struct
         have_prev = 1; slot ^= 1;
     }
     CU(cudaStreamSynchronize(pv->stream));
-    if (c->multi) CU(cudaStreamSynchronize(pv->commstream));
+    if (c->multi) { CU(cudaStreamSynchronize(pv->commstream)); CU(cudaStreamSynchronize(pv->redstream)); }
     return ACG_SUCCESS;
 }
 
@@ -644,7 +737,7 @@ int acgsolvercuda_solvempi(
         h.maxits = maxits; h.tol = tol;
         h.rr_loc[0] = h.rr[0] = rr0;
         OK(push_state(&c, &h));
-        OK(iterate(&c, maxits, tol > 0, classic_iteration));
+        OK(iterate(&c, maxits, tol > 0, 0, classic_iteration));
         OK(pull_state(&c, &h));
         cg->niterations = h.ctrl[0].iter;
         converged = h.ctrl[0].done;
@@ -706,10 +799,24 @@ static int pipelined_iteration(struct solvectx *c, int k)
     struct acgb200_devstate *st = pv->d_st;
     int *errcode = c->errcode;
     const int s = k & 1, n = pv->nowned;
-    /* one allreduce for {gamma,delta} (acg/cgcuda.c:1697), then q = A w;
-     * {gamma_0,delta_0} were reduced during setup */
-    if (k > 0) OK(allreduce(c, &st->gd_loc[s][0], &st->gd[s][0], 2));
+    /* One allreduce for {gamma,delta} (acg/cgcuda.c:1697).  The reference
+     * issues it on the compute stream ahead of q = A w, i.e. serialised; here it
+     * runs on its own stream and communicator and is only joined before the
+     * update, so it overlaps the SpMV -- the point of pipelined CG.
+     * {gamma_0,delta_0} were reduced during setup. */
+    const int side = c->multi && pv->have_redcomm;
+    if (k > 0 && c->multi) {
+        if (side) {
+            CU(cudaEventRecord(pv->ev_ready, pv->stream));
+            CU(cudaStreamWaitEvent(pv->redstream, pv->ev_ready, 0));
+            OK(acgcomm_allreduce(&st->gd_loc[s][0], &st->gd[s][0], 2, ACG_DOUBLE, ACG_SUM, pv->redstream, &pv->redcomm, errcode));
+            CU(cudaEventRecord(pv->ev_red, pv->redstream));
+        } else {
+            OK(allreduce(c, &st->gd_loc[s][0], &st->gd[s][0], 2));
+        }
+    }
     OK(apply_A(c, cg->d_w, cg->d_w, cg->d_q, NULL, SPMV_Y_AX, NULL, 1, 2, 0));
+    if (k > 0 && side) CU(cudaStreamWaitEvent(pv->stream, pv->ev_red, 0));
     prof_mark(c, &pv->blas);
     KL(acgb200_pcg_update(n, st, 1, 0, c->multi, cg->d_q, cg->d_z, cg->d_w, cg->d_t, cg->d_p, cg->d_r, c->d_x, pv->stream));
     prof_mark(c, &pv->blas);
@@ -803,7 +910,7 @@ int acgsolvercuda_solve_pipelined(
         h.gd_loc[0][1] = h.gd[0][1] = gd0[1];
         h.prev[0][0] = h.prev[0][1] = INFINITY;                    /* acg/cgcuda.c:1513-1514 */
         OK(push_state(&c, &h));
-        OK(iterate(&c, maxits, tol > 0, pipelined_iteration));
+        OK(iterate(&c, maxits, tol > 0, 1, pipelined_iteration));
         OK(pull_state(&c, &h));
         cg->niterations = h.ctrl[0].iter;
         converged = h.ctrl[0].done;
@@ -957,6 +1064,7 @@ int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info
     info->last_launches = pv->last_launches;
     info->last_spmv_ms = pv->last_spmv_ms; info->last_spmv_count = pv->last_spmv_n;
     info->last_solve_ms = pv->last_solve_ms;
+    info->last_h2d_ms = pv->last_h2d_ms; info->last_d2h_ms = pv->last_d2h_ms;
     info->num_sms = acgb200_num_sms();
     return ACG_SUCCESS;
 }

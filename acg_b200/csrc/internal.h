@@ -49,6 +49,7 @@ struct acgb200_spmvplan {
     int grid;                        /* persistent grid size */
     int smem_bytes;                  /* dynamic shared memory per CTA */
     int long_chunks;                 /* CTAs per long row */
+    int max_ctas_per_sm;             /* 0: occupancy limit */
 };
 
 /* epilogue of the SpMV kernels */

@@ -639,6 +639,7 @@ extern "C" int acgb200_spmv_configure(acgb200_spmvplan *pl)
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, pl->threads, pl->smem_bytes);
     if (err) return (int) err;
     if (per_sm < 1) per_sm = 1;
+    if (pl->max_ctas_per_sm > 0 && per_sm > pl->max_ctas_per_sm) per_sm = pl->max_ctas_per_sm;
     long long grid = (long long) acgb200_num_sms() * per_sm;
     if (grid > pl->ntiles) grid = pl->ntiles;
     if (grid < 1) grid = 1;

@@ -146,7 +146,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
-    solver = args.solver or w["solver"]
+    solver = args.solver or os.environ.get("BENCH_SOLVER") or w["solver"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     metric = "CG iterations/sec (27-pt stencil ~10M rows); SpMV achieved-HBM GB/s in roofline"

@@ -15,8 +15,10 @@ extern "C" {
 /* tunables: "profile" (0/1: CUDA-event timing of each kernel class, fills
  * tgemv/taxpy like the reference's -DACG_ENABLE_PROFILING, acg/cgcuda.c:69-73),
  * "check_every" (iterations between convergence polls), "spmv_lanes",
- * "spmv_nnz_cap", "spmv_rows_cap", "spmv_stages" (SpMV tile plan overrides,
- * read at acgsolvercuda_init).  Environment variables ACGB200_<KEY> set the
+ * "spmv_nnz_cap", "spmv_rows_cap", "spmv_stages", "spmv_threads", "spmv_unroll",
+ * "spmv_max_ctas" (SpMV tile plan overrides, read at acgsolvercuda_init), "graph"
+ * (0/1: replay iteration pairs as CUDA graphs), "redstream" (0/1: pipelined
+ * allreduce on its own stream and communicator; read at acgsolvercuda_init).  Environment variables ACGB200_<KEY> set the
  * same values at first use. */
 ACG_API int acgb200_set_option(const char *key, int value);
 
@@ -36,6 +38,8 @@ struct acgb200_info {
     double last_spmv_ms;        /* their total device time, CUDA events on the launching stream */
     double last_solve_ms;       /* device time of the last solve window (after the H2D copies and warm-up, to the
                                    end of the loop: the window of tsolve, acg/cgcuda.c:719-722,:1021), CUDA events */
+    double last_h2d_ms;         /* host time of the b, x0 upload of the last solve */
+    double last_d2h_ms;         /* host time of the x download of the last solve */
 };
 ACG_API int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info);
 

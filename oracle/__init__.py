@@ -40,7 +40,7 @@ class Oracle:
         path = os.path.join(_HERE, "liboracle.so")
         if not os.path.exists(path):
             build()
-        L = self.lib = C.CDLL(path)
+        L = self.lib = C.CDLL(path, mode=C.RTLD_LOCAL)
         L.oracle_full_csr.restype = C.c_int64
         L.oracle_full_csr.argtypes = [C.c_int, C.c_int64, _i32, _i32, _f64, C.c_double, _i64, _i32, _f64]
         L.oracle_dsymv.restype = None
@@ -115,7 +115,7 @@ class Ref:
         path = os.path.join(_HERE, "_ref", "libacgref.so")
         if not os.path.exists(path):
             build()
-        L = self.lib = C.CDLL(path)
+        L = self.lib = C.CDLL(path, mode=C.RTLD_LOCAL)
         L.ref_full_csr.argtypes = [C.c_int, C.c_int64, _i32, _i32, _f64, C.c_double, _i64, _i32, _f64,
                                    C.POINTER(C.c_int64)]
         L.ref_dsymv.argtypes = [C.c_int, C.c_int64, _i32, _i32, _f64, C.c_double, _f64, C.c_double, _f64]

@@ -231,9 +231,13 @@ int ref_partition_part(int n, int64_t nnz, const int *row, const int *col,
     sz[9] = Ap->fnpnzs; sz[10] = Ap->onpnzs;
     if (nzrows) {
         for (int i = 0; i < Ap->nprows; i++) nzrows[i] = Ap->nzrows[i];
-        for (int i = 0; i < halo.nrecipients; i++) { recipients[i] = halo.recipients[i]; sendcounts[i] = halo.sendcounts[i]; }
+        /* Before the parts are scattered to processes every neighbourrank is
+         * still 0 (acg/graph.c sets ranks when it distributes subgraphs); the
+         * neighbour's identity at this point is its part number,
+         * acg/graph.h:288 neighbourpart.  Report that. */
+        for (int i = 0; i < halo.nrecipients; i++) { recipients[i] = Ap->graph->neighbours[i].neighbourpart; sendcounts[i] = halo.sendcounts[i]; }
         for (int i = 0; i < halo.sendsize; i++) sendbufidx[i] = halo.sendbufidx[i];
-        for (int i = 0; i < halo.nsenders; i++) { senders[i] = halo.senders[i]; recvcounts[i] = halo.recvcounts[i]; }
+        for (int i = 0; i < halo.nsenders; i++) { senders[i] = Ap->graph->neighbours[i].neighbourpart; recvcounts[i] = halo.recvcounts[i]; }
         for (int i = 0; i < halo.recvsize; i++) recvbufidx[i] = halo.recvbufidx[i];
         memcpy(frowptr, Ap->frowptr, ((size_t) Ap->nprows + 1) * sizeof(int64_t));
         memcpy(fcolidx, Ap->fcolidx, (size_t) Ap->fnpnzs * sizeof(int));

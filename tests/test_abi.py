@@ -87,3 +87,25 @@ def test_binding_struct_sizes(ab):
     assert L.acgb200_sizeof(b"acgsolvercuda") == ctypes.sizeof(ab.api.acgsolvercuda)
     assert L.acgb200_sizeof(b"acgsymcsrmatrix") == ctypes.sizeof(ab.api.acgsymcsrmatrix)
     assert L.acgb200_have_mpi() == 0
+
+
+def test_reference_and_product_libraries_do_not_interpose(ab, ref):
+    """libacgref.so (the reference) and libacgb200.so export the same names.  Both
+    are linked -Bsymbolic and loaded RTLD_LOCAL, so a test process that holds both
+    really compares two implementations (an earlier build silently bound the
+    reference shim's calls to the product's symbols)."""
+    mine, theirs = ab.lib(), ref.lib
+    for name in ("acgsymcsrmatrix_init_real_double", "acgsymcsrmatrix_dsymv_init", "acgsymcsrmatrix_partition",
+                 "acgvector_alloc", "acgerrcodestr"):
+        a = ctypes.cast(getattr(mine, name), ctypes.c_void_p).value
+        b = ctypes.cast(getattr(theirs, name), ctypes.c_void_p).value
+        assert a != b, name
+    theirs.acgerrcodestr.restype = ctypes.c_char_p
+    # behavioural fingerprint: the two libraries word this message differently
+    assert mine.acgerrcodestr(16, 0) != theirs.acgerrcodestr(16, 0)
+    # and the reference shim reaches the reference's code: its init does not
+    # bounds-check under NDEBUG, the product's does (ACG_ERR_INDEX_OUT_OF_BOUNDS)
+    import numpy as np
+    r = np.array([0], np.int32); c = np.array([5], np.int32); v = np.array([1.0])
+    A = ab.api.acgsymcsrmatrix()
+    assert mine.acgsymcsrmatrix_init_real_double(ctypes.byref(A), 2, 1, 0, r, c, v) == 31

@@ -59,13 +59,18 @@ def test_partition_matches_reference(name, gen, kind, nparts, ab, ref):
         h = m.halo()
         for k in ("recipients", "sendcounts", "sendbufidx", "senders", "recvcounts", "recvbufidx"):
             assert np.array_equal(h[k], want[k]), k
-        for k in ("frowptr", "orowptr", "ocolidx", "oa"):
+        for k in ("frowptr", "orowptr"):
             assert np.array_equal(getattr(m, k), want[k]), k
-        # order of entries inside a full row may legitimately differ; compare rows as sets
-        for i in range(m.c.nownedrows):
-            a = sorted(zip(m.fcolidx[m.frowptr[i]:m.frowptr[i + 1]], m.fa[m.frowptr[i]:m.frowptr[i + 1]]))
-            b = sorted(zip(want["fcolidx"][want["frowptr"][i]:want["frowptr"][i + 1]], want["fa"][want["frowptr"][i]:want["frowptr"][i + 1]]))
-            assert a == b
+        # The order of entries inside a row may legitimately differ (the reference
+        # lists a row's own upper-triangle entries before the mirrored ones, this
+        # library follows global row order); compare rows as sets of (column, value).
+        for rp, ci, va, wrp, wci, wva, nr in (
+                (m.frowptr, m.fcolidx, m.fa, want["frowptr"], want["fcolidx"], want["fa"], m.c.nownedrows),
+                (m.orowptr, m.ocolidx, m.oa, want["orowptr"], want["ocolidx"], want["oa"], m.c.nborderrows)):
+            for i in range(nr):
+                a = sorted(zip(ci[rp[i]:rp[i + 1]], va[rp[i]:rp[i + 1]]))
+                b = sorted(zip(wci[wrp[i]:wrp[i + 1]], wva[wrp[i]:wrp[i + 1]]))
+                assert a == b
 
 
 @pytest.mark.parametrize("kind,nparts", [("slab", 4), ("random", 3)])
