@@ -110,7 +110,8 @@ class acgb200_info(C.Structure):
                                        "last_launches", "last_spmv_count")] + [("last_spmv_ms", C.c_double),
                                                                                   ("last_solve_ms", C.c_double),
                                                                                   ("last_h2d_ms", C.c_double),
-                                                                                  ("last_d2h_ms", C.c_double)]
+                                                                                  ("last_d2h_ms", C.c_double),
+                                                                                  ("last_blas_ms", C.c_double)]
 
 
 # every symbol include/acgb200/*.h declares (checked by tests/test_abi.py)

@@ -27,6 +27,7 @@
 #include "acgb200/error.h"
 #include "acgb200/ext.h"
 #include "internal.h"
+#include "p2p.h"
 
 #include <cuda_runtime_api.h>
 #include <float.h>
@@ -47,8 +48,10 @@ static struct {
     int spmv_max_ctas;  /* cap on resident SpMV CTAs per SM (0 = occupancy limit) */
     int graph;          /* replay iteration pairs as CUDA graphs */
     int redstream;      /* pipelined CG: allreduce on its own stream + communicator */
+    int p2p;            /* halo + reductions through peer memory (CUDA IPC) instead of NCCL */
+    int p2p_fuse;       /* 1: border x ghost block inside the SpMV, pushes inside the update kernels */
     int loaded;
-} cfg = { 0, 8, 0, 0, 0, 0, 0, 0, 0, 1, 1, 0 };
+} cfg = { 0, 8, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 0 };
 
 static void cfg_load(void)
 {
@@ -66,6 +69,8 @@ static void cfg_load(void)
     if ((s = getenv("ACGB200_SPMV_MAX_CTAS"))) cfg.spmv_max_ctas = atoi(s);
     if ((s = getenv("ACGB200_GRAPH"))) cfg.graph = atoi(s);
     if ((s = getenv("ACGB200_REDSTREAM"))) cfg.redstream = atoi(s);
+    if ((s = getenv("ACGB200_P2P"))) cfg.p2p = atoi(s);
+    if ((s = getenv("ACGB200_P2P_FUSE"))) cfg.p2p_fuse = atoi(s);
     if (cfg.check_every < 1) cfg.check_every = 1;
 }
 
@@ -83,6 +88,8 @@ int acgb200_set_option(const char *key, int value)
     else if (!strcmp(key, "spmv_max_ctas")) cfg.spmv_max_ctas = value;
     else if (!strcmp(key, "graph")) cfg.graph = value;
     else if (!strcmp(key, "redstream")) cfg.redstream = value;
+    else if (!strcmp(key, "p2p")) cfg.p2p = value;
+    else if (!strcmp(key, "p2p_fuse")) cfg.p2p_fuse = value;
     else return ACG_ERR_INVALID_VALUE;
     return ACG_SUCCESS;
 }
@@ -104,6 +111,7 @@ struct priv {
     int64_t fnnz, onnz;
     cudaStream_t stream, commstream, redstream;
     cudaEvent_t ev_ready, ev_halo, ev_red, ev_poll[2];
+    struct acgb200_p2p p2p;             /* peer-memory exchange (multi-GPU) */
     struct acgcomm redcomm;             /* private duplicate of the caller's communicator for reductions */
     int have_redcomm;
     double *d_b, *d_x;                  /* right-hand side / solution on the device, kept between solves */
@@ -116,6 +124,7 @@ struct priv {
     struct evpool gemv, blas;           /* profiling */
     int last_launches;                  /* kernels launched in the last solve's timed loop */
     double last_spmv_ms;                /* profiled SpMV time of the last solve */
+    double last_blas_ms;                /* profiled fused-update time of the last solve */
     int last_spmv_n;
 };
 
@@ -169,6 +178,17 @@ void acgsolvercuda_free(struct acgsolvercuda *cg)
     cg->d_rowptr = cg->d_colidx = cg->d_orowptr = cg->d_ocolidx = NULL;
     cg->d_a = cg->d_oa = NULL;
     if (pv) {
+        if (pv->stream) cudaStreamSynchronize(pv->stream);
+        if (pv->p2p.window) {
+            /* unmap the peers' windows, wait until every rank has done so, then
+             * release this rank's (collective, like the init that created it) */
+            acgb200_p2p_free(&pv->p2p);
+            if (pv->have_redcomm) { acgcomm_barrier(pv->stream, &pv->redcomm, NULL); cudaStreamSynchronize(pv->stream); }
+            cudaFree(pv->p2p.window);
+            pv->p2p.window = NULL;
+        }
+        if (pv->have_redcomm && pv->redcomm.ncclcomm) ncclCommDestroy(pv->redcomm.ncclcomm);
+        for (int i = 0; i < 2; i++) if (pv->graph[i]) cudaGraphExecDestroy(pv->graph[i]);
         cudaFree(pv->plan.d_tiles); cudaFree(pv->plan.d_longrows);
         cudaFree(pv->d_st);
         cudaFreeHost(pv->h_ctrl); cudaFreeHost(pv->h_st);
@@ -176,8 +196,6 @@ void acgsolvercuda_free(struct acgsolvercuda *cg)
         if (pv->commstream) cudaStreamDestroy(pv->commstream);
         if (pv->redstream) cudaStreamDestroy(pv->redstream);
         if (pv->ev_red) cudaEventDestroy(pv->ev_red);
-        for (int i = 0; i < 2; i++) if (pv->graph[i]) cudaGraphExecDestroy(pv->graph[i]);
-        if (pv->have_redcomm && pv->redcomm.ncclcomm) ncclCommDestroy(pv->redcomm.ncclcomm);
         cudaFree(pv->d_b); cudaFree(pv->d_x);
         if (pv->ev_ready) cudaEventDestroy(pv->ev_ready);
         if (pv->ev_halo) cudaEventDestroy(pv->ev_halo);
@@ -330,6 +348,28 @@ int acgsolvercuda_init(
             OK(acgcomm_init_nccl(&pv->redcomm, dup, errcode));
             pv->have_redcomm = 1;
         }
+        /* peer-memory exchange; all ranks must agree on whether it is usable */
+        if (cfg.p2p && commsize > 1 && comm->type == acgcomm_nccl && pv->have_redcomm) {
+            int perr = 0;
+            int ok = acgb200_p2p_init(&pv->p2p, cg->halo, A->borderrowoffset, A->nborderrows, comm, pv->stream, &perr) == ACG_SUCCESS;
+            if (!ok) (void) cudaGetLastError();
+            int *d_ok = NULL, allok = 0;
+            CU(cudaMalloc((void **) &d_ok, sizeof(int)));
+            CU(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+            ncclResult_t r = ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm->ncclcomm, pv->stream);
+            if (r != ncclSuccess) { *errcode = (int) r; return ACG_ERR_NCCL; }
+            CU(cudaMemcpyAsync(&allok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, pv->stream));
+            CU(cudaStreamSynchronize(pv->stream));
+            cudaFree(d_ok);
+            if (ok) {
+                pv->p2p.h_desc.fuse = cfg.p2p_fuse;
+                CU(cudaMemcpy(&pv->p2p.d_desc->fuse, &pv->p2p.h_desc.fuse, sizeof(int), cudaMemcpyHostToDevice));
+            }
+            if (!allok) {
+                if (getenv("ACGB200_VERBOSE")) fprintf(stderr, "acgb200: peer-memory exchange unavailable (cuda error %d), using NCCL\n", perr);
+                pv->p2p.enabled = 0;
+            }
+        }
     }
 
     pv->nowned = A->nownedrows; pv->ninner = A->ninnerrows; pv->nborder = A->nborderrows;
@@ -388,6 +428,7 @@ struct solvectx {
     double *d_b, *d_x;
     int launches;
     int capturing;            /* inside cudaStreamBeginCapture: no profiling marks */
+    int p2p;                  /* loop exchanges go through peer memory */
 };
 
 static int evpool_reserve(struct evpool *p, int n)
@@ -421,36 +462,53 @@ static double evpool_sum_ms(struct evpool *p)
  * and the border x ghost block when the matrix is distributed.  `acc` gets the
  * fused dot.  `gated`: take part in the device-side iteration control. */
 static int apply_A(struct solvectx *c, const double *x_ro, double *x_halo, double *y, const double *b,
-                   int mode, double *acc, int gated, int housekeeping, int warmup)
+                   int mode, double *acc, int gated, int housekeeping, int warmup, int pub_ch)
 {
     struct acgsolvercuda *cg = c->cg;
     struct priv *pv = c->pv;
     int *errcode = c->errcode;
-    if (c->multi) {
+    /* loop iterations exchange ghosts through peer memory (already pushed by the
+     * producer of x); set-up products (x0, r0) use the NCCL exchange */
+    const int peer = c->multi && c->p2p && gated;
+    if (c->multi && !peer) {
         /* the vector was produced on the main stream */
         CU(cudaEventRecord(pv->ev_ready, pv->stream));
         CU(cudaStreamWaitEvent(pv->commstream, pv->ev_ready, 0));
         OK(acghalo_exchange_cuda_begin(cg->halo, cg->haloexchange, pv->nvec, x_halo, ACG_DOUBLE,
                                        pv->nvec, x_halo, ACG_DOUBLE, c->comm, c->tag, errcode, warmup, pv->commstream));
-        c->launches += 1;
+        c->launches += 2;
     }
     struct acgb200_spmvargs a;
     memset(&a, 0, sizeof(a));
     a.plan = &pv->plan;
     a.rowptr = cg->d_rowptr; a.colidx = cg->d_colidx; a.a = cg->d_a;
     a.x = x_ro; a.y = y; a.b = b; a.acc = acc;
-    a.dotrows = c->multi ? pv->borderoff : pv->nowned;
+    a.dotrows = (c->multi && !peer) ? pv->borderoff : pv->nowned;
     a.mode = mode;
     if (gated) { a.ctrl_in = &pv->d_st->ctrl[0]; a.ctrl_out = &pv->d_st->ctrl[1]; }
     a.st = pv->d_st; a.housekeeping = housekeeping;
+    a.pub_ch = -1;
+    const int fused = peer && pv->p2p.h_desc.fuse;
+    if (peer && !fused) a.dotrows = pv->borderoff;
+    if (fused) {
+        /* one kernel: local block, then (for border rows) the border x ghost
+         * block with ghosts read from the window, fused dot over all rows and,
+         * if asked, publication of the dot to all ranks by the last CTA */
+        a.p2p = pv->p2p.d_desc;
+        a.od_rowoffset = pv->borderoff; a.od_nrows = pv->nborder;
+        a.orowptr = cg->d_orowptr; a.ocolidx = cg->d_ocolidx; a.oa = cg->d_oa;
+        if (pub_ch >= 0 && pv->plan.nlong == 0) a.pub_ch = pub_ch;
+    }
     prof_mark(c, &pv->gemv);
     KL(acgb200_spmv_launch(&a, pv->stream));
     c->launches += 1 + (pv->plan.nlong > 0 ? 2 : 0);
-    if (c->multi) {
-        OK(acghalo_exchange_cuda_end(cg->halo, cg->haloexchange, pv->nvec, x_halo, ACG_DOUBLE,
-                                     pv->nvec, x_halo, ACG_DOUBLE, c->comm, c->tag, errcode, warmup, pv->commstream));
-        CU(cudaEventRecord(pv->ev_halo, pv->commstream));
-        CU(cudaStreamWaitEvent(pv->stream, pv->ev_halo, 0));
+    if (c->multi && !fused) {
+        if (!peer) {
+            OK(acghalo_exchange_cuda_end(cg->halo, cg->haloexchange, pv->nvec, x_halo, ACG_DOUBLE,
+                                         pv->nvec, x_halo, ACG_DOUBLE, c->comm, c->tag, errcode, warmup, pv->commstream));
+            CU(cudaEventRecord(pv->ev_halo, pv->commstream));
+            CU(cudaStreamWaitEvent(pv->stream, pv->ev_halo, 0));
+        }
         struct acgb200_offdiagargs o;
         memset(&o, 0, sizeof(o));
         o.nrows = pv->nborder; o.rowoffset = pv->borderoff;
@@ -460,10 +518,30 @@ static int apply_A(struct solvectx *c, const double *x_ro, double *x_halo, doubl
         o.dotkind = !acc ? 0 : (mode == SPMV_R_B_AX ? 2 : (mode == SPMV_Y_AX_DOT ? 1 : 0));
         if (gated) o.ctrl_in = &pv->d_st->ctrl[1];
         o.st = pv->d_st;
+        o.p2p = peer ? pv->p2p.d_desc : NULL; o.p2p_iter_override = -1;
         KL(acgb200_offdiag_launch(&o, pv->stream));
         c->launches += (pv->nborder > 0);
     }
     prof_mark(c, &pv->gemv);
+    return ACG_SUCCESS;
+}
+
+/* push the border entries of `vec` (and/or reduction partials) into the peers'
+ * windows; see struct acgb200_postargs */
+static int post(struct solvectx *c, int ctrl_slot, int iter_override, const double *vec,
+                int ch, const double *redbase, int stride, int count, int par_off, int seq_off)
+{
+    struct priv *pv = c->pv;
+    int *errcode = c->errcode;
+    struct acgb200_postargs a;
+    memset(&a, 0, sizeof(a));
+    a.p2p = pv->p2p.d_desc;
+    a.cin = &pv->d_st->ctrl[ctrl_slot]; a.st = pv->d_st;
+    a.iter_override = iter_override;
+    a.vec = vec; a.sendbufidx = (const int *) c->cg->haloexchange->d_sendbufidx;
+    a.ch = ch; a.redbase = redbase; a.redstride = stride; a.redcount = count; a.par_off = par_off; a.seq_off = seq_off;
+    KL(acgb200_comm_post(&a, pv->stream));
+    c->launches += 1;
     return ACG_SUCCESS;
 }
 
@@ -635,14 +713,21 @@ static int classic_iteration(struct solvectx *c, int k)
     struct acgb200_devstate *st = pv->d_st;
     int *errcode = c->errcode;
     const int s = k & 1, n = pv->nowned;
-    OK(apply_A(c, cg->d_p, cg->d_p, cg->d_t, NULL, SPMV_Y_AX_DOT, &st->pap_loc[s], 1, 1, 0));
-    OK(allreduce(c, &st->pap_loc[s], &st->pap[s], 1));
+    const int peer = c->multi && c->p2p;
+    OK(apply_A(c, cg->d_p, cg->d_p, cg->d_t, NULL, SPMV_Y_AX_DOT, &st->pap_loc[s], 1, 1, 0, 0));
+    if (peer) {
+        /* (p,Ap) is published by the SpMV's last CTA; with long rows the dot is
+         * only complete after the finishing kernel, so a separate post does it */
+        if (pv->plan.nlong > 0 || !pv->p2p.h_desc.fuse) OK(post(c, 1, -1, NULL, 0, &st->pap_loc[0], 1, 1, 0, 1));
+    } else OK(allreduce(c, &st->pap_loc[s], &st->pap[s], 1));
     prof_mark(c, &pv->blas);
-    KL(acgb200_cg_update_r(n, st, 1, 1, c->multi, cg->d_t, cg->d_r, pv->stream));
-    OK(allreduce(c, &st->rr_loc[s ^ 1], &st->rr[s ^ 1], 1));
-    KL(acgb200_cg_update_xp(n, st, 1, 0, c->multi, cg->d_r, cg->d_p, c->d_x, pv->stream));
+    KL(acgb200_cg_update_r(n, st, 1, 1, c->multi, pv->p2p.d_desc && peer ? pv->p2p.d_desc : NULL, cg->d_t, cg->d_r, pv->stream));
+    if (!peer) OK(allreduce(c, &st->rr_loc[s ^ 1], &st->rr[s ^ 1], 1));
+    else if (!pv->p2p.h_desc.fuse) OK(post(c, 1, -1, NULL, 1, &st->rr_loc[0], 1, 1, 1, 1));
+    KL(acgb200_cg_update_xp(n, st, 1, 0, c->multi, peer ? pv->p2p.d_desc : NULL, cg->d_r, cg->d_p, c->d_x, pv->stream));
     prof_mark(c, &pv->blas);
-    c->launches += 2 + (c->multi ? 2 : 0);
+    if (peer && !pv->p2p.h_desc.fuse) OK(post(c, 0, -1, cg->d_p, -1, NULL, 0, 0, 0, 0));     /* p for the next SpMV */
+    c->launches += 2 + (c->multi && !peer ? 2 : 0);
     return ACG_SUCCESS;
 }
 
@@ -680,22 +765,23 @@ int acgsolvercuda_solvempi(
     const int n = pv->nowned;
     struct acgb200_devstate h;
 
-    /* warm-up: every kernel and every NCCL path once per `warmup`, on state
-     * that is overwritten below (acg/cgcuda.c:607-705); d_r stands in for x */
+    c.p2p = c.multi && pv->p2p.enabled && cfg.p2p;
+    /* warm-up: `warmup` full iterations (every kernel, every communication path)
+     * on state that is overwritten below (acg/cgcuda.c:607-705); d_r stands in
+     * for x so the initial guess is untouched */
     if (warmup > 0) {
         memset(&h, 0, sizeof(h));
         h.maxits = warmup; h.rr_loc[0] = h.rr[0] = 1.0;
         OK(push_state(&c, &h));
         double *xsave = c.d_x; c.d_x = cg->d_r;
-        for (int i = 0; i < warmup; i++) {
-            OK(apply_A(&c, cg->d_p, cg->d_p, cg->d_t, NULL, SPMV_Y_AX_DOT, &st->pap_loc[i & 1], 1, 1, 1));
-            OK(allreduce(&c, &st->pap_loc[i & 1], &st->pap[i & 1], 1));
-            KL(acgb200_cg_update_r(n, st, 1, 1, c.multi, cg->d_t, cg->d_r, pv->stream));
-            OK(allreduce(&c, &st->rr_loc[(i & 1) ^ 1], &st->rr[(i & 1) ^ 1], 1));
-            KL(acgb200_cg_update_xp(n, st, 1, 0, c.multi, cg->d_r, cg->d_p, c.d_x, pv->stream));
+        if (c.p2p) {
+            OK(acgb200_p2p_begin(&pv->p2p, warmup, pv->stream));
+            OK(post(&c, 0, 0, cg->d_p, -1, NULL, 0, 0, 0, 0));
         }
+        for (int i = 0; i < warmup; i++) OK(classic_iteration(&c, i));
         c.d_x = xsave;
         KL(acgb200_dot(n, c.d_b, c.d_b, &st->tmp_loc[0], pv->stream));
+        CU(cudaStreamSynchronize(pv->stream));
     }
     if (cfg.profile) {
         OK(evpool_reserve(&pv->gemv, 2 * (maxits + 2)));
@@ -723,7 +809,7 @@ int acgsolvercuda_solvempi(
     cg->nnrm2++; cg->nflops += 2 * (int64_t) n; cg->Bnrm2 += 8 * (int64_t) n;
 
     /* r0 = b - A x0 with (r0,r0) folded in (acg/cgcuda.c:761-799,:819-832); p = r0 */
-    OK(apply_A(&c, c.d_x, c.d_x, cg->d_r, c.d_b, SPMV_R_B_AX, &st->rr_loc[0], 0, 0, 0));
+    OK(apply_A(&c, c.d_x, c.d_x, cg->d_r, c.d_b, SPMV_R_B_AX, &st->rr_loc[0], 0, 0, 0, -1));
     CU(cudaMemcpyAsync(cg->d_p, cg->d_r, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, pv->stream));
     OK(reduce_to_host(&c, &st->rr_loc[0], &st->rr[0], 1, &rr0));
     cg->rnrm2 = cg->r0nrm2 = sqrt(rr0);
@@ -737,6 +823,11 @@ int acgsolvercuda_solvempi(
         h.maxits = maxits; h.tol = tol;
         h.rr_loc[0] = h.rr[0] = rr0;
         OK(push_state(&c, &h));
+        if (c.p2p) {
+            /* p_0 = r_0 goes to the neighbours' windows as exchange number 0 */
+            OK(acgb200_p2p_begin(&pv->p2p, maxits, pv->stream));
+            OK(post(&c, 0, 0, cg->d_p, -1, NULL, 0, 0, 0, 0));
+        }
         OK(iterate(&c, maxits, tol > 0, 0, classic_iteration));
         OK(pull_state(&c, &h));
         cg->niterations = h.ctrl[0].iter;
@@ -755,8 +846,9 @@ int acgsolvercuda_solvempi(
     pv->last_launches = c.launches;
     if (cfg.profile) {
         pv->last_spmv_ms = evpool_sum_ms(&pv->gemv); pv->last_spmv_n = pv->gemv.n / 2;
+        pv->last_blas_ms = evpool_sum_ms(&pv->blas);
         cg->tgemv += 1e-3 * pv->last_spmv_ms;
-        cg->taxpy += 1e-3 * evpool_sum_ms(&pv->blas);
+        cg->taxpy += 1e-3 * pv->last_blas_ms;
     }
     int status = ACG_SUCCESS;
     if (!converged && !(residualatol == 0 && rtol_scaled == 0)) status = ACG_ERR_NOT_CONVERGED;   /* :1099-1107 */
@@ -799,13 +891,16 @@ static int pipelined_iteration(struct solvectx *c, int k)
     struct acgb200_devstate *st = pv->d_st;
     int *errcode = c->errcode;
     const int s = k & 1, n = pv->nowned;
+    const int peer = c->multi && c->p2p;
     /* One allreduce for {gamma,delta} (acg/cgcuda.c:1697).  The reference
-     * issues it on the compute stream ahead of q = A w, i.e. serialised; here it
-     * runs on its own stream and communicator and is only joined before the
-     * update, so it overlaps the SpMV -- the point of pipelined CG.
-     * {gamma_0,delta_0} were reduced during setup. */
-    const int side = c->multi && pv->have_redcomm;
-    if (k > 0 && c->multi) {
+     * issues it on the compute stream ahead of q = A w, i.e. serialised.  Here:
+     * peer-memory mode -- the partials were pushed to every rank right after
+     * the previous update and are summed by the update kernel itself; NCCL mode
+     * -- the allreduce runs on its own stream and communicator and is only
+     * joined before the update.  Either way it overlaps the SpMV, which is the
+     * point of pipelined CG.  {gamma_0,delta_0} were reduced during setup. */
+    const int side = c->multi && !peer && pv->have_redcomm;
+    if (k > 0 && c->multi && !peer) {
         if (side) {
             CU(cudaEventRecord(pv->ev_ready, pv->stream));
             CU(cudaStreamWaitEvent(pv->redstream, pv->ev_ready, 0));
@@ -815,12 +910,17 @@ static int pipelined_iteration(struct solvectx *c, int k)
             OK(allreduce(c, &st->gd_loc[s][0], &st->gd[s][0], 2));
         }
     }
-    OK(apply_A(c, cg->d_w, cg->d_w, cg->d_q, NULL, SPMV_Y_AX, NULL, 1, 2, 0));
+    OK(apply_A(c, cg->d_w, cg->d_w, cg->d_q, NULL, SPMV_Y_AX, NULL, 1, 2, 0, -1));
     if (k > 0 && side) CU(cudaStreamWaitEvent(pv->stream, pv->ev_red, 0));
     prof_mark(c, &pv->blas);
-    KL(acgb200_pcg_update(n, st, 1, 0, c->multi, cg->d_q, cg->d_z, cg->d_w, cg->d_t, cg->d_p, cg->d_r, c->d_x, pv->stream));
+    KL(acgb200_pcg_update(n, st, 1, 0, c->multi, peer ? pv->p2p.d_desc : NULL,
+                          cg->d_q, cg->d_z, cg->d_w, cg->d_t, cg->d_p, cg->d_r, c->d_x, pv->stream));
     prof_mark(c, &pv->blas);
-    c->launches += 1 + (c->multi ? 1 : 0);
+    /* in peer-memory mode the update kernel itself pushed w's border entries
+     * and {gamma,delta} of the next iteration to the other ranks, unless fusion
+     * is switched off */
+    if (peer && !pv->p2p.h_desc.fuse) OK(post(c, 0, -1, cg->d_w, 0, &st->gd_loc[0][0], 2, 2, 0, 0));
+    c->launches += 1 + (c->multi && !peer ? 1 : 0);
     return ACG_SUCCESS;
 }
 
@@ -847,20 +947,22 @@ int acgsolvercuda_solve_pipelined(
     OK(ensure_vec(&cg->q, &cg->d_q, A, pv->nvec, errcode));
     OK(ensure_vec(&cg->z, &cg->d_z, A, pv->nvec, errcode));
 
+    c.p2p = c.multi && pv->p2p.enabled && cfg.p2p;
     if (warmup > 0) {
         memset(&h, 0, sizeof(h));
         h.maxits = warmup;
         for (int s = 0; s < 2; s++) { h.gd_loc[s][0] = h.gd[s][0] = 1; h.gd_loc[s][1] = h.gd[s][1] = 1; h.prev[s][0] = h.prev[s][1] = INFINITY; }
         OK(push_state(&c, &h));
         double *xsave = c.d_x; c.d_x = cg->d_r;
-        for (int i = 0; i < warmup; i++) {
-            OK(allreduce(&c, &st->gd_loc[i & 1][0], &st->gd[i & 1][0], 2));
-            OK(apply_A(&c, cg->d_w, cg->d_w, cg->d_q, NULL, SPMV_Y_AX, NULL, 1, 2, 1));
-            KL(acgb200_pcg_update(n, st, 1, 0, c.multi, cg->d_q, cg->d_z, cg->d_w, cg->d_t, cg->d_p, cg->d_r, c.d_x, pv->stream));
+        if (c.p2p) {
+            OK(acgb200_p2p_begin(&pv->p2p, warmup, pv->stream));
+            OK(post(&c, 0, 0, cg->d_w, -1, NULL, 0, 0, 0, 0));
         }
+        for (int i = 0; i < warmup; i++) OK(pipelined_iteration(&c, i));
         c.d_x = xsave;
         KL(acgb200_dot(n, c.d_b, c.d_b, &st->tmp_loc[0], pv->stream));
         KL(acgb200_dot2(n, cg->d_r, cg->d_w, &st->tmp_loc[0], pv->stream));
+        CU(cudaStreamSynchronize(pv->stream));
     }
     if (cfg.profile) {
         OK(evpool_reserve(&pv->gemv, 2 * (maxits + 3)));
@@ -891,8 +993,8 @@ int acgsolvercuda_solve_pipelined(
     cg->bnrm2 = sqrt(bb);
 
     /* r0 = b - A x0 ; w0 = A r0 (acg/cgcuda.c:1577-1671) */
-    OK(apply_A(&c, c.d_x, c.d_x, cg->d_r, c.d_b, SPMV_R_B_AX, NULL, 0, 0, 0));
-    OK(apply_A(&c, cg->d_r, cg->d_r, cg->d_w, NULL, SPMV_Y_AX, NULL, 0, 0, 0));
+    OK(apply_A(&c, c.d_x, c.d_x, cg->d_r, c.d_b, SPMV_R_B_AX, NULL, 0, 0, 0, -1));
+    OK(apply_A(&c, cg->d_r, cg->d_r, cg->d_w, NULL, SPMV_Y_AX, NULL, 0, 0, 0, -1));
     /* gamma0 = (r0,r0), delta0 = (w0,r0): in the reference these are the first
      * two dots of the loop (acg/cgcuda.c:1680-1697); later ones come fused out
      * of the update kernel */
@@ -910,6 +1012,11 @@ int acgsolvercuda_solve_pipelined(
         h.gd_loc[0][1] = h.gd[0][1] = gd0[1];
         h.prev[0][0] = h.prev[0][1] = INFINITY;                    /* acg/cgcuda.c:1513-1514 */
         OK(push_state(&c, &h));
+        if (c.p2p) {
+            /* w_0 goes to the neighbours' windows as exchange number 0 */
+            OK(acgb200_p2p_begin(&pv->p2p, maxits, pv->stream));
+            OK(post(&c, 0, 0, cg->d_w, -1, NULL, 0, 0, 0, 0));
+        }
         OK(iterate(&c, maxits, tol > 0, 1, pipelined_iteration));
         OK(pull_state(&c, &h));
         cg->niterations = h.ctrl[0].iter;
@@ -941,8 +1048,9 @@ int acgsolvercuda_solve_pipelined(
     pv->last_launches = c.launches;
     if (cfg.profile) {
         pv->last_spmv_ms = evpool_sum_ms(&pv->gemv); pv->last_spmv_n = pv->gemv.n / 2;
+        pv->last_blas_ms = evpool_sum_ms(&pv->blas);
         cg->tgemv += 1e-3 * pv->last_spmv_ms;
-        cg->taxpy += 1e-3 * evpool_sum_ms(&pv->blas);
+        cg->taxpy += 1e-3 * pv->last_blas_ms;
     }
     int status = ACG_SUCCESS;
     if (!converged && !(residualatol == 0 && rtol_scaled == 0)) status = ACG_ERR_NOT_CONVERGED;
@@ -1065,6 +1173,7 @@ int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info
     info->last_spmv_ms = pv->last_spmv_ms; info->last_spmv_count = pv->last_spmv_n;
     info->last_solve_ms = pv->last_solve_ms;
     info->last_h2d_ms = pv->last_h2d_ms; info->last_d2h_ms = pv->last_d2h_ms;
+    info->last_blas_ms = pv->last_blas_ms;
     info->num_sms = acgb200_num_sms();
     return ACG_SUCCESS;
 }

@@ -83,6 +83,62 @@ struct acgb200_devstate {
     double tmp_loc[2], tmp[2];
 };
 
+/* ------------------------------------------------------------------------
+ * Peer-memory exchange (NVLink 5 / NVSwitch, one process per GPU).
+ *
+ * Every rank exports one device allocation (the "window") through CUDA IPC:
+ *
+ *     uint64 hflag[MAXR]                halo sequence number, per sender rank
+ *     uint64 rflag[NCH][MAXR]           reduction sequence number, per channel/rank
+ *     double red[NCH][2][MAXR][2]       reduction partials [channel][parity][rank][2]
+ *     double ghost[2][recvsize]         ghost values, double-buffered by parity
+ *
+ * Producers store straight into their peers' windows (remote stores over
+ * NVLink) and then publish a sequence number with st.release.sys; consumers
+ * spin with ld.acquire.sys on their own window.  This replaces, inside the CG
+ * loop, the pack kernel + ncclSend/ncclRecv group + unpack of the halo exchange
+ * (acg/halo.c:1456-1627) and the ncclAllReduce of 1-2 doubles
+ * (acg/comm.c:371): see DESIGN.md section 6.
+ * ------------------------------------------------------------------------ */
+#define ACGB200_MAXR 64
+#define ACGB200_NCH 2
+
+struct acgb200_p2pdev {
+    int nranks, rank;
+    int nrecip, sendsize;                    /* halo send side: neighbours, entries */
+    int sdispls[ACGB200_MAXR + 1];           /* my send segments */
+    int peer_rdispl[ACGB200_MAXR];           /* where segment i starts in recipient i's ghost buffer */
+    double *peer_ghost[ACGB200_MAXR][2];     /* recipient i's ghost buffers */
+    unsigned long long *peer_hflag[ACGB200_MAXR];   /* recipient i's hflag slot for this rank */
+    int nsenders;
+    int senders[ACGB200_MAXR];               /* ranks this rank waits for */
+    unsigned long long *my_hflag;            /* [MAXR] */
+    double *my_ghost[2];
+    double *peer_red[ACGB200_MAXR];          /* rank r's red[][][][] base */
+    unsigned long long *peer_rflag[ACGB200_MAXR];   /* rank r's rflag[][] base */
+    double *my_red;
+    unsigned long long *my_rflag;
+    unsigned long long hbase, rbase;         /* sequence bases of the current solve */
+    unsigned int ticket;                     /* last-block detection (one kernel at a time uses it) */
+    /* inverse send map: border row b (relative to borderrowoffset) is sent to
+     * neighbours bq[e] at ghost offsets bdst[e], e in [bptr[b], bptr[b+1]) */
+    int borderoff, nborder;
+    const int *bptr, *bq, *bdst;
+    int fuse;                                /* 1: producers push/publish themselves; 0: comm_post_kernel does */
+};
+
+/* After the producer of a vector / of reduction partials: push them to the
+ * peers.  iter_override < 0: gated by *cin and using its iteration index. */
+struct acgb200_postargs {
+    struct acgb200_p2pdev *p2p;
+    const struct acgb200_ctrl *cin;
+    const struct acgb200_devstate *st;
+    int iter_override;
+    const double *vec; const int *sendbufidx;     /* halo part; vec == NULL: none */
+    int ch; const double *redbase; int redstride, redcount, par_off, seq_off;   /* reduction part; ch < 0: none */
+};
+int acgb200_comm_post(const struct acgb200_postargs *a, cudaStream_t stream);
+
 /* kernels.cu ------------------------------------------------------------- */
 
 /* choose tile parameters for a matrix with the given shape; fills everything
@@ -105,6 +161,13 @@ struct acgb200_spmvargs {
     struct acgb200_ctrl *ctrl_out;
     struct acgb200_devstate *st;          /* for per-iteration scalar housekeeping; may be NULL */
     int housekeeping;                     /* 0 none, 1 classic, 2 pipelined */
+    /* peer-memory mode: the border x ghost block is applied inside the kernel
+     * (ghost values from the window once the senders have published) and the
+     * last CTA publishes the fused dot on reduction channel pub_ch */
+    const struct acgb200_p2pdev *p2p;
+    int od_rowoffset, od_nrows;
+    const int *orowptr; const int *ocolidx; const double *oa;
+    int pub_ch;                           /* -1: do not publish */
 };
 int acgb200_spmv_launch(const struct acgb200_spmvargs *args, cudaStream_t stream);
 
@@ -121,18 +184,25 @@ struct acgb200_offdiagargs {
     const struct acgb200_ctrl *ctrl_in;
     struct acgb200_ctrl *ctrl_out;
     struct acgb200_devstate *st;
+    const struct acgb200_p2pdev *p2p;   /* not NULL: ghosts come from the peer-memory window */
+    int p2p_iter_override;              /* >= 0: wait for that halo sequence index (setup) */
 };
 int acgb200_offdiag_launch(const struct acgb200_offdiagargs *args, cudaStream_t stream);
 
 /* classic CG fused BLAS-1 (replace acg/cg-kernels-cuda.cu:119-303 and the two
  * cublasDdot calls at acg/cgcuda.c:894,933) */
+/* p2p != NULL: reductions come from / go to the peer-memory window and the
+ * kernels that produce the next SpMV input push its border entries themselves */
 int acgb200_cg_update_r(int n, struct acgb200_devstate *st, int cin, int cout, int multi,
+                        struct acgb200_p2pdev *p2p,
                         const double *t, double *r, cudaStream_t stream);
 int acgb200_cg_update_xp(int n, struct acgb200_devstate *st, int cin, int cout, int multi,
+                         struct acgb200_p2pdev *p2p,
                          const double *r, double *p, double *x, cudaStream_t stream);
 /* pipelined CG fused update + next dots (replaces acg/cg-kernels-cuda.cu:187-269
  * and the cublasDdot calls at acg/cgcuda.c:1680,1688) */
 int acgb200_pcg_update(int n, struct acgb200_devstate *st, int cin, int cout, int multi,
+                       struct acgb200_p2pdev *p2p,
                        const double *q, double *z, double *w, double *t, double *p,
                        double *r, double *x, cudaStream_t stream);
 

@@ -29,6 +29,11 @@
 #include <stdint.h>
 
 #define SPMV_THREADS 128
+/* Resident CTAs per SM the register allocator must leave room for.  Without
+ * it ptxas squeezes the kernel into 32 registers (full-occupancy default) and
+ * serialises the x gathers; shared memory limits residency to ~10 CTAs of 128
+ * threads anyway, so 48 registers cost no occupancy. */
+#define SPMV_MINB(T) ((T) >= 512 ? 2 : 1280 / (T))
 #define SPMV_MAX_STAGES 8
 #define BLAS1_THREADS 512
 
@@ -152,6 +157,150 @@ __device__ __forceinline__ Gate gate_read(const acgb200_ctrl *cin, const acgb200
 }
 
 /* ------------------------------------------------------------------------ */
+/* peer-memory exchange: flags and reductions                                */
+/* ------------------------------------------------------------------------ */
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+#define RED_IDX(ch, parity, rank) ((((ch) * 2 + (parity)) * ACGB200_MAXR + (rank)) * 2)
+
+/* Block-wide: wait until every sender has published halo sequence `seq`. */
+__device__ __forceinline__ void p2p_wait_halo(const acgb200_p2pdev *P, unsigned long long seq)
+{
+    if ((int) threadIdx.x < P->nsenders) {
+        const unsigned long long *f = P->my_hflag + P->senders[threadIdx.x];
+        while (ld_acquire_sys(f) < seq) { }
+    }
+    __syncthreads();
+}
+
+/* Block-wide: wait until every rank has published sequence `seq` on channel
+ * `ch`, then sum the partials of that parity in rank order (the same order on
+ * every rank, so all ranks get bit-identical sums).  out[0..1] in shared memory. */
+__device__ __forceinline__ void p2p_reduce(const acgb200_p2pdev *P, int ch, int parity, unsigned long long seq, double *out)
+{
+    if ((int) threadIdx.x < P->nranks) {
+        const unsigned long long *f = P->my_rflag + ch * ACGB200_MAXR + threadIdx.x;
+        while (ld_acquire_sys(f) < seq) { }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int r = 0; r < P->nranks; r++) {
+            const volatile double *s = P->my_red + RED_IDX(ch, parity, r);
+            a += s[0]; b += s[1];
+        }
+        out[0] = a; out[1] = b;
+    }
+    __syncthreads();
+}
+
+/* sum of an already complete parity slot (no waiting) */
+__device__ __forceinline__ double p2p_sum_slot(const acgb200_p2pdev *P, int ch, int parity)
+{
+    double a = 0.0;
+    for (int r = 0; r < P->nranks; r++) a += ((const volatile double *) P->my_red)[RED_IDX(ch, parity, r)];
+    return a;
+}
+
+/* True in exactly one CTA of the grid: the last one to get here.  Every CTA
+ * must have fenced its own stores (system scope) before calling. */
+__device__ __forceinline__ bool p2p_last_block(acgb200_p2pdev *P, int *flag_smem)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&P->ticket, 1u);
+        *flag_smem = (t == gridDim.x - 1);
+        if (*flag_smem) P->ticket = 0;
+    }
+    __syncthreads();
+    const bool last = *flag_smem != 0;
+    if (last) __threadfence_system();
+    return last;
+}
+
+/* last CTA: write `count` reduction partials read from `src` (device scalars
+ * completed by atomics of all CTAs) into every rank's slot, then the flags */
+__device__ __forceinline__ void p2p_publish_red(acgb200_p2pdev *P, int ch, int parity, unsigned long long seq,
+                                                double *src, int count)
+{
+    if ((int) threadIdx.x < P->nranks) {
+        double *dst = P->peer_red[threadIdx.x] + RED_IDX(ch, parity, P->rank);
+        dst[0] = atomicAdd(&src[0], 0.0);
+        dst[1] = count > 1 ? atomicAdd(&src[1], 0.0) : 0.0;
+        __threadfence_system();
+        st_release_sys(P->peer_rflag[threadIdx.x] + ch * ACGB200_MAXR + P->rank, seq);
+    }
+}
+
+__device__ __forceinline__ void p2p_publish_halo(acgb200_p2pdev *P, unsigned long long seq)
+{
+    if ((int) threadIdx.x < P->nrecip) st_release_sys(P->peer_hflag[threadIdx.x], seq);
+}
+
+/* a producer thread pushes the new value of border row `row` to the neighbours */
+__device__ __forceinline__ void p2p_push_row(const acgb200_p2pdev *P, int row, int parity, double v)
+{
+    const int b = row - P->borderoff;
+    for (int e = P->bptr[b]; e < P->bptr[b + 1]; e++) P->peer_ghost[P->bq[e]][parity][P->bdst[e]] = v;
+}
+
+/* Push halo values and/or reduction partials into the peers' windows, then
+ * publish the sequence numbers (last block to finish does the publishing). */
+__global__ void __launch_bounds__(512)
+comm_post_kernel(const acgb200_postargs A)
+{
+    __shared__ int is_last;
+    acgb200_p2pdev *P = A.p2p;
+    int iter = A.iter_override;
+    if (iter < 0) {
+        const Gate g = gate_read(A.cin, A.st);
+        if (!g.active) return;
+        iter = g.iter;
+    }
+    if (A.vec) {
+        const int parity = iter & 1;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P->sendsize; i += gridDim.x * blockDim.x) {
+            int q = 0;
+            while (i >= P->sdispls[q + 1]) q++;
+            P->peer_ghost[q][parity][P->peer_rdispl[q] + (i - P->sdispls[q])] = A.vec[A.sendbufidx[i]];
+        }
+    }
+    if (A.ch >= 0 && blockIdx.x == 0 && (int) threadIdx.x < P->nranks) {
+        const int parity = (iter + A.par_off) & 1;
+        const double *src = A.redbase + parity * A.redstride;
+        double *dst = P->peer_red[threadIdx.x] + RED_IDX(A.ch, parity, P->rank);
+        dst[0] = src[0];
+        dst[1] = A.redcount > 1 ? src[1] : 0.0;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&P->ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence_system();
+    if (A.vec && (int) threadIdx.x < P->nrecip)
+        st_release_sys(P->peer_hflag[threadIdx.x], P->hbase + (unsigned long long) iter);
+    if (A.ch >= 0 && (int) threadIdx.x < P->nranks)
+        st_release_sys(P->peer_rflag[threadIdx.x] + A.ch * ACGB200_MAXR + P->rank,
+                       P->rbase + (unsigned long long) (iter + A.seq_off));
+    if (threadIdx.x == 0) P->ticket = 0;
+}
+
+/* ------------------------------------------------------------------------ */
 /* SpMV over TMA-staged row tiles                                            */
 /* ------------------------------------------------------------------------ */
 
@@ -174,6 +323,12 @@ struct SpmvParams {
     acgb200_ctrl *ctrl_out;
     acgb200_devstate *st;
     int housekeeping;
+    acgb200_p2pdev *p2p;
+    int od_rowoffset, od_nrows;
+    const int *orowptr;
+    const int *ocolidx;
+    const double *oa;
+    int pub_ch;
 };
 
 __device__ __forceinline__ void spmv_issue(
@@ -203,12 +358,13 @@ __device__ __forceinline__ void spmv_issue(
  * valid address.
  */
 template <int G, int T, int U>
-__global__ void __launch_bounds__(T)
+__global__ void __launch_bounds__(T, SPMV_MINB(T))
 spmv_tiles_kernel(const SpmvParams P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[SPMV_MAX_STAGES];
     __shared__ double red[T / 32];
+    __shared__ int last_flag;
 
     const int tid = threadIdx.x;
     const Gate gate = gate_read(P.ctrl_in, P.st);
@@ -241,11 +397,19 @@ spmv_tiles_kernel(const SpmvParams P)
     const int lane = tid % G;
     const int grp = tid / G;
     double dot = 0.0;
+    const double *xg = NULL;            /* ghost values (peer-memory mode), set on the first border tile */
 
     int i = 0;
     for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, i++) {
         const int s = i % S;
         const acgb200_tile tl = P.tiles[t];
+        if (P.p2p && !xg && tl.row_begin + tl.nrows > P.od_rowoffset) {
+            /* first tile with border rows: from here on the neighbours' values
+             * are needed.  Border rows come last, so by now they have long
+             * arrived and the wait is a single flag read per sender. */
+            p2p_wait_halo(P.p2p, P.p2p->hbase + (unsigned long long) gate.iter);
+            xg = P.p2p->my_ghost[gate.iter & 1] - P.od_nrows;
+        }
         unsigned char *stage = smem + (size_t) s * P.stage_bytes;
         const double *vals = reinterpret_cast<const double *>(stage);
         const int *cols = reinterpret_cast<const int *>(stage + (size_t) P.sc * 8);
@@ -276,6 +440,13 @@ spmv_tiles_kernel(const SpmvParams P)
 #pragma unroll
                     for (int u = 0; u < U; u++) sum = fma((k + u * G < ke) ? v[u] : 0.0, xv[u], sum);
                 }
+                if (xg && tl.row_begin + lr >= P.od_rowoffset) {
+                    /* border x ghost block (acg/cgcuda.c:878), ocolidx rebased by
+                     * -borderrowoffset so ghosts start at od_nrows */
+                    const int ob = tl.row_begin + lr - P.od_rowoffset;
+                    for (int k = P.orowptr[ob] + lane; k < P.orowptr[ob + 1]; k += G)
+                        sum = fma(P.oa[k], xg[P.ocolidx[k]], sum);
+                }
             }
             if (G > 1) sum = group_sum<G>(sum);
             if (lr < tl.nrows && lane == 0) {
@@ -301,6 +472,12 @@ spmv_tiles_kernel(const SpmvParams P)
     if (P.acc) {
         const double v = block_sum(dot, red);
         if (tid == 0 && v != 0.0) atomicAdd(P.acc, v);
+    }
+    if (P.p2p && P.pub_ch >= 0 && P.p2p->fuse) {
+        /* the last CTA to finish sends this rank's share of the fused dot to all ranks */
+        __threadfence();
+        if (p2p_last_block(P.p2p, &last_flag))
+            p2p_publish_red(P.p2p, P.pub_ch, gate.iter & 1, P.p2p->rbase + (unsigned long long) gate.iter + 1ull, P.acc, 1);
     }
 }
 
@@ -354,14 +531,24 @@ __global__ void __launch_bounds__(256)
 offdiag_kernel(const acgb200_offdiagargs A)
 {
     __shared__ double red[8];
-    if (!gate_read(A.ctrl_in, A.st).active) return;
+    const Gate g = gate_read(A.ctrl_in, A.st);
+    if (!g.active) return;
+    /* ghost values: the tail of x (filled by ncclRecv) or, with the peer-memory
+     * exchange, this iteration's parity buffer of the window, valid once every
+     * sender has published the iteration's sequence number.  ocolidx is rebased
+     * by -borderrowoffset (acg/symcsrmatrix.c:838), ghosts start at nrows. */
+    const double *xg = A.x + A.rowoffset;
+    if (A.p2p) {
+        const int it = A.p2p_iter_override >= 0 ? A.p2p_iter_override : g.iter;
+        p2p_wait_halo(A.p2p, A.p2p->hbase + (unsigned long long) it);
+        xg = A.p2p->my_ghost[it & 1] - A.nrows;
+    }
     double dot = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.nrows; i += gridDim.x * blockDim.x) {
         const int kb = A.orowptr[i], ke = A.orowptr[i + 1];
         const int row = A.rowoffset + i;
         double sum = 0.0;
-        /* ocolidx is rebased by -borderrowoffset (acg/symcsrmatrix.c:838) */
-        for (int k = kb; k < ke; k++) sum = fma(A.oa[k], __ldg(A.x + A.rowoffset + A.ocolidx[k]), sum);
+        for (int k = kb; k < ke; k++) sum = fma(A.oa[k], xg[A.ocolidx[k]], sum);
         double v = A.y[row];
         if (kb != ke) { v = A.minus ? v - sum : v + sum; A.y[row] = v; }
         if (A.dotkind == 1) dot = fma(__ldg(A.x + row), v, dot);
@@ -379,16 +566,27 @@ offdiag_kernel(const acgb200_offdiagargs A)
 
 /* r -= alpha t with alpha = (r,r)/(p,Ap), and the new (r,r) in the same pass */
 __global__ void __launch_bounds__(BLAS1_THREADS)
-cg_update_r_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi,
+cg_update_r_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acgb200_p2pdev *P,
                    const double *__restrict__ t, double *__restrict__ r)
 {
     __shared__ double red[BLAS1_THREADS / 32];
+    __shared__ double glob[2];
+    __shared__ int last_flag;
     const Gate g = gate_read(&st->ctrl[cin], st);
     if (cin != cout && blockIdx.x == 0 && threadIdx.x == 0) st->ctrl[cout] = st->ctrl[cin];
     if (!g.active) return;
     const int s = g.iter & 1;
-    const double rr = multi ? st->rr[s] : st->rr_loc[s];
-    const double pap = multi ? st->pap[s] : st->pap_loc[s];
+    double rr, pap;
+    if (P) {
+        /* (p,Ap) of this iteration arrives on channel 0; (r,r) was completed on
+         * channel 1 one iteration ago (setup value for the first iteration) */
+        p2p_reduce(P, 0, s, P->rbase + (unsigned long long) g.iter + 1ull, glob);
+        pap = glob[0];
+        rr = g.iter > 0 ? p2p_sum_slot(P, 1, s) : st->rr[0];
+    } else {
+        rr = multi ? st->rr[s] : st->rr_loc[s];
+        pap = multi ? st->pap[s] : st->pap_loc[s];
+    }
     const double alpha = rr / pap;
     double acc = 0.0;
     const int n2 = n >> 1;
@@ -410,22 +608,38 @@ cg_update_r_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi,
     }
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) atomicAdd(&st->rr_loc[s ^ 1], acc);
+    if (P && P->fuse) {
+        __threadfence();
+        if (p2p_last_block(P, &last_flag))
+            p2p_publish_red(P, 1, s ^ 1, P->rbase + (unsigned long long) g.iter + 1ull, &st->rr_loc[s ^ 1], 1);
+    }
 }
 
 /* x += alpha p ; p = r + beta p ; decides convergence for the next iteration */
 __global__ void __launch_bounds__(BLAS1_THREADS)
-cg_update_xp_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi,
+cg_update_xp_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acgb200_p2pdev *P,
                     const double *__restrict__ r, double *__restrict__ p, double *__restrict__ x)
 {
+    __shared__ double glob[2];
+    __shared__ int last_flag;
     const Gate g = gate_read(&st->ctrl[cin], st);
     const int s = g.iter & 1;
-    const double rr = multi ? st->rr[s] : st->rr_loc[s];
-    const double rrn = multi ? st->rr[s ^ 1] : st->rr_loc[s ^ 1];
-    const double pap = multi ? st->pap[s] : st->pap_loc[s];
+    double rr, rrn, pap;
+    if (P && g.active) {
+        p2p_reduce(P, 1, s ^ 1, P->rbase + (unsigned long long) g.iter + 1ull, glob);
+        rrn = glob[0];
+        rr = g.iter > 0 ? p2p_sum_slot(P, 1, s) : st->rr[0];
+        pap = p2p_sum_slot(P, 0, s);
+    } else {
+        rr = multi ? st->rr[s] : st->rr_loc[s];
+        rrn = multi ? st->rr[s ^ 1] : st->rr_loc[s ^ 1];
+        pap = multi ? st->pap[s] : st->pap_loc[s];
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         acgb200_ctrl c = st->ctrl[cin];
         if (g.active) {
             c.iter = g.iter + 1;
+            if (P) st->rr[s ^ 1] = rrn;    /* keep the global value where the host reads it */
             /* acg/cgcuda.c:1008-1012: test ||r|| < tol with the norm, strictly */
             if (st->tol > 0.0 && sqrt(rrn) < st->tol) { c.done = 1; st->final_rr = rrn; }
             st->pap_loc[s ^ 1] = 0.0;      /* accumulator of the next SpMV */
@@ -449,11 +663,23 @@ cg_update_xp_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi,
         pv.y = fma(beta, pv.y, rv.y);
         x2[i] = xv;
         p2[i] = pv;
+        if (P && P->fuse && 2 * i + 1 >= P->borderoff) {
+            /* p is the input of the next SpMV: its border entries go straight
+             * into the neighbours' ghost buffers of the next iteration's parity */
+            if (2 * i >= P->borderoff) p2p_push_row(P, 2 * i, s ^ 1, pv.x);
+            p2p_push_row(P, 2 * i + 1, s ^ 1, pv.y);
+        }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const double pv = p[n - 1];
         x[n - 1] = fma(alpha, pv, x[n - 1]);
-        p[n - 1] = fma(beta, pv, r[n - 1]);
+        const double pn = fma(beta, pv, r[n - 1]);
+        p[n - 1] = pn;
+        if (P && P->fuse && n - 1 >= P->borderoff) p2p_push_row(P, n - 1, s ^ 1, pn);
+    }
+    if (P && P->fuse) {
+        __threadfence_system();
+        if (p2p_last_block(P, &last_flag)) p2p_publish_halo(P, P->hbase + (unsigned long long) g.iter + 1ull);
     }
 }
 
@@ -461,16 +687,25 @@ cg_update_xp_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi,
  * w-=alpha z (acg/cg-kernels-cuda.cu:201-214), plus gamma'=(r,r), delta'=(w,r)
  * of the updated vectors for the next iteration. */
 __global__ void __launch_bounds__(BLAS1_THREADS)
-pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi,
+pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acgb200_p2pdev *P,
                   const double *__restrict__ q, double *__restrict__ z, double *__restrict__ w,
                   double *__restrict__ t, double *__restrict__ p, double *__restrict__ r,
                   double *__restrict__ x)
 {
     __shared__ double red[BLAS1_THREADS / 32];
+    __shared__ double glob[2];
+    __shared__ int last_flag;
     const Gate g = gate_read(&st->ctrl[cin], st);
     const int s = g.iter & 1;
-    const double gamma = multi ? st->gd[s][0] : st->gd_loc[s][0];
-    const double delta = multi ? st->gd[s][1] : st->gd_loc[s][1];
+    double gamma, delta;
+    if (P && g.active && g.iter > 0) {
+        /* {gamma,delta} pushed by every rank after its previous update */
+        p2p_reduce(P, 0, s, P->rbase + (unsigned long long) g.iter, glob);
+        gamma = glob[0]; delta = glob[1];
+    } else {
+        gamma = multi ? st->gd[s][0] : st->gd_loc[s][0];
+        delta = multi ? st->gd[s][1] : st->gd_loc[s][1];
+    }
     const double gamma_prev = st->prev[s][0], alpha_prev = st->prev[s][1];
     /* acg/cgcuda.c:1764-1772: the test precedes the update */
     const bool conv = st->tol > 0.0 && sqrt(gamma) < st->tol;
@@ -479,6 +714,7 @@ pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi,
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         acgb200_ctrl c = st->ctrl[cin];
         if (g.active) {
+            if (P) { st->gd[s][0] = gamma; st->gd[s][1] = delta; }   /* for the host's final report */
             if (conv) { c.done = 1; st->final_rr = gamma; }
             else { c.iter = g.iter + 1; st->prev[s ^ 1][0] = gamma; st->prev[s ^ 1][1] = alpha; }
         }
@@ -497,12 +733,24 @@ pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi,
         r[i] = rv; w[i] = wv;
         g2 = fma(rv, rv, g2);
         d2 = fma(wv, rv, d2);
+        /* w is the input of the next SpMV: border entries go to the neighbours */
+        if (P && P->fuse && i >= P->borderoff) p2p_push_row(P, i, s ^ 1, wv);
     }
     g2 = block_sum(g2, red);
     d2 = block_sum(d2, red);
     if (threadIdx.x == 0) {
         atomicAdd(&st->gd_loc[s ^ 1][0], g2);
         atomicAdd(&st->gd_loc[s ^ 1][1], d2);
+    }
+    if (P && P->fuse) {
+        /* last CTA: this rank's {gamma,delta} of the next iteration to every
+         * rank, and the halo sequence number to the neighbours */
+        __threadfence_system();
+        if (p2p_last_block(P, &last_flag)) {
+            const unsigned long long it1 = (unsigned long long) g.iter + 1ull;
+            p2p_publish_red(P, 0, s ^ 1, P->rbase + it1, &st->gd_loc[s ^ 1][0], 2);
+            p2p_publish_halo(P, P->hbase + it1);
+        }
     }
 }
 
@@ -660,6 +908,8 @@ extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t strea
         P.rowptr = a->rowptr; P.colidx = a->colidx; P.a = a->a; P.x = a->x; P.y = a->y; P.b = a->b;
         P.acc = a->acc; P.dotrows = a->dotrows; P.mode = a->mode;
         P.ctrl_in = a->ctrl_in; P.ctrl_out = a->ctrl_out; P.st = a->st; P.housekeeping = a->housekeeping;
+        P.p2p = (acgb200_p2pdev *) a->p2p; P.od_rowoffset = a->od_rowoffset; P.od_nrows = a->od_nrows;
+        P.orowptr = a->orowptr; P.ocolidx = a->ocolidx; P.oa = a->oa; P.pub_ch = a->p2p ? a->pub_ch : -1;
         spmv_variant(pl->lanes_per_row, pl->threads, pl->unroll)<<<pl->grid, pl->threads, pl->smem_bytes, stream>>>(P);
         cudaError_t err = cudaGetLastError();
         if (err) return (int) err;
@@ -695,24 +945,40 @@ extern "C" int acgb200_offdiag_launch(const acgb200_offdiagargs *a, cudaStream_t
 }
 
 extern "C" int acgb200_cg_update_r(int n, acgb200_devstate *st, int cin, int cout, int multi,
+                                   acgb200_p2pdev *p2p,
                                    const double *t, double *r, cudaStream_t stream)
 {
-    cg_update_r_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, st, cin, cout, multi, t, r);
+    cg_update_r_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, st, cin, cout, multi, p2p, t, r);
     return (int) cudaGetLastError();
 }
 
 extern "C" int acgb200_cg_update_xp(int n, acgb200_devstate *st, int cin, int cout, int multi,
+                                    acgb200_p2pdev *p2p,
                                     const double *r, double *p, double *x, cudaStream_t stream)
 {
-    cg_update_xp_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, st, cin, cout, multi, r, p, x);
+    cg_update_xp_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, st, cin, cout, multi, p2p, r, p, x);
     return (int) cudaGetLastError();
 }
 
 extern "C" int acgb200_pcg_update(int n, acgb200_devstate *st, int cin, int cout, int multi,
+                                  acgb200_p2pdev *p2p,
                                   const double *q, double *z, double *w, double *t, double *p,
                                   double *r, double *x, cudaStream_t stream)
 {
-    pcg_update_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, st, cin, cout, multi, q, z, w, t, p, r, x);
+    pcg_update_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, st, cin, cout, multi, p2p, q, z, w, t, p, r, x);
+    return (int) cudaGetLastError();
+}
+
+extern "C" int acgb200_comm_post(const acgb200_postargs *a, cudaStream_t stream)
+{
+    int grid = 1;
+    if (a->vec) {
+        /* sendsize is only known on the device descriptor's host mirror; the caller
+         * passes it through redstride when there is no reduction part -- keep it
+         * simple: a handful of CTAs is enough for halos of 10^4-10^5 entries */
+        grid = 8;
+    }
+    comm_post_kernel<<<grid, 512, 0, stream>>>(*a);
     return (int) cudaGetLastError();
 }
 

@@ -1,0 +1,165 @@
+/*
+ * p2p.c -- set-up of the peer-memory exchange (CUDA IPC over NVLink/NVSwitch).
+ *
+ * One process per GPU; the only bootstrap channel is the NCCL communicator the
+ * caller passed in: the IPC handle of this rank's window and the layout facts
+ * its peers need are all-gathered with ncclAllGather.  See internal.h for the
+ * window layout and kernels.cu (comm_post_kernel, p2p_wait_halo, p2p_reduce)
+ * for the data path.
+ */
+#include "acgb200/error.h"
+#include "acgb200/halo.h"
+#include "internal.h"
+#include "p2p.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+struct record {                       /* what every rank tells every other rank */
+    cudaIpcMemHandle_t handle;
+    int recvsize;
+    int rdispl_for[ACGB200_MAXR];     /* offset of sender q's segment in my ghost buffer, -1: not a neighbour */
+};
+
+static size_t off_hflag(void) { return 0; }
+static size_t off_rflag(void) { return off_hflag() + ACGB200_MAXR * sizeof(unsigned long long); }
+static size_t off_red(void) { return off_rflag() + ACGB200_NCH * ACGB200_MAXR * sizeof(unsigned long long); }
+static size_t off_ghost(void) { return off_red() + (size_t) ACGB200_NCH * 2 * ACGB200_MAXR * 2 * sizeof(double); }
+static size_t ghost_stride(int recvsize) { return (((size_t) (recvsize > 0 ? recvsize : 1) + 15) & ~(size_t) 15) * sizeof(double); }
+
+void acgb200_p2p_free(struct acgb200_p2p *p)
+{
+    if (!p) return;
+    for (int r = 0; r < p->nranks; r++)
+        if (r != p->rank && p->peer_base[r]) cudaIpcCloseMemHandle(p->peer_base[r]);
+    cudaFree((void *) p->h_desc.bptr); cudaFree((void *) p->h_desc.bq); cudaFree((void *) p->h_desc.bdst);
+    cudaFree(p->d_desc);
+    /* the window itself is freed by the caller after a barrier (peers may still
+     * have it mapped) */
+}
+
+int acgb200_p2p_init(struct acgb200_p2p *p, const struct acghalo *halo, int borderoff, int nborder,
+                     const struct acgcomm *comm, cudaStream_t stream, int *errcode)
+{
+    memset(p, 0, sizeof(*p));
+    int nranks = 1, rank = 0;
+    int err = acgcomm_size(comm, &nranks); if (err) return err;
+    err = acgcomm_rank(comm, &rank); if (err) return err;
+    if (nranks < 2 || nranks > ACGB200_MAXR || comm->type != acgcomm_nccl) return ACG_ERR_NOT_SUPPORTED;
+    if (halo->nrecipients > ACGB200_MAXR || halo->nsenders > ACGB200_MAXR) return ACG_ERR_NOT_SUPPORTED;
+    p->nranks = nranks; p->rank = rank;
+
+#define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { if (errcode) *errcode = (int) e_; return ACG_ERR_CUDA; } } while (0)
+    p->window_bytes = off_ghost() + 2 * ghost_stride(halo->recvsize);
+    CUP(cudaMalloc(&p->window, p->window_bytes));
+    CUP(cudaMemset(p->window, 0, p->window_bytes));
+
+    /* all-gather the records */
+    struct record mine, *all = malloc((size_t) nranks * sizeof(*all));
+    if (!all) return ACG_ERR_ERRNO;
+    memset(&mine, 0, sizeof(mine));
+    CUP(cudaIpcGetMemHandle(&mine.handle, p->window));
+    mine.recvsize = halo->recvsize;
+    for (int q = 0; q < ACGB200_MAXR; q++) mine.rdispl_for[q] = -1;
+    for (int j = 0; j < halo->nsenders; j++) mine.rdispl_for[halo->senders[j]] = halo->rdispls[j];
+    void *d_mine = NULL, *d_all = NULL;
+    CUP(cudaMalloc(&d_mine, sizeof(mine)));
+    CUP(cudaMalloc(&d_all, (size_t) nranks * sizeof(mine)));
+    CUP(cudaMemcpyAsync(d_mine, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream));
+    ncclResult_t nr = ncclAllGather(d_mine, d_all, sizeof(mine), ncclChar, comm->ncclcomm, stream);
+    if (nr != ncclSuccess) { if (errcode) *errcode = (int) nr; free(all); return ACG_ERR_NCCL; }
+    CUP(cudaMemcpyAsync(all, d_all, (size_t) nranks * sizeof(mine), cudaMemcpyDeviceToHost, stream));
+    CUP(cudaStreamSynchronize(stream));
+    cudaFree(d_mine); cudaFree(d_all);
+
+    /* map every peer's window */
+    for (int r = 0; r < nranks; r++) {
+        if (r == rank) { p->peer_base[r] = p->window; continue; }
+        cudaError_t e = cudaIpcOpenMemHandle(&p->peer_base[r], all[r].handle, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { if (errcode) *errcode = (int) e; free(all); return ACG_ERR_CUDA; }
+    }
+
+    /* device descriptor */
+    struct acgb200_p2pdev *d = &p->h_desc;
+    memset(d, 0, sizeof(*d));
+    d->nranks = nranks; d->rank = rank;
+    d->nrecip = halo->nrecipients; d->sendsize = halo->sendsize;
+    for (int i = 0; i < halo->nrecipients; i++) {
+        const int q = halo->recipients[i];
+        d->sdispls[i] = halo->sdispls[i];
+        d->peer_rdispl[i] = all[q].rdispl_for[rank];
+        if (d->peer_rdispl[i] < 0) { free(all); return ACG_ERR_INVALID_VALUE; }   /* asymmetric pattern */
+        char *base = p->peer_base[q];
+        d->peer_ghost[i][0] = (double *) (base + off_ghost());
+        d->peer_ghost[i][1] = (double *) (base + off_ghost() + ghost_stride(all[q].recvsize));
+        d->peer_hflag[i] = (unsigned long long *) (base + off_hflag()) + rank;
+    }
+    d->sdispls[halo->nrecipients] = halo->sendsize;
+    d->nsenders = halo->nsenders;
+    for (int j = 0; j < halo->nsenders; j++) d->senders[j] = halo->senders[j];
+    char *me = p->window;
+    d->my_hflag = (unsigned long long *) (me + off_hflag());
+    d->my_ghost[0] = (double *) (me + off_ghost());
+    d->my_ghost[1] = (double *) (me + off_ghost() + ghost_stride(halo->recvsize));
+    for (int r = 0; r < nranks; r++) {
+        char *base = p->peer_base[r];
+        d->peer_red[r] = (double *) (base + off_red());
+        d->peer_rflag[r] = (unsigned long long *) (base + off_rflag());
+    }
+    d->my_red = (double *) (me + off_red());
+    d->my_rflag = (unsigned long long *) (me + off_rflag());
+    d->hbase = d->rbase = 1;
+    /* inverse send map: which (neighbour, ghost offset) pairs each border row feeds */
+    d->borderoff = borderoff; d->nborder = nborder;
+    {
+        int *bptr = calloc((size_t) nborder + 2, sizeof(int));
+        int *bq = malloc((size_t) (halo->sendsize > 0 ? halo->sendsize : 1) * sizeof(int));
+        int *bdst = malloc((size_t) (halo->sendsize > 0 ? halo->sendsize : 1) * sizeof(int));
+        if (!bptr || !bq || !bdst) { free(bptr); free(bq); free(bdst); free(all); return ACG_ERR_ERRNO; }
+        for (int i = 0; i < halo->sendsize; i++) {
+            const int b = halo->sendbufidx[i] - borderoff;
+            if (b < 0 || b >= nborder) { free(bptr); free(bq); free(bdst); free(all); return ACG_ERR_INVALID_VALUE; }
+            bptr[b + 2]++;
+        }
+        for (int b = 0; b < nborder; b++) bptr[b + 2] += bptr[b + 1];
+        for (int q = 0; q < halo->nrecipients; q++) {
+            for (int i = halo->sdispls[q]; i < halo->sdispls[q] + halo->sendcounts[q]; i++) {
+                const int b = halo->sendbufidx[i] - borderoff;
+                const int e = bptr[b + 1]++;
+                bq[e] = q;
+                bdst[e] = d->peer_rdispl[q] + (i - halo->sdispls[q]);
+            }
+        }
+        int *d_bptr = NULL, *d_bq = NULL, *d_bdst = NULL;
+        const size_t ne = (size_t) (halo->sendsize > 0 ? halo->sendsize : 1);
+        CUP(cudaMalloc((void **) &d_bptr, ((size_t) nborder + 1) * sizeof(int)));
+        CUP(cudaMalloc((void **) &d_bq, ne * sizeof(int)));
+        CUP(cudaMalloc((void **) &d_bdst, ne * sizeof(int)));
+        CUP(cudaMemcpy(d_bptr, bptr, ((size_t) nborder + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        CUP(cudaMemcpy(d_bq, bq, (size_t) halo->sendsize * sizeof(int), cudaMemcpyHostToDevice));
+        CUP(cudaMemcpy(d_bdst, bdst, (size_t) halo->sendsize * sizeof(int), cudaMemcpyHostToDevice));
+        d->bptr = d_bptr; d->bq = d_bq; d->bdst = d_bdst;
+        free(bptr); free(bq); free(bdst);
+    }
+    free(all);
+    CUP(cudaMalloc((void **) &p->d_desc, sizeof(*d)));
+    CUP(cudaMemcpy(p->d_desc, d, sizeof(*d), cudaMemcpyHostToDevice));
+    p->seq = 1;
+    p->enabled = 1;
+    return ACG_SUCCESS;
+#undef CUP
+}
+
+/* start a new solve: fresh sequence bases above everything published so far
+ * (identical on all ranks, which make identical call sequences) */
+int acgb200_p2p_begin(struct acgb200_p2p *p, int maxits, cudaStream_t stream)
+{
+    p->seq += 4;
+    p->h_desc.hbase = p->h_desc.rbase = p->seq;
+    p->seq += (unsigned long long) maxits + 4;
+    /* hbase and rbase are adjacent: one 16-byte copy */
+    cudaError_t e = cudaMemcpyAsync(&p->d_desc->hbase, &p->h_desc.hbase, 2 * sizeof(unsigned long long),
+                                    cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    return e == cudaSuccess ? ACG_SUCCESS : ACG_ERR_CUDA;
+}

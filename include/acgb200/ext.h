@@ -40,6 +40,7 @@ struct acgb200_info {
                                    end of the loop: the window of tsolve, acg/cgcuda.c:719-722,:1021), CUDA events */
     double last_h2d_ms;         /* host time of the b, x0 upload of the last solve */
     double last_d2h_ms;         /* host time of the x download of the last solve */
+    double last_blas_ms;        /* device time of the fused vector-update kernels of the last solve (profile=1) */
 };
 ACG_API int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info);
 

@@ -11,7 +11,7 @@ import json,sys
 name=sys.argv[1]
 try:
     d=json.loads(open(f'gpurun_out/var_{name}.json').read().strip().splitlines()[-1])
-    print(f"{name}: value {d['value']:.1f} it/s e2e {d['e2e']['value']:.1f} ms/step {d['ms_per_step']:.2f} spmv {d['roofline']['ms_per_launch']:.4f} ms launches {d['gpu_launches']} resid {d['residual_after_step']:.6f}", flush=True)
+    print(f"{name}: value {d['value']:.1f} it/s e2e {d['e2e']['value']:.1f} ms/step {d['ms_per_step']:.2f} spmv {d['roofline']['ms_per_launch']:.4f} upd {d['roofline']['update_ms_per_iteration']:.4f} ms launches {d['gpu_launches']} resid {d['residual_after_step']:.6f}", flush=True)
 except Exception as e:
     print(name, "parse fail", e); print(open(f'gpurun_out/var_{name}.err').read()[-1500:])
 PY
