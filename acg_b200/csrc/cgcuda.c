@@ -1129,6 +1129,49 @@ int acgsolvercuda_fwrite(FILE *f, const struct acgsolvercuda *cg, int indent)
     return ACG_SUCCESS;
 }
 
+#ifdef ACG_HAVE_MPI
+/* acg/cgcuda.h:293 (acg/cgcuda.c:1948-2216): the same report on `root`, with
+ * times taken as the maximum and flop/byte/message counters as the sum over the
+ * ranks of `comm` -- the aggregation the reference performs with
+ * MPI_Reduce (:1990-2012).  `verbose` adds one halo line per rank. */
+int acgsolvercuda_fwritempi(FILE *f, const struct acgsolvercuda *cg, int indent, int verbose, MPI_Comm comm, int root)
+{
+    int rank = 0, size = 1;
+    MPI_Comm_rank(comm, &rank);
+    MPI_Comm_size(comm, &size);
+    struct acgsolvercuda agg = *cg;
+    double tin[8] = { cg->tsolve, cg->tgemv, cg->tdot, cg->tnrm2, cg->taxpy, cg->tcopy, cg->tallreduce, cg->thalo }, tout[8];
+    int64_t cin[16] = { cg->nflops, cg->Bgemv, cg->Bdot, cg->Bnrm2, cg->Baxpy, cg->Bcopy, cg->Ballreduce, cg->Bhalo,
+                        cg->nhalomsgs, 0, 0, 0, 0, 0, 0, 0 }, cout[16];
+    memcpy(tout, tin, sizeof(tin)); memcpy(cout, cin, sizeof(cin));
+    if (MPI_Reduce(tin, tout, 8, MPI_DOUBLE, MPI_MAX, root, comm)) return ACG_ERR_MPI;
+    if (MPI_Reduce(cin, cout, 16, MPI_INT64_T, MPI_SUM, root, comm)) return ACG_ERR_MPI;
+    if (rank == root) {
+        agg.tsolve = tout[0]; agg.tgemv = tout[1]; agg.tdot = tout[2]; agg.tnrm2 = tout[3];
+        agg.taxpy = tout[4]; agg.tcopy = tout[5]; agg.tallreduce = tout[6]; agg.thalo = tout[7];
+        agg.nflops = cout[0]; agg.Bgemv = cout[1]; agg.Bdot = cout[2]; agg.Bnrm2 = cout[3]; agg.Baxpy = cout[4];
+        agg.Bcopy = cout[5]; agg.Ballreduce = cout[6]; agg.Bhalo = cout[7]; agg.nhalomsgs = cout[8];
+        int err = acgsolvercuda_fwrite(f, &agg, indent);
+        if (err) return err;
+        fprintf(f, "%*sprocesses: %d\n", indent, "", size);
+    }
+    if (verbose > 0 && cg->halo) {
+        /* per-rank halo volume (the reference prints these under -v, :2060-2100) */
+        int64_t mine[4] = { cg->halo->nrecipients, cg->halo->sendsize, cg->halo->nsenders, cg->halo->recvsize };
+        int64_t *all = rank == root ? malloc((size_t) size * sizeof(mine)) : NULL;
+        if (MPI_Gather(mine, 4, MPI_INT64_T, all, 4, MPI_INT64_T, root, comm)) { free(all); return ACG_ERR_MPI; }
+        if (rank == root) {
+            fprintf(f, "%*shalo exchange pattern (rank: recipients sendsize senders recvsize):\n", indent, "");
+            for (int r = 0; r < size; r++)
+                fprintf(f, "%*s  %d: %" PRId64 " %" PRId64 " %" PRId64 " %" PRId64 "\n", indent, "", r,
+                        all[4 * r], all[4 * r + 1], all[4 * r + 2], all[4 * r + 3]);
+            free(all);
+        }
+    }
+    return ACG_SUCCESS;
+}
+#endif
+
 /* ------------------------------------------------------------------------ */
 /* extensions (include/acgb200/ext.h)                                        */
 /* ------------------------------------------------------------------------ */

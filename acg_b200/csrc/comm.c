@@ -23,6 +23,19 @@ const char *acgcommtypestr(enum acgcommtype t)
     }
 }
 
+/* acg/comm.h:188-240 */
+const char *acgdatatypestr(enum acgdatatype datatype) { return datatype == ACG_DOUBLE ? "double" : "unknown"; }
+const char *acgopstr(enum acgop op) { return op == ACG_SUM ? "sum" : "unknown"; }
+ncclDataType_t acgdatatype_nccl(enum acgdatatype datatype) { (void) datatype; return ncclDouble; }
+ncclRedOp_t acgop_nccl(enum acgop op) { (void) op; return ncclSum; }
+
+int acgdatatype_size(enum acgdatatype datatype, int *size)
+{
+    if (datatype != ACG_DOUBLE) return ACG_ERR_INVALID_VALUE;
+    *size = (int) sizeof(double);
+    return ACG_SUCCESS;
+}
+
 int acgcomm_init_nccl(struct acgcomm *comm, ncclComm_t ncclcomm, int *ncclerrcode)
 {
     (void) ncclerrcode;
@@ -94,7 +107,14 @@ int acgcomm_allreduce(const void *src, void *dst, int count, enum acgdatatype da
         if (r != ncclSuccess) { if (errcode) *errcode = (int) r; return ACG_ERR_NCCL; }
         return ACG_SUCCESS;
     }
-    if (comm->type == acgcomm_mpi) return ACG_ERR_MPI_NOT_SUPPORTED;
+    if (comm->type == acgcomm_mpi) {
+        /* MPI carries no data in this build; a one-rank MPI communicator (the
+         * reference driver's default --comm mpi on a single GPU) is a no-op */
+        int size = 1;
+        if (acgcomm_size(comm, &size) == ACG_SUCCESS && size == 1)
+            return acgcomm_allreduce(src, dst, count, datatype, op, stream, NULL, errcode);
+        return ACG_ERR_MPI_NOT_SUPPORTED;
+    }
     if (comm->type == acgcomm_nvshmem) return ACG_ERR_NVSHMEM_NOT_SUPPORTED;
     return ACG_ERR_INVALID_VALUE;
 }
@@ -108,6 +128,10 @@ int acgcomm_barrier(cudaStream_t stream, const struct acgcomm *comm, int *errcod
         if (r != ncclSuccess) { if (errcode) *errcode = (int) r; return ACG_ERR_NCCL; }
         return ACG_SUCCESS;
     }
-    if (comm->type == acgcomm_mpi) return ACG_ERR_MPI_NOT_SUPPORTED;
+    if (comm->type == acgcomm_mpi) {
+        int size = 1;
+        if (acgcomm_size(comm, &size) == ACG_SUCCESS && size == 1) return ACG_SUCCESS;
+        return ACG_ERR_MPI_NOT_SUPPORTED;
+    }
     return ACG_ERR_INVALID_VALUE;
 }

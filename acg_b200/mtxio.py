@@ -1,0 +1,36 @@
+"""Matrix Market output in the two encodings the reference driver reads
+(acg/mtxfile.c): plain text and aCG's binary variant (``--binary``: the text
+header and size line, then ``rowidx[nnz]``, ``colidx[nnz]`` as 1-based int32 and
+``a[nnz]`` as float64, acg/mtxfile.c:1107-1127; tools mtx2bin/mtx2bin.c:538-549
+produce the same layout).  Input is the upper-triangle COO of acg_b200.matgen."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def write_symmetric(path: str, n: int, rows, cols, vals, binary: bool = True) -> None:
+    rows = np.ascontiguousarray(rows, np.int32)
+    cols = np.ascontiguousarray(cols, np.int32)
+    vals = np.ascontiguousarray(vals, np.float64)
+    with open(path, "wb") as f:
+        f.write(b"%%MatrixMarket matrix coordinate real symmetric\n")
+        f.write(f"{n} {n} {len(vals)}\n".encode())
+        if binary:
+            (rows + 1).tofile(f)
+            (cols + 1).tofile(f)
+            vals.tofile(f)
+        else:
+            for i, j, a in zip(rows, cols, vals):
+                f.write(f"{i + 1} {j + 1} {a:.17g}\n".encode())
+
+
+def write_vector(path: str, x, binary: bool = True) -> None:
+    x = np.ascontiguousarray(x, np.float64)
+    with open(path, "wb") as f:
+        f.write(b"%%MatrixMarket vector array real general\n")
+        f.write(f"{len(x)}\n".encode())
+        if binary:
+            x.tofile(f)
+        else:
+            for a in x:
+                f.write(f"{a:.17g}\n".encode())

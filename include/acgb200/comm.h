@@ -47,6 +47,13 @@ struct acgcomm {
 enum acgdatatype { ACG_DOUBLE };
 enum acgop { ACG_SUM };
 
+/* acg/comm.h:188-240 */
+ACG_API const char *acgdatatypestr(enum acgdatatype datatype);
+ACG_API int acgdatatype_size(enum acgdatatype datatype, int *size);
+ACG_API ncclDataType_t acgdatatype_nccl(enum acgdatatype datatype);
+ACG_API const char *acgopstr(enum acgop op);
+ACG_API ncclRedOp_t acgop_nccl(enum acgop op);
+
 /* acg/comm.h:135 -- wraps (does not own) an existing NCCL communicator */
 ACG_API int acgcomm_init_nccl(struct acgcomm *comm, ncclComm_t ncclcomm, int *ncclerrcode);
 #if defined(ACG_HAVE_MPI)

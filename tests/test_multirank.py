@@ -16,10 +16,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _launch(nproc, extra, timeout=600):
+def _launch(nproc, extra, timeout=600, env_extra=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), WORKER] + extra
-    env = dict(os.environ, OMP_NUM_THREADS="2")
+    env = dict(os.environ, OMP_NUM_THREADS="2", **(env_extra or {}))
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     sys.stdout.write(p.stdout[-4000:])
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
@@ -49,11 +49,19 @@ def _ngpu():
         return 0
 
 
+# exchange back-ends of the CG loop: peer memory with pushes fused into the
+# kernels (default), peer memory with separate post kernels, NCCL only
+BACKENDS = {"p2p-fused": {}, "p2p-unfused": {"ACGB200_P2P_FUSE": "0"}, "nccl": {"ACGB200_P2P": "0"},
+            "nccl-nograph": {"ACGB200_P2P": "0", "ACGB200_GRAPH": "0"}}
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize("backend", list(BACKENDS))
 @pytest.mark.parametrize("matrix,size,partition", [("27pt", 24, "block"), ("7pt", 20, "slab"), ("rmat", 5000, "random")])
-def test_nccl_multi_gpu(matrix, size, partition):
+def test_multi_gpu(matrix, size, partition, backend):
     n = _ngpu()
     if n < 2:
         pytest.skip("needs at least 2 GPUs on the box (gpurun --gpus 2)")
-    _launch(min(n, 4) if n >= 4 and matrix == "27pt" else 2,
-            ["--mode", "gpu", "--matrix", matrix, "--size", str(size), "--partition", partition] + _its(matrix))
+    _launch(min(n, 8) if n >= 4 and matrix == "27pt" else 2,
+            ["--mode", "gpu", "--matrix", matrix, "--size", str(size), "--partition", partition] + _its(matrix),
+            env_extra=BACKENDS[backend])

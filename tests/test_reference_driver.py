@@ -1,0 +1,66 @@
+"""The UNMODIFIED reference driver cuda/acg-cuda.c linked against libacgb200_mpi.so.
+
+CPU part (build container, where /root/reference exists): the driver and the
+reference's host layer compile from where they lie and link against the library
+with no undefined symbol (tools/build_driver.sh) -- the "drop-in" claim of
+INTEGRATION.md, option A.  GPU part: the prebuilt binary (oracle/_ref/driver/,
+shipped by gpurun) reads a Matrix Market file, solves on the B200 through
+acgsolvercuda_init/_solvempi/_solve_pipelined/_fwritempi and prints x; iteration
+count, norms and solution are compared with the oracle.
+"""
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from acg_b200 import matgen as mg
+from acg_b200 import mtxio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "driver", "acg-cuda")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cuda"), reason="reference tree not present (GPU box)")
+def test_unmodified_driver_links_against_library():
+    p = subprocess.run(["bash", os.path.join(ROOT, "tools", "build_driver.sh")], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "undefined reference" not in p.stderr
+    v = subprocess.run([DRIVER, "--version"], capture_output=True, text=True)
+    assert v.returncode == 0 and "acg-cuda" in v.stdout
+    # the solver symbols resolve to the library, not to reference objects
+    nm = subprocess.run(["nm", "-D", "--undefined-only", DRIVER], capture_output=True, text=True).stdout
+    for sym in ("acgsolvercuda_init", "acgsolvercuda_solvempi", "acgsolvercuda_solve_pipelined",
+                "acgsolvercuda_fwritempi", "acgsolvercuda_free", "acgcomm_init_nccl", "acgcomm_init_mpi"):
+        assert re.search(rf"\bU {sym}\b", nm), sym
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver,method", [("acg", "cg"), ("acg-pipelined", "cg_pipelined")])
+def test_driver_solves_on_gpu(solver, method, oracle):
+    if not os.path.exists(DRIVER):
+        pytest.skip("driver binary not built (needs the reference tree at build time)")
+    n, r, c, v = mg.stencil3d_27pt(20)
+    csr = oracle.full_csr(n, r, c, v)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "A.mtx")
+        mtxio.write_symmetric(path, n, r, c, v, binary=True)
+        p = subprocess.run([DRIVER, path, "--binary", "--solver", solver, "--max-iterations", "200",
+                            "--residual-rtol", "1e-9", "--warmup", "2", "--numfmt", "%.17g"],
+                           capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-3000:]
+    rep = p.stderr
+    its = int(re.search(r"^\s*iterations: ([\d,]+)", rep, re.M).group(1).replace(",", ""))
+    rnrm2 = float(re.search(r"^\s*residual 2-norm: (\S+)", rep, re.M).group(1))
+    r0 = float(re.search(r"^\s*initial residual 2-norm: (\S+)", rep, re.M).group(1))
+    # the driver's default right-hand side is all ones (cuda/acg-cuda.c:1949-1967)
+    want = getattr(oracle, method)(csr, np.ones(n), maxits=200, rtol=1e-9)
+    assert its == want["niterations"]
+    assert r0 == pytest.approx(want["r0nrm2"], rel=1e-13)
+    assert rnrm2 / r0 == pytest.approx(want["rnrm2"] / want["r0nrm2"], rel=1e-6, abs=1e-10)
+    lines = [l for l in p.stdout.splitlines() if l and not l.startswith("%")]
+    x = np.array([float(t) for t in lines[1:]])
+    assert int(lines[0].split()[0]) == n and len(x) == n
+    assert np.abs(x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()

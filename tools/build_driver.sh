@@ -1,0 +1,28 @@
+#!/bin/bash
+# Build the UNMODIFIED reference driver cuda/acg-cuda.c against libacgb200_mpi.so.
+#
+# Everything compiled here comes from /root/reference where it lies (nothing is
+# copied into the repository); outputs go to oracle/_ref/driver/ (git-ignored,
+# shipped to the GPU box by gpurun).  The reference's CUDA solver sources
+# (acg/cgcuda.c, acg/cg-kernels-cuda.cu, acg/halo.cu, acg/comm.c and the NVSHMEM
+# wrappers) are NOT compiled: their symbols come from the library.  mpi.h is the
+# single-process stand-in compat/mpi/mpi.h, so the binary runs on one rank.
+set -e
+REF=${REF:-/root/reference}
+ROOT=$(cd "$(dirname "$0")/.." && pwd)
+OUT=$ROOT/oracle/_ref/driver
+CUDA=${CUDA:-/usr/local/cuda}
+mkdir -p "$OUT"
+make -s -C "$ROOT/acg_b200/csrc" mpi
+DEFS="-D_GNU_SOURCE -DHAVE_CLOCK_GETTIME -DACG_HAVE_OPENMP -DACG_HAVE_MPI -DACG_HAVE_NCCL -DACG_HAVE_CUBLAS -DACG_HAVE_CUSPARSE"
+INC="-I$REF -I$ROOT/compat/mpi -I$CUDA/include"
+/usr/bin/gcc -O2 -g -fopenmp $DEFS -DACG_HAVE_CUDA $INC -c "$REF/cuda/acg-cuda.c" -o "$OUT/acg-cuda.o"
+# host layer of the reference, unchanged; halo.c without ACG_HAVE_CUDA = pattern code only;
+# cgpetsc.c without PETSc = the reference's own 'not supported' stubs
+for f in vector symcsrmatrix graph halo error fmtspec mtxfile metis prefixsum sort cgpetsc; do
+  /usr/bin/gcc -O2 -g -fopenmp $DEFS $INC -c "$REF/acg/$f.c" -o "$OUT/$f.o"
+done
+/usr/bin/gcc -fopenmp -o "$OUT/acg-cuda" "$OUT"/*.o \
+  -L"$ROOT/acg_b200" -lacgb200_mpi -Wl,-rpath,'$ORIGIN/../../../acg_b200' \
+  -L"$CUDA/lib64" -lcublas -lcusparse -lcudart -lnccl -lm
+echo "built $OUT/acg-cuda"
