@@ -256,7 +256,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "e2e": {"value": total_iters / host_s_max, "unit": "iterations/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "whole acgsolvercuda_solve* call with pinned host b, x (cudaMalloc, H2D, solve, D2H, cudaFree)"},
+                    "note": "whole acgsolvercuda_solve* call with pinned host b, x: H2D of b and x0, set-up, iterations, D2H of x"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "spmv_tiles_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
