@@ -133,7 +133,7 @@ EXPORTS = [
     "acgsolvercuda_fwrite",
     "acgb200_set_option", "acgsolvercuda_spmv", "acgsolvercuda_info", "acgb200_sizeof", "acgb200_have_mpi",
     "acgb200_nccl_unique_id", "acgb200_comm_init_rank", "acgb200_comm_destroy",
-    "acgb200_host_register", "acgb200_host_unregister",
+    "acgb200_host_register", "acgb200_host_unregister", "acgb200_spmv_plan_host", "acgb200_p2p_inverse_map",
 ]
 
 
@@ -191,6 +191,8 @@ def lib() -> C.CDLL:
     L.acgb200_nccl_unique_id.argtypes = [C.c_void_p]
     L.acgb200_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.acgb200_host_unregister.argtypes = [C.c_void_p]
+    L.acgb200_p2p_inverse_map.argtypes = [P(acghalo), C.c_int, C.c_int, i32p, i32p, i32p, i32p]
+    L.acgb200_spmv_plan_host.argtypes = [C.c_int, i64p, P(acgb200_info), i32p, C.c_int, i32p, C.c_int]
     L.acgb200_comm_init_rank.argtypes = [P(acgcomm), C.c_int, C.c_void_p, C.c_int, P(C.c_int)]
     L.acgb200_comm_destroy.argtypes = [P(acgcomm)]
     L.acgcomm_size.argtypes = [P(acgcomm), P(C.c_int)]
@@ -206,6 +208,19 @@ def _check(code, where, detail=0):
 
 def set_option(key: str, value: int) -> None:
     _check(lib().acgb200_set_option(key.encode(), int(value)), f"acgb200_set_option({key})")
+
+
+def spmv_plan_host(rowptr) -> dict:
+    """Tile plan of the SpMV for a CSR row-pointer array (host only, no device)."""
+    rowptr = np.ascontiguousarray(rowptr, np.int64)
+    n = len(rowptr) - 1
+    tiles = np.zeros(4 * (n + 1), np.int32)
+    longrows = np.zeros(n + 1, np.int32)
+    inf = acgb200_info()
+    _check(lib().acgb200_spmv_plan_host(n, rowptr, C.byref(inf), tiles, n + 1, longrows, n + 1), "acgb200_spmv_plan_host")
+    nt, nl = inf.spmv_ntiles, inf.spmv_nlong
+    return dict(lanes=inf.spmv_lanes_per_row, rows_cap=inf.spmv_rows_cap, nnz_cap=inf.spmv_nnz_cap,
+                stages=inf.spmv_stages, tiles=tiles[:4 * nt].reshape(nt, 4).copy(), longrows=longrows[:nl].copy())
 
 
 def _view(ptr, n, dtype):
@@ -299,6 +314,22 @@ class SymCsrMatrix:
         lib().acgvector_setzero(C.byref(v.c))
         v._owns = True
         return v
+
+    def p2p_inverse_map(self, rdispl_at_recipient) -> dict:
+        """Inverse send map of the peer-memory exchange for this part (host only)."""
+        h = acghalo()
+        _check(lib().acgsymcsrmatrix_halo(C.byref(self.c), C.byref(h)), "acgsymcsrmatrix_halo")
+        nb = self.c.nborderrows
+        bptr = np.zeros(nb + 1, np.int32)
+        bq = np.zeros(max(h.sendsize, 1), np.int32)
+        bdst = np.zeros(max(h.sendsize, 1), np.int32)
+        rd = np.ascontiguousarray(rdispl_at_recipient, np.int32)
+        code = lib().acgb200_p2p_inverse_map(C.byref(h), self.c.borderrowoffset, nb, rd if len(rd) else np.zeros(1, np.int32),
+                                             bptr, bq, bdst)
+        n = h.sendsize
+        lib().acghalo_free(C.byref(h))
+        _check(code, "acgb200_p2p_inverse_map")
+        return dict(bptr=bptr, bq=bq[:n], bdst=bdst[:n])
 
     def halo(self) -> dict:
         h = acghalo()

@@ -189,7 +189,7 @@ void acgsolvercuda_free(struct acgsolvercuda *cg)
         }
         if (pv->have_redcomm && pv->redcomm.ncclcomm) ncclCommDestroy(pv->redcomm.ncclcomm);
         for (int i = 0; i < 2; i++) if (pv->graph[i]) cudaGraphExecDestroy(pv->graph[i]);
-        cudaFree(pv->plan.d_tiles); cudaFree(pv->plan.d_longrows);
+        cudaFree(pv->plan.d_tiles); cudaFree(pv->plan.d_longrows); cudaFree(pv->plan.d_long_scratch);
         cudaFree(pv->d_st);
         cudaFreeHost(pv->h_ctrl); cudaFreeHost(pv->h_st);
         if (pv->stream) cudaStreamDestroy(pv->stream);
@@ -209,13 +209,13 @@ void acgsolvercuda_free(struct acgsolvercuda *cg)
     }
 }
 
-/* cut rows [0,nrows) into TMA tiles; see internal.h */
-static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr, int *errcode)
+/* Cut rows [0,nrows) into TMA tiles (see internal.h): greedy, row-aligned, at
+ * most rows_cap rows and nnz_cap nonzeros per tile; rows longer than nnz_cap go
+ * to the long-row list.  Host-only, no CUDA: testable without a device. */
+static int cut_tiles(const struct acgb200_spmvplan *pl, const int64_t *rowptr,
+                     struct acgb200_tile *tiles, int *ntiles, int *longrows, int *nlong)
 {
     const int n = pl->nrows;
-    struct acgb200_tile *tiles = malloc(((size_t) n + 1) * sizeof(*tiles));
-    int *longrows = malloc(((size_t) n + 1) * sizeof(*longrows));
-    if (!tiles || !longrows) { free(tiles); free(longrows); return ACG_ERR_ERRNO; }
     int nt = 0, nl = 0, r = 0;
     while (r < n) {
         int64_t len = rowptr[r + 1] - rowptr[r];
@@ -228,6 +228,7 @@ static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr, int *
             cnt += len; r++;
         }
         const int64_t kb = rowptr[start], ke = rowptr[r];
+        if (ke > INT32_MAX) return ACG_ERR_INDEX_OUT_OF_BOUNDS;
         const int64_t k_al = kb & ~(int64_t) 3;
         tiles[nt].row_begin = start;
         tiles[nt].nrows = r - start;
@@ -235,18 +236,69 @@ static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr, int *
         tiles[nt].nnz_al = (int) (((ke - k_al) + 3) & ~(int64_t) 3);
         nt++;
     }
+    *ntiles = nt; *nlong = nl;
+    return ACG_SUCCESS;
+}
+
+static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr, int *errcode)
+{
+    const int n = pl->nrows;
+    struct acgb200_tile *tiles = malloc(((size_t) n + 1) * sizeof(*tiles));
+    int *longrows = malloc(((size_t) n + 1) * sizeof(*longrows));
+    if (!tiles || !longrows) { free(tiles); free(longrows); return ACG_ERR_ERRNO; }
+    int nt = 0, nl = 0;
+    int err = cut_tiles(pl, rowptr, tiles, &nt, longrows, &nl);
+    if (err) { free(tiles); free(longrows); return err; }
     pl->ntiles = nt; pl->nlong = nl;
-    pl->d_tiles = NULL; pl->d_longrows = NULL;
+    pl->d_tiles = NULL; pl->d_longrows = NULL; pl->d_long_scratch = NULL;
+    cudaError_t e = cudaSuccess;
     if (nt > 0) {
-        CU(cudaMalloc((void **) &pl->d_tiles, (size_t) nt * sizeof(*tiles)));
-        CU(cudaMemcpy(pl->d_tiles, tiles, (size_t) nt * sizeof(*tiles), cudaMemcpyHostToDevice));
+        e = cudaMalloc((void **) &pl->d_tiles, (size_t) nt * sizeof(*tiles));
+        if (!e) e = cudaMemcpy(pl->d_tiles, tiles, (size_t) nt * sizeof(*tiles), cudaMemcpyHostToDevice);
     }
-    if (nl > 0) {
-        CU(cudaMalloc((void **) &pl->d_longrows, (size_t) nl * sizeof(int)));
-        CU(cudaMemcpy(pl->d_longrows, longrows, (size_t) nl * sizeof(int), cudaMemcpyHostToDevice));
+    if (!e && nl > 0) {
+        e = cudaMalloc((void **) &pl->d_longrows, (size_t) nl * sizeof(int));
+        if (!e) e = cudaMemcpy(pl->d_longrows, longrows, (size_t) nl * sizeof(int), cudaMemcpyHostToDevice);
+        if (!e) e = cudaMalloc((void **) &pl->d_long_scratch, (size_t) nl * (size_t) pl->long_chunks * sizeof(double));
     }
     free(tiles); free(longrows);
+    CU(e);
     return ACG_SUCCESS;
+}
+
+/* ext.h: the tile plan the solver would build for a CSR row-pointer array,
+ * computed on the host without touching a device */
+int acgb200_spmv_plan_host(int nrows, const int64_t *rowptr, struct acgb200_info *info,
+                           int *tiles4, int maxtiles, int *longrows, int maxlong)
+{
+    struct acgb200_spmvplan pl;
+    memset(&pl, 0, sizeof(pl));
+    int64_t maxlen = 0;
+    for (int i = 0; i < nrows; i++) if (rowptr[i + 1] - rowptr[i] > maxlen) maxlen = rowptr[i + 1] - rowptr[i];
+    acgb200_spmv_choose(&pl, nrows, rowptr[nrows] - rowptr[0], maxlen);
+    cfg_load();
+    if (cfg.spmv_lanes > 0) pl.lanes_per_row = cfg.spmv_lanes;
+    if (cfg.spmv_nnz_cap > 0) pl.nnz_cap = cfg.spmv_nnz_cap;
+    if (cfg.spmv_rows_cap > 0) pl.rows_cap = cfg.spmv_rows_cap;
+    struct acgb200_tile *tiles = malloc(((size_t) nrows + 1) * sizeof(*tiles));
+    int *lr = malloc(((size_t) nrows + 1) * sizeof(*lr));
+    if (!tiles || !lr) { free(tiles); free(lr); return ACG_ERR_ERRNO; }
+    int nt = 0, nl = 0;
+    int err = cut_tiles(&pl, rowptr, tiles, &nt, lr, &nl);
+    if (!err && (nt > maxtiles || nl > maxlong)) err = ACG_ERR_NO_BUFFER_SPACE;
+    if (!err) {
+        for (int t = 0; t < nt; t++) {
+            tiles4[4 * t] = tiles[t].row_begin; tiles4[4 * t + 1] = tiles[t].nrows;
+            tiles4[4 * t + 2] = tiles[t].k_al; tiles4[4 * t + 3] = tiles[t].nnz_al;
+        }
+        memcpy(longrows, lr, (size_t) nl * sizeof(int));
+        memset(info, 0, sizeof(*info));
+        info->spmv_lanes_per_row = pl.lanes_per_row; info->spmv_rows_cap = pl.rows_cap;
+        info->spmv_nnz_cap = pl.nnz_cap; info->spmv_stages = pl.nstages;
+        info->spmv_ntiles = nt; info->spmv_nlong = nl;
+    }
+    free(tiles); free(lr);
+    return err;
 }
 
 /* upload a host int64 row-pointer array narrowed to int32 (acg/cgcuda.c:262-272)
@@ -291,17 +343,26 @@ static int upload_block(int **d_col, double **d_val, const acgidx_t *col, const 
     return ACG_SUCCESS;
 }
 
+static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, const struct acgcomm *comm);
+
 int acgsolvercuda_init(
     struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A,
     cublasHandle_t cublas, cusparseHandle_t cusparse, const struct acgcomm *comm)
 {
     (void) cublas; (void) cusparse;
-    int errcode_ = 0, *errcode = &errcode_;
+    memset(cg, 0, sizeof(*cg));
     cfg_load();
     if (!A->frowptr || !A->fcolidx || !A->fa) return ACG_ERR_INVALID_VALUE;   /* needs acgsymcsrmatrix_dsymv_init */
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return ACG_ERR_CUDA;   /* no CPU fallback */
-    memset(cg, 0, sizeof(*cg));
+    int err = init_impl(cg, A, comm);
+    if (err) acgsolvercuda_free(cg);       /* releases whatever was set up before the failure */
+    return err;
+}
+
+static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, const struct acgcomm *comm)
+{
+    int errcode_ = 0, *errcode = &errcode_;
     struct priv *pv = calloc(1, sizeof(*pv));
     if (!pv) return ACG_ERR_ERRNO;
     pv->key = cg; pv->next = registry; registry = pv;

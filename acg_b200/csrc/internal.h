@@ -46,6 +46,7 @@ struct acgb200_spmvplan {
     struct acgb200_tile *d_tiles;    /* [ntiles] */
     int nlong;                       /* rows with more than nnz_cap nonzeros */
     int *d_longrows;                 /* [nlong] */
+    double *d_long_scratch;          /* [nlong * long_chunks] partial sums of the long-row kernels */
     int grid;                        /* persistent grid size */
     int smem_bytes;                  /* dynamic shared memory per CTA */
     int long_chunks;                 /* CTAs per long row */

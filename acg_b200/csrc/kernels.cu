@@ -895,9 +895,6 @@ extern "C" int acgb200_spmv_configure(acgb200_spmvplan *pl)
     return 0;
 }
 
-static double *g_long_scratch = NULL;
-static size_t g_long_scratch_len = 0;
-
 extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t stream)
 {
     const acgb200_spmvplan *pl = a->plan;
@@ -915,18 +912,12 @@ extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t strea
         if (err) return (int) err;
     }
     if (pl->nlong > 0) {
-        const size_t need = (size_t) pl->nlong * pl->long_chunks;
-        if (need > g_long_scratch_len) {
-            cudaFree(g_long_scratch);
-            cudaError_t err = cudaMalloc((void **) &g_long_scratch, need * sizeof(double));
-            if (err) return (int) err;
-            g_long_scratch_len = need;
-        }
+        if (!pl->d_long_scratch) return (int) cudaErrorInvalidValue;
         spmv_long_partial_kernel<<<pl->nlong * pl->long_chunks, 256, 0, stream>>>(
-            pl->nlong, pl->d_longrows, pl->long_chunks, a->rowptr, a->colidx, a->a, a->x, g_long_scratch,
+            pl->nlong, pl->d_longrows, pl->long_chunks, a->rowptr, a->colidx, a->a, a->x, pl->d_long_scratch,
             a->ctrl_in, a->st);
         spmv_long_finish_kernel<<<(pl->nlong + 127) / 128, 128, 0, stream>>>(
-            pl->nlong, pl->d_longrows, pl->long_chunks, g_long_scratch, a->x, a->y, a->b, a->acc,
+            pl->nlong, pl->d_longrows, pl->long_chunks, pl->d_long_scratch, a->x, a->y, a->b, a->acc,
             a->dotrows, a->mode, a->ctrl_in, a->st);
         cudaError_t err = cudaGetLastError();
         if (err) return (int) err;
@@ -971,13 +962,9 @@ extern "C" int acgb200_pcg_update(int n, acgb200_devstate *st, int cin, int cout
 
 extern "C" int acgb200_comm_post(const acgb200_postargs *a, cudaStream_t stream)
 {
-    int grid = 1;
-    if (a->vec) {
-        /* sendsize is only known on the device descriptor's host mirror; the caller
-         * passes it through redstride when there is no reduction part -- keep it
-         * simple: a handful of CTAs is enough for halos of 10^4-10^5 entries */
-        grid = 8;
-    }
+    /* a handful of CTAs moves a halo of 10^4-10^5 doubles in a few microseconds;
+     * a reduction-only post needs one */
+    const int grid = a->vec ? 8 : 1;
     comm_post_kernel<<<grid, 512, 0, stream>>>(*a);
     return (int) cudaGetLastError();
 }

@@ -27,6 +27,36 @@ static size_t off_red(void) { return off_rflag() + ACGB200_NCH * ACGB200_MAXR * 
 static size_t off_ghost(void) { return off_red() + (size_t) ACGB200_NCH * 2 * ACGB200_MAXR * 2 * sizeof(double); }
 static size_t ghost_stride(int recvsize) { return (((size_t) (recvsize > 0 ? recvsize : 1) + 15) & ~(size_t) 15) * sizeof(double); }
 
+/*
+ * Inverse of the halo send list: for border row b (relative to borderoff) the
+ * entries e in [bptr[b], bptr[b+1]) name the recipient index bq[e] and the
+ * position bdst[e] in that recipient's ghost buffer (its rdispl for this sender
+ * plus the offset inside the segment).  Host-only, no CUDA.
+ */
+int acgb200_p2p_inverse_map(const struct acghalo *halo, int borderoff, int nborder,
+                            const int *rdispl_at_recipient, int *bptr, int *bq, int *bdst)
+{
+    int *cnt = calloc((size_t) nborder + 2, sizeof(int));
+    if (!cnt) return ACG_ERR_ERRNO;
+    for (int i = 0; i < halo->sendsize; i++) {
+        const int b = halo->sendbufidx[i] - borderoff;
+        if (b < 0 || b >= nborder) { free(cnt); return ACG_ERR_INVALID_VALUE; }
+        cnt[b + 2]++;
+    }
+    for (int b = 0; b < nborder; b++) cnt[b + 2] += cnt[b + 1];
+    for (int q = 0; q < halo->nrecipients; q++) {
+        for (int i = halo->sdispls[q]; i < halo->sdispls[q] + halo->sendcounts[q]; i++) {
+            const int b = halo->sendbufidx[i] - borderoff;
+            const int e = cnt[b + 1]++;
+            bq[e] = q;
+            bdst[e] = rdispl_at_recipient[q] + (i - halo->sdispls[q]);
+        }
+    }
+    memcpy(bptr, cnt, ((size_t) nborder + 1) * sizeof(int));
+    free(cnt);
+    return ACG_SUCCESS;
+}
+
 void acgb200_p2p_free(struct acgb200_p2p *p)
 {
     if (!p) return;
@@ -112,26 +142,14 @@ int acgb200_p2p_init(struct acgb200_p2p *p, const struct acghalo *halo, int bord
     /* inverse send map: which (neighbour, ghost offset) pairs each border row feeds */
     d->borderoff = borderoff; d->nborder = nborder;
     {
-        int *bptr = calloc((size_t) nborder + 2, sizeof(int));
-        int *bq = malloc((size_t) (halo->sendsize > 0 ? halo->sendsize : 1) * sizeof(int));
-        int *bdst = malloc((size_t) (halo->sendsize > 0 ? halo->sendsize : 1) * sizeof(int));
-        if (!bptr || !bq || !bdst) { free(bptr); free(bq); free(bdst); free(all); return ACG_ERR_ERRNO; }
-        for (int i = 0; i < halo->sendsize; i++) {
-            const int b = halo->sendbufidx[i] - borderoff;
-            if (b < 0 || b >= nborder) { free(bptr); free(bq); free(bdst); free(all); return ACG_ERR_INVALID_VALUE; }
-            bptr[b + 2]++;
-        }
-        for (int b = 0; b < nborder; b++) bptr[b + 2] += bptr[b + 1];
-        for (int q = 0; q < halo->nrecipients; q++) {
-            for (int i = halo->sdispls[q]; i < halo->sdispls[q] + halo->sendcounts[q]; i++) {
-                const int b = halo->sendbufidx[i] - borderoff;
-                const int e = bptr[b + 1]++;
-                bq[e] = q;
-                bdst[e] = d->peer_rdispl[q] + (i - halo->sdispls[q]);
-            }
-        }
-        int *d_bptr = NULL, *d_bq = NULL, *d_bdst = NULL;
         const size_t ne = (size_t) (halo->sendsize > 0 ? halo->sendsize : 1);
+        int *bptr = malloc(((size_t) nborder + 1) * sizeof(int));
+        int *bq = malloc(ne * sizeof(int));
+        int *bdst = malloc(ne * sizeof(int));
+        if (!bptr || !bq || !bdst) { free(bptr); free(bq); free(bdst); free(all); return ACG_ERR_ERRNO; }
+        err = acgb200_p2p_inverse_map(halo, borderoff, nborder, d->peer_rdispl, bptr, bq, bdst);
+        if (err) { free(bptr); free(bq); free(bdst); free(all); return err; }
+        int *d_bptr = NULL, *d_bq = NULL, *d_bdst = NULL;
         CUP(cudaMalloc((void **) &d_bptr, ((size_t) nborder + 1) * sizeof(int)));
         CUP(cudaMalloc((void **) &d_bq, ne * sizeof(int)));
         CUP(cudaMalloc((void **) &d_bdst, ne * sizeof(int)));

@@ -44,6 +44,21 @@ struct acgb200_info {
 };
 ACG_API int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info);
 
+/* The SpMV tile plan acgsolvercuda_init would build for a CSR row-pointer array
+ * (int64, nrows+1 entries), computed on the host without a device: tiles4 gets
+ * {row_begin, nrows, k_al, nnz_al} per tile, longrows the rows that exceed a
+ * tile; info->spmv_* describe the plan.  For tests of the host logic. */
+ACG_API int acgb200_spmv_plan_host(int nrows, const int64_t *rowptr, struct acgb200_info *info,
+                                   int *tiles4, int maxtiles, int *longrows, int maxlong);
+
+/* Inverse send map of the peer-memory halo exchange (host logic of p2p.c): for
+ * border row b, entries [bptr[b], bptr[b+1]) give the recipient index bq[e] and
+ * the destination offset bdst[e] in that recipient's ghost buffer;
+ * rdispl_at_recipient[i] is recipient i's receive displacement for this sender.
+ * bptr: nborder+1 ints, bq/bdst: halo->sendsize ints. */
+ACG_API int acgb200_p2p_inverse_map(const struct acghalo *halo, int borderoff, int nborder,
+                                    const int *rdispl_at_recipient, int *bptr, int *bq, int *bdst);
+
 /* struct sizes, for bindings: "acgsolvercuda", "acgsymcsrmatrix", "acgvector",
  * "acgcomm", "acghalo"; returns 0 for unknown names */
 ACG_API size_t acgb200_sizeof(const char *name);

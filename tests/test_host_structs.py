@@ -147,3 +147,69 @@ def test_solver_refuses_without_device(ab):
     with pytest.raises(ab.AcgError) as e:
         ab.SolverCuda(A)
     assert e.value.code == 4
+
+
+@pytest.mark.parametrize("name,gen", GENS + [("rmat-long", lambda: mg.rmat_spd(20000, 400000, seed=8)),
+                                             ("dense-rows", lambda: mg.random_spd(400, 0.5, 2)),
+                                             ("n1", lambda: mg.poisson1d_3pt(1))],
+                         ids=[g[0] for g in GENS] + ["rmat-long", "dense-rows", "n1"])
+def test_spmv_tile_plan_invariants(name, gen, ab, oracle):
+    """The SpMV tile plan (host logic of the CUDA path): every row is in exactly
+    one tile or in the long-row list, tiles respect both caps, and every slice
+    meets the 16-byte rule of cp.async.bulk (starts/lengths multiples of 4
+    elements) while covering the tile's nonzeros."""
+    n, r, c, v = gen()
+    rowptr = oracle.full_csr(n, r, c, v)[0]
+    plan = ab.spmv_plan_host(rowptr)
+    lens = np.diff(rowptr)
+    G, rows_cap, nnz_cap = plan["lanes"], plan["rows_cap"], plan["nnz_cap"]
+    assert G in (1, 2, 4, 8, 16, 32) and rows_cap == 128 // G and nnz_cap % 4 == 0 and plan["stages"] == 2
+    covered = np.zeros(n, int)
+    covered[plan["longrows"]] += 1
+    assert np.all(lens[plan["longrows"]] > nnz_cap)
+    prev_end = 0
+    for row_begin, nrows, k_al, nnz_al in plan["tiles"]:
+        assert 1 <= nrows <= rows_cap and row_begin >= prev_end
+        prev_end = row_begin + nrows
+        covered[row_begin:row_begin + nrows] += 1
+        kb, ke = rowptr[row_begin], rowptr[row_begin + nrows]
+        assert ke - kb <= nnz_cap and np.all(lens[row_begin:row_begin + nrows] <= nnz_cap)
+        assert k_al % 4 == 0 and nnz_al % 4 == 0 and k_al <= kb < k_al + 4 and k_al + nnz_al >= ke
+        assert nnz_al <= nnz_cap + 8          # fits the shared-memory stage (stage_slots in kernels.cu)
+    assert np.all(covered == 1)
+    if name == "rmat-long":
+        assert len(plan["longrows"]) > 0
+    if name == "27pt":
+        assert G == 4
+    if name == "7pt":
+        assert G == 1
+
+
+@pytest.mark.parametrize("kind,nparts", [("slab", 2), ("random", 4), ("cyclic", 3)])
+def test_peer_memory_push_addressing(kind, nparts, ab):
+    """Host logic of the peer-memory halo exchange (p2p.c): pushing every border
+    row through the inverse send map into the recipients' ghost buffers fills
+    each ghost slot exactly once with the value of the global row it mirrors."""
+    n, r, c, v = mg.stencil3d_27pt(6, 7, 5)
+    A = ab.SymCsrMatrix.init_real_double(n, r, c, v)
+    parts = A.partition(nparts, _parts(kind, n, nparts))
+    halos = [m.halo() for m in parts]
+    x = np.random.default_rng(0).standard_normal(n)
+    ghost = [np.full(m.c.nghostrows, np.nan) for m in parts]
+    writes = [np.zeros(m.c.nghostrows, int) for m in parts]
+    for p, m in enumerate(parts):
+        h = halos[p]
+        # what rank p learns from the all-gather: where its segment starts at each recipient
+        rd = [int(halos[q]["rdispls"][list(halos[q]["senders"]).index(p)]) for q in h["recipients"]]
+        inv = m.p2p_inverse_map(rd)
+        assert inv["bptr"][0] == 0 and inv["bptr"][-1] == len(h["sendbufidx"])
+        xl = x[m.nzrows[:m.c.nownedrows]]
+        for b in range(m.c.nborderrows):
+            assert inv["bptr"][b + 1] > inv["bptr"][b]          # every border row has a recipient
+            for e in range(inv["bptr"][b], inv["bptr"][b + 1]):
+                q = int(h["recipients"][inv["bq"][e]])
+                ghost[q][inv["bdst"][e]] = xl[m.c.borderrowoffset + b]
+                writes[q][inv["bdst"][e]] += 1
+    for p, m in enumerate(parts):
+        assert np.all(writes[p] == 1)
+        assert np.array_equal(ghost[p], x[m.nzrows[m.c.nownedrows:]])
