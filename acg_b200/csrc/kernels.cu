@@ -504,15 +504,29 @@ spmv_long_partial_kernel(int nlong, const int *longrows, int chunks,
 
 __global__ void spmv_long_finish_kernel(int nlong, const int *longrows, int chunks, const double *scratch,
                                         const double *x, double *y, const double *b, double *acc,
-                                        int dotrows, int mode, const acgb200_ctrl *cin, const acgb200_devstate *st)
+                                        int dotrows, int mode, const acgb200_ctrl *cin, const acgb200_devstate *st,
+                                        const acgb200_p2pdev *p2p, int od_rowoffset, int od_nrows,
+                                        const int *orowptr, const int *ocolidx, const double *oa)
 {
-    if (!gate_read(cin, st).active) return;
+    const Gate g = gate_read(cin, st);
+    if (!g.active) return;
+    /* peer-memory mode: long rows that are border rows also get their
+     * border x ghost entries here (the tile kernel only sees rows in tiles) */
+    const double *xg = NULL;
+    if (p2p) {
+        p2p_wait_halo(p2p, p2p->hbase + (unsigned long long) g.iter);
+        xg = p2p->my_ghost[g.iter & 1] - od_nrows;
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double dot = 0.0;
     if (i < nlong) {
         const int row = longrows[i];
         double sum = 0.0;
         for (int c = 0; c < chunks; c++) sum += scratch[(size_t) i * chunks + c];
+        if (xg && row >= od_rowoffset) {
+            const int ob = row - od_rowoffset;
+            for (int k = orowptr[ob]; k < orowptr[ob + 1]; k++) sum = fma(oa[k], xg[ocolidx[k]], sum);
+        }
         if (mode == SPMV_R_B_AX) {
             const double v = b[row] - sum; y[row] = v;
             if (row < dotrows) dot = v * v;
@@ -918,7 +932,8 @@ extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t strea
             a->ctrl_in, a->st);
         spmv_long_finish_kernel<<<(pl->nlong + 127) / 128, 128, 0, stream>>>(
             pl->nlong, pl->d_longrows, pl->long_chunks, pl->d_long_scratch, a->x, a->y, a->b, a->acc,
-            a->dotrows, a->mode, a->ctrl_in, a->st);
+            a->dotrows, a->mode, a->ctrl_in, a->st,
+            a->p2p, a->od_rowoffset, a->od_nrows, a->orowptr, a->ocolidx, a->oa);
         cudaError_t err = cudaGetLastError();
         if (err) return (int) err;
     }
