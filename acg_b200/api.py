@@ -111,7 +111,9 @@ class acgb200_info(C.Structure):
                                                                                   ("last_solve_ms", C.c_double),
                                                                                   ("last_h2d_ms", C.c_double),
                                                                                   ("last_d2h_ms", C.c_double),
-                                                                                  ("last_blas_ms", C.c_double)]
+                                                                                  ("last_blas_ms", C.c_double),
+                                                                                  ("spmv_compressed_tiles", C.c_int),
+                                                                                  ("spmv_min_bytes", C.c_int64)]
 
 
 # every symbol include/acgb200/*.h declares (checked by tests/test_abi.py)
@@ -133,7 +135,7 @@ EXPORTS = [
     "acgsolvercuda_fwrite",
     "acgb200_set_option", "acgsolvercuda_spmv", "acgsolvercuda_info", "acgb200_sizeof", "acgb200_have_mpi",
     "acgb200_nccl_unique_id", "acgb200_comm_init_rank", "acgb200_comm_destroy",
-    "acgb200_host_register", "acgb200_host_unregister", "acgb200_spmv_plan_host", "acgb200_p2p_inverse_map",
+    "acgb200_host_register", "acgb200_host_unregister", "acgb200_spmv_plan_host", "acgb200_p2p_inverse_map", "acgb200_patterns_host",
 ]
 
 
@@ -191,6 +193,8 @@ def lib() -> C.CDLL:
     L.acgb200_nccl_unique_id.argtypes = [C.c_void_p]
     L.acgb200_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.acgb200_host_unregister.argtypes = [C.c_void_p]
+    u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+    L.acgb200_patterns_host.argtypes = [C.c_int, i64p, i32p, C.c_int, P(C.c_int), P(C.c_int), i32p, i32p, u16p, P(C.c_int64)]
     L.acgb200_p2p_inverse_map.argtypes = [P(acghalo), C.c_int, C.c_int, i32p, i32p, i32p, i32p]
     L.acgb200_spmv_plan_host.argtypes = [C.c_int, i64p, P(acgb200_info), i32p, C.c_int, i32p, C.c_int]
     L.acgb200_comm_init_rank.argtypes = [P(acgcomm), C.c_int, C.c_void_p, C.c_int, P(C.c_int)]
@@ -208,6 +212,21 @@ def _check(code, where, detail=0):
 
 def set_option(key: str, value: int) -> None:
     _check(lib().acgb200_set_option(key.encode(), int(value)), f"acgb200_set_option({key})")
+
+
+def patterns_host(rowptr, colidx, max_entries: int = 4096) -> dict:
+    """Row-pattern dictionary of a 0-based CSR matrix (host only, compress.c)."""
+    rowptr = np.ascontiguousarray(rowptr, np.int64)
+    colidx = np.ascontiguousarray(colidx, np.int32)
+    n = len(rowptr) - 1
+    npat, nent, nm = C.c_int(0), C.c_int(0), C.c_int64(0)
+    patptr = np.zeros(max_entries + 2, np.int32)
+    patoff = np.zeros(max_entries + 1, np.int32)
+    patid = np.zeros(max(n, 1), np.uint16)
+    _check(lib().acgb200_patterns_host(n, rowptr, colidx, max_entries, C.byref(npat), C.byref(nent), patptr, patoff,
+                                       patid, C.byref(nm)), "acgb200_patterns_host")
+    return dict(npat=npat.value, patptr=patptr[:npat.value + 1].copy(), patoff=patoff[:nent.value].copy(),
+                patid=patid[:n].copy(), nmatched=nm.value)
 
 
 def spmv_plan_host(rowptr) -> dict:

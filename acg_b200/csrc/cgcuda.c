@@ -50,8 +50,9 @@ static struct {
     int redstream;      /* pipelined CG: allreduce on its own stream + communicator */
     int p2p;            /* halo + reductions through peer memory (CUDA IPC) instead of NCCL */
     int p2p_fuse;       /* 1: border x ghost block inside the SpMV, pushes inside the update kernels */
+    int spmv_compress;  /* 1: index-free tiles where the rows' patterns repeat (opt-in, compress.c) */
     int loaded;
-} cfg = { 0, 8, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 0 };
+} cfg = { 0, 8, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0 };
 
 static void cfg_load(void)
 {
@@ -71,6 +72,7 @@ static void cfg_load(void)
     if ((s = getenv("ACGB200_REDSTREAM"))) cfg.redstream = atoi(s);
     if ((s = getenv("ACGB200_P2P"))) cfg.p2p = atoi(s);
     if ((s = getenv("ACGB200_P2P_FUSE"))) cfg.p2p_fuse = atoi(s);
+    if ((s = getenv("ACGB200_SPMV_COMPRESS"))) cfg.spmv_compress = atoi(s);
     if (cfg.check_every < 1) cfg.check_every = 1;
 }
 
@@ -90,6 +92,7 @@ int acgb200_set_option(const char *key, int value)
     else if (!strcmp(key, "redstream")) cfg.redstream = value;
     else if (!strcmp(key, "p2p")) cfg.p2p = value;
     else if (!strcmp(key, "p2p_fuse")) cfg.p2p_fuse = value;
+    else if (!strcmp(key, "spmv_compress")) cfg.spmv_compress = value;
     else return ACG_ERR_INVALID_VALUE;
     return ACG_SUCCESS;
 }
@@ -190,6 +193,7 @@ void acgsolvercuda_free(struct acgsolvercuda *cg)
         if (pv->have_redcomm && pv->redcomm.ncclcomm) ncclCommDestroy(pv->redcomm.ncclcomm);
         for (int i = 0; i < 2; i++) if (pv->graph[i]) cudaGraphExecDestroy(pv->graph[i]);
         cudaFree(pv->plan.d_tiles); cudaFree(pv->plan.d_longrows); cudaFree(pv->plan.d_long_scratch);
+        cudaFree(pv->plan.d_patptr); cudaFree(pv->plan.d_patoff); cudaFree(pv->plan.d_patid);
         cudaFree(pv->d_st);
         cudaFreeHost(pv->h_ctrl); cudaFreeHost(pv->h_st);
         if (pv->stream) cudaStreamDestroy(pv->stream);
@@ -240,7 +244,7 @@ static int cut_tiles(const struct acgb200_spmvplan *pl, const int64_t *rowptr,
     return ACG_SUCCESS;
 }
 
-static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr, int *errcode)
+static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr, const struct acgb200_patterns *pat, int *errcode)
 {
     const int n = pl->nrows;
     struct acgb200_tile *tiles = malloc(((size_t) n + 1) * sizeof(*tiles));
@@ -252,6 +256,29 @@ static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr, int *
     pl->ntiles = nt; pl->nlong = nl;
     pl->d_tiles = NULL; pl->d_longrows = NULL; pl->d_long_scratch = NULL;
     cudaError_t e = cudaSuccess;
+    pl->compressed = 0; pl->ncompressed_tiles = 0;
+    if (pat && pat->npat > 0) {
+        /* a tile drops its column indices if every one of its rows is in the dictionary */
+        for (int t = 0; t < nt; t++) {
+            int all = 1;
+            for (int r = tiles[t].row_begin; r < tiles[t].row_begin + tiles[t].nrows && all; r++)
+                all = pat->patid[r] != ACGB200_NOPATTERN;
+            if (all) { tiles[t].nrows |= ACGB200_TILE_COMPRESSED; pl->ncompressed_tiles++; }
+        }
+        if (2 * (int64_t) pl->ncompressed_tiles >= nt) {
+            pl->compressed = 1; pl->npat = pat->npat; pl->nentries = pat->nentries;
+            e = cudaMalloc((void **) &pl->d_patptr, ((size_t) pat->npat + 1) * sizeof(int));
+            if (!e) e = cudaMemcpy(pl->d_patptr, pat->patptr, ((size_t) pat->npat + 1) * sizeof(int), cudaMemcpyHostToDevice);
+            if (!e) e = cudaMalloc((void **) &pl->d_patoff, (size_t) (pat->nentries > 0 ? pat->nentries : 1) * sizeof(int));
+            if (!e) e = cudaMemcpy(pl->d_patoff, pat->patoff, (size_t) pat->nentries * sizeof(int), cudaMemcpyHostToDevice);
+            if (!e) e = cudaMalloc((void **) &pl->d_patid, ((size_t) n + 16) * sizeof(unsigned short));
+            if (!e) e = cudaMemset(pl->d_patid, 0, ((size_t) n + 16) * sizeof(unsigned short));
+            if (!e) e = cudaMemcpy(pl->d_patid, pat->patid, (size_t) n * sizeof(unsigned short), cudaMemcpyHostToDevice);
+        } else {
+            for (int t = 0; t < nt; t++) tiles[t].nrows &= ~ACGB200_TILE_COMPRESSED;
+            pl->ncompressed_tiles = 0;
+        }
+    }
     if (nt > 0) {
         e = cudaMalloc((void **) &pl->d_tiles, (size_t) nt * sizeof(*tiles));
         if (!e) e = cudaMemcpy(pl->d_tiles, tiles, (size_t) nt * sizeof(*tiles), cudaMemcpyHostToDevice);
@@ -263,6 +290,21 @@ static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr, int *
     }
     free(tiles); free(longrows);
     CU(e);
+    return ACG_SUCCESS;
+}
+
+/* ext.h: row-pattern dictionary of a CSR matrix, host only (compress.c) */
+int acgb200_patterns_host(int nrows, const int64_t *rowptr, const int *colidx, int max_entries,
+                          int *npat, int *nentries, int *patptr, int *patoff, unsigned short *patid, int64_t *nmatched)
+{
+    struct acgb200_patterns pat;
+    int err = acgb200_patterns_build(nrows, rowptr, colidx, max_entries, &pat);
+    if (err) return err;
+    *npat = pat.npat; *nentries = pat.nentries; *nmatched = pat.nrows_matched;
+    memcpy(patptr, pat.patptr, ((size_t) pat.npat + 1) * sizeof(int));
+    memcpy(patoff, pat.patoff, (size_t) pat.nentries * sizeof(int));
+    memcpy(patid, pat.patid, (size_t) nrows * sizeof(unsigned short));
+    acgb200_patterns_free(&pat);
     return ACG_SUCCESS;
 }
 
@@ -470,7 +512,15 @@ static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, 
     if (cfg.spmv_stages > 0) pv->plan.nstages = cfg.spmv_stages > 8 ? 8 : cfg.spmv_stages;
     if (cfg.spmv_threads > 0) pv->plan.threads = cfg.spmv_threads;
     if (cfg.spmv_unroll > 0) pv->plan.unroll = cfg.spmv_unroll;
-    OK(build_tiles(&pv->plan, A->frowptr, errcode));
+    {
+        struct acgb200_patterns pat;
+        memset(&pat, 0, sizeof(pat));
+        if (cfg.spmv_compress && A->rowidxbase == 0)
+            OK(acgb200_patterns_build(A->nownedrows, A->frowptr, A->fcolidx, 4096, &pat));
+        int err = build_tiles(&pv->plan, A->frowptr, pat.npat > 0 ? &pat : NULL, errcode);
+        acgb200_patterns_free(&pat);
+        if (err) return err;
+    }
     pv->plan.max_ctas_per_sm = cfg.spmv_max_ctas;
     KL(acgb200_spmv_configure(&pv->plan));
     return ACG_SUCCESS;
@@ -1279,5 +1329,7 @@ int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info
     info->last_h2d_ms = pv->last_h2d_ms; info->last_d2h_ms = pv->last_d2h_ms;
     info->last_blas_ms = pv->last_blas_ms;
     info->num_sms = acgb200_num_sms();
+    info->spmv_compressed_tiles = pv->plan.ncompressed_tiles;
+    info->spmv_min_bytes = acgb200_spmv_min_bytes(&pv->plan);
     return ACG_SUCCESS;
 }

@@ -1,0 +1,135 @@
+/*
+ * compress.c -- row-pattern dictionary for index-free SpMV tiles (host side).
+ *
+ * Column indices are a third of the CSR stream (4 of 12 bytes per nonzero).
+ * Matrices from stencils and other structured discretisations repeat a small
+ * number of row "patterns" -- the sequence of offsets col - row of a row's
+ * nonzeros: 27 of them describe every row of the 27-point stencil on a box.
+ * A row whose pattern is in the dictionary needs no column indices at all: a
+ * 2-byte pattern id per row replaces 4 bytes per nonzero.  Rows with patterns
+ * outside the dictionary (irregular matrices, rows next to a partition
+ * boundary after the [interior|border] reordering) keep their indices; a tile
+ * of the SpMV plan is "compressed" only if all of its rows are in the
+ * dictionary.  Nothing here is specific to stencils: the dictionary is found
+ * by hashing the rows of whatever matrix is given, and an unstructured matrix
+ * simply ends up with no compressed tiles.
+ *
+ * Status: opt-in (ACGB200_SPMV_COMPRESS=1 / option "spmv_compress"); the host
+ * logic is tested on the CPU, the kernel that consumes it
+ * (spmv_ctiles_kernel) has not been measured yet.
+ */
+#include "acgb200/error.h"
+#include "internal.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+struct slot { uint64_t hash; int row; int len; int64_t count; int id; };
+
+static uint64_t row_hash(const int *col, int64_t kb, int64_t ke, int row)
+{
+    uint64_t h = 1469598103934665603ull ^ (uint64_t) (ke - kb);
+    for (int64_t k = kb; k < ke; k++) {
+        h ^= (uint64_t) (uint32_t) (col[k] - row);
+        h *= 1099511628211ull;
+    }
+    return h ? h : 1;
+}
+
+static int same_pattern(const int64_t *rp, const int *col, int r1, int r2)
+{
+    const int64_t n1 = rp[r1 + 1] - rp[r1];
+    if (n1 != rp[r2 + 1] - rp[r2]) return 0;
+    for (int64_t j = 0; j < n1; j++)
+        if (col[rp[r1] + j] - r1 != col[rp[r2] + j] - r2) return 0;
+    return 1;
+}
+
+static int by_count_desc(const void *a, const void *b)
+{
+    const struct slot *x = a, *y = b;
+    if (x->count != y->count) return x->count > y->count ? -1 : 1;
+    return (x->row > y->row) - (x->row < y->row);       /* deterministic order */
+}
+
+void acgb200_patterns_free(struct acgb200_patterns *p)
+{
+    free(p->patptr); free(p->patoff); free(p->patid);
+    memset(p, 0, sizeof(*p));
+}
+
+/*
+ * Build the dictionary for rows [0,nrows) of a CSR matrix with 0-based
+ * columns.  At most 65535 patterns totalling at most max_entries offsets are
+ * kept, most frequent first.  patid[r] == ACGB200_NOPATTERN marks a row whose
+ * pattern was not kept.
+ */
+int acgb200_patterns_build(int nrows, const int64_t *rowptr, const int *colidx, int max_entries,
+                           struct acgb200_patterns *out)
+{
+    memset(out, 0, sizeof(*out));
+    const size_t cap = 1u << 17;          /* open addressing; distinct patterns tracked <= cap/2 */
+    struct slot *tab = calloc(cap, sizeof(*tab));
+    out->patid = malloc((size_t) (nrows > 0 ? nrows : 1) * sizeof(*out->patid));
+    if (!tab || !out->patid) { free(tab); acgb200_patterns_free(out); return ACG_ERR_ERRNO; }
+    size_t used = 0;
+    /* pass 1: count patterns */
+    for (int r = 0; r < nrows; r++) {
+        const uint64_t h = row_hash(colidx, rowptr[r], rowptr[r + 1], r);
+        size_t i = (size_t) (h & (cap - 1));
+        for (;;) {
+            if (tab[i].hash == 0) {
+                if (used >= cap / 2) break;             /* table full: this pattern is not tracked */
+                tab[i].hash = h; tab[i].row = r; tab[i].len = (int) (rowptr[r + 1] - rowptr[r]);
+                tab[i].count = 1; tab[i].id = -1; used++;
+                break;
+            }
+            if (tab[i].hash == h && same_pattern(rowptr, colidx, tab[i].row, r)) { tab[i].count++; break; }
+            i = (i + 1) & (cap - 1);
+        }
+    }
+    /* choose the most frequent patterns that fit */
+    struct slot *sel = malloc((used ? used : 1) * sizeof(*sel));
+    if (!sel) { free(tab); acgb200_patterns_free(out); return ACG_ERR_ERRNO; }
+    size_t ns = 0;
+    for (size_t i = 0; i < cap; i++) if (tab[i].hash) sel[ns++] = tab[i];
+    qsort(sel, ns, sizeof(*sel), by_count_desc);
+    int npat = 0, nent = 0;
+    for (size_t i = 0; i < ns && npat < 65535; i++) {
+        if (nent + sel[i].len > max_entries) continue;
+        sel[i].id = npat++; nent += sel[i].len;
+    }
+    out->npat = npat; out->nentries = nent;
+    out->patptr = malloc(((size_t) npat + 1) * sizeof(int));
+    out->patoff = malloc((size_t) (nent > 0 ? nent : 1) * sizeof(int));
+    if (!out->patptr || !out->patoff) { free(sel); free(tab); acgb200_patterns_free(out); return ACG_ERR_ERRNO; }
+    int pos = 0;
+    for (size_t i = 0; i < ns; i++) {
+        if (sel[i].id < 0) continue;
+        out->patptr[sel[i].id] = pos;
+        const int r = sel[i].row;
+        for (int64_t k = rowptr[r]; k < rowptr[r + 1]; k++) out->patoff[pos++] = colidx[k] - r;
+        /* write the id back into the hash table entry of this pattern */
+        size_t j = (size_t) (sel[i].hash & (cap - 1));
+        while (!(tab[j].hash == sel[i].hash && tab[j].row == sel[i].row)) j = (j + 1) & (cap - 1);
+        tab[j].id = sel[i].id;
+    }
+    out->patptr[npat] = pos;
+    free(sel);
+    /* pass 2: ids per row */
+    int64_t matched = 0;
+    for (int r = 0; r < nrows; r++) {
+        const uint64_t h = row_hash(colidx, rowptr[r], rowptr[r + 1], r);
+        size_t i = (size_t) (h & (cap - 1));
+        int id = -1;
+        while (tab[i].hash) {
+            if (tab[i].hash == h && same_pattern(rowptr, colidx, tab[i].row, r)) { id = tab[i].id; break; }
+            i = (i + 1) & (cap - 1);
+        }
+        out->patid[r] = id >= 0 ? (unsigned short) id : ACGB200_NOPATTERN;
+        matched += id >= 0;
+    }
+    out->nrows_matched = matched;
+    free(tab);
+    return ACG_SUCCESS;
+}

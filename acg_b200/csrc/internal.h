@@ -51,7 +51,28 @@ struct acgb200_spmvplan {
     int smem_bytes;                  /* dynamic shared memory per CTA */
     int long_chunks;                 /* CTAs per long row */
     int max_ctas_per_sm;             /* 0: occupancy limit */
+    /* index-free tiles (opt-in, see compress.c) */
+    int compressed;                  /* 1: tiles flagged ACGB200_TILE_COMPRESSED carry no column indices */
+    int npat, nentries;
+    int *d_patptr, *d_patoff;
+    unsigned short *d_patid;         /* [nrows] (+16 pad) */
+    int ncompressed_tiles;
 };
+
+/* row-pattern dictionary (compress.c): rows whose pattern id is not
+ * ACGB200_NOPATTERN need no column indices, col = row + patoff[patptr[id] + j] */
+#define ACGB200_NOPATTERN 0xFFFFu
+#define ACGB200_TILE_COMPRESSED 0x40000000      /* flag in acgb200_tile.nrows */
+struct acgb200_patterns {
+    int npat, nentries;
+    int *patptr;                 /* [npat+1] */
+    int *patoff;                 /* [nentries] */
+    unsigned short *patid;       /* [nrows] */
+    int64_t nrows_matched;
+};
+int acgb200_patterns_build(int nrows, const int64_t *rowptr, const int *colidx, int max_entries,
+                           struct acgb200_patterns *out);
+void acgb200_patterns_free(struct acgb200_patterns *p);
 
 /* epilogue of the SpMV kernels */
 enum acgb200_spmvmode {
@@ -170,6 +191,8 @@ struct acgb200_spmvargs {
     const int *orowptr; const int *ocolidx; const double *oa;
     int pub_ch;                           /* -1: do not publish */
 };
+/* bytes one SpMV launch must move at least, given the plan (for reports) */
+int64_t acgb200_spmv_min_bytes(const struct acgb200_spmvplan *plan);
 int acgb200_spmv_launch(const struct acgb200_spmvargs *args, cudaStream_t stream);
 
 /* y[rowoffset+i] (+)= sum_k oa[k]*x[xoffset + ocolidx[k]], i in [0,nrows): the

@@ -481,6 +481,173 @@ spmv_tiles_kernel(const SpmvParams P)
     }
 }
 
+/* ------------------------------------------------------------------------ */
+/* SpMV over index-free ("compressed") tiles -- opt-in, see compress.c         */
+/* ------------------------------------------------------------------------ */
+
+struct CmpParams {
+    const unsigned short *patid;   /* [nrows] pattern id per row */
+    const int *patptr;             /* [npat+1] */
+    const int *patoff;             /* [nentries] col - row */
+    int npat, nentries;
+    int pc;                        /* pattern-id slots per stage (multiple of 8) */
+    int rc;                        /* row-pointer slots per stage (multiple of 4) */
+};
+
+/* stage layout: values [8*sc] | row pointers [4*rc] | pattern ids [2*pc] */
+__device__ __forceinline__ void cspmv_issue(
+    const SpmvParams &P, const CmpParams &C, const acgb200_tile &tl, unsigned char *stage, uint64_t *bar, uint64_t pol)
+{
+    const int nrows = tl.nrows & ~ACGB200_TILE_COMPRESSED;
+    const bool cmp = (tl.nrows & ACGB200_TILE_COMPRESSED) != 0;
+    const int row_al = tl.row_begin & ~3;
+    const int nrp = (tl.row_begin + nrows + 1 - row_al + 3) & ~3;
+    const int row_al8 = tl.row_begin & ~7;
+    const int npid = (tl.row_begin + nrows - row_al8 + 7) & ~7;
+    double *vals = reinterpret_cast<double *>(stage);
+    int *rptr = reinterpret_cast<int *>(stage + (size_t) P.sc * 8);
+    unsigned short *pid = reinterpret_cast<unsigned short *>(stage + (size_t) P.sc * 8 + (size_t) C.rc * 4);
+    mbar_arrive_expect_tx(bar, (uint32_t) tl.nnz_al * 8u + (uint32_t) nrp * 4u + (cmp ? (uint32_t) npid * 2u : 0u));
+    if (tl.nnz_al > 0) bulk_g2s(vals, P.a + tl.k_al, (uint32_t) tl.nnz_al * 8u, bar, pol);
+    bulk_g2s(rptr, P.rowptr + row_al, (uint32_t) nrp * 4u, bar, pol);
+    if (cmp) bulk_g2s(pid, C.patid + row_al8, (uint32_t) npid * 2u, bar, pol);
+}
+
+/*
+ * Same structure as spmv_tiles_kernel.  A compressed tile streams 8 B per
+ * nonzero (values only) plus 6 B per row (row pointer, pattern id); column
+ * indices are rebuilt as row + offset from the pattern table held in shared
+ * memory.  Tiles that are not compressed (rows with patterns outside the
+ * dictionary) read their column indices straight from global memory -- they
+ * are rare by construction (the plan is only used when almost all tiles
+ * compress).
+ */
+template <int G, int T, int U>
+__global__ void __launch_bounds__(T, SPMV_MINB(T))
+spmv_ctiles_kernel(const SpmvParams P, const CmpParams C)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[SPMV_MAX_STAGES];
+    __shared__ double red[T / 32];
+    __shared__ int last_flag;
+
+    const int tid = threadIdx.x;
+    const Gate gate = gate_read(P.ctrl_in, P.st);
+    if (blockIdx.x == 0 && tid == 0 && P.ctrl_in) {
+        *P.ctrl_out = *P.ctrl_in;
+        if (gate.active) {
+            const int s = gate.iter & 1;
+            if (P.housekeeping == 1) P.st->rr_loc[s ^ 1] = 0.0;
+            if (P.housekeeping == 2) { P.st->gd_loc[s ^ 1][0] = 0.0; P.st->gd_loc[s ^ 1][1] = 0.0; }
+        }
+    }
+    if (!gate.active) return;
+
+    const int S = P.nstages;
+    /* pattern table behind the stage ring */
+    int *patptr_s = reinterpret_cast<int *>(smem + (size_t) S * P.stage_bytes);
+    int *patoff_s = patptr_s + ((C.npat + 1 + 3) & ~3);
+    for (int i = tid; i <= C.npat; i += T) patptr_s[i] = C.patptr[i];
+    for (int i = tid; i < C.nentries; i += T) patoff_s[i] = C.patoff[i];
+
+    uint64_t pol = 0;
+    if (tid == 0) {
+        pol = l2_policy_evict_first();
+        for (int s = 0; s < S; s++) mbar_init(&full_bar[s], 1);
+        mbar_init_fence();
+        for (int s = 0; s < S; s++) {
+            const int t = blockIdx.x + s * gridDim.x;
+            if (t < P.ntiles) cspmv_issue(P, C, P.tiles[t], smem + (size_t) s * P.stage_bytes, &full_bar[s], pol);
+        }
+    }
+    __syncthreads();
+
+    constexpr int RPP = T / G;
+    const int lane = tid % G;
+    const int grp = tid / G;
+    double dot = 0.0;
+    const double *xg = NULL;
+
+    int i = 0;
+    for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, i++) {
+        const int s = i % S;
+        const acgb200_tile tl = P.tiles[t];
+        const int nrows = tl.nrows & ~ACGB200_TILE_COMPRESSED;
+        const bool cmp = (tl.nrows & ACGB200_TILE_COMPRESSED) != 0;
+        if (P.p2p && !xg && tl.row_begin + nrows > P.od_rowoffset) {
+            p2p_wait_halo(P.p2p, P.p2p->hbase + (unsigned long long) gate.iter);
+            xg = P.p2p->my_ghost[gate.iter & 1] - P.od_nrows;
+        }
+        unsigned char *stage = smem + (size_t) s * P.stage_bytes;
+        const double *vals = reinterpret_cast<const double *>(stage);
+        const int *rp = reinterpret_cast<const int *>(stage + (size_t) P.sc * 8) + (tl.row_begin & 3);
+        const unsigned short *pid = reinterpret_cast<const unsigned short *>(stage + (size_t) P.sc * 8 + (size_t) C.rc * 4)
+                                    + (tl.row_begin & 7);
+
+        mbar_wait(&full_bar[s], (uint32_t) ((i / S) & 1));
+
+        for (int base = 0; base < nrows; base += RPP) {
+            const int lr = base + grp;
+            double sum = 0.0;
+            if (lr < nrows) {
+                const int row = tl.row_begin + lr;
+                const int kb = rp[lr] - tl.k_al;
+                const int ke = rp[lr + 1] - tl.k_al;
+                /* compressed: offsets of this row's pattern; raw: indices from global memory */
+                const int *offs = cmp ? patoff_s + patptr_s[pid[lr]] - kb : NULL;
+                const int *gcol = P.colidx + tl.k_al;
+                for (int k = kb + lane; k < ke; k += U * G) {
+                    int c[U];
+                    double v[U], xv[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int kk = min(k + u * G, ke - 1);
+                        c[u] = cmp ? row + offs[kk] : __ldg(gcol + kk);
+                        v[u] = vals[kk];
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; u++) xv[u] = ld_x(P.x + c[u]);
+#pragma unroll
+                    for (int u = 0; u < U; u++) sum = fma((k + u * G < ke) ? v[u] : 0.0, xv[u], sum);
+                }
+                if (xg && row >= P.od_rowoffset) {
+                    const int ob = row - P.od_rowoffset;
+                    for (int k = P.orowptr[ob] + lane; k < P.orowptr[ob + 1]; k += G)
+                        sum = fma(P.oa[k], xg[P.ocolidx[k]], sum);
+                }
+            }
+            if (G > 1) sum = group_sum<G>(sum);
+            if (lr < nrows && lane == 0) {
+                const int row = tl.row_begin + lr;
+                if (P.mode == SPMV_R_B_AX) {
+                    const double v = P.b[row] - sum;
+                    P.y[row] = v;
+                    if (row < P.dotrows) dot = fma(v, v, dot);
+                } else {
+                    P.y[row] = sum;
+                    if (P.mode == SPMV_Y_AX_DOT && row < P.dotrows) dot = fma(__ldg(P.x + row), sum, dot);
+                }
+            }
+        }
+
+        __syncthreads();
+        if (tid == 0) {
+            const int tn = t + S * gridDim.x;
+            if (tn < P.ntiles) cspmv_issue(P, C, P.tiles[tn], stage, &full_bar[s], pol);
+        }
+    }
+
+    if (P.acc) {
+        const double v = block_sum(dot, red);
+        if (tid == 0 && v != 0.0) atomicAdd(P.acc, v);
+    }
+    if (P.p2p && P.pub_ch >= 0 && P.p2p->fuse) {
+        __threadfence();
+        if (p2p_last_block(P.p2p, &last_flag))
+            p2p_publish_red(P.p2p, P.pub_ch, gate.iter & 1, P.p2p->rbase + (unsigned long long) gate.iter + 1ull, P.acc, 1);
+    }
+}
+
 /* ---- long rows: several CTAs per row, partials to scratch, then a finisher -- */
 
 __global__ void __launch_bounds__(256)
@@ -853,12 +1020,37 @@ static spmv_fn spmv_variant(int G, int T, int U)
     return NULL;
 }
 
+typedef void (*cspmv_fn)(const SpmvParams, const CmpParams);
+
+static cspmv_fn cspmv_variant(int G, int T, int U)
+{
+    if (U != 8) return NULL;
+#define X(g, t) if (G == g && T == t) return spmv_ctiles_kernel<g, t, 8>;
+    X(1, 128) X(2, 128) X(4, 128) X(8, 128) X(16, 128) X(32, 128) X(4, 256) X(2, 256) X(1, 64)
+#undef X
+    return NULL;
+}
+
 static inline int stage_slots(const acgb200_spmvplan *pl) { return (pl->nnz_cap + 8 + 3) & ~3; }
+static inline int stage_rslots(const acgb200_spmvplan *pl) { return (pl->rows_cap + 1 + 8 + 3) & ~3; }
+static inline int stage_pslots(const acgb200_spmvplan *pl) { return (pl->rows_cap + 16 + 7) & ~7; }
 static inline int stage_bytes(const acgb200_spmvplan *pl)
 {
     const int sc = stage_slots(pl);
-    const int rc = (pl->rows_cap + 1 + 8 + 3) & ~3;
+    const int rc = stage_rslots(pl);
+    if (pl->compressed) return (sc * 8 + rc * 4 + stage_pslots(pl) * 2 + 127) & ~127;
     return (sc * 12 + rc * 4 + 127) & ~127;
+}
+static inline int table_bytes(const acgb200_spmvplan *pl)
+{
+    return pl->compressed ? (((pl->npat + 1 + 3) & ~3) + ((pl->nentries + 3) & ~3)) * 4 : 0;
+}
+
+extern "C" int64_t acgb200_spmv_min_bytes(const acgb200_spmvplan *pl)
+{
+    /* values + (indices unless the tile is compressed) + per row: row pointer, y, x (+ pattern id) */
+    const double frac = pl->ntiles > 0 && pl->compressed ? (double) pl->ncompressed_tiles / pl->ntiles : 0.0;
+    return (int64_t) (pl->nnz * (8.0 + 4.0 * (1.0 - frac)) + pl->nrows * (20.0 + 2.0 * frac));
 }
 
 /*
@@ -892,9 +1084,10 @@ extern "C" void acgb200_spmv_choose(acgb200_spmvplan *pl, int nrows, int64_t nnz
 
 extern "C" int acgb200_spmv_configure(acgb200_spmvplan *pl)
 {
-    spmv_fn fn = spmv_variant(pl->lanes_per_row, pl->threads, pl->unroll);
+    const void *fn = pl->compressed ? (const void *) cspmv_variant(pl->lanes_per_row, pl->threads, pl->unroll)
+                                    : (const void *) spmv_variant(pl->lanes_per_row, pl->threads, pl->unroll);
     if (!fn) return (int) cudaErrorInvalidConfiguration;
-    pl->smem_bytes = stage_bytes(pl) * pl->nstages;
+    pl->smem_bytes = stage_bytes(pl) * pl->nstages + table_bytes(pl);
     cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes);
     if (err) return (int) err;
     int per_sm = 0;
@@ -921,7 +1114,15 @@ extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t strea
         P.ctrl_in = a->ctrl_in; P.ctrl_out = a->ctrl_out; P.st = a->st; P.housekeeping = a->housekeeping;
         P.p2p = (acgb200_p2pdev *) a->p2p; P.od_rowoffset = a->od_rowoffset; P.od_nrows = a->od_nrows;
         P.orowptr = a->orowptr; P.ocolidx = a->ocolidx; P.oa = a->oa; P.pub_ch = a->p2p ? a->pub_ch : -1;
-        spmv_variant(pl->lanes_per_row, pl->threads, pl->unroll)<<<pl->grid, pl->threads, pl->smem_bytes, stream>>>(P);
+        if (pl->compressed) {
+            CmpParams C;
+            C.patid = pl->d_patid; C.patptr = pl->d_patptr; C.patoff = pl->d_patoff;
+            C.npat = pl->npat; C.nentries = pl->nentries;
+            C.pc = stage_pslots(pl); C.rc = stage_rslots(pl);
+            cspmv_variant(pl->lanes_per_row, pl->threads, pl->unroll)<<<pl->grid, pl->threads, pl->smem_bytes, stream>>>(P, C);
+        } else {
+            spmv_variant(pl->lanes_per_row, pl->threads, pl->unroll)<<<pl->grid, pl->threads, pl->smem_bytes, stream>>>(P);
+        }
         cudaError_t err = cudaGetLastError();
         if (err) return (int) err;
     }

@@ -16,7 +16,8 @@ extern "C" {
  * tgemv/taxpy like the reference's -DACG_ENABLE_PROFILING, acg/cgcuda.c:69-73),
  * "check_every" (iterations between convergence polls), "spmv_lanes",
  * "spmv_nnz_cap", "spmv_rows_cap", "spmv_stages", "spmv_threads", "spmv_unroll",
- * "spmv_max_ctas" (SpMV tile plan overrides, read at acgsolvercuda_init), "graph"
+ * "spmv_max_ctas" (SpMV tile plan overrides, read at acgsolvercuda_init), "spmv_compress"
+ * (0/1, default 0: drop the column indices of tiles whose rows repeat a pattern, compress.c), "graph"
  * (0/1: replay iteration pairs as CUDA graphs), "redstream" (0/1: pipelined
  * allreduce on its own stream and communicator; read at acgsolvercuda_init).  Environment variables ACGB200_<KEY> set the
  * same values at first use. */
@@ -41,6 +42,8 @@ struct acgb200_info {
     double last_h2d_ms;         /* host time of the b, x0 upload of the last solve */
     double last_d2h_ms;         /* host time of the x download of the last solve */
     double last_blas_ms;        /* device time of the fused vector-update kernels of the last solve (profile=1) */
+    int spmv_compressed_tiles;  /* tiles that carry no column indices (option "spmv_compress") */
+    int64_t spmv_min_bytes;     /* bytes one SpMV launch must move at least, given the plan */
 };
 ACG_API int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info);
 
@@ -50,6 +53,14 @@ ACG_API int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_in
  * tile; info->spmv_* describe the plan.  For tests of the host logic. */
 ACG_API int acgb200_spmv_plan_host(int nrows, const int64_t *rowptr, struct acgb200_info *info,
                                    int *tiles4, int maxtiles, int *longrows, int maxlong);
+
+/* Row-pattern dictionary of a 0-based CSR matrix (host logic of the index-free
+ * SpMV tiles, compress.c).  patptr needs max_entries+1 ints (at most that many
+ * patterns), patoff max_entries ints, patid nrows entries; 0xFFFF in patid
+ * marks a row whose pattern is not in the dictionary. */
+ACG_API int acgb200_patterns_host(int nrows, const int64_t *rowptr, const int *colidx, int max_entries,
+                                  int *npat, int *nentries, int *patptr, int *patoff, unsigned short *patid,
+                                  int64_t *nmatched);
 
 /* Inverse send map of the peer-memory halo exchange (host logic of p2p.c): for
  * border row b, entries [bptr[b], bptr[b+1]) give the recipient index bq[e] and

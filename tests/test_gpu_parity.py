@@ -223,3 +223,31 @@ def test_full_size_properties(kind, ab):
         # CG minimises the A-norm of the error monotonically: closer to the all-ones solution
         assert np.linalg.norm(x.x - 1.0) < np.linalg.norm(ones)
     cg.free()
+
+
+@pytest.mark.skipif(os.environ.get("ACGB200_TEST_EXPERIMENTAL") != "1",
+                    reason="index-free SpMV tiles are opt-in and not yet validated on hardware "
+                           "(set ACGB200_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("name,gen", [CASES[0], CASES[1], CASES[2], CASES[5]], ids=[CASES[i][0] for i in (0, 1, 2, 5)])
+def test_compressed_tiles_match_oracle(name, gen, ab, oracle):
+    """Option spmv_compress=1 (compress.c, spmv_ctiles_kernel): same results."""
+    n, r, c, v = gen()
+    ab.set_option("spmv_compress", 1)
+    try:
+        A, cg = _solver(ab, n, r, c, v)
+    finally:
+        ab.set_option("spmv_compress", 0)
+    csr = (A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy())
+    x = np.random.default_rng(1).standard_normal(n)
+    y, _ = cg.spmv(x)
+    want = oracle.dsymv(csr, 1.0, x, 0.0, np.zeros(n))
+    scale = oracle.dsymv((csr[0], csr[1], np.abs(csr[2])), 1.0, np.abs(x), 0.0, np.zeros(n))
+    assert np.all(np.abs(y - want) <= SPMV_RTOL * scale + 1e-300)
+    if name != "rmat-longrows":
+        assert cg.info()["spmv_compressed_tiles"] > 0
+        b = A.vector(); b.x[:] = 1.0
+        xs = A.vector()
+        ref = oracle.cg(csr, b.x, maxits=300, rtol=1e-9)
+        assert cg.solvempi(b, xs, maxits=300, residualrtol=1e-9) == 0 and cg.c.niterations == ref["niterations"]
+        assert np.abs(xs.x - ref["x"]).max() <= 1e-9 * np.abs(ref["x"]).max()
+    cg.free()

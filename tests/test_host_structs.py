@@ -213,3 +213,40 @@ def test_peer_memory_push_addressing(kind, nparts, ab):
     for p, m in enumerate(parts):
         assert np.all(writes[p] == 1)
         assert np.array_equal(ghost[p], x[m.nzrows[m.c.nownedrows:]])
+
+
+@pytest.mark.parametrize("name,gen,full", [
+    ("27pt", lambda: mg.stencil3d_27pt(9, 8, 7), True),
+    ("7pt", lambda: mg.laplace3d_7pt(8, 9, 10), True),
+    ("1d5", lambda: mg.poisson1d_5pt(500), True),
+    ("rmat", lambda: mg.rmat_spd(3000, 30000, seed=2), False),
+])
+def test_row_pattern_dictionary(name, gen, full, ab, oracle):
+    """Host logic of the index-free SpMV tiles (compress.c): rebuilding the
+    column indices of every matched row from (row, pattern id, pattern table)
+    gives back the CSR column indices exactly; stencil matrices match fully
+    with a few dozen patterns, a power-law matrix mostly does not."""
+    n, r, c, v = gen()
+    rowptr, colidx, _ = oracle.full_csr(n, r, c, v)
+    d = ab.patterns_host(rowptr, colidx, max_entries=4096)
+    assert d["patptr"][0] == 0 and d["patptr"][-1] == len(d["patoff"]) <= 4096
+    matched = 0
+    for row in range(n):
+        pid = int(d["patid"][row])
+        if pid == 0xFFFF:
+            continue
+        matched += 1
+        offs = d["patoff"][d["patptr"][pid]:d["patptr"][pid + 1]]
+        assert np.array_equal(row + offs, colidx[rowptr[row]:rowptr[row + 1]])
+    assert matched == d["nmatched"]
+    if full:
+        assert matched == n and d["npat"] <= 125
+    else:
+        assert matched < n
+    # partitioned: interior rows keep their patterns, rows touching reordered border rows may not
+    if name == "27pt":
+        A = ab.SymCsrMatrix.init_real_double(n, r, c, v)
+        part = A.partition(2, _parts("slab", n, 2))[0].dsymv_init(0.0)
+        no = part.c.nownedrows
+        dp = ab.patterns_host(part.frowptr[:no + 1].copy(), part.fcolidx[:part.frowptr[no]].copy())
+        assert dp["nmatched"] >= 0.5 * no
