@@ -124,7 +124,7 @@ EXPORTS = [
     "acgvector_set_constant_real_double", "acgvector_copy", "acgvector_daxpy", "acgvector_dnrm2",
     "acgvector_usga", "acgvector_ussc",
     "acgsymcsrmatrix_init_real_double", "acgsymcsrmatrix_init_rowwise_real_double", "acgsymcsrmatrix_free",
-    "acgsymcsrmatrix_vector", "acgsymcsrmatrix_partition", "acgsymcsrmatrix_halo", "acgsymcsrmatrix_dsymv_init",
+    "acgsymcsrmatrix_vector", "acgsymcsrmatrix_partition", "acgsymcsrmatrix_partition_rows", "acgsymcsrmatrix_halo", "acgsymcsrmatrix_dsymv_init",
     "acgcommtypestr", "acgcomm_init_nccl", "acgcomm_free", "acgcomm_size", "acgcomm_rank", "acgcomm_barrier",
     "acgcomm_allreduce",
     "acghalo_free", "acghaloexchange_init_cuda", "acghaloexchange_free", "acghaloexchange_profile",
@@ -166,6 +166,7 @@ def lib() -> C.CDLL:
     L.acgsymcsrmatrix_free.argtypes = [P(acgsymcsrmatrix)]
     L.acgsymcsrmatrix_vector.argtypes = [P(acgsymcsrmatrix), P(acgvector)]
     L.acgsymcsrmatrix_partition.argtypes = [P(acgsymcsrmatrix), C.c_int, i32p, P(acgsymcsrmatrix), C.c_int]
+    L.acgsymcsrmatrix_partition_rows.argtypes = [P(acgsymcsrmatrix), C.c_int, C.c_int, i32p, P(C.c_int), C.c_int, C.c_int]
     L.acgsymcsrmatrix_halo.argtypes = [P(acgsymcsrmatrix), P(acghalo)]
     L.acgsymcsrmatrix_dsymv_init.argtypes = [P(acgsymcsrmatrix), C.c_double]
     L.acghalo_free.restype = None
@@ -314,6 +315,14 @@ class SymCsrMatrix:
     def dsymv_init(self, eps: float = 0.0):
         _check(lib().acgsymcsrmatrix_dsymv_init(C.byref(self.c), eps), "acgsymcsrmatrix_dsymv_init")
         return self
+
+    def partition_rows(self, nparts: int, kway: bool = False, seed: int = 0):
+        """acgsymcsrmatrix_partition_rows: METIS row->part map; returns (rowparts, edge cut)."""
+        rowparts = np.zeros(max(self.c.nprows, 1), np.int32)
+        cut = C.c_int(0)
+        _check(lib().acgsymcsrmatrix_partition_rows(C.byref(self.c), nparts, 1 if kway else 0, rowparts, C.byref(cut), seed, 0),
+               "acgsymcsrmatrix_partition_rows")
+        return rowparts[:self.c.nprows], cut.value
 
     def partition(self, nparts: int, rowparts) -> list["SymCsrMatrix"]:
         rowparts = np.ascontiguousarray(rowparts, np.int32)

@@ -10,7 +10,8 @@ object broadcast, NCCL for the data path inside libacgb200):
 * ``nccl_comm()``        -- unique id from rank 0, broadcast, ``Comm.init_nccl``
 * ``local_part()``       -- every rank builds the (synthetic) matrix, partitions
                             it with the same row->part map and keeps its part
-* ``block_partition()``  -- geometric px*py*pz row->part map for stencil grids
+* ``block_partition()``  -- geometric px*py*pz row->part map for stencil grids;
+                            ``rowparts="metis"`` uses acgsymcsrmatrix_partition_rows
 """
 from __future__ import annotations
 
@@ -74,6 +75,9 @@ def local_part(n, rows, cols, vals, rowparts, rank: int, world: int, eps: float 
     A = SymCsrMatrix.init_real_double(n, rows, cols, vals)
     if world == 1:
         return A.dsymv_init(eps)
+    if isinstance(rowparts, str) and rowparts == "metis":
+        # METIS is deterministic for a fixed seed: every rank computes the same map
+        rowparts, _ = A.partition_rows(world, kway=False, seed=0)
     parts = A.partition(world, rowparts)
     A.free()
     mine = parts[rank]

@@ -144,6 +144,8 @@ def main():
     ap.add_argument("--iters", type=int, default=100, help="CG iterations per step (reference default --max-iterations 100)")
     ap.add_argument("--cpu-iters", type=int, default=5, help="iterations per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partition", default="block", choices=["block", "metis"],
+                    help="row partition for N>1: geometric blocks or METIS (acgsymcsrmatrix_partition_rows)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     solver = args.solver or os.environ.get("BENCH_SOLVER") or w["solver"]
@@ -152,7 +154,8 @@ def main():
     metric = "CG iterations/sec (27-pt stencil ~10M rows); SpMV achieved-HBM GB/s in roofline"
     config = {"workload": f"{w['kind']} stencil {w['N']}^3, FP64, b=1, x0=0, {solver} CG, {args.iters} iterations/step, "
                           f"tolerances off", "n": w["N"] ** 3, "solver": solver, "iters_per_step": args.iters,
-              "partition": f"{world} geometric block(s)" if world > 1 else "none",
+              "partition": (f"{world} parts, " + ("METIS recursive" if args.partition == "metis" else "geometric blocks"))
+                           if world > 1 else "none",
               "l2": "inputs larger than L2 (CSR 3.6 GB per SpMV vs 126 MB L2), no flush needed"}
 
     if args.impl == "reference":
@@ -180,7 +183,9 @@ def main():
 
     n, r, c, v = make_matrix(w)
     N = w["N"]
-    rowparts = abdist.block_partition(N, N, N, *abdist.grid_factors(world)) if world > 1 else None
+    rowparts = None
+    if world > 1:
+        rowparts = "metis" if args.partition == "metis" else abdist.block_partition(N, N, N, *abdist.grid_factors(world))
     A = abdist.local_part(n, r, c, v, rowparts, rank, world)
     del r, c, v
     nnz_local = int(A.c.fnpnzs + A.c.onpnzs)

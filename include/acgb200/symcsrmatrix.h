@@ -95,6 +95,13 @@ ACG_API int acgsymcsrmatrix_init_rowwise_real_double(
 ACG_API void acgsymcsrmatrix_free(struct acgsymcsrmatrix *A);
 /* acg/symcsrmatrix.h:405 -- vector compatible with A (owned + ghost entries) */
 ACG_API int acgsymcsrmatrix_vector(const struct acgsymcsrmatrix *A, struct acgvector *x);
+/* acg/metis.h:39-43 */
+enum metis_partitioner { metis_partgraphrecursive, metis_partgraphkway };
+/* acg/symcsrmatrix.h:419 -- row->part map (0-based part numbers) from METIS on
+ * the matrix graph; objval receives the edge cut */
+ACG_API int acgsymcsrmatrix_partition_rows(
+    struct acgsymcsrmatrix *A, int nparts, enum metis_partitioner partitioner,
+    int *rowparts, acgidx_t *objval, acgidx_t seed, int verbose);
 /* acg/symcsrmatrix.h:435 -- split by a row->part map into nparts submatrices
  * with [interior|border|ghost] local order and neighbour lists */
 ACG_API int acgsymcsrmatrix_partition(

@@ -84,6 +84,8 @@ def main():
         n, r, c, v = mg.rmat_spd(N, 12 * N, seed=4)
     if args.partition == "block" and args.matrix != "rmat":
         rowparts = abdist.block_partition(N, N, N, *abdist.grid_factors(world))
+    elif args.partition == "metis":
+        rowparts = "metis"
     elif args.partition == "random":
         rowparts = np.random.default_rng(3).integers(0, world, n).astype(np.int32)
     else:

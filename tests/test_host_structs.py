@@ -250,3 +250,36 @@ def test_row_pattern_dictionary(name, gen, full, ab, oracle):
         no = part.c.nownedrows
         dp = ab.patterns_host(part.frowptr[:no + 1].copy(), part.fcolidx[:part.frowptr[no]].copy())
         assert dp["nmatched"] >= 0.5 * no
+
+
+@pytest.mark.parametrize("kway", [False, True])
+def test_metis_row_partition(kway, ab, oracle):
+    """acgsymcsrmatrix_partition_rows (METIS from the CUDA toolkit's static
+    archive): valid, balanced, low-cut, reproducible; and it feeds
+    acgsymcsrmatrix_partition like any other row->part map."""
+    N = 16
+    n, r, c, v = mg.stencil3d_27pt(N)
+    A = ab.SymCsrMatrix.init_real_double(n, r, c, v)
+    try:
+        parts, cut = A.partition_rows(8, kway=kway, seed=0)
+    except ab.AcgError as e:
+        if e.code == 19:
+            pytest.skip("library built without METIS")
+        raise
+    assert parts.min() == 0 and parts.max() == 7
+    sizes = np.bincount(parts, minlength=8)
+    assert sizes.max() <= 1.05 * n / 8 + 1
+    # edge cut as METIS reports it == edges of the pattern whose ends differ
+    off = r != c
+    assert cut == int(np.sum(parts[r[off]] != parts[c[off]]))
+    # a 2x2x2 block split cuts 3 planes; METIS should be within 2x of that
+    from acg_b200 import dist as abdist
+    blk = abdist.block_partition(N, N, N, 2, 2, 2)
+    assert cut <= 2 * int(np.sum(blk[r[off]] != blk[c[off]]))
+    again, cut2 = A.partition_rows(8, kway=kway, seed=0)
+    assert np.array_equal(parts, again) and cut == cut2
+    one, cut1 = A.partition_rows(1)
+    assert np.all(one == 0) and cut1 == 0
+    subs = A.partition(8, parts)
+    assert sum(m.c.nownedrows for m in subs) == n
+    assert sum(m.c.ninterfacenzs for m in subs) == 2 * cut
