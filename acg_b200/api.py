@@ -135,7 +135,7 @@ EXPORTS = [
     "acgsolvercuda_fwrite",
     "acgb200_set_option", "acgsolvercuda_spmv", "acgsolvercuda_info", "acgb200_sizeof", "acgb200_have_mpi",
     "acgb200_nccl_unique_id", "acgb200_comm_init_rank", "acgb200_comm_destroy",
-    "acgb200_host_register", "acgb200_host_unregister", "acgb200_spmv_plan_host", "acgb200_p2p_inverse_map", "acgb200_patterns_host",
+    "acgb200_host_register", "acgb200_host_unregister", "acgb200_spmv_plan_host", "acgb200_p2p_inverse_map", "acgb200_patterns_host", "acgb200_stencil_part",
 ]
 
 
@@ -168,6 +168,7 @@ def lib() -> C.CDLL:
     L.acgsymcsrmatrix_partition.argtypes = [P(acgsymcsrmatrix), C.c_int, i32p, P(acgsymcsrmatrix), C.c_int]
     L.acgsymcsrmatrix_partition_rows.argtypes = [P(acgsymcsrmatrix), C.c_int, C.c_int, i32p, P(C.c_int), C.c_int, C.c_int]
     L.acgsymcsrmatrix_halo.argtypes = [P(acgsymcsrmatrix), P(acghalo)]
+    L.acgb200_stencil_part.argtypes = [C.c_int] * 8 + [P(acgsymcsrmatrix)]
     L.acgsymcsrmatrix_dsymv_init.argtypes = [P(acgsymcsrmatrix), C.c_double]
     L.acghalo_free.restype = None
     L.acghalo_free.argtypes = [P(acghalo)]
@@ -312,6 +313,14 @@ class SymCsrMatrix:
         self._owns = True
         return self
 
+    @classmethod
+    def stencil_part(cls, kind: int, nx: int, ny: int, nz: int, px: int, py: int, pz: int, part: int):
+        """One part of a block-partitioned 7/27-point stencil matrix, built without the global matrix."""
+        self = cls()
+        _check(lib().acgb200_stencil_part(kind, nx, ny, nz, px, py, pz, part, C.byref(self.c)), "acgb200_stencil_part")
+        self._owns = True
+        return self
+
     def dsymv_init(self, eps: float = 0.0):
         _check(lib().acgsymcsrmatrix_dsymv_init(C.byref(self.c), eps), "acgsymcsrmatrix_dsymv_init")
         return self
@@ -375,6 +384,12 @@ class SymCsrMatrix:
         return out
 
     # read-only numpy views of the arrays the device path consumes
+    @property
+    def rowptr(self): return _view(self.c.rowptr, self.c.nprows + 1, np.int64)
+    @property
+    def colidx(self): return _view(self.c.colidx, self.c.npnzs, np.int32)
+    @property
+    def a(self): return _view(self.c.a, self.c.npnzs, np.float64)
     @property
     def nzrows(self): return _view(self.c.nzrows, self.c.nprows, np.int32)
     @property

@@ -68,6 +68,16 @@ def grid_factors(nparts: int) -> tuple[int, int, int]:
     return best
 
 
+def local_stencil_part(kind: int, nx: int, ny: int, nz: int, rank: int, world: int, eps: float = 0.0):
+    """This rank's part of a 7/27-point stencil matrix on an nx*ny*nz box under the
+    geometric block partition, generated directly (acgb200_stencil_part): no process
+    ever holds the global matrix.  Array-for-array identical to
+    ``local_part(..., block_partition(...))`` (tests/test_host_structs.py)."""
+    from .api import SymCsrMatrix
+    px, py, pz = grid_factors(world)
+    return SymCsrMatrix.stencil_part(kind, nx, ny, nz, px, py, pz, rank).dsymv_init(eps)
+
+
 def local_part(n, rows, cols, vals, rowparts, rank: int, world: int, eps: float = 0.0):
     """This rank's submatrix (full storage initialised), as the reference's
     rank 0 would have scattered it (acg/symcsrmatrix.c:685 + :1238)."""

@@ -50,6 +50,7 @@ WORKLOADS = {
     "7pt-256": dict(kind="7pt", N=256, solver="classic"),          # configs[1]
     "27pt-128": dict(kind="27pt", N=128, solver="pipelined"),      # quick check
     "27pt-64": dict(kind="27pt", N=64, solver="pipelined"),
+    "27pt-448": dict(kind="27pt", N=448, solver="pipelined"),      # configs[3]: 8 GPUs only (weak-scaled x8 point)
 }
 
 
@@ -181,13 +182,16 @@ def main():
     import torch.distributed as dist
     comm = abdist.nccl_comm(rank, world)
 
-    n, r, c, v = make_matrix(w)
     N = w["N"]
-    rowparts = None
-    if world > 1:
-        rowparts = "metis" if args.partition == "metis" else abdist.block_partition(N, N, N, *abdist.grid_factors(world))
-    A = abdist.local_part(n, r, c, v, rowparts, rank, world)
-    del r, c, v
+    if world > 1 and args.partition == "block":
+        # every rank builds only its own block (no global matrix anywhere)
+        A = abdist.local_stencil_part(27 if w["kind"] == "27pt" else 7, N, N, N, rank, world)
+    else:
+        if N ** 3 * (27 if w["kind"] == "27pt" else 7) >= 2 ** 31:
+            raise SystemExit(f"bench.py: {args.workload} does not fit 32-bit indices on {world} GPU(s)")
+        n, r, c, v = make_matrix(w)
+        A = abdist.local_part(n, r, c, v, "metis" if world > 1 else None, rank, world)
+        del r, c, v
     nnz_local = int(A.c.fnpnzs + A.c.onpnzs)
     cg = ab.SolverCuda(A, comm)
     b = A.vector(); b.x[:] = 1.0

@@ -54,6 +54,14 @@ ACG_API int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_in
 ACG_API int acgb200_spmv_plan_host(int nrows, const int64_t *rowptr, struct acgb200_info *info,
                                    int *tiles4, int maxtiles, int *longrows, int maxlong);
 
+/* One part of the block-partitioned 7- or 27-point stencil matrix on an
+ * nx*ny*nz box (diag 6 / 26, neighbours -1, lexicographic numbering, px*py*pz
+ * geometric blocks, part = bi + px*(bj + py*bk)), built directly without a
+ * global matrix: array-for-array what acgsymcsrmatrix_partition yields for that
+ * part (stencil.c).  Follow with acgsymcsrmatrix_dsymv_init. */
+ACG_API int acgb200_stencil_part(int kind, int nx, int ny, int nz, int px, int py, int pz, int part,
+                                 struct acgsymcsrmatrix *A);
+
 /* Row-pattern dictionary of a 0-based CSR matrix (host logic of the index-free
  * SpMV tiles, compress.c).  patptr needs max_entries+1 ints (at most that many
  * patterns), patoff max_entries ints, patid nrows entries; 0xFFFF in patid

@@ -283,3 +283,50 @@ def test_metis_row_partition(kway, ab, oracle):
     subs = A.partition(8, parts)
     assert sum(m.c.nownedrows for m in subs) == n
     assert sum(m.c.ninterfacenzs for m in subs) == 2 * cut
+
+
+@pytest.mark.parametrize("kind,dims,procs", [
+    (27, (8, 8, 8), (2, 2, 2)),
+    (27, (7, 9, 5), (2, 1, 3)),
+    (27, (6, 6, 6), (1, 1, 2)),
+    (7, (9, 7, 8), (3, 2, 2)),
+    (7, (6, 6, 6), (1, 1, 1)),
+])
+def test_stencil_part_matches_partition(kind, dims, procs, ab):
+    """acgb200_stencil_part (no global matrix) == partition of the global stencil
+    matrix by the same block map, array for array."""
+    from acg_b200 import dist as abdist
+    nx, ny, nz = dims
+    px, py, pz = procs
+    n, r, c, v = (mg.stencil3d_27pt if kind == 27 else mg.laplace3d_7pt)(nx, ny, nz)
+    A = ab.SymCsrMatrix.init_real_double(n, r, c, v)
+    nparts = px * py * pz
+    want = A.partition(nparts, abdist.block_partition(nx, ny, nz, px, py, pz)) if nparts > 1 else [A]
+    for p in range(nparts):
+        m = ab.SymCsrMatrix.stencil_part(kind, nx, ny, nz, px, py, pz, p)
+        w = want[p]
+        for k in ("nrows", "nprows", "nnzs", "npnzs", "nownedrows", "ninnerrows", "nborderrows", "borderrowoffset",
+                  "nghostrows", "ghostrowoffset", "ninnernzs", "ninterfacenzs"):
+            assert getattr(m.c, k) == getattr(w.c, k), k
+        if nparts > 1:
+            assert np.array_equal(m.nzrows, w.nzrows)
+        assert np.array_equal(m.rowptr, w.rowptr) and np.array_equal(m.colidx, w.colidx) and np.array_equal(m.a, w.a)
+        hm, hw = m.halo(), w.halo()
+        for k in hm:
+            assert np.array_equal(hm[k], hw[k]), k
+        m.dsymv_init(0.0); w.dsymv_init(0.0)
+        for k in ("frowptr", "fcolidx", "fa", "orowptr", "ocolidx", "oa"):
+            assert np.array_equal(getattr(m, k), getattr(w, k)), k
+        m.free()
+
+
+def test_stencil_part_large_is_cheap(ab):
+    """One eighth of the 27-point 448^3 problem (BASELINE config 4) has the sizes
+    SURVEY.md section 8 lists -- checked on a scaled-down box with the same formulas."""
+    N = 64
+    m = ab.SymCsrMatrix.stencil_part(27, N, N, N, 2, 2, 2, 0)
+    h = N // 2
+    assert m.c.nownedrows == h ** 3
+    assert m.c.nghostrows == 3 * h * h + 3 * h + 1          # three faces, three edges, one corner
+    assert m.c.nborderrows == h ** 3 - (h - 1) ** 3
+    assert len(m.halo()["recipients"]) == 7
