@@ -786,7 +786,12 @@ static int iterate(struct solvectx *c, int maxits, int poll, int kind, int (*iss
     struct priv *pv = c->pv;
     int *errcode = c->errcode;
     int issued = 0, slot = 0, have_prev = 0, since_poll = 0;
-    const int use_graph = cfg.graph && !cfg.profile && maxits >= 6;
+    /* Replays are used on one GPU and with the peer-memory exchange (kernel nodes
+     * only).  With the NCCL exchange the iteration also contains collectives on
+     * two communicators and three streams; that combination ran in the
+     * benchmarks but its test matrix is not closed yet, so it is only captured
+     * on request (option "graph" = 2). */
+    const int use_graph = cfg.graph && !cfg.profile && maxits >= 6 && (!c->multi || c->p2p || cfg.graph >= 2);
     while (issued < maxits) {
         if (use_graph && issued >= 2 && maxits - issued >= 2) {
             if (!pv->graph[kind] || pv->graph_multi[kind] != c->multi) OK(capture_pair(c, kind, issue));

@@ -53,7 +53,7 @@ def _ngpu():
 # exchange back-ends of the CG loop: peer memory with pushes fused into the
 # kernels (default), peer memory with separate post kernels, NCCL only
 BACKENDS = {"p2p-fused": {}, "p2p-unfused": {"ACGB200_P2P_FUSE": "0"}, "nccl": {"ACGB200_P2P": "0"},
-            "nccl-nograph": {"ACGB200_P2P": "0", "ACGB200_GRAPH": "0"}}
+            "nccl-graph": {"ACGB200_P2P": "0", "ACGB200_GRAPH": "2"}}
 
 
 # The default back-end is always tested; the others only when
