@@ -135,7 +135,7 @@ EXPORTS = [
     "acgsolvercuda_fwrite",
     "acgb200_set_option", "acgsolvercuda_spmv", "acgsolvercuda_info", "acgb200_sizeof", "acgb200_have_mpi",
     "acgb200_nccl_unique_id", "acgb200_comm_init_rank", "acgb200_comm_destroy",
-    "acgb200_host_register", "acgb200_host_unregister", "acgb200_spmv_plan_host", "acgb200_p2p_inverse_map", "acgb200_patterns_host", "acgb200_stencil_part",
+    "acgb200_host_register", "acgb200_host_unregister", "acgb200_spmv_plan_host", "acgb200_spmv_plan_host2", "acgb200_p2p_inverse_map", "acgb200_patterns_host", "acgb200_stencil_part",
 ]
 
 
@@ -198,6 +198,7 @@ def lib() -> C.CDLL:
     u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
     L.acgb200_patterns_host.argtypes = [C.c_int, i64p, i32p, C.c_int, P(C.c_int), P(C.c_int), i32p, i32p, u16p, P(C.c_int64)]
     L.acgb200_p2p_inverse_map.argtypes = [P(acghalo), C.c_int, C.c_int, i32p, i32p, i32p, i32p]
+    L.acgb200_spmv_plan_host2.argtypes = [C.c_int, i64p, C.c_void_p, P(acgb200_info), i32p, C.c_int, i32p, C.c_int]
     L.acgb200_spmv_plan_host.argtypes = [C.c_int, i64p, P(acgb200_info), i32p, C.c_int, i32p, C.c_int]
     L.acgb200_comm_init_rank.argtypes = [P(acgcomm), C.c_int, C.c_void_p, C.c_int, P(C.c_int)]
     L.acgb200_comm_destroy.argtypes = [P(acgcomm)]
@@ -231,17 +232,25 @@ def patterns_host(rowptr, colidx, max_entries: int = 4096) -> dict:
                 patid=patid[:n].copy(), nmatched=nm.value)
 
 
-def spmv_plan_host(rowptr) -> dict:
-    """Tile plan of the SpMV for a CSR row-pointer array (host only, no device)."""
+def spmv_plan_host(rowptr, colidx=None) -> dict:
+    """Tile plan of the SpMV for a CSR row-pointer array (host only, no device).
+    With ``colidx`` the compression decision is included: ``compressed[t]``."""
     rowptr = np.ascontiguousarray(rowptr, np.int64)
     n = len(rowptr) - 1
     tiles = np.zeros(4 * (n + 1), np.int32)
     longrows = np.zeros(n + 1, np.int32)
     inf = acgb200_info()
-    _check(lib().acgb200_spmv_plan_host(n, rowptr, C.byref(inf), tiles, n + 1, longrows, n + 1), "acgb200_spmv_plan_host")
+    cptr = None
+    if colidx is not None:
+        colidx = np.ascontiguousarray(colidx, np.int32)
+        cptr = colidx.ctypes.data_as(C.c_void_p)
+    _check(lib().acgb200_spmv_plan_host2(n, rowptr, cptr, C.byref(inf), tiles, n + 1, longrows, n + 1), "acgb200_spmv_plan_host")
     nt, nl = inf.spmv_ntiles, inf.spmv_nlong
+    t4 = tiles[:4 * nt].reshape(nt, 4).copy()
+    compressed = (t4[:, 1] & 0x40000000) != 0
+    t4[:, 1] &= ~np.int32(0x40000000)
     return dict(lanes=inf.spmv_lanes_per_row, rows_cap=inf.spmv_rows_cap, nnz_cap=inf.spmv_nnz_cap,
-                stages=inf.spmv_stages, tiles=tiles[:4 * nt].reshape(nt, 4).copy(), longrows=longrows[:nl].copy())
+                stages=inf.spmv_stages, tiles=t4, longrows=longrows[:nl].copy(), compressed=compressed)
 
 
 def _view(ptr, n, dtype):

@@ -309,9 +309,18 @@ int acgb200_patterns_host(int nrows, const int64_t *rowptr, const int *colidx, i
 }
 
 /* ext.h: the tile plan the solver would build for a CSR row-pointer array,
- * computed on the host without touching a device */
+ * computed on the host without touching a device.  With colidx != NULL the
+ * row-pattern dictionary is built too and tiles whose rows are all in it are
+ * flagged ACGB200_TILE_COMPRESSED in their nrows field, exactly as
+ * acgsolvercuda_init does under option "spmv_compress". */
 int acgb200_spmv_plan_host(int nrows, const int64_t *rowptr, struct acgb200_info *info,
                            int *tiles4, int maxtiles, int *longrows, int maxlong)
+{
+    return acgb200_spmv_plan_host2(nrows, rowptr, NULL, info, tiles4, maxtiles, longrows, maxlong);
+}
+
+int acgb200_spmv_plan_host2(int nrows, const int64_t *rowptr, const int *colidx, struct acgb200_info *info,
+                            int *tiles4, int maxtiles, int *longrows, int maxlong)
 {
     struct acgb200_spmvplan pl;
     memset(&pl, 0, sizeof(pl));
@@ -325,9 +334,23 @@ int acgb200_spmv_plan_host(int nrows, const int64_t *rowptr, struct acgb200_info
     struct acgb200_tile *tiles = malloc(((size_t) nrows + 1) * sizeof(*tiles));
     int *lr = malloc(((size_t) nrows + 1) * sizeof(*lr));
     if (!tiles || !lr) { free(tiles); free(lr); return ACG_ERR_ERRNO; }
-    int nt = 0, nl = 0;
+    int nt = 0, nl = 0, ncomp = 0;
     int err = cut_tiles(&pl, rowptr, tiles, &nt, lr, &nl);
     if (!err && (nt > maxtiles || nl > maxlong)) err = ACG_ERR_NO_BUFFER_SPACE;
+    if (!err && colidx) {
+        struct acgb200_patterns pat;
+        err = acgb200_patterns_build(nrows, rowptr, colidx, 4096, &pat);
+        if (!err) {
+            for (int t = 0; t < nt; t++) {
+                int all = pat.npat > 0;
+                for (int r = tiles[t].row_begin; r < tiles[t].row_begin + tiles[t].nrows && all; r++)
+                    all = pat.patid[r] != ACGB200_NOPATTERN;
+                if (all) { tiles[t].nrows |= ACGB200_TILE_COMPRESSED; ncomp++; }
+            }
+            if (2 * (int64_t) ncomp < nt) { for (int t = 0; t < nt; t++) tiles[t].nrows &= ~ACGB200_TILE_COMPRESSED; ncomp = 0; }
+            acgb200_patterns_free(&pat);
+        }
+    }
     if (!err) {
         for (int t = 0; t < nt; t++) {
             tiles4[4 * t] = tiles[t].row_begin; tiles4[4 * t + 1] = tiles[t].nrows;
@@ -337,7 +360,7 @@ int acgb200_spmv_plan_host(int nrows, const int64_t *rowptr, struct acgb200_info
         memset(info, 0, sizeof(*info));
         info->spmv_lanes_per_row = pl.lanes_per_row; info->spmv_rows_cap = pl.rows_cap;
         info->spmv_nnz_cap = pl.nnz_cap; info->spmv_stages = pl.nstages;
-        info->spmv_ntiles = nt; info->spmv_nlong = nl;
+        info->spmv_ntiles = nt; info->spmv_nlong = nl; info->spmv_compressed_tiles = ncomp;
     }
     free(tiles); free(lr);
     return err;

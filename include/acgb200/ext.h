@@ -53,6 +53,10 @@ ACG_API int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_in
  * tile; info->spmv_* describe the plan.  For tests of the host logic. */
 ACG_API int acgb200_spmv_plan_host(int nrows, const int64_t *rowptr, struct acgb200_info *info,
                                    int *tiles4, int maxtiles, int *longrows, int maxlong);
+/* same, and with colidx != NULL (0-based) also the compression decision: tiles whose
+ * rows are all in the row-pattern dictionary have bit 30 set in their nrows field */
+ACG_API int acgb200_spmv_plan_host2(int nrows, const int64_t *rowptr, const int *colidx, struct acgb200_info *info,
+                                    int *tiles4, int maxtiles, int *longrows, int maxlong);
 
 /* One part of the block-partitioned 7- or 27-point stencil matrix on an
  * nx*ny*nz box (diag 6 / 26, neighbours -1, lexicographic numbering, px*py*pz

@@ -330,3 +330,54 @@ def test_stencil_part_large_is_cheap(ab):
     assert m.c.nghostrows == 3 * h * h + 3 * h + 1          # three faces, three edges, one corner
     assert m.c.nborderrows == h ** 3 - (h - 1) ** 3
     assert len(m.halo()["recipients"]) == 7
+
+
+@pytest.mark.parametrize("name,gen", [("27pt", lambda: mg.stencil3d_27pt(10, 9, 11)), ("7pt", lambda: mg.laplace3d_7pt(12)),
+                                      ("27pt-part", None)], ids=["27pt", "7pt", "27pt-part"])
+def test_compressed_tile_arithmetic_emulated(name, gen, ab, oracle):
+    """Emulation of the index arithmetic of spmv_ctiles_kernel on the CPU, from
+    exactly the arrays the device gets (tile descriptors with their aligned
+    slice starts, pattern ids, pattern table): y = A x tile by tile."""
+    if gen is None:
+        from acg_b200 import dist as abdist
+        n, r, c, v = mg.stencil3d_27pt(12)
+        A = ab.SymCsrMatrix.init_real_double(n, r, c, v)
+        part = A.partition(2, abdist.block_partition(12, 12, 12, 1, 1, 2))[1].dsymv_init(0.0)
+        no = part.c.nownedrows
+        rowptr = part.frowptr[:no + 1].copy(); colidx = part.fcolidx[:rowptr[no]].copy(); vals = part.fa[:rowptr[no]].copy()
+        nvec = no
+    else:
+        n, r, c, v = gen()
+        rowptr, colidx, vals = oracle.full_csr(n, r, c, v)
+        no = nvec = n
+    plan = ab.spmv_plan_host(rowptr, colidx)
+    pat = ab.patterns_host(rowptr, colidx)
+    assert plan["compressed"].sum() > 0.5 * len(plan["tiles"])
+    x = np.random.default_rng(3).standard_normal(nvec)
+    y = np.zeros(no)
+    patid_dev = np.concatenate([pat["patid"], np.zeros(16, np.uint16)])         # device array is padded
+    for (row_begin, nrows, k_al, nnz_al), cmp in zip(plan["tiles"], plan["compressed"]):
+        # what cspmv_issue stages: values slice, row-pointer slice, pattern-id slice
+        vals_s = np.concatenate([vals, np.zeros(16)])[k_al:k_al + nnz_al]
+        row_al = row_begin & ~3
+        nrp = (row_begin + nrows + 1 - row_al + 3) & ~3
+        rptr_s = np.concatenate([rowptr, np.full(8, rowptr[-1])])[row_al:row_al + nrp]
+        row_al8 = row_begin & ~7
+        npid = (row_begin + nrows - row_al8 + 7) & ~7
+        pid_s = patid_dev[row_al8:row_al8 + npid]
+        rp = rptr_s[row_begin & 3:]
+        pid = pid_s[row_begin & 7:]
+        for lr in range(nrows):
+            row = row_begin + lr
+            kb, ke = rp[lr] - k_al, rp[lr + 1] - k_al
+            assert 0 <= kb <= ke <= nnz_al
+            if cmp:
+                base = pat["patptr"][pid[lr]] - kb                 # offs = patoff_s + patptr_s[pid] - kb
+                cols = np.array([row + pat["patoff"][base + kk] for kk in range(kb, ke)], dtype=np.int64)
+            else:
+                cols = colidx[k_al + kb:k_al + ke]                 # gcol = colidx + k_al
+            y[row] = vals_s[kb:ke] @ x[cols] if ke > kb else 0.0
+    want = np.zeros(no)
+    for i in range(no):
+        want[i] = vals[rowptr[i]:rowptr[i + 1]] @ x[colidx[rowptr[i]:rowptr[i + 1]]]
+    assert np.allclose(y, want, rtol=1e-14, atol=1e-14)
