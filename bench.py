@@ -134,6 +134,32 @@ def cpu_reference(w, steps, warmup, iters, solver_note):
                 seconds=tot)
 
 
+def reference_gpu(w, iters, solver):
+    """The stock reference GPU solver (acg/cgcuda.c: cusparseSpMV + cublasDdot + its own axpy
+    kernels), built unmodified for sm_100a by tools/build_driver.sh, on the same matrix through a
+    binary Matrix Market file.  Optional extra arm (--with-reference-gpu): the kernel to beat."""
+    import re
+    import tempfile
+    from acg_b200 import mtxio
+    exe = os.path.join(ROOT, "oracle", "_ref", "driver_ref", "acg-cuda-ref")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/driver_ref/acg-cuda-ref not built (needs the reference tree at build time)"}
+    n, r, c, v = make_matrix(w)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "A.mtx")
+        mtxio.write_symmetric(path, n, r, c, v, binary=True)
+        del r, c, v
+        p = subprocess.run([exe, path, "--binary", "--solver", "acg-pipelined" if solver == "pipelined" else "acg",
+                            "--max-iterations", str(iters), "--residual-rtol", "0", "--warmup", "10", "-q"],
+                           capture_output=True, text=True)
+    if p.returncode != 0:
+        return {"unavailable": "reference GPU solver failed: " + p.stderr[-300:]}
+    t = float(re.search(r"total solver time: ([\d.,]+) seconds", p.stderr).group(1).replace(",", ""))
+    its = int(re.search(r"^\s*iterations: ([\d,]+)", p.stderr, re.M).group(1).replace(",", ""))
+    return {"value": its / t, "unit": "iterations/s", "iterations": its, "tsolve_s": t,
+            "what": "unmodified aCG GPU solver (cuSPARSE SpMV, cuBLAS dot), 'total solver time' of its own report"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -145,6 +171,8 @@ def main():
     ap.add_argument("--iters", type=int, default=100, help="CG iterations per step (reference default --max-iterations 100)")
     ap.add_argument("--cpu-iters", type=int, default=5, help="iterations per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--with-reference-gpu", action="store_true",
+                    help="also run the stock reference GPU solver (cuSPARSE/cuBLAS) on the same matrix (1 GPU, adds minutes)")
     ap.add_argument("--partition", default="block", choices=["block", "metis"],
                     help="row partition for N>1: geometric blocks or METIS (acgsymcsrmatrix_partition_rows)")
     args = ap.parse_args()
@@ -281,6 +309,9 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(w, 1, 0, args.cpu_iters,
                                                  "" if solver == "classic" else "; GPU arm runs pipelined CG")
+        if world == 1 and args.with_reference_gpu:
+            cg.free(); b.free(); x.free(); A.free()          # give the memory back first
+            line["reference_gpu"] = reference_gpu(w, args.iters, solver)
         print(json.dumps(line), flush=True)
     cg.free(); b.free(); x.free()
     comm.destroy()

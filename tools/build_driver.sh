@@ -26,3 +26,19 @@ done
   -L"$ROOT/acg_b200" -lacgb200_mpi -Wl,-rpath,'$ORIGIN/../../../acg_b200' \
   -L"$CUDA/lib64" -lcublas -lcusparse -lcudart -lnccl -lm
 echo "built $OUT/acg-cuda"
+
+# The stock reference GPU solver (its own cgcuda.c: cusparseSpMV + cublasDdot + its axpy kernels) with the same
+# single-process MPI stand-in, for sm_100a: the "kernel to beat" arm (bench.py --with-reference-gpu).
+REFOUT=$ROOT/oracle/_ref/driver_ref
+mkdir -p "$REFOUT"
+/usr/bin/gcc -O2 -fopenmp $DEFS -DACG_HAVE_CUDA $INC -c "$REF/cuda/acg-cuda.c" -o "$REFOUT/acg-cuda.o"
+for f in vector symcsrmatrix graph halo comm error fmtspec mtxfile metis prefixsum sort cgpetsc cgcuda cg; do
+  /usr/bin/gcc -O2 -fopenmp $DEFS -DACG_HAVE_CUDA $INC -c "$REF/acg/$f.c" -o "$REFOUT/$f.o"
+done
+for f in cg-kernels-cuda halo comm-nvshmem nvshmem; do
+  "$CUDA/bin/nvcc" -O3 -gencode arch=compute_100a,code=sm_100a -rdc=true -Xcompiler -fopenmp $DEFS -DACG_HAVE_CUDA $INC \
+      -c "$REF/acg/$f.cu" -o "$REFOUT/$f.cu.o"
+done
+"$CUDA/bin/nvcc" -gencode arch=compute_100a,code=sm_100a -Xcompiler -fopenmp -o "$REFOUT/acg-cuda-ref" "$REFOUT"/*.o \
+  -lcublas -lcusparse -lnccl -lm -lcudadevrt
+echo "built $REFOUT/acg-cuda-ref"
