@@ -97,6 +97,10 @@ int acgb200_stencil_part(int kind, int nx, int ny, int nz, int px, int py, int p
     for (size_t i = 0; i < (size_t) sx * sy * sz; i++) shell[i] = -1;
     for (int z = g.z0; z < g.z1; z++) for (int y = g.y0; y < g.y1; y++) for (int x = g.x0; x < g.x1; x++) {
         int border = 0;
+        if (x > g.x0 && x < g.x1 - 1 && y > g.y0 && y < g.y1 - 1 && z > g.z0 && z < g.z1 - 1) {
+            ninner++;                            /* off the faces of the box: interior */
+            continue;
+        }
         for (int dz = -1; dz <= 1; dz++) for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) {
             if (!is_stencil(&g, dx, dy, dz)) continue;
             const int X = x + dx, Y = y + dy, Z = z + dz;
@@ -162,7 +166,7 @@ int acgb200_stencil_part(int kind, int nx, int ny, int nz, int px, int py, int p
             A->a = malloc(ne * sizeof(double));
             if (!gr->srcnodeidx || !gr->dstnodeidx || !A->a) goto fail;
         }
-        #pragma omp parallel for collapse(2) if (pass == 1)
+        #pragma omp parallel for collapse(2)
         for (int z = g.z0; z < g.z1; z++) for (int y = g.y0; y < g.y1; y++) for (int x = g.x0; x < g.x1; x++) {
             const int lu = loc[BOX(x, y, z)];
             int64_t pos = pass == 1 ? gr->srcnodeptr[lu] : 0;
@@ -184,7 +188,9 @@ int acgb200_stencil_part(int kind, int nx, int ny, int nz, int px, int py, int p
             }
         }
     }
-    /* edge statistics (serial: shared counters) */
+    /* edge statistics */
+    int64_t ninneredges = 0, ninterfaceedges = 0;
+    #pragma omp parallel for collapse(2) reduction(+:ninneredges, ninterfaceedges)
     for (int z = g.z0; z < g.z1; z++) for (int y = g.y0; y < g.y1; y++) for (int x = g.x0; x < g.x1; x++) {
         const int lu = loc[BOX(x, y, z)];
         for (int dz = -1; dz <= 1; dz++) for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) {
@@ -194,15 +200,18 @@ int acgb200_stencil_part(int kind, int nx, int ny, int nz, int px, int py, int p
             const int lower = dz < 0 || (dz == 0 && (dy < 0 || (dy == 0 && dx < 0)));
             if (in_box(&g, X, Y, Z)) {
                 if (lower) continue;
-                gr->ninneredges++;
-                if (isb[BOX(x, y, z)]) gr->nbordernodeinneredges[lu - ninner]++;
-                if (isb[BOX(X, Y, Z)] && !(dx == 0 && dy == 0 && dz == 0)) gr->nbordernodeinneredges[loc[BOX(X, Y, Z)] - ninner]++;
+                ninneredges++;
+                if (isb[BOX(x, y, z)])
+                    __atomic_fetch_add(&gr->nbordernodeinneredges[lu - ninner], 1, __ATOMIC_RELAXED);
+                if (isb[BOX(X, Y, Z)] && !(dx == 0 && dy == 0 && dz == 0))
+                    __atomic_fetch_add(&gr->nbordernodeinneredges[loc[BOX(X, Y, Z)] - ninner], 1, __ATOMIC_RELAXED);
             } else {
-                gr->ninterfaceedges++;
-                gr->nbordernodeinterfaceedges[lu - ninner]++;
+                ninterfaceedges++;
+                __atomic_fetch_add(&gr->nbordernodeinterfaceedges[lu - ninner], 1, __ATOMIC_RELAXED);
             }
         }
     }
+    gr->ninneredges = ninneredges; gr->ninterfaceedges = ninterfaceedges;
     /* neighbours: one per foreign owner among the ghosts, ascending */
     {
         int nn = 0;

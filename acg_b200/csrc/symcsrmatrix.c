@@ -24,6 +24,9 @@
 
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 /* ------------------------------------------------------------------------ */
 /* graph bookkeeping                                                         */
@@ -182,6 +185,20 @@ int acgsymcsrmatrix_vector(const struct acgsymcsrmatrix *A, struct acgvector *x)
  * is the reference's (acg/symcsrmatrix.c:792-812): packed rows are visited in
  * increasing order and each entry (i,j) is appended to row i and, if i != j,
  * to row j -- so tests can compare the arrays verbatim.
+ *
+ * Full-storage expansion, threaded.  The result is the one the serial fill
+ * produces (row r holds its entries ordered by the packed row they came from:
+ * mirrored entries (i,r) at position i, its own packed entries at position r),
+ * so the order of the products in every SpMV row -- and hence every bit of the
+ * GPU result -- does not depend on the thread count:
+ *   1. counts: own entries per row directly, mirrored ones with atomic adds;
+ *      per packed row the [min,max] local-block column is recorded;
+ *   2. serial prefix sum;
+ *   3. fill: thread t owns a contiguous range of target rows (balanced by
+ *      entries) and walks the packed rows in order, taking row i itself when i is
+ *      in its range and the mirrored entries whose column falls in the range;
+ *      rows whose column span misses the range are skipped on the two recorded
+ *      bounds, so a banded matrix is read about once in total.
  */
 int acgsymcsrmatrix_dsymv_init(struct acgsymcsrmatrix *A, double eps)
 {
@@ -189,15 +206,28 @@ int acgsymcsrmatrix_dsymv_init(struct acgsymcsrmatrix *A, double eps)
     const int base = A->rowidxbase;
     const int64_t *rp = A->rowptr;
     const acgidx_t *cj = A->colidx;
+    const double *av = A->a;
     free(A->frowptr); free(A->fcolidx); free(A->fa);
     free(A->orowptr); free(A->ocolidx); free(A->oa);
+    A->fcolidx = NULL; A->fa = NULL; A->orowptr = NULL; A->ocolidx = NULL; A->oa = NULL;
     A->frowptr = calloc((size_t) n + 1, sizeof(*A->frowptr));
-    if (!A->frowptr) return ACG_ERR_ERRNO;
+    acgidx_t *span = malloc((size_t) (n > 0 ? n : 1) * 2 * sizeof(*span));
+    if (!A->frowptr || !span) { free(span); return ACG_ERR_ERRNO; }
+    int64_t *cnt = A->frowptr + 1;
+#pragma omp parallel for schedule(static)
     for (acgidx_t i = 0; i < n; i++) {
+        int64_t own = 0;
+        acgidx_t lo = ghost0, hi = -1;
         for (int64_t k = rp[i]; k < rp[i + 1]; k++) {
             const acgidx_t j = cj[k] - base;
-            if (j < ghost0) { A->frowptr[i + 1]++; if (i != j) A->frowptr[j + 1]++; }
+            if (j >= ghost0) continue;
+            own++;
+            if (j < lo) lo = j;
+            if (j > hi) hi = j;
+            if (j != i) __atomic_fetch_add(&cnt[j], 1, __ATOMIC_RELAXED);
         }
+        if (own) __atomic_fetch_add(&cnt[i], own, __ATOMIC_RELAXED);
+        span[2 * (size_t) i] = lo; span[2 * (size_t) i + 1] = hi;
     }
     for (acgidx_t i = 0; i < n; i++) A->frowptr[i + 1] += A->frowptr[i];
     A->fnpnzs = A->frowptr[n];
@@ -205,30 +235,58 @@ int acgsymcsrmatrix_dsymv_init(struct acgsymcsrmatrix *A, double eps)
     A->fcolidx = malloc(fcap * sizeof(*A->fcolidx));
     A->fa = malloc(fcap * sizeof(*A->fa));
     int64_t *cur = malloc((size_t) (n > 0 ? n : 1) * sizeof(*cur));
-    if (!A->fcolidx || !A->fa || !cur) { free(cur); return ACG_ERR_ERRNO; }
+    if (!A->fcolidx || !A->fa || !cur) { free(cur); free(span); return ACG_ERR_ERRNO; }
     memcpy(cur, A->frowptr, (size_t) n * sizeof(*cur));
-    for (acgidx_t i = 0; i < n; i++) {
-        for (int64_t k = rp[i]; k < rp[i + 1]; k++) {
-            const acgidx_t j = cj[k] - base;
-            if (j >= ghost0) continue;
-            int64_t l = cur[i]++;
-            A->fcolidx[l] = j + base;
-            A->fa[l] = A->a[k] + (i == j ? eps : 0.0);
-            if (i != j) {
-                l = cur[j]++;
-                A->fcolidx[l] = i + base;
-                A->fa[l] = A->a[k];
+    const int64_t *frp = A->frowptr;
+    acgidx_t *fcj = A->fcolidx;
+    double *fav = A->fa;
+#pragma omp parallel
+    {
+        int nt = 1, t = 0;
+#ifdef _OPENMP
+        nt = omp_get_num_threads(); t = omp_get_thread_num();
+#endif
+        /* target rows [ra, rb): equal shares of the full-storage entries */
+        acgidx_t ra = 0, rb = n;
+        if (nt > 1) {
+            const int64_t tot = frp[n];
+            const int64_t wa = tot / nt * t, wb = (t == nt - 1) ? tot : tot / nt * (t + 1);
+            acgidx_t lo = 0, hi = n;
+            while (lo < hi) { acgidx_t m = lo + (hi - lo) / 2; if (frp[m] < wa) lo = m + 1; else hi = m; }
+            ra = lo; hi = n;
+            while (lo < hi) { acgidx_t m = lo + (hi - lo) / 2; if (frp[m] < wb) lo = m + 1; else hi = m; }
+            rb = (t == nt - 1) ? n : lo;
+        }
+        for (acgidx_t i = 0; i < n && ra < rb; i++) {
+            const int mine = i >= ra && i < rb;
+            if (!mine && (span[2 * (size_t) i + 1] < ra || span[2 * (size_t) i] >= rb)) continue;
+            for (int64_t k = rp[i]; k < rp[i + 1]; k++) {
+                const acgidx_t j = cj[k] - base;
+                if (j >= ghost0) continue;
+                if (mine) {
+                    const int64_t l = cur[i]++;
+                    fcj[l] = j + base;
+                    fav[l] = av[k] + (i == j ? eps : 0.0);
+                }
+                if (j != i && j >= ra && j < rb) {
+                    const int64_t l = cur[j]++;
+                    fcj[l] = i + base;
+                    fav[l] = av[k];
+                }
             }
         }
     }
-    free(cur);
+    free(cur); free(span);
 
     const acgidx_t no = A->nborderrows + A->nghostrows;
     A->orowptr = calloc((size_t) no + 1, sizeof(*A->orowptr));
     if (!A->orowptr) return ACG_ERR_ERRNO;
+#pragma omp parallel for schedule(static)
     for (acgidx_t i = 0; i < no; i++) {
+        int64_t c = 0;
         for (int64_t k = rp[border0 + i]; k < rp[border0 + i + 1]; k++)
-            if (cj[k] - base >= ghost0) A->orowptr[i + 1]++;
+            if (cj[k] - base >= ghost0) c++;
+        A->orowptr[i + 1] = c;
     }
     for (acgidx_t i = 0; i < no; i++) A->orowptr[i + 1] += A->orowptr[i];
     A->onpnzs = A->orowptr[no];
@@ -236,13 +294,14 @@ int acgsymcsrmatrix_dsymv_init(struct acgsymcsrmatrix *A, double eps)
     A->ocolidx = malloc(ocap * sizeof(*A->ocolidx));
     A->oa = malloc(ocap * sizeof(*A->oa));
     if (!A->ocolidx || !A->oa) return ACG_ERR_ERRNO;
+#pragma omp parallel for schedule(static)
     for (acgidx_t i = 0; i < no; i++) {
         int64_t l = A->orowptr[i];
         for (int64_t k = rp[border0 + i]; k < rp[border0 + i + 1]; k++) {
             const acgidx_t j = cj[k] - base;
             if (j < ghost0) continue;
             A->ocolidx[l] = j + base - border0;
-            A->oa[l] = A->a[k];
+            A->oa[l] = av[k];
             l++;
         }
     }

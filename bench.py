@@ -211,8 +211,10 @@ def main():
     comm = abdist.nccl_comm(rank, world)
 
     N = w["N"]
-    if world > 1 and args.partition == "block":
-        # every rank builds only its own block (no global matrix anywhere)
+    if args.partition == "block":
+        # every rank builds only its own block (no global matrix anywhere); one rank = the whole box
+        if (N ** 3 * (27 if w["kind"] == "27pt" else 7)) // world >= 2 ** 31:
+            raise SystemExit(f"bench.py: {args.workload} does not fit 32-bit indices on {world} GPU(s)")
         A = abdist.local_stencil_part(27 if w["kind"] == "27pt" else 7, N, N, N, rank, world)
     else:
         if N ** 3 * (27 if w["kind"] == "27pt" else 7) >= 2 ** 31:

@@ -381,3 +381,38 @@ def test_compressed_tile_arithmetic_emulated(name, gen, ab, oracle):
     for i in range(no):
         want[i] = vals[rowptr[i]:rowptr[i + 1]] @ x[colidx[rowptr[i]:rowptr[i + 1]]]
     assert np.allclose(y, want, rtol=1e-14, atol=1e-14)
+
+
+_FS_HASH = r"""
+import hashlib, sys
+import numpy as np
+import acg_b200 as ab
+from acg_b200 import matgen as mg
+m = hashlib.sha256()
+n, r, c, v = mg.rmat_spd(2048, 20000, seed=5)
+A = ab.SymCsrMatrix.init_real_double(n, r, c, v)
+mats = [ab.SymCsrMatrix.init_real_double(n, c, r, v).dsymv_init(0.5)]           # lower-triangle input
+mats += [p.dsymv_init(0.25) for p in A.partition(3, (np.arange(n) * 31 % 3).astype(np.int32))]
+mats += [ab.SymCsrMatrix.stencil_part(27, 11, 12, 13, 2, 1, 2, q).dsymv_init(0.0) for q in range(4)]
+for M in mats:
+    for k in ("frowptr", "fcolidx", "fa", "orowptr", "ocolidx", "oa"):
+        m.update(np.ascontiguousarray(getattr(M, k)).tobytes())
+print(m.hexdigest())
+"""
+
+
+def test_full_storage_independent_of_thread_count():
+    """The threaded expansion in acgsymcsrmatrix_dsymv_init and the threaded stencil
+    generator give byte-identical arrays for any OMP_NUM_THREADS (the entry order
+    inside a row fixes the summation order of the SpMV)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    seen = set()
+    for nt in ("1", "3", "8"):
+        env = dict(os.environ, OMP_NUM_THREADS=nt, PYTHONPATH=root)
+        out = subprocess.run([sys.executable, "-c", _FS_HASH], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        seen.add(out.stdout.strip().splitlines()[-1])
+    assert len(seen) == 1, seen
