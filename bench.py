@@ -55,9 +55,17 @@ WORKLOADS = {
 
 
 def make_matrix(w):
-    from acg_b200 import matgen
+    """Upper-triangle COO of the whole stencil matrix (for the reference arms): the
+    one-part output of the threaded generator, the same entries as acg_b200.matgen's."""
+    import acg_b200 as ab
     N = w["N"]
-    return matgen.stencil3d_27pt(N) if w["kind"] == "27pt" else matgen.laplace3d_7pt(N)
+    A = ab.SymCsrMatrix.stencil_part(27 if w["kind"] == "27pt" else 7, N, N, N, 1, 1, 1, 0)
+    rp = A.rowptr
+    rows = np.repeat(np.arange(A.c.nprows, dtype=np.int32), np.diff(rp).astype(np.int64))
+    cols, vals = A.colidx.copy(), A.a.copy()
+    n = int(A.c.nprows)
+    A.free()
+    return n, rows, cols, vals
 
 
 def peaks():
@@ -185,7 +193,11 @@ def main():
                           f"tolerances off", "n": w["N"] ** 3, "solver": solver, "iters_per_step": args.iters,
               "partition": (f"{world} parts, " + ("METIS recursive" if args.partition == "metis" else "geometric blocks"))
                            if world > 1 else "none",
-              "l2": "inputs larger than L2 (CSR 3.6 GB per SpMV vs 126 MB L2), no flush needed"}
+              "l2": None}
+    k = 27 if w["kind"] == "27pt" else 7
+    csr_gb = 12.0 * ((3 * w["N"] - 2) ** 3 if k == 27 else 7 * w["N"] ** 3 - 6 * w["N"] ** 2) / world / 1e9
+    config["l2"] = (f"inputs larger than L2 (CSR {csr_gb:.2f} GB per SpMV per GPU vs 126 MB L2), no flush needed"
+                    if csr_gb > 0.26 else f"CSR {csr_gb:.2f} GB per GPU: partly L2-resident, not a roofline-valid size")
 
     if args.impl == "reference":
         if rank != 0:
