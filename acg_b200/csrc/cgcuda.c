@@ -51,8 +51,10 @@ static struct {
     int p2p;            /* halo + reductions through peer memory (CUDA IPC) instead of NCCL */
     int p2p_fuse;       /* 1: border x ghost block inside the SpMV, pushes inside the update kernels */
     int spmv_compress;  /* 1: index-free tiles where the rows' patterns repeat (opt-in, compress.c) */
+    int blas1_ctas;     /* CTAs per SM of the fused BLAS-1 kernels (0 = one full wave, from the occupancy) */
+    int pdl;            /* 1: programmatic dependent launch along the iteration chain (opt-in) */
     int loaded;
-} cfg = { 0, 8, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0 };
+} cfg = { .check_every = 8, .graph = 1, .redstream = 1, .p2p = 1, .p2p_fuse = 1 };
 
 static void cfg_load(void)
 {
@@ -73,7 +75,11 @@ static void cfg_load(void)
     if ((s = getenv("ACGB200_P2P"))) cfg.p2p = atoi(s);
     if ((s = getenv("ACGB200_P2P_FUSE"))) cfg.p2p_fuse = atoi(s);
     if ((s = getenv("ACGB200_SPMV_COMPRESS"))) cfg.spmv_compress = atoi(s);
+    if ((s = getenv("ACGB200_BLAS1_CTAS"))) cfg.blas1_ctas = atoi(s);
     if (cfg.check_every < 1) cfg.check_every = 1;
+    if ((s = getenv("ACGB200_PDL"))) cfg.pdl = atoi(s);
+    acgb200_blas1_set_ctas_per_sm(cfg.blas1_ctas);
+    acgb200_set_pdl(cfg.pdl);
 }
 
 int acgb200_set_option(const char *key, int value)
@@ -93,6 +99,8 @@ int acgb200_set_option(const char *key, int value)
     else if (!strcmp(key, "p2p")) cfg.p2p = value;
     else if (!strcmp(key, "p2p_fuse")) cfg.p2p_fuse = value;
     else if (!strcmp(key, "spmv_compress")) cfg.spmv_compress = value;
+    else if (!strcmp(key, "blas1_ctas")) { cfg.blas1_ctas = value; acgb200_blas1_set_ctas_per_sm(value); }
+    else if (!strcmp(key, "pdl")) { cfg.pdl = value; acgb200_set_pdl(value); }
     else return ACG_ERR_INVALID_VALUE;
     return ACG_SUCCESS;
 }

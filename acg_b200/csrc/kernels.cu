@@ -104,6 +104,18 @@ __device__ __forceinline__ double ld_x(const double *p)
     return v;
 }
 
+/* Programmatic dependent launch (opt-in, ACGB200_PDL=1).  Every kernel of the
+ * iteration chain starts with this: wait until the preceding kernel of the
+ * stream has completed and flushed (nothing in global memory is touched before),
+ * then let the next kernel's CTAs be scheduled as soon as SM resources free up,
+ * so its launch latency and CTA ramp overlap this kernel's tail.  Both
+ * instructions are no-ops for a kernel launched without the attribute. */
+__device__ __forceinline__ void pdl_prologue()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 /* ------------------------------------------------------------------------ */
 /* reductions                                                                */
 /* ------------------------------------------------------------------------ */
@@ -367,6 +379,7 @@ spmv_tiles_kernel(const SpmvParams P)
     __shared__ int last_flag;
 
     const int tid = threadIdx.x;
+    pdl_prologue();
     const Gate gate = gate_read(P.ctrl_in, P.st);
     if (blockIdx.x == 0 && tid == 0 && P.ctrl_in) {
         *P.ctrl_out = *P.ctrl_in;
@@ -532,6 +545,7 @@ spmv_ctiles_kernel(const SpmvParams P, const CmpParams C)
     __shared__ int last_flag;
 
     const int tid = threadIdx.x;
+    pdl_prologue();
     const Gate gate = gate_read(P.ctrl_in, P.st);
     if (blockIdx.x == 0 && tid == 0 && P.ctrl_in) {
         *P.ctrl_out = *P.ctrl_in;
@@ -753,6 +767,7 @@ cg_update_r_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, ac
     __shared__ double red[BLAS1_THREADS / 32];
     __shared__ double glob[2];
     __shared__ int last_flag;
+    pdl_prologue();
     const Gate g = gate_read(&st->ctrl[cin], st);
     if (cin != cout && blockIdx.x == 0 && threadIdx.x == 0) st->ctrl[cout] = st->ctrl[cin];
     if (!g.active) return;
@@ -803,6 +818,7 @@ cg_update_xp_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, a
 {
     __shared__ double glob[2];
     __shared__ int last_flag;
+    pdl_prologue();
     const Gate g = gate_read(&st->ctrl[cin], st);
     const int s = g.iter & 1;
     double rr, rrn, pap;
@@ -876,6 +892,7 @@ pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acg
     __shared__ double red[BLAS1_THREADS / 32];
     __shared__ double glob[2];
     __shared__ int last_flag;
+    pdl_prologue();
     const Gate g = gate_read(&st->ctrl[cin], st);
     const int s = g.iter & 1;
     double gamma, delta;
@@ -987,14 +1004,46 @@ extern "C" int acgb200_num_sms(void)
     return g_num_sms;
 }
 
-static int blas1_grid(int n)
+/* CTAs per SM for the BLAS-1 kernels: 0 = as many as are resident at once */
+static int g_blas1_ctas_per_sm = 0;
+
+extern "C" void acgb200_blas1_set_ctas_per_sm(int v) { g_blas1_ctas_per_sm = v < 0 ? 0 : v; }
+
+/* One wave of grid-stride CTAs: SMs x resident CTAs of that kernel (a grid that
+ * is not a multiple of it ends in a partial wave at a fraction of the memory
+ * parallelism), fewer when the vector is short.  `slot` caches the occupancy. */
+static int blas1_grid(int n, const void *fn, int *slot)
 {
+    if (*slot == 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, BLAS1_THREADS, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 2;
+        *slot = per_sm;
+    }
     const int per = BLAS1_THREADS * 2;
     long long want = ((long long) n + per - 1) / per;
-    const long long cap = (long long) acgb200_num_sms() * 4;
+    const long long cap = (long long) acgb200_num_sms() * (g_blas1_ctas_per_sm > 0 ? g_blas1_ctas_per_sm : *slot);
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     return (int) want;
+}
+
+/* kernel launch, with the programmatic-dependency attribute when PDL is on */
+static int g_pdl = 0;
+
+extern "C" void acgb200_set_pdl(int v) { g_pdl = v != 0; }
+
+template <typename... Params, typename... Args>
+static cudaError_t launch_chain(void (*kernel)(Params...), int grid, int block, size_t smem, cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned) grid); lc.blockDim = dim3((unsigned) block);
+    lc.dynamicSmemBytes = smem; lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr; lc.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&lc, kernel, args...);
 }
 
 typedef void (*spmv_fn)(const SpmvParams);
@@ -1121,7 +1170,9 @@ extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t strea
             C.pc = stage_pslots(pl); C.rc = stage_rslots(pl);
             cspmv_variant(pl->lanes_per_row, pl->threads, pl->unroll)<<<pl->grid, pl->threads, pl->smem_bytes, stream>>>(P, C);
         } else {
-            spmv_variant(pl->lanes_per_row, pl->threads, pl->unroll)<<<pl->grid, pl->threads, pl->smem_bytes, stream>>>(P);
+            const cudaError_t le = launch_chain(spmv_variant(pl->lanes_per_row, pl->threads, pl->unroll),
+                                                pl->grid, pl->threads, (size_t) pl->smem_bytes, stream, P);
+            if (le) return (int) le;
         }
         cudaError_t err = cudaGetLastError();
         if (err) return (int) err;
@@ -1155,16 +1206,18 @@ extern "C" int acgb200_cg_update_r(int n, acgb200_devstate *st, int cin, int cou
                                    acgb200_p2pdev *p2p,
                                    const double *t, double *r, cudaStream_t stream)
 {
-    cg_update_r_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, st, cin, cout, multi, p2p, t, r);
-    return (int) cudaGetLastError();
+    static int occ = 0;
+    return (int) launch_chain(cg_update_r_kernel, blas1_grid(n, (const void *) cg_update_r_kernel, &occ), BLAS1_THREADS, 0, stream,
+                              n, st, cin, cout, multi, p2p, t, r);
 }
 
 extern "C" int acgb200_cg_update_xp(int n, acgb200_devstate *st, int cin, int cout, int multi,
                                     acgb200_p2pdev *p2p,
                                     const double *r, double *p, double *x, cudaStream_t stream)
 {
-    cg_update_xp_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, st, cin, cout, multi, p2p, r, p, x);
-    return (int) cudaGetLastError();
+    static int occ = 0;
+    return (int) launch_chain(cg_update_xp_kernel, blas1_grid(n, (const void *) cg_update_xp_kernel, &occ), BLAS1_THREADS, 0, stream,
+                              n, st, cin, cout, multi, p2p, r, p, x);
 }
 
 extern "C" int acgb200_pcg_update(int n, acgb200_devstate *st, int cin, int cout, int multi,
@@ -1172,8 +1225,9 @@ extern "C" int acgb200_pcg_update(int n, acgb200_devstate *st, int cin, int cout
                                   const double *q, double *z, double *w, double *t, double *p,
                                   double *r, double *x, cudaStream_t stream)
 {
-    pcg_update_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, st, cin, cout, multi, p2p, q, z, w, t, p, r, x);
-    return (int) cudaGetLastError();
+    static int occ = 0;
+    return (int) launch_chain(pcg_update_kernel, blas1_grid(n, (const void *) pcg_update_kernel, &occ), BLAS1_THREADS, 0, stream,
+                              n, st, cin, cout, multi, p2p, q, z, w, t, p, r, x);
 }
 
 extern "C" int acgb200_comm_post(const acgb200_postargs *a, cudaStream_t stream)
@@ -1187,13 +1241,15 @@ extern "C" int acgb200_comm_post(const acgb200_postargs *a, cudaStream_t stream)
 
 extern "C" int acgb200_dot(int n, const double *x, const double *y, double *acc, cudaStream_t stream)
 {
-    dot_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, x, y, acc);
+    static int occ = 0;
+    dot_kernel<<<blas1_grid(n, (const void *) dot_kernel, &occ), BLAS1_THREADS, 0, stream>>>(n, x, y, acc);
     return (int) cudaGetLastError();
 }
 
 extern "C" int acgb200_dot2(int n, const double *r, const double *w, double *acc2, cudaStream_t stream)
 {
-    dot2_kernel<<<blas1_grid(n), BLAS1_THREADS, 0, stream>>>(n, r, w, acc2);
+    static int occ = 0;
+    dot2_kernel<<<blas1_grid(n, (const void *) dot2_kernel, &occ), BLAS1_THREADS, 0, stream>>>(n, r, w, acc2);
     return (int) cudaGetLastError();
 }
 

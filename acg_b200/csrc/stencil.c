@@ -20,6 +20,7 @@
 #include "acgb200/error.h"
 #include "acgb200/ext.h"
 #include "acgb200/symcsrmatrix.h"
+#include "hostmem.h"
 
 #include <stdlib.h>
 #include <string.h>
@@ -81,8 +82,8 @@ int acgb200_stencil_part(int kind, int nx, int ny, int nz, int px, int py, int p
 
     /* local numbers of the box (owned) and of its one-cell shell (ghost candidates) */
     const int sx = bx + 2, sy = by + 2, sz = bz + 2;
-    int *loc = malloc((size_t) (nown > 0 ? nown : 1) * sizeof(int));
-    int *shell = malloc((size_t) sx * sy * sz * sizeof(int));
+    int *loc = acgb200_bigalloc((size_t) (nown > 0 ? nown : 1) * sizeof(int));
+    int *shell = acgb200_bigalloc((size_t) sx * sy * sz * sizeof(int));
     unsigned char *isb = calloc((size_t) (nown > 0 ? nown : 1), 1);
     struct gpair *gh = NULL;
     struct acggraph *gr = calloc(1, sizeof(*gr));
@@ -161,9 +162,9 @@ int acgb200_stencil_part(int kind, int nx, int ny, int nz, int px, int py, int p
             for (int64_t i = 0; i < npn; i++) { gr->nodenedges[i] = gr->srcnodeptr[i + 1]; gr->srcnodeptr[i + 1] += gr->srcnodeptr[i]; }
             gr->npedges = gr->srcnodeptr[npn];
             const size_t ne = (size_t) (gr->npedges > 0 ? gr->npedges : 1);
-            gr->srcnodeidx = malloc(ne * sizeof(acgidx_t));
-            gr->dstnodeidx = malloc(ne * sizeof(acgidx_t));
-            A->a = malloc(ne * sizeof(double));
+            gr->srcnodeidx = acgb200_bigalloc(ne * sizeof(acgidx_t));
+            gr->dstnodeidx = acgb200_bigalloc(ne * sizeof(acgidx_t));
+            A->a = acgb200_bigalloc(ne * sizeof(double));
             if (!gr->srcnodeidx || !gr->dstnodeidx || !A->a) goto fail;
         }
         #pragma omp parallel for collapse(2)

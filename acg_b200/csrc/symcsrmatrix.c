@@ -21,6 +21,7 @@
 #include "acgb200/error.h"
 #include "acgb200/halo.h"
 #include "acgb200/symcsrmatrix.h"
+#include "hostmem.h"
 
 #include <stdlib.h>
 #include <string.h>
@@ -210,8 +211,8 @@ int acgsymcsrmatrix_dsymv_init(struct acgsymcsrmatrix *A, double eps)
     free(A->frowptr); free(A->fcolidx); free(A->fa);
     free(A->orowptr); free(A->ocolidx); free(A->oa);
     A->fcolidx = NULL; A->fa = NULL; A->orowptr = NULL; A->ocolidx = NULL; A->oa = NULL;
-    A->frowptr = calloc((size_t) n + 1, sizeof(*A->frowptr));
-    acgidx_t *span = malloc((size_t) (n > 0 ? n : 1) * 2 * sizeof(*span));
+    A->frowptr = acgb200_bigcalloc((size_t) n + 1, sizeof(*A->frowptr));
+    acgidx_t *span = acgb200_bigalloc((size_t) (n > 0 ? n : 1) * 2 * sizeof(*span));
     if (!A->frowptr || !span) { free(span); return ACG_ERR_ERRNO; }
     int64_t *cnt = A->frowptr + 1;
 #pragma omp parallel for schedule(static)
@@ -232,9 +233,9 @@ int acgsymcsrmatrix_dsymv_init(struct acgsymcsrmatrix *A, double eps)
     for (acgidx_t i = 0; i < n; i++) A->frowptr[i + 1] += A->frowptr[i];
     A->fnpnzs = A->frowptr[n];
     const size_t fcap = (size_t) (A->fnpnzs > 0 ? A->fnpnzs : 1);
-    A->fcolidx = malloc(fcap * sizeof(*A->fcolidx));
-    A->fa = malloc(fcap * sizeof(*A->fa));
-    int64_t *cur = malloc((size_t) (n > 0 ? n : 1) * sizeof(*cur));
+    A->fcolidx = acgb200_bigalloc(fcap * sizeof(*A->fcolidx));
+    A->fa = acgb200_bigalloc(fcap * sizeof(*A->fa));
+    int64_t *cur = acgb200_bigalloc((size_t) (n > 0 ? n : 1) * sizeof(*cur));
     if (!A->fcolidx || !A->fa || !cur) { free(cur); free(span); return ACG_ERR_ERRNO; }
     memcpy(cur, A->frowptr, (size_t) n * sizeof(*cur));
     const int64_t *frp = A->frowptr;

@@ -251,3 +251,26 @@ def test_compressed_tiles_match_oracle(name, gen, ab, oracle):
         assert cg.solvempi(b, xs, maxits=300, residualrtol=1e-9) == 0 and cg.c.niterations == ref["niterations"]
         assert np.abs(xs.x - ref["x"]).max() <= 1e-9 * np.abs(ref["x"]).max()
     cg.free()
+
+
+@pytest.mark.skipif(os.environ.get("ACGB200_TEST_EXPERIMENTAL") != "1",
+                    reason="programmatic dependent launch is opt-in and not yet validated on hardware "
+                           "(set ACGB200_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("method", ["solvempi", "solve_pipelined"])
+def test_pdl_matches_oracle(method, ab, oracle):
+    """Option pdl=1 (griddepcontrol along the iteration chain, also inside the captured
+    graphs): same iterates as the default launches."""
+    n, r, c, v = mg.stencil3d_27pt(24)
+    A, cg = _solver(ab, n, r, c, v)
+    csr = (A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy())
+    b = A.vector(); b.x[:] = np.random.default_rng(5).standard_normal(n)
+    want = (oracle.cg if method == "solvempi" else oracle.cg_pipelined)(csr, b.x, maxits=300, rtol=1e-9)
+    ab.set_option("pdl", 1)
+    try:
+        x = A.vector()
+        assert getattr(cg, method)(b, x, maxits=300, residualrtol=1e-9) == 0
+    finally:
+        ab.set_option("pdl", 0)
+    assert cg.c.niterations == want["niterations"]
+    assert np.abs(x.x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
+    cg.free()
