@@ -508,8 +508,28 @@ class SolverCuda:
         return self._solve("solve_pipelined", b, x, maxits, diffatol, diffrtol, residualatol, residualrtol, warmup,
                            raise_on_not_converged)
 
-    def solve_device(self, b, x, **kw):
-        return self._solve("solve_device", b, x, kw.get("maxits", 100), 0, 0, 0, 0, 0, True)
+    def solve_device(self, b, x, maxits=100, diffatol=0.0, diffrtol=0.0, residualatol=0.0, residualrtol=0.0,
+                     warmup=0, raise_on_not_converged=False):
+        """acgsolvercuda_solve_device: the classic loop (control and communication are
+        device-resident in every loop of this library); NVSHMEM communicators are refused."""
+        return self._solve("solve_device", b, x, maxits, diffatol, diffrtol, residualatol, residualrtol, warmup,
+                           raise_on_not_converged)
+
+    def solve_device_pipelined(self, b, x, maxits=100, diffatol=0.0, diffrtol=0.0, residualatol=0.0,
+                               residualrtol=0.0, warmup=0, raise_on_not_converged=False):
+        return self._solve("solve_device_pipelined", b, x, maxits, diffatol, diffrtol, residualatol, residualrtol,
+                           warmup, raise_on_not_converged)
+
+    def solve(self, b, x, maxits=100, diffatol=0.0, diffrtol=0.0, residualatol=0.0, residualrtol=0.0, warmup=0,
+              raise_on_not_converged=False):
+        """acgsolvercuda_solve (acg/cgcuda.h:165, declared but not defined in the reference):
+        classic CG on one GPU without a communicator."""
+        code = lib().acgsolvercuda_solve(C.byref(self.c), C.byref(self.A.c), C.byref(b.c), C.byref(x.c), int(maxits),
+                                         float(diffatol), float(diffrtol), float(residualatol), float(residualrtol),
+                                         int(warmup))
+        if code != ACG_SUCCESS and (raise_on_not_converged or code != ACG_ERR_NOT_CONVERGED):
+            raise AcgError(code, "acgsolvercuda_solve", 0)
+        return code
 
     def spmv(self, x: np.ndarray, nrep: int = 0):
         """y = A x on the device (host arrays in/out); returns (y, ms_per_spmv)."""

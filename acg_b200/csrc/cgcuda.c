@@ -32,6 +32,7 @@
 #include <cuda_runtime_api.h>
 #include <float.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -139,19 +140,38 @@ struct priv {
     int last_spmv_n;
 };
 
+/* The public struct has no room for private state (its layout is the
+ * reference's), so it lives in a registry keyed by the solver's address.  The
+ * lock only guards the list: one solver is driven by one host thread, as in the
+ * reference, but different solvers may live on different threads. */
 static struct priv *registry = NULL;
+static pthread_mutex_t registry_lock = PTHREAD_MUTEX_INITIALIZER;
 
 static struct priv *priv_of(const struct acgsolvercuda *cg)
 {
-    for (struct priv *p = registry; p; p = p->next) if (p->key == cg) return p;
-    return NULL;
+    struct priv *found = NULL;
+    pthread_mutex_lock(&registry_lock);
+    for (struct priv *p = registry; p; p = p->next) if (p->key == cg) { found = p; break; }
+    pthread_mutex_unlock(&registry_lock);
+    return found;
+}
+
+static void priv_add(struct priv *pv)
+{
+    pthread_mutex_lock(&registry_lock);
+    pv->next = registry; registry = pv;
+    pthread_mutex_unlock(&registry_lock);
 }
 
 static void priv_drop(const struct acgsolvercuda *cg)
 {
+    struct priv *d = NULL;
+    pthread_mutex_lock(&registry_lock);
     for (struct priv **pp = &registry; *pp; pp = &(*pp)->next) {
-        if ((*pp)->key == cg) { struct priv *d = *pp; *pp = d->next; free(d); return; }
+        if ((*pp)->key == cg) { d = *pp; *pp = d->next; break; }
     }
+    pthread_mutex_unlock(&registry_lock);
+    free(d);
 }
 
 static double wall(void)
@@ -438,15 +458,16 @@ static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, 
     int errcode_ = 0, *errcode = &errcode_;
     struct priv *pv = calloc(1, sizeof(*pv));
     if (!pv) return ACG_ERR_ERRNO;
-    pv->key = cg; pv->next = registry; registry = pv;
+    pv->key = cg;
+    priv_add(pv);
 
     /* host-side work vectors, as the reference keeps them (acg/cgcuda.c:145-153) */
     OK(acgsymcsrmatrix_vector(A, &cg->r)); acgvector_setzero(&cg->r);
     OK(acgsymcsrmatrix_vector(A, &cg->p)); acgvector_setzero(&cg->p);
     OK(acgsymcsrmatrix_vector(A, &cg->t)); acgvector_setzero(&cg->t);
 
-    cg->halo = malloc(sizeof(*cg->halo));
-    cg->haloexchange = malloc(sizeof(*cg->haloexchange));
+    cg->halo = calloc(1, sizeof(*cg->halo));            /* zeroed: acgsolvercuda_free may run before they are filled */
+    cg->haloexchange = calloc(1, sizeof(*cg->haloexchange));
     if (!cg->halo || !cg->haloexchange) return ACG_ERR_ERRNO;
     OK(acgsymcsrmatrix_halo(A, cg->halo));
     {
@@ -491,10 +512,11 @@ static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, 
             CU(cudaMalloc((void **) &d_ok, sizeof(int)));
             CU(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
             ncclResult_t r = ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm->ncclcomm, pv->stream);
-            if (r != ncclSuccess) { *errcode = (int) r; return ACG_ERR_NCCL; }
-            CU(cudaMemcpyAsync(&allok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, pv->stream));
-            CU(cudaStreamSynchronize(pv->stream));
+            if (r != ncclSuccess) { cudaFree(d_ok); *errcode = (int) r; return ACG_ERR_NCCL; }
+            cudaError_t ce = cudaMemcpyAsync(&allok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, pv->stream);
+            if (!ce) ce = cudaStreamSynchronize(pv->stream);
             cudaFree(d_ok);
+            CU(ce);
             if (ok) {
                 pv->p2p.h_desc.fuse = cfg.p2p_fuse;
                 CU(cudaMemcpy(&pv->p2p.d_desc->fuse, &pv->p2p.h_desc.fuse, sizeof(int), cudaMemcpyHostToDevice));
@@ -1205,18 +1227,37 @@ int acgsolvercuda_solve_pipelined(
 }
 
 /* ------------------------------------------------------------------------ */
-/* device-resident variants: NVSHMEM-only in the reference                   */
+/* device-resident variants                                                  */
 /* ------------------------------------------------------------------------ */
 
+/*
+ * acg/cg-kernels-cuda.cu:998 / :1713.  In the reference these are the solvers
+ * whose iteration never returns to the host: one cooperative kernel per solve,
+ * scalars and the convergence test on the device, halo values and reductions
+ * moved by device-initiated NVSHMEM operations; they require an NVSHMEM
+ * communicator and a build with NVSHMEM (ACG_ERR_NVSHMEM_NOT_SUPPORTED
+ * otherwise, :1012, :1727).
+ *
+ * In this library those three properties already hold for the loops behind
+ * acgsolvercuda_solvempi / _solve_pipelined: scalars and the stopping test live
+ * in the device control ring, the host only replays a captured two-iteration
+ * graph and looks at the control word every few iterations, and between GPUs
+ * the kernels themselves store halo values and reduction partials into the
+ * peers' memory.  So with a null or NCCL communicator the device entry points
+ * run those loops (same results, same report); what is *not* built is the fusion
+ * of an iteration's two or three kernels into one persistent kernel with grid
+ * barriers.  An NVSHMEM communicator is refused as in a
+ * reference build without NVSHMEM.
+ */
 int acgsolvercuda_solve_device(
     struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A,
     const struct acgvector *b, struct acgvector *x,
     int maxits, double diffatol, double diffrtol, double residualatol, double residualrtol,
     int warmup, struct acgcomm *comm, int *errcode)
 {
-    (void) cg; (void) A; (void) b; (void) x; (void) maxits; (void) diffatol; (void) diffrtol;
-    (void) residualatol; (void) residualrtol; (void) warmup; (void) comm; (void) errcode;
-    return ACG_ERR_NVSHMEM_NOT_SUPPORTED;      /* acg/cg-kernels-cuda.cu:1012 */
+    if (comm && comm->type == acgcomm_nvshmem) return ACG_ERR_NVSHMEM_NOT_SUPPORTED;
+    return acgsolvercuda_solvempi(cg, A, b, x, maxits, diffatol, diffrtol, residualatol, residualrtol,
+                                  warmup, comm, 0, errcode, NULL, NULL, 0);
 }
 
 int acgsolvercuda_solve_device_pipelined(
@@ -1225,9 +1266,9 @@ int acgsolvercuda_solve_device_pipelined(
     int maxits, double diffatol, double diffrtol, double residualatol, double residualrtol,
     int warmup, struct acgcomm *comm, int *errcode)
 {
-    (void) cg; (void) A; (void) b; (void) x; (void) maxits; (void) diffatol; (void) diffrtol;
-    (void) residualatol; (void) residualrtol; (void) warmup; (void) comm; (void) errcode;
-    return ACG_ERR_NVSHMEM_NOT_SUPPORTED;      /* acg/cg-kernels-cuda.cu:1727 */
+    if (comm && comm->type == acgcomm_nvshmem) return ACG_ERR_NVSHMEM_NOT_SUPPORTED;
+    return acgsolvercuda_solve_pipelined(cg, A, b, x, maxits, diffatol, diffrtol, residualatol, residualrtol,
+                                         warmup, comm, 0, errcode, NULL, NULL);
 }
 
 /* ------------------------------------------------------------------------ */

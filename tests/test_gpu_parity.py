@@ -150,9 +150,14 @@ def test_interface_behaviour(ab):
     with pytest.raises(ab.AcgError) as e:
         cg.solvempi(b, x, maxits=5, diffatol=1e-3)
     assert e.value.code == 26                                             # ACG_ERR_NOT_SUPPORTED
-    with pytest.raises(ab.AcgError) as e:
-        cg.solve_device(b, x)
-    assert e.value.code == 16                                             # ACG_ERR_NVSHMEM_NOT_SUPPORTED
+    cg.comm.c.type = 4                                                    # acgcomm_nvshmem
+    try:
+        for call in (cg.solve_device, cg.solve_device_pipelined):
+            with pytest.raises(ab.AcgError) as e:
+                call(b, x)
+            assert e.value.code == 16                                         # ACG_ERR_NVSHMEM_NOT_SUPPORTED
+    finally:
+        cg.comm.c.type = 0
     # already-converged initial guess: zero iterations, success
     xs = A.vector(); xs.x[:] = np.random.default_rng(0).standard_normal(n)
     bb = A.vector(); bb.x[:], _ = cg.spmv(xs.x)
@@ -160,6 +165,25 @@ def test_interface_behaviour(ab):
     assert cg.c.nsolves == 3 and cg.c.ntotaliterations == 2   # the rejected call returns before counting (acg/cgcuda.c:424)
     rep = cg.report()
     assert "total solver time:" in rep and "iterations: 0" in rep and "gemv:" in rep
+    cg.free()
+
+
+@pytest.mark.parametrize("entry,twin", [("solve_device", "solvempi"), ("solve_device_pipelined", "solve_pipelined"),
+                                        ("solve", "solvempi")])
+def test_device_and_plain_entry_points(entry, twin, ab, oracle):
+    """acgsolvercuda_solve_device{,_pipelined} (acg/cg-kernels-cuda.cu:998,:1713) with a
+    non-NVSHMEM communicator and acgsolvercuda_solve (acg/cgcuda.h:165) run the
+    device-controlled loops: same iteration count, norms and solution as the oracle."""
+    n, r, c, v = mg.stencil3d_27pt(16)
+    A, cg = _solver(ab, n, r, c, v)
+    csr = (A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy())
+    b = A.vector(); b.x[:] = np.random.default_rng(11).standard_normal(n)
+    want = (oracle.cg_pipelined if "pipelined" in twin else oracle.cg)(csr, b.x, maxits=200, rtol=1e-9)
+    x = A.vector()
+    assert getattr(cg, entry)(b, x, maxits=200, residualrtol=1e-9) == 0
+    assert cg.c.niterations == want["niterations"] and cg.c.nsolves == 1
+    assert cg.c.rnrm2 / cg.c.r0nrm2 == pytest.approx(want["rnrm2"] / want["r0nrm2"], rel=1e-6, abs=RES_RTOL)
+    assert np.abs(x.x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
     cg.free()
 
 

@@ -38,7 +38,8 @@ def test_unmodified_driver_links_against_library():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("solver,method", [("acg", "cg"), ("acg-pipelined", "cg_pipelined")])
+@pytest.mark.parametrize("solver,method", [("acg", "cg"), ("acg-pipelined", "cg_pipelined"),
+                                           ("acg-device", "cg"), ("acg-device-pipelined", "cg_pipelined")])
 def test_driver_solves_on_gpu(solver, method, oracle):
     if not os.path.exists(DRIVER):
         pytest.skip("driver binary not built (needs the reference tree at build time)")
