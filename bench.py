@@ -49,6 +49,7 @@ WORKLOADS = {
     "27pt-224": dict(kind="27pt", N=224, solver="pipelined"),     # BASELINE.json configs[2]  (metric config)
     "7pt-256": dict(kind="7pt", N=256, solver="classic"),          # configs[1]
     "27pt-128": dict(kind="27pt", N=128, solver="pipelined"),      # quick check
+    "27pt-112": dict(kind="27pt", N=112, solver="pipelined"),      # one rank's share of 27pt-224 on 8 GPUs, without the exchange
     "27pt-64": dict(kind="27pt", N=64, solver="pipelined"),
     "27pt-448": dict(kind="27pt", N=448, solver="pipelined"),      # configs[3]: 8 GPUs only (weak-scaled x8 point)
 }
