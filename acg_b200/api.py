@@ -116,6 +116,11 @@ class acgb200_info(C.Structure):
                                                                                   ("spmv_min_bytes", C.c_int64)]
 
 
+class acgb200_mtxinfo(C.Structure):
+    _fields_ = [("nrows", C.c_int64), ("ncols", C.c_int64), ("nnzs", C.c_int64), ("data_offset", C.c_int64),
+                ("field", C.c_int), ("symmetric", C.c_int)]
+
+
 # every symbol include/acgb200/*.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "acgerrcodestr",
@@ -136,6 +141,7 @@ EXPORTS = [
     "acgb200_set_option", "acgsolvercuda_spmv", "acgsolvercuda_info", "acgb200_sizeof", "acgb200_have_mpi",
     "acgb200_nccl_unique_id", "acgb200_comm_init_rank", "acgb200_comm_destroy",
     "acgb200_host_register", "acgb200_host_unregister", "acgb200_spmv_plan_host", "acgb200_spmv_plan_host2", "acgb200_p2p_inverse_map", "acgb200_patterns_host", "acgb200_stencil_part",
+    "acgb200_mtx_info", "acgb200_mtx_read", "acgb200_mtx_read_part", "acgb200_comm_matrix_row",
 ]
 
 
@@ -169,6 +175,11 @@ def lib() -> C.CDLL:
     L.acgsymcsrmatrix_partition_rows.argtypes = [P(acgsymcsrmatrix), C.c_int, C.c_int, i32p, P(C.c_int), C.c_int, C.c_int]
     L.acgsymcsrmatrix_halo.argtypes = [P(acgsymcsrmatrix), P(acghalo)]
     L.acgb200_stencil_part.argtypes = [C.c_int] * 8 + [P(acgsymcsrmatrix)]
+    L.acgb200_mtx_info.argtypes = [C.c_char_p, P(acgb200_mtxinfo)]
+    L.acgb200_comm_matrix_row.argtypes = [P(acgsymcsrmatrix), C.c_int, np.ctypeslib.ndpointer(np.int64, flags="C")]
+    L.acgb200_mtx_read.argtypes = [C.c_char_p, C.c_int, P(acgsymcsrmatrix)]
+    L.acgb200_mtx_read_part.argtypes = [C.c_char_p, C.c_int, np.ctypeslib.ndpointer(np.int32, flags="C"), C.c_int,
+                                        P(acgsymcsrmatrix)]
     L.acgsymcsrmatrix_dsymv_init.argtypes = [P(acgsymcsrmatrix), C.c_double]
     L.acghalo_free.restype = None
     L.acghalo_free.argtypes = [P(acghalo)]
@@ -211,6 +222,13 @@ def lib() -> C.CDLL:
 def _check(code, where, detail=0):
     if code != ACG_SUCCESS:
         raise AcgError(code, where, detail)
+
+
+def mtx_info(path: str) -> dict:
+    """acgb200_mtx_info: sizes and data offset of a Matrix Market coordinate file."""
+    inf = acgb200_mtxinfo()
+    _check(lib().acgb200_mtx_info(os.fsencode(path), C.byref(inf)), "acgb200_mtx_info")
+    return {k: getattr(inf, k) for k, _ in acgb200_mtxinfo._fields_}
 
 
 def set_option(key: str, value: int) -> None:
@@ -323,6 +341,26 @@ class SymCsrMatrix:
         return self
 
     @classmethod
+    def read_mtx(cls, path: str, binary: bool = True):
+        """acgb200_mtx_read: a "matrix coordinate real symmetric" Matrix Market file, text
+        or aCG binary (acg/mtxfile.c:1107-1127), as a 0-based packed matrix."""
+        self = cls()
+        _check(lib().acgb200_mtx_read(os.fsencode(path), 1 if binary else 0, C.byref(self.c)), "acgb200_mtx_read")
+        self._owns = True
+        return self
+
+    @classmethod
+    def read_mtx_part(cls, path: str, nparts: int, rowparts, part: int):
+        """acgb200_mtx_read_part: this part of a row partition straight from a binary
+        file; no process holds the whole matrix."""
+        self = cls()
+        rowparts = np.ascontiguousarray(rowparts, np.int32)
+        _check(lib().acgb200_mtx_read_part(os.fsencode(path), nparts, rowparts, part, C.byref(self.c)),
+               "acgb200_mtx_read_part")
+        self._owns = True
+        return self
+
+    @classmethod
     def stencil_part(cls, kind: int, nx: int, ny: int, nz: int, px: int, py: int, pz: int, part: int):
         """One part of a block-partitioned 7/27-point stencil matrix, built without the global matrix."""
         self = cls()
@@ -353,6 +391,13 @@ class SymCsrMatrix:
             m._owns = True
             out.append(m)
         return out
+
+    def comm_matrix_row(self, nparts: int) -> np.ndarray:
+        """Border values this part sends to every other part per halo exchange
+        (one row of the driver's --output-comm-matrix, cuda/acg-cuda.c:1713-1775)."""
+        row = np.zeros(nparts, np.int64)
+        _check(lib().acgb200_comm_matrix_row(C.byref(self.c), nparts, row), "acgb200_comm_matrix_row")
+        return row
 
     def vector(self) -> Vector:
         v = Vector()

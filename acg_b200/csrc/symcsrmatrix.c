@@ -605,3 +605,21 @@ int acgsymcsrmatrix_halo(const struct acgsymcsrmatrix *A, struct acghalo *halo)
     }
     return ACG_SUCCESS;
 }
+
+/* ext.h: one row of the communication matrix the reference driver prints with
+ * --output-comm-matrix (cuda/acg-cuda.c:1713-1775): entry (p,q) is the number
+ * of border values part p sends to part q in one halo exchange.  `row` has
+ * nparts entries.  Parts made by this library carry the peer in
+ * neighbourrank (the state after the reference's scatter, acg/graph.c:1767-1779). */
+int acgb200_comm_matrix_row(const struct acgsymcsrmatrix *A, int nparts, int64_t *row)
+{
+    const struct acggraph *g = A->graph;
+    for (int q = 0; q < nparts; q++) row[q] = 0;
+    if (!g) return ACG_SUCCESS;
+    for (int i = 0; i < g->nneighbours; i++) {
+        const int q = g->neighbours[i].neighbourrank;
+        if (q < 0 || q >= nparts) return ACG_ERR_INDEX_OUT_OF_BOUNDS;
+        row[q] += g->neighbours[i].nbordernodes;
+    }
+    return ACG_SUCCESS;
+}

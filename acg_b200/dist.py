@@ -12,6 +12,9 @@ object broadcast, NCCL for the data path inside libacgb200):
                             it with the same row->part map and keeps its part
 * ``block_partition()``  -- geometric px*py*pz row->part map for stencil grids;
                             ``rowparts="metis"`` uses acgsymcsrmatrix_partition_rows
+* ``local_stencil_part()`` / ``local_part_from_file()`` -- a rank's part built
+                            directly (generator / streamed binary Matrix Market
+                            file) without anybody holding the global matrix
 """
 from __future__ import annotations
 
@@ -95,3 +98,34 @@ def local_part(n, rows, cols, vals, rowparts, rank: int, world: int, eps: float 
         if p != rank:
             m.free()
     return mine.dsymv_init(eps)
+
+
+def contiguous_partition(n: int, nparts: int) -> np.ndarray:
+    """Row -> part map of nparts contiguous, equally sized row blocks."""
+    return (np.arange(n, dtype=np.int64) * nparts // max(n, 1)).astype(np.int32)
+
+
+def local_part_from_file(path: str, rowparts, rank: int, world: int, eps: float = 0.0):
+    """This rank's part of the matrix in a binary Matrix Market file
+    (acgb200_mtx_read_part): every rank streams the file and keeps the entries of
+    its own rows -- the reference reads on rank 0 and scatters
+    (cuda/acg-cuda.c:1297-1304, :1516-1782).  ``rowparts``: an array, or "rows"
+    for contiguous row blocks."""
+    from .api import SymCsrMatrix, mtx_info
+    if world == 1:
+        return SymCsrMatrix.read_mtx(path, binary=True).dsymv_init(eps)
+    if isinstance(rowparts, str) and rowparts == "rows":
+        rowparts = contiguous_partition(mtx_info(path)["nrows"], world)
+    return SymCsrMatrix.read_mtx_part(path, world, rowparts, rank).dsymv_init(eps)
+
+
+def comm_matrix(A, rank: int, world: int) -> np.ndarray:
+    """world x world matrix of halo send counts, assembled from every rank's row
+    (the driver's --output-comm-matrix, cuda/acg-cuda.c:1713-1775)."""
+    row = A.comm_matrix_row(world)
+    if world == 1:
+        return row.reshape(1, 1)
+    import torch.distributed as dist
+    rows = [None] * world
+    dist.all_gather_object(rows, row)
+    return np.stack(rows)

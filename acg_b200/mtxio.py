@@ -34,3 +34,16 @@ def write_vector(path: str, x, binary: bool = True) -> None:
         else:
             for a in x:
                 f.write(f"{a:.17g}\n".encode())
+
+
+def write_comm_matrix(path: str, counts) -> None:
+    """The communication matrix in the form the reference driver prints it
+    (cuda/acg-cuda.c:1741-1748): "matrix coordinate integer general", part numbers
+    1-based in the file (acg/mtxfile.c:1471-1472), one entry per (sender, recipient) pair."""
+    counts = np.asarray(counts)
+    p, q = np.nonzero(counts)
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate integer general\n")
+        f.write(f"{counts.shape[0]} {counts.shape[1]} {len(p)}\n")
+        for i, j in zip(p, q):
+            f.write(f"{i + 1} {j + 1} {int(counts[i, j])}\n")

@@ -66,6 +66,32 @@ ACG_API int acgb200_spmv_plan_host2(int nrows, const int64_t *rowptr, const int 
 ACG_API int acgb200_stencil_part(int kind, int nx, int ny, int nz, int px, int py, int pz, int part,
                                  struct acgsymcsrmatrix *A);
 
+/* Matrix Market ingest (mtxfile.c): text, and aCG's binary encoding -- header and
+ * size line as text, then rowidx[nnz], colidx[nnz] (1-based acgidx_t), a[nnz]
+ * (double); acg/mtxfile.c:1107-1127, written by mtx2bin (mtx2bin/mtx2bin.c:538-549),
+ * read by `acg-cuda --binary` (cuda/acg-cuda.c:1297-1304).  Only "matrix
+ * coordinate real symmetric" files are accepted.  Matrices come out 0-based. */
+struct acgb200_mtxinfo {
+    int64_t nrows, ncols, nnzs;
+    int64_t data_offset;      /* first byte after the size line */
+    int field;                /* 0 real, 1 integer, 2 pattern, 3 other */
+    int symmetric;
+};
+ACG_API int acgb200_mtx_info(const char *path, struct acgb200_mtxinfo *info);
+ACG_API int acgb200_mtx_read(const char *path, int binary, struct acgsymcsrmatrix *A);
+/* Part `part` of the row partition `rowparts` (nrows entries in [0,nparts)) of a
+ * binary file, array for array what acgsymcsrmatrix_partition returns for that
+ * part, without any process holding the whole matrix: the file is streamed and
+ * only entries with an end in `part` are kept -- the per-rank replacement of the
+ * reference's read-on-root + scatter (cuda/acg-cuda.c:1516-1782). */
+ACG_API int acgb200_mtx_read_part(const char *path, int nparts, const int *rowparts, int part,
+                                  struct acgsymcsrmatrix *A);
+
+/* Row p of the communication matrix (cuda/acg-cuda.c:1713-1775, the driver's
+ * --output-comm-matrix): row[q] = border values part A sends to part q per halo
+ * exchange; nparts entries. */
+ACG_API int acgb200_comm_matrix_row(const struct acgsymcsrmatrix *A, int nparts, int64_t *row);
+
 /* Row-pattern dictionary of a 0-based CSR matrix (host logic of the index-free
  * SpMV tiles, compress.c).  patptr needs max_entries+1 ints (at most that many
  * patterns), patoff max_entries ints, patid nrows entries; 0xFFFF in patid

@@ -11,6 +11,7 @@ mode gpu : the product path: NCCL communicator inside libacgb200, device SpMV /
 import argparse
 import os
 import sys
+import tempfile
 
 import numpy as np
 import torch
@@ -90,7 +91,21 @@ def main():
         rowparts = np.random.default_rng(3).integers(0, world, n).astype(np.int32)
     else:
         rowparts = (np.arange(n) * world // n).astype(np.int32)
-    m = abdist.local_part(n, r, c, v, rowparts, rank, world)
+    if args.partition == "file":
+        # ingest path: rank 0 writes aCG's binary Matrix Market file, then every rank
+        # streams it and keeps its own row block (acgb200_mtx_read_part) -- nobody
+        # partitions the whole matrix
+        from acg_b200 import mtxio
+        path = os.path.join(tempfile.gettempdir(), f"acgb200_dist_{os.environ.get('MASTER_PORT', '0')}.mtx")
+        if rank == 0:
+            mtxio.write_symmetric(path, n, r, c, v, binary=True)
+        dist.barrier()
+        m = abdist.local_part_from_file(path, "rows", rank, world)
+        dist.barrier()
+        if rank == 0:
+            os.remove(path)
+    else:
+        m = abdist.local_part(n, r, c, v, rowparts, rank, world)
     no = m.c.nownedrows
     rng = np.random.default_rng(11)
     bglob = rng.standard_normal(n)

@@ -416,3 +416,24 @@ def test_full_storage_independent_of_thread_count():
         assert out.returncode == 0, out.stderr[-2000:]
         seen.add(out.stdout.strip().splitlines()[-1])
     assert len(seen) == 1, seen
+
+
+def test_comm_matrix(ab, tmp_path):
+    """Communication matrix (cuda/acg-cuda.c:1713-1775): entry (p,q) = border values p
+    sends q; symmetric for a structurally symmetric matrix, and equal to what q
+    receives from p."""
+    from acg_b200 import dist as abdist, mtxio
+    n, r, c, v = mg.stencil3d_27pt(8)
+    parts = ab.SymCsrMatrix.init_real_double(n, r, c, v).partition(8, abdist.block_partition(8, 8, 8, 2, 2, 2))
+    M = np.stack([p.comm_matrix_row(8) for p in parts])
+    assert np.array_equal(M, M.T) and np.all(np.diag(M) == 0)
+    assert M[0, 1] == 16 and M[0, 3] == 4 and M[0, 7] == 1            # face, edge, corner of a 4^3 block
+    for p, m in enumerate(parts):
+        h = m.halo()
+        for q, cnt in zip(h["senders"], h["recvcounts"]):
+            assert M[q, p] == cnt
+    path = str(tmp_path / "comm.mtx")
+    mtxio.write_comm_matrix(path, M)
+    lines = open(path).read().splitlines()
+    assert lines[0] == "%%MatrixMarket matrix coordinate integer general" and lines[1] == f"8 8 {np.count_nonzero(M)}"
+    assert "1 2 16" in lines                                           # 1-based in the file

@@ -31,6 +31,7 @@ def _launch(nproc, extra, timeout=240, env_extra=None):
     (3, "7pt", 9, "slab"),
     (2, "rmat", 600, "random"),
     (3, "rmat", 900, "metis"),
+    (3, "27pt", 9, "file"),          # parts streamed from a binary Matrix Market file
 ])
 def test_gloo_host_logic(nproc, matrix, size, partition):
     _launch(nproc, ["--mode", "cpu", "--matrix", matrix, "--size", str(size), "--partition", partition] + _its(matrix))
