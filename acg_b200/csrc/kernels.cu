@@ -920,19 +920,28 @@ pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acg
     }
     if (!g.active || conv) return;
     double g2 = 0.0, d2 = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double zv = fma(beta, z[i], q[i]);
-        const double tv = fma(beta, t[i], w[i]);
-        const double pv = fma(beta, p[i], r[i]);
-        const double rv = fma(-alpha, tv, r[i]);
-        const double wv = fma(-alpha, zv, w[i]);
-        z[i] = zv; t[i] = tv; p[i] = pv;
-        x[i] = fma(alpha, pv, x[i]);
-        r[i] = rv; w[i] = wv;
-        g2 = fma(rv, rv, g2);
-        d2 = fma(wv, rv, d2);
-        /* w is the input of the next SpMV: border entries go to the neighbours */
-        if (P && P->fuse && i >= P->borderoff) p2p_push_row(P, i, s ^ 1, wv);
+    /* Peer-memory mode: border rows first.  Their new w values are stored into
+     * the neighbours' ghost buffers (w is the input of the next SpMV), and
+     * issuing those NVLink stores at the start lets them drain under the
+     * interior rows instead of in front of the closing system fence. */
+    const bool push = P && P->fuse;
+    const int first = push ? P->borderoff : 0;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+    for (int pass = 0; pass < 2; pass++) {
+        const int lo = pass == 0 ? first : 0, hi = pass == 0 ? n : first;
+        for (int i = lo + gtid; i < hi; i += gstride) {
+            const double zv = fma(beta, z[i], q[i]);
+            const double tv = fma(beta, t[i], w[i]);
+            const double pv = fma(beta, p[i], r[i]);
+            const double rv = fma(-alpha, tv, r[i]);
+            const double wv = fma(-alpha, zv, w[i]);
+            z[i] = zv; t[i] = tv; p[i] = pv;
+            x[i] = fma(alpha, pv, x[i]);
+            r[i] = rv; w[i] = wv;
+            g2 = fma(rv, rv, g2);
+            d2 = fma(wv, rv, d2);
+            if (push && pass == 0) p2p_push_row(P, i, s ^ 1, wv);
+        }
     }
     g2 = block_sum(g2, red);
     d2 = block_sum(d2, red);

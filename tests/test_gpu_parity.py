@@ -50,6 +50,37 @@ def test_spmv_matches_oracle(name, gen, ab, oracle):
     cg.free()
 
 
+def test_spmv_ragged_rows(ab, oracle):
+    """Rows with no entries at all, single-entry rows, rows longer than a tile
+    (long-row path) and a dense last row next to each other: y = A x entry by entry."""
+    n = 5000
+    rng = np.random.default_rng(12)
+    rows, cols = [], []
+    for i in range(0, n, 3):                       # every third row has a diagonal entry; the others are empty so far
+        rows.append(i); cols.append(i)
+    hub = 7                                        # one row touching 60 % of the columns
+    for j in rng.choice(np.arange(hub + 1, n), size=3000, replace=False):
+        rows.append(hub); cols.append(int(j))
+    for j in range(0, n - 1, 2):                   # dense-ish last column = last row of the full matrix
+        rows.append(j); cols.append(n - 1)
+    r = np.array(rows, np.int32); c = np.array(cols, np.int32)
+    key = np.unique(r.astype(np.int64) * n + c)
+    r, c = (key // n).astype(np.int32), (key % n).astype(np.int32)
+    v = rng.standard_normal(len(r))
+    A, cg = _solver(ab, n, r, c, v)
+    lens = np.diff(A.frowptr)
+    assert (lens == 0).sum() > 100 and lens.max() > 2000
+    csr = (A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy())
+    x = rng.standard_normal(n)
+    y, _ = cg.spmv(x)
+    want = oracle.dsymv(csr, 1.0, x, 0.0, np.zeros(n))
+    scale = oracle.dsymv((csr[0], csr[1], np.abs(csr[2])), 1.0, np.abs(x), 0.0, np.zeros(n))
+    assert np.all(np.abs(y - want) <= SPMV_RTOL * scale + 1e-300)
+    assert np.all(y[lens == 0] == 0.0)
+    assert cg.info()["spmv_nlong"] >= 1
+    cg.free()
+
+
 @pytest.mark.parametrize("method", ["solvempi", "solve_pipelined"])
 @pytest.mark.parametrize("name,gen", CASES[:3] + [CASES[4]] + CASES[6:], ids=[c[0] for c in CASES[:3] + [CASES[4]] + CASES[6:]])
 def test_cg_matches_oracle(name, gen, method, ab, oracle):
