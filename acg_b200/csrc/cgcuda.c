@@ -54,6 +54,7 @@ static struct {
     int spmv_compress;  /* 1: index-free tiles where the rows' patterns repeat (opt-in, compress.c) */
     int blas1_ctas;     /* CTAs per SM of the fused BLAS-1 kernels (0 = one full wave, from the occupancy) */
     int pdl;            /* 1: programmatic dependent launch along the iteration chain (opt-in) */
+    int pcg_fused;      /* 1: pipelined CG as one kernel per iteration (SpMV + update fused, opt-in) */
     int loaded;
 } cfg = { .check_every = 8, .graph = 1, .redstream = 1, .p2p = 1, .p2p_fuse = 1 };
 
@@ -79,6 +80,7 @@ static void cfg_load(void)
     if ((s = getenv("ACGB200_BLAS1_CTAS"))) cfg.blas1_ctas = atoi(s);
     if (cfg.check_every < 1) cfg.check_every = 1;
     if ((s = getenv("ACGB200_PDL"))) cfg.pdl = atoi(s);
+    if ((s = getenv("ACGB200_PCG_FUSED"))) cfg.pcg_fused = atoi(s);
     acgb200_blas1_set_ctas_per_sm(cfg.blas1_ctas);
     acgb200_set_pdl(cfg.pdl);
 }
@@ -102,6 +104,7 @@ int acgb200_set_option(const char *key, int value)
     else if (!strcmp(key, "spmv_compress")) cfg.spmv_compress = value;
     else if (!strcmp(key, "blas1_ctas")) { cfg.blas1_ctas = value; acgb200_blas1_set_ctas_per_sm(value); }
     else if (!strcmp(key, "pdl")) { cfg.pdl = value; acgb200_set_pdl(value); }
+    else if (!strcmp(key, "pcg_fused")) cfg.pcg_fused = value;
     else return ACG_ERR_INVALID_VALUE;
     return ACG_SUCCESS;
 }
@@ -127,9 +130,12 @@ struct priv {
     struct acgcomm redcomm;             /* private duplicate of the caller's communicator for reductions */
     int have_redcomm;
     double *d_b, *d_x;                  /* right-hand side / solution on the device, kept between solves */
-    cudaGraphExec_t graph[2];           /* [0] classic, [1] pipelined: two iterations (parity 0 then 1) */
-    int graph_multi[2];
-    int graph_launches[2];              /* kernel/NCCL launches inside one replay */
+    cudaGraphExec_t graph[3];           /* [0] classic, [1] pipelined, [2] pipelined as one kernel per iteration:
+                                         * two iterations each (parity 0 then 1) */
+    int graph_multi[3];
+    int graph_launches[3];              /* kernel/NCCL launches inside one replay */
+    double *d_w2;                       /* second w buffer of the one-kernel pipelined iteration */
+    int fused_grid;                     /* its grid (0: not available for this plan) */
     double last_h2d_ms, last_d2h_ms;    /* host time spent before / after the solve window */
     cudaEvent_t ev_t0, ev_t1;           /* device-side bracket of the solve window */
     double last_solve_ms;
@@ -219,7 +225,8 @@ void acgsolvercuda_free(struct acgsolvercuda *cg)
             pv->p2p.window = NULL;
         }
         if (pv->have_redcomm && pv->redcomm.ncclcomm) ncclCommDestroy(pv->redcomm.ncclcomm);
-        for (int i = 0; i < 2; i++) if (pv->graph[i]) cudaGraphExecDestroy(pv->graph[i]);
+        for (int i = 0; i < 3; i++) if (pv->graph[i]) cudaGraphExecDestroy(pv->graph[i]);
+        cudaFree(pv->d_w2);
         cudaFree(pv->plan.d_tiles); cudaFree(pv->plan.d_longrows); cudaFree(pv->plan.d_long_scratch);
         cudaFree(pv->plan.d_patptr); cudaFree(pv->plan.d_patoff); cudaFree(pv->plan.d_patid);
         cudaFree(pv->d_st);
@@ -1093,6 +1100,32 @@ static int pipelined_iteration(struct solvectx *c, int k)
     return ACG_SUCCESS;
 }
 
+/* One launch per iteration: q = A w fused with the update (kernels.cu,
+ * pcg_fused_kernel).  Iteration k reads control word k&1 and w buffer k&1. */
+static int fused_iteration(struct solvectx *c, int k)
+{
+    struct acgsolvercuda *cg = c->cg;
+    struct priv *pv = c->pv;
+    int *errcode = c->errcode;
+    const int peer = c->multi && c->p2p;
+    struct acgb200_spmvargs a;
+    memset(&a, 0, sizeof(a));
+    a.plan = &pv->plan;
+    a.rowptr = cg->d_rowptr; a.colidx = cg->d_colidx; a.a = cg->d_a;
+    a.st = pv->d_st;
+    if (peer) {
+        a.p2p = pv->p2p.d_desc;
+        a.od_rowoffset = pv->borderoff; a.od_nrows = pv->nborder;
+        a.orowptr = cg->d_orowptr; a.ocolidx = cg->d_ocolidx; a.oa = cg->d_oa;
+    }
+    prof_mark(c, &pv->gemv);
+    KL(acgb200_pcg_fused_launch(&a, pv->fused_grid, k & 1, c->multi, cg->d_z, cg->d_t, cg->d_p, cg->d_r, c->d_x,
+                                cg->d_w, pv->d_w2, pv->stream));
+    prof_mark(c, &pv->gemv);
+    c->launches += 1;
+    return ACG_SUCCESS;
+}
+
 int acgsolvercuda_solve_pipelined(
     struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A,
     const struct acgvector *b, struct acgvector *x,
@@ -1117,6 +1150,19 @@ int acgsolvercuda_solve_pipelined(
     OK(ensure_vec(&cg->z, &cg->d_z, A, pv->nvec, errcode));
 
     c.p2p = c.multi && pv->p2p.enabled && cfg.p2p;
+    /* one kernel per iteration: on one GPU, or with the fused peer-memory exchange */
+    int fused = 0;
+    if (cfg.pcg_fused && (!c.multi || (c.p2p && pv->p2p.h_desc.fuse))) {
+        if (!pv->fused_grid) pv->fused_grid = acgb200_pcg_fused_grid(&pv->plan);
+        if (pv->fused_grid > 0) {
+            if (!pv->d_w2) {
+                CU(cudaMalloc((void **) &pv->d_w2, ((size_t) pv->nvec + 2) * sizeof(double)));
+                CU(cudaMemsetAsync(pv->d_w2, 0, ((size_t) pv->nvec + 2) * sizeof(double), pv->stream));
+            }
+            fused = 1;
+        }
+    }
+    int (*const iteration)(struct solvectx *, int) = fused ? fused_iteration : pipelined_iteration;
     if (warmup > 0) {
         memset(&h, 0, sizeof(h));
         h.maxits = warmup;
@@ -1127,7 +1173,7 @@ int acgsolvercuda_solve_pipelined(
             OK(acgb200_p2p_begin(&pv->p2p, warmup, pv->stream));
             OK(post(&c, 0, 0, cg->d_w, -1, NULL, 0, 0, 0, 0));
         }
-        for (int i = 0; i < warmup; i++) OK(pipelined_iteration(&c, i));
+        for (int i = 0; i < warmup; i++) OK(iteration(&c, i));
         c.d_x = xsave;
         KL(acgb200_dot(n, c.d_b, c.d_b, &st->tmp_loc[0], pv->stream));
         KL(acgb200_dot2(n, cg->d_r, cg->d_w, &st->tmp_loc[0], pv->stream));
@@ -1186,14 +1232,18 @@ int acgsolvercuda_solve_pipelined(
             OK(acgb200_p2p_begin(&pv->p2p, maxits, pv->stream));
             OK(post(&c, 0, 0, cg->d_w, -1, NULL, 0, 0, 0, 0));
         }
-        OK(iterate(&c, maxits, tol > 0, 1, pipelined_iteration));
+        OK(iterate(&c, maxits, tol > 0, fused ? 2 : 1, iteration));
         OK(pull_state(&c, &h));
-        cg->niterations = h.ctrl[0].iter;
-        converged = h.ctrl[0].done;
+        /* the one-kernel iteration alternates between two control words: the
+         * later one counts */
+        const struct acgb200_ctrl *fc = &h.ctrl[0];
+        if (fused && (h.ctrl[1].done || h.ctrl[1].iter > h.ctrl[0].iter)) fc = &h.ctrl[1];
+        cg->niterations = fc->iter;
+        converged = fc->done;
         /* the reference reports sqrt(gamma) of the last *tested* iterate
          * (acg/cgcuda.c:1760): gamma_k at convergence, gamma_{maxits-1} otherwise */
         const int kk = converged ? cg->niterations : (cg->niterations > 0 ? cg->niterations - 1 : 0);
-        const double g = converged ? h.final_rr : (kk == 0 ? gd0[0] : (c.multi ? h.gd[kk & 1][0] : h.gd_loc[kk & 1][0]));
+        const double g = converged ? h.final_rr : (kk == 0 ? gd0[0] : ((c.multi || fused) ? h.gd[kk & 1][0] : h.gd_loc[kk & 1][0]));
         cg->rnrm2 = sqrt(g);
         cg->ntotaliterations += cg->niterations;
     }

@@ -103,6 +103,8 @@ struct acgb200_devstate {
     double prev[2][2];               /* {gamma_{k-1}, alpha_{k-1}} read by update k from slot k&1 */
     /* setup-time reductions */
     double tmp_loc[2], tmp[2];
+    unsigned int ticket;             /* last-CTA detection of the one-kernel iteration (single GPU) */
+    unsigned int pad1;
 };
 
 /* ------------------------------------------------------------------------
@@ -229,6 +231,14 @@ int acgb200_pcg_update(int n, struct acgb200_devstate *st, int cin, int cout, in
                        struct acgb200_p2pdev *p2p,
                        const double *q, double *z, double *w, double *t, double *p,
                        double *r, double *x, cudaStream_t stream);
+
+/* one kernel per pipelined iteration (opt-in): q = A w fused with the update;
+ * w is double-buffered (w0: parity 0).  grid from acgb200_pcg_fused_grid (0: the
+ * plan has no fused variant). */
+int acgb200_pcg_fused_grid(const struct acgb200_spmvplan *plan);
+int acgb200_pcg_fused_launch(const struct acgb200_spmvargs *args, int grid, int cin, int multi,
+                             double *z, double *t, double *p, double *r, double *x,
+                             double *w0, double *w1, cudaStream_t stream);
 
 /* setup-time helpers */
 int acgb200_dot(int n, const double *x, const double *y, double *acc, cudaStream_t stream); /* acc += x.y */

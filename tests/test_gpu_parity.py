@@ -329,3 +329,38 @@ def test_pdl_matches_oracle(method, ab, oracle):
     assert cg.c.niterations == want["niterations"]
     assert np.abs(x.x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
     cg.free()
+
+
+@pytest.mark.skipif(os.environ.get("ACGB200_TEST_EXPERIMENTAL") != "1",
+                    reason="the one-kernel pipelined iteration is opt-in and not yet validated on hardware "
+                           "(set ACGB200_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("name,gen", [CASES[0], CASES[1], CASES[2], CASES[4], CASES[7]],
+                         ids=[CASES[i][0] for i in (0, 1, 2, 4, 7)])
+def test_fused_pipelined_iteration_matches_oracle(name, gen, ab, oracle):
+    """Option pcg_fused=1 (pcg_fused_kernel: q = A w and the vector update in one launch,
+    w double-buffered): same iterates, iteration count, norms and return codes as the
+    two-kernel pipelined loop, with and without tolerances, odd and even iteration counts."""
+    n, r, c, v = gen()
+    A, cg = _solver(ab, n, r, c, v)
+    csr = (A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy())
+    b = A.vector(); b.x[:] = np.random.default_rng(5).standard_normal(n)
+    ab.set_option("pcg_fused", 1)
+    try:
+        want = oracle.cg_pipelined(csr, b.x, maxits=300, rtol=1e-9)
+        x = A.vector()
+        assert cg.solve_pipelined(b, x, maxits=300, residualrtol=1e-9, warmup=1) == 0
+        assert cg.c.niterations == want["niterations"]
+        assert cg.c.rnrm2 / cg.c.r0nrm2 == pytest.approx(want["rnrm2"] / want["r0nrm2"], rel=1e-6, abs=RES_RTOL)
+        assert np.abs(x.x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
+        for its in (1, 2, 7, 12):                                   # tolerances off: exactly `its` iterations
+            if n < 4 and its > 2:
+                continue
+            want = oracle.cg_pipelined(csr, b.x, maxits=its, rtol=0.0)
+            x = A.vector()
+            assert cg.solve_pipelined(b, x, maxits=its) == 0 and cg.c.niterations == its
+            assert cg.c.rnrm2 == pytest.approx(want["rnrm2"], rel=1e-8)
+            assert np.abs(x.x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
+        assert cg.solve_pipelined(b, x, maxits=2, residualrtol=1e-30) == 39     # ACG_ERR_NOT_CONVERGED
+    finally:
+        ab.set_option("pcg_fused", 0)
+    cg.free()

@@ -54,7 +54,8 @@ def _ngpu():
 # exchange back-ends of the CG loop: peer memory with pushes fused into the
 # kernels (default), peer memory with separate post kernels, NCCL only
 BACKENDS = {"p2p-fused": {}, "p2p-unfused": {"ACGB200_P2P_FUSE": "0"}, "nccl": {"ACGB200_P2P": "0"},
-            "nccl-graph": {"ACGB200_P2P": "0", "ACGB200_GRAPH": "2"}}
+            "nccl-graph": {"ACGB200_P2P": "0", "ACGB200_GRAPH": "2"},
+            "one-kernel": {"ACGB200_PCG_FUSED": "1"}, "pdl": {"ACGB200_PDL": "1"}}
 
 
 # The default back-end is always tested; the others only when

@@ -5,16 +5,18 @@ cd "$(dirname "$0")/.."
 source tools/run_variants.sh
 set -x
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-ACGB200_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "pdl or compressed" 2>&1 | tail -5
+ACGB200_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "pdl or compressed or fused" 2>&1 | tail -5
 set +x
 run base 1
 run oldgrid 1 ACGB200_BLAS1_CTAS=4
 run pdl 1 ACGB200_PDL=1
 run compress 1 ACGB200_SPMV_COMPRESS=1
+run onekernel 1 ACGB200_PCG_FUSED=1
+run onekernel_pdl 1 ACGB200_PCG_FUSED=1 ACGB200_PDL=1
 run classic 1 BENCH_SOLVER=classic
 run classic_pdl 1 BENCH_SOLVER=classic ACGB200_PDL=1
 # one rank's share of the 8-GPU problem without any exchange: what the small size alone costs
-for v in "s112 X=1" "s112_pdl ACGB200_PDL=1" "s112_oldgrid ACGB200_BLAS1_CTAS=4"; do
+for v in "s112 X=1" "s112_pdl ACGB200_PDL=1" "s112_oldgrid ACGB200_BLAS1_CTAS=4" "s112_onekernel ACGB200_PCG_FUSED=1"; do
   set -- $v; name=$1; shift
   env "$@" timeout 300 python bench.py --workload 27pt-112 --no-cpu-baseline --steps 8 --warmup 3 > gpurun_out/var_$name.json 2> gpurun_out/var_$name.err
   python - "$name" <<'PY'
