@@ -283,3 +283,36 @@ fail:
     }
     return err;
 }
+
+/* ext.h: geometric row -> part map of an nx*ny*nz lexicographic grid cut into
+ * px*py*pz blocks (part = bi + px*(bj + py*bk)) -- the partition
+ * acgb200_stencil_part assumes, usable with acgsymcsrmatrix_partition or
+ * acgb200_mtx_read_part for any matrix on such a grid; the alternative to the
+ * METIS call in acg/graph.c:510 when the geometry is known. */
+int acgb200_partition_rows_grid(int nx, int ny, int nz, int px, int py, int pz, int *rowparts)
+{
+    if (nx < 1 || ny < 1 || nz < 1 || px < 1 || py < 1 || pz < 1 || px > nx || py > ny || pz > nz)
+        return ACG_ERR_INVALID_VALUE;
+    #pragma omp parallel for collapse(2)
+    for (int z = 0; z < nz; z++) for (int y = 0; y < ny; y++) {
+        const int base = px * (blk_of(y, ny, py) + py * blk_of(z, nz, pz));
+        int *row = rowparts + ((size_t) z * ny + y) * nx;
+        for (int x = 0; x < nx; x++) row[x] = blk_of(x, nx, px) + base;
+    }
+    return ACG_SUCCESS;
+}
+
+/* ext.h: px*py*pz = nparts, as cubic as possible, px <= py <= pz */
+void acgb200_grid_factors(int nparts, int *px, int *py, int *pz)
+{
+    int best[3] = { 1, 1, nparts };
+    for (int a = 1; a <= nparts; a++) {
+        if (nparts % a) continue;
+        for (int b = a; b <= nparts / a; b++) {
+            if ((nparts / a) % b) continue;
+            const int c = nparts / a / b;
+            if (c >= b && (c - a) < (best[2] - best[0])) { best[0] = a; best[1] = b; best[2] = c; }
+        }
+    }
+    *px = best[0]; *py = best[1]; *pz = best[2];
+}

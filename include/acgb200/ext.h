@@ -66,6 +66,13 @@ ACG_API int acgb200_spmv_plan_host2(int nrows, const int64_t *rowptr, const int 
 ACG_API int acgb200_stencil_part(int kind, int nx, int ny, int nz, int px, int py, int pz, int part,
                                  struct acgsymcsrmatrix *A);
 
+/* Geometric row -> part map of an nx*ny*nz lexicographic grid in px*py*pz blocks
+ * (the partition acgb200_stencil_part assumes; the alternative to the METIS call
+ * of acg/graph.c:510 when the geometry is known), and the most cubic
+ * factorisation px <= py <= pz of a part count. */
+ACG_API int acgb200_partition_rows_grid(int nx, int ny, int nz, int px, int py, int pz, int *rowparts);
+ACG_API void acgb200_grid_factors(int nparts, int *px, int *py, int *pz);
+
 /* Matrix Market ingest (mtxfile.c): text, and aCG's binary encoding -- header and
  * size line as text, then rowidx[nnz], colidx[nnz] (1-based acgidx_t), a[nnz]
  * (double); acg/mtxfile.c:1107-1127, written by mtx2bin (mtx2bin/mtx2bin.c:538-549),

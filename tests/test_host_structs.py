@@ -437,3 +437,19 @@ def test_comm_matrix(ab, tmp_path):
     lines = open(path).read().splitlines()
     assert lines[0] == "%%MatrixMarket matrix coordinate integer general" and lines[1] == f"8 8 {np.count_nonzero(M)}"
     assert "1 2 16" in lines                                           # 1-based in the file
+
+
+def test_grid_partition_matches_python_helpers(ab):
+    """acgb200_partition_rows_grid / acgb200_grid_factors (C) == dist.block_partition / grid_factors."""
+    import ctypes as C
+    from acg_b200 import dist as abdist
+    L = ab.lib()
+    for nparts in (1, 2, 3, 4, 6, 8, 12, 16, 27, 64):
+        px, py, pz = C.c_int(), C.c_int(), C.c_int()
+        L.acgb200_grid_factors(nparts, C.byref(px), C.byref(py), C.byref(pz))
+        assert (px.value, py.value, pz.value) == abdist.grid_factors(nparts)
+    for dims, procs in (((10, 9, 8), (2, 3, 1)), ((7, 7, 7), (3, 3, 3)), ((5, 4, 6), (1, 1, 1))):
+        out = np.zeros(dims[0] * dims[1] * dims[2], np.int32)
+        assert L.acgb200_partition_rows_grid(*dims, *procs, out) == 0
+        assert np.array_equal(out, abdist.block_partition(*dims, *procs))
+    assert L.acgb200_partition_rows_grid(4, 4, 4, 5, 1, 1, np.zeros(64, np.int32)) != 0
