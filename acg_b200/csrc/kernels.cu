@@ -27,6 +27,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #define SPMV_THREADS 128
 /* Resident CTAs per SM the register allocator must leave room for.  Without
@@ -495,204 +496,6 @@ spmv_tiles_kernel(const SpmvParams P)
 }
 
 /* ------------------------------------------------------------------------ */
-/* One kernel per pipelined-CG iteration (opt-in, option "pcg_fused")          */
-/* ------------------------------------------------------------------------ */
-
-/*
- * q = A w and the whole vector update of acg/cg-kernels-cuda.cu:201-214 in one
- * pass: a row's update needs only that row's q, so it runs as the epilogue of
- * the row's tile and q never goes to memory.  The SpMV gathers w at arbitrary
- * columns while w is being updated, hence w is double-buffered by iteration
- * parity (gathers read one buffer, the epilogue writes the other); z, t, p, x, r
- * are only touched at the tile's own rows.  Per row this moves 96 B of vectors
- * instead of 8 (q written) + 104 (update) B, and an iteration is one launch and
- * one grid-wide dependency instead of two -- which is what counts once a rank's
- * share of the matrix takes 0.1 ms.
- *
- * The scalars are those of the two-kernel path: {gamma,delta} of this iteration
- * were accumulated by the previous launch (peer-memory mode: published by its
- * last CTA to every rank and summed here in rank order), alpha and beta follow,
- * the stopping test precedes the update (acg/cgcuda.c:1764-1772).  Unlike that
- * path the reduction is needed at the *start* of the launch, so it no longer
- * overlaps the SpMV: algebraically the iteration is unchanged, the latency
- * hiding of pipelined CG is traded for the launch and the q traffic (between
- * GPUs of one NVSwitch domain the exposed latency is a few microseconds).
- *
- * Accumulators: slot s^1 of gd_loc collects {gamma,delta} of the next
- * iteration; slot s, read by every CTA at its start, is cleared by the last
- * CTA to finish, ready for the launch after this one.
- */
-struct FusedParams {
-    double *z, *t, *p, *r, *x;
-    double *w0, *w1;        /* w of even / odd iterations */
-    int cin;                /* control word read; cin^1 is written */
-    int multi;
-};
-
-template <int G, int T, int U>
-__global__ void __launch_bounds__(T, SPMV_MINB(T))
-pcg_fused_kernel(const SpmvParams P, const FusedParams F)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full_bar[SPMV_MAX_STAGES];
-    __shared__ double red[T / 32];
-    __shared__ double glob[2];
-    __shared__ double qs[2][T / G];          /* q of the current / previous tile (rows_cap <= T/G) */
-    __shared__ int last_flag;
-
-    const int tid = threadIdx.x;
-    pdl_prologue();
-    acgb200_devstate *st = P.st;
-    acgb200_p2pdev *PP = P.p2p;
-    const Gate gate = gate_read(&st->ctrl[F.cin], st);
-    const int s = gate.iter & 1;
-    double gamma, delta;
-    if (PP && gate.active && gate.iter > 0) {
-        p2p_reduce(PP, 0, s, PP->rbase + (unsigned long long) gate.iter, glob);
-        gamma = glob[0]; delta = glob[1];
-    } else {
-        gamma = F.multi ? st->gd[s][0] : st->gd_loc[s][0];
-        delta = F.multi ? st->gd[s][1] : st->gd_loc[s][1];
-    }
-    const double gamma_prev = st->prev[s][0], alpha_prev = st->prev[s][1];
-    const bool conv = st->tol > 0.0 && sqrt(gamma) < st->tol;
-    const double beta = gamma / gamma_prev;
-    const double alpha = gamma / (delta - beta * gamma / alpha_prev);
-    if (blockIdx.x == 0 && tid == 0) {
-        acgb200_ctrl c = st->ctrl[F.cin];
-        if (gate.active) {
-            st->gd[s][0] = gamma; st->gd[s][1] = delta;      /* where the host finds the last tested gamma */
-            if (conv) { c.done = 1; st->final_rr = gamma; }
-            else { c.iter = gate.iter + 1; st->prev[s ^ 1][0] = gamma; st->prev[s ^ 1][1] = alpha; }
-        }
-        st->ctrl[F.cin ^ 1] = c;
-    }
-    if (!gate.active || conv) return;
-
-    const double *wold = s ? F.w1 : F.w0;
-    double *wnew = s ? F.w0 : F.w1;
-    const int S = P.nstages;
-    if (tid == 0) {
-        const uint64_t pol = l2_policy_evict_first();
-        for (int i = 0; i < S; i++) mbar_init(&full_bar[i], 1);
-        mbar_init_fence();
-        for (int i = 0; i < S; i++) {
-            const int t = blockIdx.x + i * gridDim.x;
-            if (t < P.ntiles) spmv_issue(P, P.tiles[t], smem + (size_t) i * P.stage_bytes, &full_bar[i], pol);
-        }
-    }
-    __syncthreads();
-
-    constexpr int RPP = T / G;
-    const int lane = tid % G;
-    const int grp = tid / G;
-    const bool push = PP != NULL;            /* launched only with the fused exchange */
-    double g2 = 0.0, d2 = 0.0;
-    const double *xg = NULL;
-
-    int i = 0;
-    for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, i++) {
-        const int sidx = i % S;
-        const acgb200_tile tl = P.tiles[t];
-        if (PP && !xg && tl.row_begin + tl.nrows > P.od_rowoffset) {
-            p2p_wait_halo(PP, PP->hbase + (unsigned long long) gate.iter);
-            xg = PP->my_ghost[s] - P.od_nrows;
-        }
-        unsigned char *stage = smem + (size_t) sidx * P.stage_bytes;
-        const double *vals = reinterpret_cast<const double *>(stage);
-        const int *cols = reinterpret_cast<const int *>(stage + (size_t) P.sc * 8);
-        const int *rp = reinterpret_cast<const int *>(stage + (size_t) P.sc * 12) + (tl.row_begin & 3);
-        double *qt = qs[i & 1];
-
-        mbar_wait(&full_bar[sidx], (uint32_t) ((i / S) & 1));
-
-        for (int base = 0; base < tl.nrows; base += RPP) {
-            const int lr = base + grp;
-            double sum = 0.0;
-            if (lr < tl.nrows) {
-                const int kb = rp[lr] - tl.k_al;
-                const int ke = rp[lr + 1] - tl.k_al;
-                for (int k = kb + lane; k < ke; k += U * G) {
-                    int c[U];
-                    double v[U], xv[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const int kk = min(k + u * G, ke - 1);
-                        c[u] = cols[kk];
-                        v[u] = vals[kk];
-                    }
-                    /* plain loads: w is rewritten by every launch, but never the buffer being gathered */
-#pragma unroll
-                    for (int u = 0; u < U; u++) xv[u] = ld_x(wold + c[u]);
-#pragma unroll
-                    for (int u = 0; u < U; u++) sum = fma((k + u * G < ke) ? v[u] : 0.0, xv[u], sum);
-                }
-                if (xg && tl.row_begin + lr >= P.od_rowoffset) {
-                    const int ob = tl.row_begin + lr - P.od_rowoffset;
-                    for (int k = P.orowptr[ob] + lane; k < P.orowptr[ob + 1]; k += G)
-                        sum = fma(P.oa[k], xg[P.ocolidx[k]], sum);
-                }
-            }
-            if (G > 1) sum = group_sum<G>(sum);
-            if (lr < tl.nrows && lane == 0) qt[lr] = sum;
-        }
-
-        __syncthreads();        /* q of the tile is in shared memory; stage sidx is free */
-        if (tid == 0) {
-            const int tn = t + S * gridDim.x;
-            if (tn < P.ntiles) spmv_issue(P, P.tiles[tn], stage, &full_bar[sidx], l2_policy_evict_first());
-        }
-        /* update of the tile's rows, one thread per row, coalesced; the duty
-         * rotates over the warps so that no warp is the straggler of every tile.
-         * qs is double-buffered by tile parity: the next tile's q goes to the
-         * other half, and the barrier above of that tile orders this read
-         * before the half is written again. */
-        for (int lr = (tid + T - (i * 32) % T) % T; lr < tl.nrows; lr += T) {
-            const int row = tl.row_begin + lr;
-            const double qv = qt[lr];
-            const double wv0 = wold[row], rv0 = F.r[row];
-            const double zv = fma(beta, F.z[row], qv);
-            const double tv = fma(beta, F.t[row], wv0);
-            const double pv = fma(beta, F.p[row], rv0);
-            const double rv = fma(-alpha, tv, rv0);
-            const double wv = fma(-alpha, zv, wv0);
-            F.z[row] = zv; F.t[row] = tv; F.p[row] = pv;
-            F.x[row] = fma(alpha, pv, F.x[row]);
-            F.r[row] = rv; wnew[row] = wv;
-            g2 = fma(rv, rv, g2);
-            d2 = fma(wv, rv, d2);
-            if (push && row >= PP->borderoff) p2p_push_row(PP, row, s ^ 1, wv);
-        }
-    }
-
-    g2 = block_sum(g2, red);
-    d2 = block_sum(d2, red);
-    if (tid == 0) {
-        atomicAdd(&st->gd_loc[s ^ 1][0], g2);
-        atomicAdd(&st->gd_loc[s ^ 1][1], d2);
-    }
-    if (PP) {
-        __threadfence_system();
-        if (p2p_last_block(PP, &last_flag)) {
-            const unsigned long long it1 = (unsigned long long) gate.iter + 1ull;
-            p2p_publish_red(PP, 0, s ^ 1, PP->rbase + it1, &st->gd_loc[s ^ 1][0], 2);
-            p2p_publish_halo(PP, PP->hbase + it1);
-            if (tid == 0) { st->gd_loc[s][0] = 0.0; st->gd_loc[s][1] = 0.0; }
-        }
-    } else {
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned int tk = atomicAdd(&st->ticket, 1u);
-            if (tk == gridDim.x - 1) {
-                st->ticket = 0;
-                st->gd_loc[s][0] = 0.0; st->gd_loc[s][1] = 0.0;
-            }
-        }
-    }
-}
-
-/* ------------------------------------------------------------------------ */
 /* SpMV over index-free ("compressed") tiles -- opt-in, see compress.c         */
 /* ------------------------------------------------------------------------ */
 
@@ -857,6 +660,233 @@ spmv_ctiles_kernel(const SpmvParams P, const CmpParams C)
         __threadfence();
         if (p2p_last_block(P.p2p, &last_flag))
             p2p_publish_red(P.p2p, P.pub_ch, gate.iter & 1, P.p2p->rbase + (unsigned long long) gate.iter + 1ull, P.acc, 1);
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* One kernel per pipelined-CG iteration (opt-in, option "pcg_fused")          */
+/* ------------------------------------------------------------------------ */
+
+/*
+ * q = A w and the whole vector update of acg/cg-kernels-cuda.cu:201-214 in one
+ * pass: a row's update needs only that row's q, so it runs as the epilogue of
+ * the row's tile and q never goes to memory.  The SpMV gathers w at arbitrary
+ * columns while w is being updated, hence w is double-buffered by iteration
+ * parity (gathers read one buffer, the epilogue writes the other); z, t, p, x, r
+ * are only touched at the tile's own rows.  Per row this moves 96 B of vectors
+ * instead of 8 (q written) + 104 (update) B, and an iteration is one launch and
+ * one grid-wide dependency instead of two -- which is what counts once a rank's
+ * share of the matrix takes 0.1 ms.
+ *
+ * The scalars are those of the two-kernel path: {gamma,delta} of this iteration
+ * were accumulated by the previous launch (peer-memory mode: published by its
+ * last CTA to every rank and summed here in rank order), alpha and beta follow,
+ * the stopping test precedes the update (acg/cgcuda.c:1764-1772).  Unlike that
+ * path the reduction is needed at the *start* of the launch, so it no longer
+ * overlaps the SpMV: algebraically the iteration is unchanged, the latency
+ * hiding of pipelined CG is traded for the launch and the q traffic (between
+ * GPUs of one NVSwitch domain the exposed latency is a few microseconds).
+ *
+ * Accumulators: slot s^1 of gd_loc collects {gamma,delta} of the next
+ * iteration; slot s, read by every CTA at its start, is cleared by the last
+ * CTA to finish, ready for the launch after this one.
+ */
+struct FusedParams {
+    double *z, *t, *p, *r, *x;
+    double *w0, *w1;        /* w of even / odd iterations */
+    int cin;                /* control word read; cin^1 is written */
+    int multi;
+};
+
+template <int G, int T, int U, bool CMP>
+__global__ void __launch_bounds__(T, SPMV_MINB(T))
+pcg_fused_kernel(const SpmvParams P, const CmpParams C, const FusedParams F)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[SPMV_MAX_STAGES];
+    __shared__ double red[T / 32];
+    __shared__ double glob[2];
+    __shared__ double qs[2][T / G];          /* q of the current / previous tile (rows_cap <= T/G) */
+    __shared__ double ab[2];                 /* alpha, beta: kept out of the registers of the gather loop */
+    __shared__ int last_flag;
+
+    const int tid = threadIdx.x;
+    pdl_prologue();
+    acgb200_devstate *st = P.st;
+    acgb200_p2pdev *PP = P.p2p;
+    const Gate gate = gate_read(&st->ctrl[F.cin], st);
+    const int s = gate.iter & 1;
+    double gamma, delta;
+    if (PP && gate.active && gate.iter > 0) {
+        p2p_reduce(PP, 0, s, PP->rbase + (unsigned long long) gate.iter, glob);
+        gamma = glob[0]; delta = glob[1];
+    } else {
+        gamma = F.multi ? st->gd[s][0] : st->gd_loc[s][0];
+        delta = F.multi ? st->gd[s][1] : st->gd_loc[s][1];
+    }
+    const double gamma_prev = st->prev[s][0], alpha_prev = st->prev[s][1];
+    const bool conv = st->tol > 0.0 && sqrt(gamma) < st->tol;
+    if (tid == 0) {
+        const double beta = gamma / gamma_prev;
+        ab[1] = beta;
+        ab[0] = gamma / (delta - beta * gamma / alpha_prev);
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        const double alpha = ab[0];
+        acgb200_ctrl c = st->ctrl[F.cin];
+        if (gate.active) {
+            st->gd[s][0] = gamma; st->gd[s][1] = delta;      /* where the host finds the last tested gamma */
+            if (conv) { c.done = 1; st->final_rr = gamma; }
+            else { c.iter = gate.iter + 1; st->prev[s ^ 1][0] = gamma; st->prev[s ^ 1][1] = alpha; }
+        }
+        st->ctrl[F.cin ^ 1] = c;
+    }
+    if (!gate.active || conv) return;
+
+    const double *wold = s ? F.w1 : F.w0;
+    const int S = P.nstages;
+    /* index-free tiles (CMP): pattern table behind the stage ring, as in spmv_ctiles_kernel */
+    int *patptr_s = reinterpret_cast<int *>(smem + (size_t) S * P.stage_bytes);
+    int *patoff_s = patptr_s + ((C.npat + 1 + 3) & ~3);
+    if (CMP) {
+        for (int j = tid; j <= C.npat; j += T) patptr_s[j] = C.patptr[j];
+        for (int j = tid; j < C.nentries; j += T) patoff_s[j] = C.patoff[j];
+    }
+    if (tid == 0) {
+        const uint64_t pol = l2_policy_evict_first();
+        for (int i = 0; i < S; i++) mbar_init(&full_bar[i], 1);
+        mbar_init_fence();
+        for (int i = 0; i < S; i++) {
+            const int t = blockIdx.x + i * gridDim.x;
+            if (t < P.ntiles) {
+                if (CMP) cspmv_issue(P, C, P.tiles[t], smem + (size_t) i * P.stage_bytes, &full_bar[i], pol);
+                else spmv_issue(P, P.tiles[t], smem + (size_t) i * P.stage_bytes, &full_bar[i], pol);
+            }
+        }
+    }
+    __syncthreads();
+
+    constexpr int RPP = T / G;
+    const int lane = tid % G;
+    const int grp = tid / G;
+    const bool push = PP != NULL;            /* launched only with the fused exchange */
+    double g2 = 0.0, d2 = 0.0;
+    const double *xg = NULL;
+
+    int i = 0;
+    for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, i++) {
+        const int sidx = i % S;
+        acgb200_tile tl = P.tiles[t];
+        const bool cmp = CMP && (tl.nrows & ACGB200_TILE_COMPRESSED) != 0;
+        tl.nrows &= ~ACGB200_TILE_COMPRESSED;
+        if (PP && !xg && tl.row_begin + tl.nrows > P.od_rowoffset) {
+            p2p_wait_halo(PP, PP->hbase + (unsigned long long) gate.iter);
+            xg = PP->my_ghost[s] - P.od_nrows;
+        }
+        unsigned char *stage = smem + (size_t) sidx * P.stage_bytes;
+        const double *vals = reinterpret_cast<const double *>(stage);
+        /* stage layout: values | column indices | row pointers, or (CMP) values | row pointers | pattern ids */
+        const int *cols = reinterpret_cast<const int *>(stage + (size_t) P.sc * 8);
+        const int *rp = (CMP ? reinterpret_cast<const int *>(stage + (size_t) P.sc * 8)
+                             : reinterpret_cast<const int *>(stage + (size_t) P.sc * 12)) + (tl.row_begin & 3);
+        const unsigned short *pid = reinterpret_cast<const unsigned short *>(stage + (size_t) P.sc * 8 + (size_t) C.rc * 4)
+                                    + (tl.row_begin & 7);
+        const int *gcol = P.colidx + tl.k_al;
+        double *qt = qs[i & 1];
+
+        mbar_wait(&full_bar[sidx], (uint32_t) ((i / S) & 1));
+
+        for (int base = 0; base < tl.nrows; base += RPP) {
+            const int lr = base + grp;
+            double sum = 0.0;
+            if (lr < tl.nrows) {
+                const int row = tl.row_begin + lr;
+                const int kb = rp[lr] - tl.k_al;
+                const int ke = rp[lr + 1] - tl.k_al;
+                const int *offs = cmp ? patoff_s + patptr_s[pid[lr]] - kb : NULL;
+                for (int k = kb + lane; k < ke; k += U * G) {
+                    int c[U];
+                    double v[U], xv[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int kk = min(k + u * G, ke - 1);
+                        if (CMP) c[u] = cmp ? row + offs[kk] : __ldg(gcol + kk);
+                        else c[u] = cols[kk];
+                        v[u] = vals[kk];
+                    }
+                    /* read-only path: the buffer being gathered is not written by this launch */
+#pragma unroll
+                    for (int u = 0; u < U; u++) xv[u] = ld_x(wold + c[u]);
+#pragma unroll
+                    for (int u = 0; u < U; u++) sum = fma((k + u * G < ke) ? v[u] : 0.0, xv[u], sum);
+                }
+                if (xg && row >= P.od_rowoffset) {
+                    const int ob = row - P.od_rowoffset;
+                    for (int k = P.orowptr[ob] + lane; k < P.orowptr[ob + 1]; k += G)
+                        sum = fma(P.oa[k], xg[P.ocolidx[k]], sum);
+                }
+            }
+            if (G > 1) sum = group_sum<G>(sum);
+            if (lr < tl.nrows && lane == 0) qt[lr] = sum;
+        }
+
+        __syncthreads();        /* q of the tile is in shared memory; stage sidx is free */
+        if (tid == 0) {
+            const int tn = t + S * gridDim.x;
+            if (tn < P.ntiles) {
+                if (CMP) cspmv_issue(P, C, P.tiles[tn], stage, &full_bar[sidx], l2_policy_evict_first());
+                else spmv_issue(P, P.tiles[tn], stage, &full_bar[sidx], l2_policy_evict_first());
+            }
+        }
+        /* update of the tile's rows, one thread per row, coalesced; the duty
+         * rotates over the warps so that no warp is the straggler of every tile.
+         * qs is double-buffered by tile parity: the next tile's q goes to the
+         * other half, and the barrier above of that tile orders this read
+         * before the half is written again. */
+        for (int lr = (tid + T - (i * 32) % T) % T; lr < tl.nrows; lr += T) {
+            const int row = tl.row_begin + lr;
+            const double alpha = ab[0], beta = ab[1];
+            double *wnew = s ? F.w0 : F.w1;
+            const double qv = qt[lr];
+            const double wv0 = wold[row], rv0 = F.r[row];
+            const double zv = fma(beta, F.z[row], qv);
+            const double tv = fma(beta, F.t[row], wv0);
+            const double pv = fma(beta, F.p[row], rv0);
+            const double rv = fma(-alpha, tv, rv0);
+            const double wv = fma(-alpha, zv, wv0);
+            F.z[row] = zv; F.t[row] = tv; F.p[row] = pv;
+            F.x[row] = fma(alpha, pv, F.x[row]);
+            F.r[row] = rv; wnew[row] = wv;
+            g2 = fma(rv, rv, g2);
+            d2 = fma(wv, rv, d2);
+            if (push && row >= PP->borderoff) p2p_push_row(PP, row, s ^ 1, wv);
+        }
+    }
+
+    g2 = block_sum(g2, red);
+    d2 = block_sum(d2, red);
+    if (tid == 0) {
+        atomicAdd(&st->gd_loc[s ^ 1][0], g2);
+        atomicAdd(&st->gd_loc[s ^ 1][1], d2);
+    }
+    if (PP) {
+        __threadfence_system();
+        if (p2p_last_block(PP, &last_flag)) {
+            const unsigned long long it1 = (unsigned long long) gate.iter + 1ull;
+            p2p_publish_red(PP, 0, s ^ 1, PP->rbase + it1, &st->gd_loc[s ^ 1][0], 2);
+            p2p_publish_halo(PP, PP->hbase + it1);
+            if (tid == 0) { st->gd_loc[s][0] = 0.0; st->gd_loc[s][1] = 0.0; }
+        }
+    } else {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int tk = atomicAdd(&st->ticket, 1u);
+            if (tk == gridDim.x - 1) {
+                st->ticket = 0;
+                st->gd_loc[s][0] = 0.0; st->gd_loc[s][1] = 0.0;
+            }
+        }
     }
 }
 
@@ -1399,12 +1429,12 @@ extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t strea
     return 0;
 }
 
-typedef void (*fused_fn)(const SpmvParams, const FusedParams);
+typedef void (*fused_fn)(const SpmvParams, const CmpParams, const FusedParams);
 
-static fused_fn fused_variant(int G, int T, int U)
+static fused_fn fused_variant(int G, int T, int U, int compressed)
 {
     if (U != 8 || T != 128) return NULL;
-#define X(g) if (G == g) return pcg_fused_kernel<g, 128, 8>;
+#define X(g) if (G == g) return compressed ? pcg_fused_kernel<g, 128, 8, true> : pcg_fused_kernel<g, 128, 8, false>;
     X(1) X(2) X(4) X(8) X(16) X(32)
 #undef X
     return NULL;
@@ -1413,8 +1443,8 @@ static fused_fn fused_variant(int G, int T, int U)
 /* grid of the fused kernel for this plan (0: no variant / does not fit) */
 extern "C" int acgb200_pcg_fused_grid(const acgb200_spmvplan *pl)
 {
-    fused_fn fn = fused_variant(pl->lanes_per_row, pl->threads, pl->unroll);
-    if (!fn || pl->compressed || pl->nlong > 0 || pl->rows_cap > pl->threads / pl->lanes_per_row) return 0;
+    fused_fn fn = fused_variant(pl->lanes_per_row, pl->threads, pl->unroll, pl->compressed);
+    if (!fn || pl->nlong > 0 || pl->rows_cap > pl->threads / pl->lanes_per_row) return 0;
     if (cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes) != cudaSuccess) return 0;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) fn, pl->threads, pl->smem_bytes) != cudaSuccess || per_sm < 1)
@@ -1430,7 +1460,7 @@ extern "C" int acgb200_pcg_fused_launch(const acgb200_spmvargs *a, int grid, int
                                         double *w0, double *w1, cudaStream_t stream)
 {
     const acgb200_spmvplan *pl = a->plan;
-    fused_fn fn = fused_variant(pl->lanes_per_row, pl->threads, pl->unroll);
+    fused_fn fn = fused_variant(pl->lanes_per_row, pl->threads, pl->unroll, pl->compressed);
     if (!fn || grid < 1) return (int) cudaErrorInvalidConfiguration;
     SpmvParams P;
     P.tiles = pl->d_tiles; P.ntiles = pl->ntiles;
@@ -1440,9 +1470,16 @@ extern "C" int acgb200_pcg_fused_launch(const acgb200_spmvargs *a, int grid, int
     P.ctrl_in = NULL; P.ctrl_out = NULL; P.st = a->st; P.housekeeping = 0;
     P.p2p = (acgb200_p2pdev *) a->p2p; P.od_rowoffset = a->od_rowoffset; P.od_nrows = a->od_nrows;
     P.orowptr = a->orowptr; P.ocolidx = a->ocolidx; P.oa = a->oa; P.pub_ch = -1;
+    CmpParams C;
+    memset(&C, 0, sizeof(C));
+    if (pl->compressed) {
+        C.patid = pl->d_patid; C.patptr = pl->d_patptr; C.patoff = pl->d_patoff;
+        C.npat = pl->npat; C.nentries = pl->nentries;
+        C.pc = stage_pslots(pl); C.rc = stage_rslots(pl);
+    }
     FusedParams F;
     F.z = z; F.t = t; F.p = p; F.r = r; F.x = x; F.w0 = w0; F.w1 = w1; F.cin = cin; F.multi = multi;
-    return (int) launch_chain(fn, grid, pl->threads, (size_t) pl->smem_bytes, stream, P, F);
+    return (int) launch_chain(fn, grid, pl->threads, (size_t) pl->smem_bytes, stream, P, C, F);
 }
 
 extern "C" int acgb200_offdiag_launch(const acgb200_offdiagargs *a, cudaStream_t stream)

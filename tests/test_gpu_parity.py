@@ -334,14 +334,19 @@ def test_pdl_matches_oracle(method, ab, oracle):
 @pytest.mark.skipif(os.environ.get("ACGB200_TEST_EXPERIMENTAL") != "1",
                     reason="the one-kernel pipelined iteration is opt-in and not yet validated on hardware "
                            "(set ACGB200_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("compress", [0, 1], ids=["csr-tiles", "index-free-tiles"])
 @pytest.mark.parametrize("name,gen", [CASES[0], CASES[1], CASES[2], CASES[4], CASES[7]],
                          ids=[CASES[i][0] for i in (0, 1, 2, 4, 7)])
-def test_fused_pipelined_iteration_matches_oracle(name, gen, ab, oracle):
+def test_fused_pipelined_iteration_matches_oracle(name, gen, compress, ab, oracle):
     """Option pcg_fused=1 (pcg_fused_kernel: q = A w and the vector update in one launch,
     w double-buffered): same iterates, iteration count, norms and return codes as the
     two-kernel pipelined loop, with and without tolerances, odd and even iteration counts."""
     n, r, c, v = gen()
-    A, cg = _solver(ab, n, r, c, v)
+    ab.set_option("spmv_compress", compress)
+    try:
+        A, cg = _solver(ab, n, r, c, v)
+    finally:
+        ab.set_option("spmv_compress", 0)
     csr = (A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy())
     b = A.vector(); b.x[:] = np.random.default_rng(5).standard_normal(n)
     ab.set_option("pcg_fused", 1)

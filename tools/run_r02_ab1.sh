@@ -13,6 +13,7 @@ run pdl 1 ACGB200_PDL=1
 run compress 1 ACGB200_SPMV_COMPRESS=1
 run onekernel 1 ACGB200_PCG_FUSED=1
 run onekernel_pdl 1 ACGB200_PCG_FUSED=1 ACGB200_PDL=1
+run onekernel_compress 1 ACGB200_PCG_FUSED=1 ACGB200_SPMV_COMPRESS=1
 run classic 1 BENCH_SOLVER=classic
 run classic_pdl 1 BENCH_SOLVER=classic ACGB200_PDL=1
 # one rank's share of the 8-GPU problem without any exchange: what the small size alone costs
