@@ -106,3 +106,26 @@ def test_stock_reference_gpu_solver_pins_the_oracle(solver, method, oracle):
     x = np.array([float(t) for t in lines[1:]])
     assert len(x) == n
     assert np.abs(x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", ["acg", "acg-pipelined"])
+def test_driver_manufactured_solution(solver):
+    """KAT-4 (cuda/acg-cuda.c:1969-1979, :2090-2130, :2376-2385): the driver draws a random
+    unit vector x*, sets b = A x* with the reference's host SpMV, solves on the GPU through
+    the library and prints ||x*|| and ||x - x*||.  With a residual tolerance of 1e-10 on a
+    well-conditioned matrix the error must fall by many orders of magnitude."""
+    if not os.path.exists(DRIVER):
+        pytest.skip("driver binary not built (needs the reference tree at build time)")
+    n, r, c, v = mg.stencil3d_27pt(24)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "A.mtx")
+        mtxio.write_symmetric(path, n, r, c, v, binary=True)
+        p = subprocess.run([DRIVER, path, "--binary", "--solver", solver, "--max-iterations", "500",
+                            "--residual-rtol", "1e-10", "--manufactured-solution", "--seed", "7", "-q"],
+                           capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-3000:]
+    e0 = float(re.search(r"^initial error 2-norm: (\S+)", p.stderr, re.M).group(1))
+    e1 = float(re.search(r"^error 2-norm: (\S+)", p.stderr, re.M).group(1))
+    assert e0 == pytest.approx(1.0, rel=1e-12)            # x* is normalised
+    assert e1 < 1e-7 * e0
