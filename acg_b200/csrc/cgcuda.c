@@ -875,6 +875,12 @@ static int iterate(struct solvectx *c, int maxits, int poll, int kind, int (*iss
     }
     CU(cudaStreamSynchronize(pv->stream));
     if (c->multi) { CU(cudaStreamSynchronize(pv->commstream)); CU(cudaStreamSynchronize(pv->redstream)); }
+    if (c->multi && c->p2p) {
+        /* a kernel that waited in vain for a peer gave up instead of hanging the GPU */
+        int gaveup = 0;
+        OK(acgb200_p2p_timed_out(&pv->p2p, pv->stream, &gaveup));
+        if (gaveup) { *errcode = (int) cudaErrorLaunchTimeout; return ACG_ERR_CUDA; }
+    }
     return ACG_SUCCESS;
 }
 

@@ -143,6 +143,9 @@ struct acgb200_p2pdev {
     double *my_red;
     unsigned long long *my_rflag;
     unsigned long long hbase, rbase;         /* sequence bases of the current solve */
+    unsigned long long timed_out;            /* set by a kernel whose wait for a peer exceeded timeout_ns; sticky
+                                              * for the solve (hbase, rbase, timed_out are reset by one copy) */
+    unsigned long long timeout_ns;           /* 0: wait for ever */
     unsigned int ticket;                     /* last-block detection (one kernel at a time uses it) */
     /* inverse send map: border row b (relative to borderrowoffset) is sent to
      * neighbours bq[e] at ghost offsets bdst[e], e in [bptr[b], bptr[b+1]) */

@@ -187,13 +187,37 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 
 #define RED_IDX(ch, parity, rank) ((((ch) * 2 + (parity)) * ACGB200_MAXR + (rank)) * 2)
 
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+/* Spin until *f >= seq.  A peer that never publishes (it failed, or a protocol
+ * error) must not hang the GPU: after timeout_ns the waiter raises the sticky
+ * timed_out flag of its descriptor and gives up, every later wait of the solve
+ * returns at once, and the host turns the flag into an error (the iterates are
+ * garbage from then on).  The clock is only read every 1024 polls. */
+__device__ __forceinline__ void p2p_spin(const unsigned long long *f, unsigned long long seq, const acgb200_p2pdev *P)
+{
+    unsigned long long t0 = 0;
+    unsigned int polls = 0;
+    volatile unsigned long long *flag = const_cast<volatile unsigned long long *>(&P->timed_out);
+    while (ld_acquire_sys(f) < seq) {
+        if ((++polls & 1023u) != 0) continue;
+        if (*flag) return;
+        if (P->timeout_ns == 0) continue;
+        const unsigned long long now = global_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > P->timeout_ns) { *flag = 1ull; __threadfence_system(); return; }
+    }
+}
+
 /* Block-wide: wait until every sender has published halo sequence `seq`. */
 __device__ __forceinline__ void p2p_wait_halo(const acgb200_p2pdev *P, unsigned long long seq)
 {
-    if ((int) threadIdx.x < P->nsenders) {
-        const unsigned long long *f = P->my_hflag + P->senders[threadIdx.x];
-        while (ld_acquire_sys(f) < seq) { }
-    }
+    if ((int) threadIdx.x < P->nsenders) p2p_spin(P->my_hflag + P->senders[threadIdx.x], seq, P);
     __syncthreads();
 }
 
@@ -202,10 +226,7 @@ __device__ __forceinline__ void p2p_wait_halo(const acgb200_p2pdev *P, unsigned 
  * every rank, so all ranks get bit-identical sums).  out[0..1] in shared memory. */
 __device__ __forceinline__ void p2p_reduce(const acgb200_p2pdev *P, int ch, int parity, unsigned long long seq, double *out)
 {
-    if ((int) threadIdx.x < P->nranks) {
-        const unsigned long long *f = P->my_rflag + ch * ACGB200_MAXR + threadIdx.x;
-        while (ld_acquire_sys(f) < seq) { }
-    }
+    if ((int) threadIdx.x < P->nranks) p2p_spin(P->my_rflag + ch * ACGB200_MAXR + threadIdx.x, seq, P);
     __syncthreads();
     if (threadIdx.x == 0) {
         double a = 0.0, b = 0.0;

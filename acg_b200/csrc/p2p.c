@@ -139,6 +139,14 @@ int acgb200_p2p_init(struct acgb200_p2p *p, const struct acghalo *halo, int bord
     d->my_red = (double *) (me + off_red());
     d->my_rflag = (unsigned long long *) (me + off_rflag());
     d->hbase = d->rbase = 1;
+    {
+        /* watchdog of the device-side waits (kernels.cu, p2p_spin): generous, its
+         * job is to turn a dead peer into an error instead of a hung GPU */
+        const char *t = getenv("ACGB200_P2P_TIMEOUT_MS");
+        const long long ms = t ? atoll(t) : 30000;
+        d->timeout_ns = ms > 0 ? (unsigned long long) ms * 1000000ull : 0ull;
+        d->timed_out = 0;
+    }
     /* inverse send map: which (neighbour, ghost offset) pairs each border row feeds */
     d->borderoff = borderoff; d->nborder = nborder;
     {
@@ -175,9 +183,20 @@ int acgb200_p2p_begin(struct acgb200_p2p *p, int maxits, cudaStream_t stream)
     p->seq += 4;
     p->h_desc.hbase = p->h_desc.rbase = p->seq;
     p->seq += (unsigned long long) maxits + 4;
-    /* hbase and rbase are adjacent: one 16-byte copy */
-    cudaError_t e = cudaMemcpyAsync(&p->d_desc->hbase, &p->h_desc.hbase, 2 * sizeof(unsigned long long),
+    /* hbase, rbase and the watchdog flag are adjacent: one 24-byte copy */
+    p->h_desc.timed_out = 0;
+    cudaError_t e = cudaMemcpyAsync(&p->d_desc->hbase, &p->h_desc.hbase, 3 * sizeof(unsigned long long),
                                     cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    return e == cudaSuccess ? ACG_SUCCESS : ACG_ERR_CUDA;
+}
+
+/* after a solve: did any wait for a peer time out? */
+int acgb200_p2p_timed_out(struct acgb200_p2p *p, cudaStream_t stream, int *flag)
+{
+    unsigned long long v = 0;
+    cudaError_t e = cudaMemcpyAsync(&v, &p->d_desc->timed_out, sizeof(v), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    *flag = v != 0;
     return e == cudaSuccess ? ACG_SUCCESS : ACG_ERR_CUDA;
 }

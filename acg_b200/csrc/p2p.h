@@ -21,6 +21,8 @@ int acgb200_p2p_init(struct acgb200_p2p *p, const struct acghalo *halo, int bord
                      const struct acgcomm *comm, cudaStream_t stream, int *errcode);
 int acgb200_p2p_begin(struct acgb200_p2p *p, int maxits, cudaStream_t stream);
 void acgb200_p2p_free(struct acgb200_p2p *p);
+/* after a solve: *flag = 1 if a device-side wait for a peer gave up (ACGB200_P2P_TIMEOUT_MS, default 30 s) */
+int acgb200_p2p_timed_out(struct acgb200_p2p *p, cudaStream_t stream, int *flag);
 int acgb200_p2p_inverse_map(const struct acghalo *halo, int borderoff, int nborder,
                             const int *rdispl_at_recipient, int *bptr, int *bq, int *bdst);
 
