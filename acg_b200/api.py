@@ -141,7 +141,7 @@ EXPORTS = [
     "acgb200_set_option", "acgsolvercuda_spmv", "acgsolvercuda_info", "acgb200_sizeof", "acgb200_have_mpi",
     "acgb200_nccl_unique_id", "acgb200_comm_init_rank", "acgb200_comm_destroy",
     "acgb200_host_register", "acgb200_host_unregister", "acgb200_spmv_plan_host", "acgb200_spmv_plan_host2", "acgb200_p2p_inverse_map", "acgb200_patterns_host", "acgb200_stencil_part",
-    "acgb200_mtx_info", "acgb200_mtx_read", "acgb200_mtx_read_part", "acgb200_comm_matrix_row", "acgb200_partition_rows_grid", "acgb200_grid_factors",
+    "acgb200_mtx_info", "acgb200_mtx_read", "acgb200_mtx_read_part", "acgb200_comm_matrix_row", "acgb200_partition_rows_grid", "acgb200_grid_factors", "acgb200_rmat_spd",
 ]
 
 
@@ -179,6 +179,7 @@ def lib() -> C.CDLL:
     L.acgb200_partition_rows_grid.argtypes = [C.c_int] * 6 + [np.ctypeslib.ndpointer(np.int32, flags="C")]
     L.acgb200_grid_factors.argtypes = [C.c_int, P(C.c_int), P(C.c_int), P(C.c_int)]
     L.acgb200_grid_factors.restype = None
+    L.acgb200_rmat_spd.argtypes = [C.c_int64, C.c_int64, C.c_uint64, P(C.c_double), P(acgsymcsrmatrix)]
     L.acgb200_comm_matrix_row.argtypes = [P(acgsymcsrmatrix), C.c_int, np.ctypeslib.ndpointer(np.int64, flags="C")]
     L.acgb200_mtx_read.argtypes = [C.c_char_p, C.c_int, P(acgsymcsrmatrix)]
     L.acgb200_mtx_read_part.argtypes = [C.c_char_p, C.c_int, np.ctypeslib.ndpointer(np.int32, flags="C"), C.c_int,
@@ -340,6 +341,14 @@ class SymCsrMatrix:
         a = np.ascontiguousarray(a, np.float64)
         _check(lib().acgsymcsrmatrix_init_real_double(C.byref(self.c), n, len(a), idxbase, rowidx, colidx, a),
                "acgsymcsrmatrix_init_real_double")
+        self._owns = True
+        return self
+
+    @classmethod
+    def rmat_spd(cls, n: int, nedges: int, seed: int = 42):
+        """acgb200_rmat_spd: threaded R-MAT power-law SPD matrix (BASELINE config 5)."""
+        self = cls()
+        _check(lib().acgb200_rmat_spd(n, nedges, seed, None, C.byref(self.c)), "acgb200_rmat_spd")
         self._owns = True
         return self
 

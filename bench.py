@@ -52,6 +52,9 @@ WORKLOADS = {
     "27pt-112": dict(kind="27pt", N=112, solver="pipelined"),      # one rank's share of 27pt-224 on 8 GPUs, without the exchange
     "27pt-64": dict(kind="27pt", N=64, solver="pipelined"),
     "27pt-448": dict(kind="27pt", N=448, solver="pipelined"),      # configs[3]: 8 GPUs only (weak-scaled x8 point)
+    # configs[4]: power-law rows (long-row path, gathers without locality); contiguous row blocks or METIS for N>1
+    "rmat-20M": dict(kind="rmat", N=20_000_000, edges=200_000_000, solver="pipelined"),
+    "rmat-2M": dict(kind="rmat", N=2_000_000, edges=20_000_000, solver="pipelined"),
 }
 
 
@@ -60,13 +63,29 @@ def make_matrix(w):
     one-part output of the threaded generator, the same entries as acg_b200.matgen's."""
     import acg_b200 as ab
     N = w["N"]
-    A = ab.SymCsrMatrix.stencil_part(27 if w["kind"] == "27pt" else 7, N, N, N, 1, 1, 1, 0)
+    if w["kind"] == "rmat":
+        A = ab.SymCsrMatrix.rmat_spd(N, w["edges"], seed=42)
+    else:
+        A = ab.SymCsrMatrix.stencil_part(27 if w["kind"] == "27pt" else 7, N, N, N, 1, 1, 1, 0)
     rp = A.rowptr
     rows = np.repeat(np.arange(A.c.nprows, dtype=np.int32), np.diff(rp).astype(np.int64))
     cols, vals = A.colidx.copy(), A.a.copy()
     n = int(A.c.nprows)
     A.free()
     return n, rows, cols, vals
+
+
+def rhs(w, gidx):
+    """Right-hand side at the given global row numbers: all ones (the driver's default,
+    cuda/acg-cuda.c:1949-1967) -- except for the R-MAT matrix, whose rows sum to 1 so that
+    b = 1 is an eigenvector and CG would finish in one step."""
+    if w["kind"] == "rmat":
+        return 1.0 + 0.5 * np.sin(0.37 * np.asarray(gidx, dtype=np.float64))
+    return np.ones(len(gidx))
+
+
+def rhs_name(w):
+    return "b_i=1+sin(0.37i)/2" if w["kind"] == "rmat" else "b=1"
 
 
 def peaks():
@@ -115,7 +134,7 @@ def cpu_reference(w, steps, warmup, iters, solver_note):
     oracle port when oracle/_ref was not built."""
     from oracle import Oracle, Ref, ref_available
     n, r, c, v = make_matrix(w)
-    b = np.ones(n)
+    b = rhs(w, np.arange(n))
     out = []
     if ref_available():
         R = Ref()
@@ -137,8 +156,9 @@ def cpu_reference(w, steps, warmup, iters, solver_note):
                 out.append(time.perf_counter() - t0)
     tot = sum(out)
     return dict(value=len(out) * iters / tot, unit="iterations/s", cores=cores, kind=kind,
-                sample=f"{len(out)} x {iters} classic CG iterations (acgsolver_solve) on the full {w['kind']} "
-                       f"{w['N']}^3 matrix, b=1, x0=0; OpenMP dsymv on {cores} threads, BLAS-1 serial as in the reference"
+                sample=f"{len(out)} x {iters} classic CG iterations (acgsolver_solve) on the full "
+                       + (f"R-MAT n={w['N']}" if w["kind"] == "rmat" else f"{w['kind']} {w['N']}^3")
+                       + f" matrix, {rhs_name(w)}, x0=0; OpenMP dsymv on {cores} threads, BLAS-1 serial as in the reference"
                        f"{solver_note}",
                 seconds=tot)
 
@@ -190,13 +210,20 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     metric = "CG iterations/sec (27-pt stencil ~10M rows); SpMV achieved-HBM GB/s in roofline"
-    config = {"workload": f"{w['kind']} stencil {w['N']}^3, FP64, b=1, x0=0, {solver} CG, {args.iters} iterations/step, "
-                          f"tolerances off", "n": w["N"] ** 3, "solver": solver, "iters_per_step": args.iters,
-              "partition": (f"{world} parts, " + ("METIS recursive" if args.partition == "metis" else "geometric blocks"))
+    what = (f"R-MAT power-law SPD, n={w['N']}, {w['edges']} draws" if w["kind"] == "rmat"
+            else f"{w['kind']} stencil {w['N']}^3")
+    config = {"workload": f"{what}, FP64, {rhs_name(w)}, x0=0, {solver} CG, {args.iters} iterations/step, "
+                          f"tolerances off", "n": w["N"] if w["kind"] == "rmat" else w["N"] ** 3,
+              "solver": solver, "iters_per_step": args.iters,
+              "partition": (f"{world} parts, " + ("METIS recursive" if args.partition == "metis" else
+                                                  ("contiguous row blocks" if w["kind"] == "rmat" else "geometric blocks")))
                            if world > 1 else "none",
               "l2": None}
     k = 27 if w["kind"] == "27pt" else 7
-    csr_gb = 12.0 * ((3 * w["N"] - 2) ** 3 if k == 27 else 7 * w["N"] ** 3 - 6 * w["N"] ** 2) / world / 1e9
+    if w["kind"] == "rmat":
+        csr_gb = 12.0 * 2.1 * w["edges"] / world / 1e9
+    else:
+        csr_gb = 12.0 * ((3 * w["N"] - 2) ** 3 if k == 27 else 7 * w["N"] ** 3 - 6 * w["N"] ** 2) / world / 1e9
     config["l2"] = (f"inputs larger than L2 (CSR {csr_gb:.2f} GB per SpMV per GPU vs 126 MB L2), no flush needed"
                     if csr_gb > 0.26 else f"CSR {csr_gb:.2f} GB per GPU: partly L2-resident, not a roofline-valid size")
 
@@ -224,7 +251,19 @@ def main():
     comm = abdist.nccl_comm(rank, world)
 
     N = w["N"]
-    if args.partition == "block":
+    if w["kind"] == "rmat":
+        # power-law graph: no geometry; every rank generates the (deterministic) matrix and keeps its part
+        A = ab.SymCsrMatrix.rmat_spd(N, w["edges"], seed=42)
+        if world > 1:
+            rowparts = A.partition_rows(world, seed=0)[0] if args.partition == "metis" else abdist.contiguous_partition(N, world)
+            parts = A.partition(world, rowparts)
+            A.free()
+            A = parts[rank]
+            for p, m in enumerate(parts):
+                if p != rank:
+                    m.free()
+        A.dsymv_init(0.0)
+    elif args.partition == "block":
         # every rank builds only its own block (no global matrix anywhere); one rank = the whole box
         if (N ** 3 * (27 if w["kind"] == "27pt" else 7)) // world >= 2 ** 31:
             raise SystemExit(f"bench.py: {args.workload} does not fit 32-bit indices on {world} GPU(s)")
@@ -237,7 +276,11 @@ def main():
         del r, c, v
     nnz_local = int(A.c.fnpnzs + A.c.onpnzs)
     cg = ab.SolverCuda(A, comm)
-    b = A.vector(); b.x[:] = 1.0
+    b = A.vector()
+    nown = A.c.nownedrows
+    gidx = A.nzrows[:nown] if len(A.nzrows) >= nown else np.arange(nown)     # global row numbers of the owned rows
+    b.x[:] = 0.0
+    b.x[:nown] = rhs(w, gidx)
     x = A.vector()
     b.pin(); x.pin()
     h2d = 2 * b.c.num_nonzeros * 8

@@ -66,6 +66,13 @@ ACG_API int acgb200_spmv_plan_host2(int nrows, const int64_t *rowptr, const int 
 ACG_API int acgb200_stencil_part(int kind, int nx, int ny, int nz, int px, int py, int pz, int part,
                                  struct acgsymcsrmatrix *A);
 
+/* R-MAT style power-law SPD matrix (BASELINE config 5): n vertices, `nedges`
+ * draws with quadrant probabilities abcd (NULL: 0.57, 0.19, 0.19, 0.05),
+ * symmetrised, deduplicated, off-diagonal -1, diagonal degree+1.  Threaded; the
+ * result does not depend on the thread count (rmat.c). */
+ACG_API int acgb200_rmat_spd(int64_t n, int64_t nedges, uint64_t seed, const double *abcd,
+                             struct acgsymcsrmatrix *A);
+
 /* Geometric row -> part map of an nx*ny*nz lexicographic grid in px*py*pz blocks
  * (the partition acgb200_stencil_part assumes; the alternative to the METIS call
  * of acg/graph.c:510 when the geometry is known), and the most cubic

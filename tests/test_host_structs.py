@@ -1,6 +1,8 @@
 """Host-side data structures of libacgb200 (no GPU): packed/full storage,
 row partition, halo pattern.  Checked against the reference build where it is
 available and against the invariants of SURVEY.md §8(c) KAT-5 everywhere."""
+import os
+
 import numpy as np
 import pytest
 
@@ -453,3 +455,47 @@ def test_grid_partition_matches_python_helpers(ab):
         assert L.acgb200_partition_rows_grid(*dims, *procs, out) == 0
         assert np.array_equal(out, abdist.block_partition(*dims, *procs))
     assert L.acgb200_partition_rows_grid(4, 4, 4, 5, 1, 1, np.zeros(64, np.int32)) != 0
+
+
+_RMAT_HASH = r"""
+import hashlib
+import numpy as np
+import acg_b200 as ab
+A = ab.SymCsrMatrix.rmat_spd(50000, 400000, seed=9)
+m = hashlib.sha256()
+for k in ("rowptr", "colidx", "a"):
+    m.update(np.ascontiguousarray(getattr(A, k)).tobytes())
+print(m.hexdigest())
+"""
+
+
+def test_rmat_generator(ab, oracle):
+    """acgb200_rmat_spd (BASELINE config 5): packed upper triangle with sorted, duplicate-free
+    rows; diagonal = degree + 1, off-diagonal -1 (every row of the full matrix sums to 1, so
+    A is strictly diagonally dominant, hence SPD); heavy-tailed degrees; the same matrix for
+    any thread count and a different one for another seed."""
+    import subprocess
+    import sys
+    n = 50000
+    A = ab.SymCsrMatrix.rmat_spd(n, 400000, seed=9)
+    rp, ci, va = A.rowptr.copy(), A.colidx.copy(), A.a.copy()
+    assert A.c.nprows == n and rp[-1] == len(ci)
+    for i in (0, 1, 17, n - 1):
+        row = ci[rp[i]:rp[i + 1]]
+        assert row[0] == i and np.all(np.diff(row) > 0)          # diagonal first, then ascending, no duplicates
+    A.dsymv_init(0.0)
+    y = oracle.dsymv((A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy()), 1.0, np.ones(n), 0.0, np.zeros(n))
+    assert np.allclose(y, 1.0, rtol=0, atol=1e-9)
+    deg = np.diff(A.frowptr) - 1
+    assert deg.max() > 50 * deg.mean()                             # power law: a few very long rows
+    assert 350000 < (len(ci) - n) <= 400000                        # few collisions, self-loops dropped
+    B = ab.SymCsrMatrix.rmat_spd(n, 400000, seed=10)
+    assert not np.array_equal(B.colidx, ci)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    seen = set()
+    for nt in ("1", "5"):
+        out = subprocess.run([sys.executable, "-c", _RMAT_HASH], env=dict(os.environ, OMP_NUM_THREADS=nt, PYTHONPATH=root),
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        seen.add(out.stdout.strip().splitlines()[-1])
+    assert len(seen) == 1
