@@ -113,7 +113,9 @@ class acgb200_info(C.Structure):
                                                                                   ("last_d2h_ms", C.c_double),
                                                                                   ("last_blas_ms", C.c_double),
                                                                                   ("spmv_compressed_tiles", C.c_int),
-                                                                                  ("spmv_min_bytes", C.c_int64)]
+                                                                                  ("spmv_min_bytes", C.c_int64),
+                                                                                  ("spmv_nmedium", C.c_int),
+                                                                                  ("pad0", C.c_int)]
 
 
 class acgb200_mtxinfo(C.Structure):
@@ -272,7 +274,8 @@ def spmv_plan_host(rowptr, colidx=None) -> dict:
     compressed = (t4[:, 1] & 0x40000000) != 0
     t4[:, 1] &= ~np.int32(0x40000000)
     return dict(lanes=inf.spmv_lanes_per_row, rows_cap=inf.spmv_rows_cap, nnz_cap=inf.spmv_nnz_cap,
-                stages=inf.spmv_stages, tiles=t4, longrows=longrows[:nl].copy(), compressed=compressed)
+                stages=inf.spmv_stages, tiles=t4, longrows=longrows[:nl].copy(), compressed=compressed,
+                nmedium=inf.spmv_nmedium)
 
 
 def _view(ptr, n, dtype):

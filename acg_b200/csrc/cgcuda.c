@@ -55,6 +55,7 @@ static struct {
     int blas1_ctas;     /* CTAs per SM of the fused BLAS-1 kernels (0 = one full wave, from the occupancy) */
     int pdl;            /* 1: programmatic dependent launch along the iteration chain (opt-in) */
     int pcg_fused;      /* 1: pipelined CG as one kernel per iteration (SpMV + update fused, opt-in) */
+    int spmv_medium;    /* > 0: rows longer than this (and shorter than a tile) get a warp each (opt-in) */
     int loaded;
 } cfg = { .check_every = 8, .graph = 1, .redstream = 1, .p2p = 1, .p2p_fuse = 1 };
 
@@ -81,6 +82,7 @@ static void cfg_load(void)
     if (cfg.check_every < 1) cfg.check_every = 1;
     if ((s = getenv("ACGB200_PDL"))) cfg.pdl = atoi(s);
     if ((s = getenv("ACGB200_PCG_FUSED"))) cfg.pcg_fused = atoi(s);
+    if ((s = getenv("ACGB200_SPMV_MEDIUM"))) cfg.spmv_medium = atoi(s);
     acgb200_blas1_set_ctas_per_sm(cfg.blas1_ctas);
     acgb200_set_pdl(cfg.pdl);
 }
@@ -105,6 +107,7 @@ int acgb200_set_option(const char *key, int value)
     else if (!strcmp(key, "blas1_ctas")) { cfg.blas1_ctas = value; acgb200_blas1_set_ctas_per_sm(value); }
     else if (!strcmp(key, "pdl")) { cfg.pdl = value; acgb200_set_pdl(value); }
     else if (!strcmp(key, "pcg_fused")) cfg.pcg_fused = value;
+    else if (!strcmp(key, "spmv_medium")) cfg.spmv_medium = value < 0 ? 0 : value;
     else return ACG_ERR_INVALID_VALUE;
     return ACG_SUCCESS;
 }
@@ -227,7 +230,7 @@ void acgsolvercuda_free(struct acgsolvercuda *cg)
         if (pv->have_redcomm && pv->redcomm.ncclcomm) ncclCommDestroy(pv->redcomm.ncclcomm);
         for (int i = 0; i < 3; i++) if (pv->graph[i]) cudaGraphExecDestroy(pv->graph[i]);
         cudaFree(pv->d_w2);
-        cudaFree(pv->plan.d_tiles); cudaFree(pv->plan.d_longrows); cudaFree(pv->plan.d_long_scratch);
+        cudaFree(pv->plan.d_tiles); cudaFree(pv->plan.d_longrows); cudaFree(pv->plan.d_long_scratch); cudaFree(pv->plan.d_medrows);
         cudaFree(pv->plan.d_patptr); cudaFree(pv->plan.d_patoff); cudaFree(pv->plan.d_patid);
         cudaFree(pv->d_st);
         cudaFreeHost(pv->h_ctrl); cudaFreeHost(pv->h_st);
@@ -252,18 +255,21 @@ void acgsolvercuda_free(struct acgsolvercuda *cg)
  * most rows_cap rows and nnz_cap nonzeros per tile; rows longer than nnz_cap go
  * to the long-row list.  Host-only, no CUDA: testable without a device. */
 static int cut_tiles(const struct acgb200_spmvplan *pl, const int64_t *rowptr,
-                     struct acgb200_tile *tiles, int *ntiles, int *longrows, int *nlong)
+                     struct acgb200_tile *tiles, int *ntiles, int *longrows, int *nlong, int *medrows, int *nmed)
 {
     const int n = pl->nrows;
-    int nt = 0, nl = 0, r = 0;
+    /* rows above `out` leave the tiles: the long ones (> nnz_cap) always, the medium ones on request */
+    const int64_t out = pl->med_thr > 0 && pl->med_thr < pl->nnz_cap ? pl->med_thr : pl->nnz_cap;
+    int nt = 0, nl = 0, nm = 0, r = 0;
     while (r < n) {
         int64_t len = rowptr[r + 1] - rowptr[r];
         if (len > pl->nnz_cap) { longrows[nl++] = r++; continue; }
+        if (len > out) { medrows[nm++] = r++; continue; }
         const int start = r;
         int64_t cnt = 0;
         while (r < n && r - start < pl->rows_cap) {
             len = rowptr[r + 1] - rowptr[r];
-            if (len > pl->nnz_cap || cnt + len > pl->nnz_cap) break;
+            if (len > out || cnt + len > pl->nnz_cap) break;
             cnt += len; r++;
         }
         const int64_t kb = rowptr[start], ke = rowptr[r];
@@ -275,7 +281,7 @@ static int cut_tiles(const struct acgb200_spmvplan *pl, const int64_t *rowptr,
         tiles[nt].nnz_al = (int) (((ke - k_al) + 3) & ~(int64_t) 3);
         nt++;
     }
-    *ntiles = nt; *nlong = nl;
+    *ntiles = nt; *nlong = nl; *nmed = nm;
     return ACG_SUCCESS;
 }
 
@@ -284,12 +290,13 @@ static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr, const
     const int n = pl->nrows;
     struct acgb200_tile *tiles = malloc(((size_t) n + 1) * sizeof(*tiles));
     int *longrows = malloc(((size_t) n + 1) * sizeof(*longrows));
-    if (!tiles || !longrows) { free(tiles); free(longrows); return ACG_ERR_ERRNO; }
-    int nt = 0, nl = 0;
-    int err = cut_tiles(pl, rowptr, tiles, &nt, longrows, &nl);
-    if (err) { free(tiles); free(longrows); return err; }
-    pl->ntiles = nt; pl->nlong = nl;
-    pl->d_tiles = NULL; pl->d_longrows = NULL; pl->d_long_scratch = NULL;
+    int *medrows = malloc(((size_t) n + 1) * sizeof(*medrows));
+    if (!tiles || !longrows || !medrows) { free(tiles); free(longrows); free(medrows); return ACG_ERR_ERRNO; }
+    int nt = 0, nl = 0, nm = 0;
+    int err = cut_tiles(pl, rowptr, tiles, &nt, longrows, &nl, medrows, &nm);
+    if (err) { free(tiles); free(longrows); free(medrows); return err; }
+    pl->ntiles = nt; pl->nlong = nl; pl->nmed = nm;
+    pl->d_tiles = NULL; pl->d_longrows = NULL; pl->d_long_scratch = NULL; pl->d_medrows = NULL;
     cudaError_t e = cudaSuccess;
     pl->compressed = 0; pl->ncompressed_tiles = 0;
     if (pat && pat->npat > 0) {
@@ -323,7 +330,11 @@ static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr, const
         if (!e) e = cudaMemcpy(pl->d_longrows, longrows, (size_t) nl * sizeof(int), cudaMemcpyHostToDevice);
         if (!e) e = cudaMalloc((void **) &pl->d_long_scratch, (size_t) nl * (size_t) pl->long_chunks * sizeof(double));
     }
-    free(tiles); free(longrows);
+    if (!e && nm > 0) {
+        e = cudaMalloc((void **) &pl->d_medrows, (size_t) nm * sizeof(int));
+        if (!e) e = cudaMemcpy(pl->d_medrows, medrows, (size_t) nm * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    free(tiles); free(longrows); free(medrows);
     CU(e);
     return ACG_SUCCESS;
 }
@@ -366,11 +377,13 @@ int acgb200_spmv_plan_host2(int nrows, const int64_t *rowptr, const int *colidx,
     if (cfg.spmv_lanes > 0) pl.lanes_per_row = cfg.spmv_lanes;
     if (cfg.spmv_nnz_cap > 0) pl.nnz_cap = cfg.spmv_nnz_cap;
     if (cfg.spmv_rows_cap > 0) pl.rows_cap = cfg.spmv_rows_cap;
+    pl.med_thr = cfg.spmv_medium;
     struct acgb200_tile *tiles = malloc(((size_t) nrows + 1) * sizeof(*tiles));
     int *lr = malloc(((size_t) nrows + 1) * sizeof(*lr));
-    if (!tiles || !lr) { free(tiles); free(lr); return ACG_ERR_ERRNO; }
-    int nt = 0, nl = 0, ncomp = 0;
-    int err = cut_tiles(&pl, rowptr, tiles, &nt, lr, &nl);
+    int *mr = malloc(((size_t) nrows + 1) * sizeof(*mr));
+    if (!tiles || !lr || !mr) { free(tiles); free(lr); free(mr); return ACG_ERR_ERRNO; }
+    int nt = 0, nl = 0, nm = 0, ncomp = 0;
+    int err = cut_tiles(&pl, rowptr, tiles, &nt, lr, &nl, mr, &nm);
     if (!err && (nt > maxtiles || nl > maxlong)) err = ACG_ERR_NO_BUFFER_SPACE;
     if (!err && colidx) {
         struct acgb200_patterns pat;
@@ -396,8 +409,9 @@ int acgb200_spmv_plan_host2(int nrows, const int64_t *rowptr, const int *colidx,
         info->spmv_lanes_per_row = pl.lanes_per_row; info->spmv_rows_cap = pl.rows_cap;
         info->spmv_nnz_cap = pl.nnz_cap; info->spmv_stages = pl.nstages;
         info->spmv_ntiles = nt; info->spmv_nlong = nl; info->spmv_compressed_tiles = ncomp;
+        info->spmv_nmedium = nm;
     }
-    free(tiles); free(lr);
+    free(tiles); free(lr); free(mr);
     return err;
 }
 
@@ -572,6 +586,7 @@ static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, 
     if (cfg.spmv_stages > 0) pv->plan.nstages = cfg.spmv_stages > 8 ? 8 : cfg.spmv_stages;
     if (cfg.spmv_threads > 0) pv->plan.threads = cfg.spmv_threads;
     if (cfg.spmv_unroll > 0) pv->plan.unroll = cfg.spmv_unroll;
+    pv->plan.med_thr = cfg.spmv_medium;
     {
         struct acgb200_patterns pat;
         memset(&pat, 0, sizeof(pat));
@@ -668,11 +683,11 @@ static int apply_A(struct solvectx *c, const double *x_ro, double *x_halo, doubl
         a.p2p = pv->p2p.d_desc;
         a.od_rowoffset = pv->borderoff; a.od_nrows = pv->nborder;
         a.orowptr = cg->d_orowptr; a.ocolidx = cg->d_ocolidx; a.oa = cg->d_oa;
-        if (pub_ch >= 0 && pv->plan.nlong == 0) a.pub_ch = pub_ch;
+        if (pub_ch >= 0 && pv->plan.nlong == 0 && pv->plan.nmed == 0) a.pub_ch = pub_ch;
     }
     prof_mark(c, &pv->gemv);
     KL(acgb200_spmv_launch(&a, pv->stream));
-    c->launches += 1 + (pv->plan.nlong > 0 ? 2 : 0);
+    c->launches += 1 + (pv->plan.nlong > 0 ? 2 : 0) + (pv->plan.nmed > 0 ? 1 : 0);
     if (c->multi && !fused) {
         if (!peer) {
             OK(acghalo_exchange_cuda_end(cg->halo, cg->haloexchange, pv->nvec, x_halo, ACG_DOUBLE,
@@ -900,7 +915,7 @@ static int classic_iteration(struct solvectx *c, int k)
     if (peer) {
         /* (p,Ap) is published by the SpMV's last CTA; with long rows the dot is
          * only complete after the finishing kernel, so a separate post does it */
-        if (pv->plan.nlong > 0 || !pv->p2p.h_desc.fuse) OK(post(c, 1, -1, NULL, 0, &st->pap_loc[0], 1, 1, 0, 1));
+        if (pv->plan.nlong > 0 || pv->plan.nmed > 0 || !pv->p2p.h_desc.fuse) OK(post(c, 1, -1, NULL, 0, &st->pap_loc[0], 1, 1, 0, 1));
     } else OK(allreduce(c, &st->pap_loc[s], &st->pap[s], 1));
     prof_mark(c, &pv->blas);
     KL(acgb200_cg_update_r(n, st, 1, 1, c->multi, pv->p2p.d_desc && peer ? pv->p2p.d_desc : NULL, cg->d_t, cg->d_r, pv->stream));
@@ -1463,6 +1478,7 @@ int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info
     info->last_blas_ms = pv->last_blas_ms;
     info->num_sms = acgb200_num_sms();
     info->spmv_compressed_tiles = pv->plan.ncompressed_tiles;
+    info->spmv_nmedium = pv->plan.nmed;
     info->spmv_min_bytes = acgb200_spmv_min_bytes(&pv->plan);
     return ACG_SUCCESS;
 }

@@ -46,6 +46,12 @@ struct acgb200_spmvplan {
     struct acgb200_tile *d_tiles;    /* [ntiles] */
     int nlong;                       /* rows with more than nnz_cap nonzeros */
     int *d_longrows;                 /* [nlong] */
+    /* medium rows (opt-in, option "spmv_medium" = threshold): rows with more than med_thr and at most
+     * nnz_cap nonzeros are left out of the tiles and get one warp each (spmv_medium_kernel); inside a
+     * tile such a row would keep one G-lane group busy while the rest of the CTA idles */
+    int med_thr;                     /* 0: off */
+    int nmed;
+    int *d_medrows;                  /* [nmed] */
     double *d_long_scratch;          /* [nlong * long_chunks] partial sums of the long-row kernels */
     int grid;                        /* persistent grid size */
     int smem_bytes;                  /* dynamic shared memory per CTA */

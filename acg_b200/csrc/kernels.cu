@@ -969,6 +969,71 @@ __global__ void spmv_long_finish_kernel(int nlong, const int *longrows, int chun
     if (acc && (threadIdx.x & 31) == 0 && dot != 0.0) atomicAdd(acc, dot);
 }
 
+/* ---- medium rows: one warp per row, straight from global memory (opt-in) ----- */
+
+/*
+ * Rows that would monopolise one G-lane group of a tile (a few hundred to a
+ * couple of thousand nonzeros, the body of a power-law degree distribution) are
+ * taken out of the tiles by the planner when option "spmv_medium" is set and
+ * processed here: a warp walks its row with coalesced 32-wide accesses, four
+ * gathers in flight per lane, and applies the same epilogue as the tile kernel.
+ * Persistent grid, warps stride over the list; one atomic per CTA for the dot.
+ */
+__global__ void __launch_bounds__(256)
+spmv_medium_kernel(int nmed, const int *medrows,
+                   const int *rowptr, const int *colidx, const double *a, const double *x,
+                   double *y, const double *b, double *acc, int dotrows, int mode,
+                   const acgb200_ctrl *cin, const acgb200_devstate *st,
+                   const acgb200_p2pdev *p2p, int od_rowoffset, int od_nrows,
+                   const int *orowptr, const int *ocolidx, const double *oa)
+{
+    __shared__ double red[8];
+    const Gate g = gate_read(cin, st);
+    if (!g.active) return;
+    const double *xg = NULL;
+    if (p2p) {
+        p2p_wait_halo(p2p, p2p->hbase + (unsigned long long) g.iter);
+        xg = p2p->my_ghost[g.iter & 1] - od_nrows;
+    }
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    double dot = 0.0;
+    for (int i = warp; i < nmed; i += nwarps) {
+        const int row = medrows[i];
+        const int kb = rowptr[row], ke = rowptr[row + 1];
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int k = kb + lane;
+        for (; k + 96 < ke; k += 128) {
+            const double x0 = __ldg(x + colidx[k]), x1 = __ldg(x + colidx[k + 32]);
+            const double x2 = __ldg(x + colidx[k + 64]), x3 = __ldg(x + colidx[k + 96]);
+            s0 = fma(a[k], x0, s0); s1 = fma(a[k + 32], x1, s1);
+            s2 = fma(a[k + 64], x2, s2); s3 = fma(a[k + 96], x3, s3);
+        }
+        for (; k < ke; k += 32) s0 = fma(a[k], __ldg(x + colidx[k]), s0);
+        double sum = (s0 + s1) + (s2 + s3);
+        if (xg && row >= od_rowoffset) {
+            const int ob = row - od_rowoffset;
+            for (int j = orowptr[ob] + lane; j < orowptr[ob + 1]; j += 32) sum = fma(oa[j], xg[ocolidx[j]], sum);
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) {
+            if (mode == SPMV_R_B_AX) {
+                const double v = b[row] - sum;
+                y[row] = v;
+                if (row < dotrows) dot = fma(v, v, dot);
+            } else {
+                y[row] = sum;
+                if (mode == SPMV_Y_AX_DOT && row < dotrows) dot = fma(x[row], sum, dot);
+            }
+        }
+    }
+    if (acc) {
+        dot = block_sum(dot, red);
+        if (threadIdx.x == 0 && dot != 0.0) atomicAdd(acc, dot);
+    }
+}
+
 /* ---- border x ghost block: thread per border row, direct from global -------- */
 
 __global__ void __launch_bounds__(256)
@@ -1435,6 +1500,17 @@ extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t strea
         cudaError_t err = cudaGetLastError();
         if (err) return (int) err;
     }
+    if (pl->nmed > 0) {
+        long long grid = ((long long) pl->nmed + 7) / 8;
+        const long long cap = (long long) acgb200_num_sms() * 8;
+        if (grid > cap) grid = cap;
+        spmv_medium_kernel<<<(int) grid, 256, 0, stream>>>(
+            pl->nmed, pl->d_medrows, a->rowptr, a->colidx, a->a, a->x, a->y, a->b, a->acc,
+            a->dotrows, a->mode, a->ctrl_in, a->st,
+            a->p2p, a->od_rowoffset, a->od_nrows, a->orowptr, a->ocolidx, a->oa);
+        cudaError_t err = cudaGetLastError();
+        if (err) return (int) err;
+    }
     if (pl->nlong > 0) {
         if (!pl->d_long_scratch) return (int) cudaErrorInvalidValue;
         spmv_long_partial_kernel<<<pl->nlong * pl->long_chunks, 256, 0, stream>>>(
@@ -1465,7 +1541,7 @@ static fused_fn fused_variant(int G, int T, int U, int compressed)
 extern "C" int acgb200_pcg_fused_grid(const acgb200_spmvplan *pl)
 {
     fused_fn fn = fused_variant(pl->lanes_per_row, pl->threads, pl->unroll, pl->compressed);
-    if (!fn || pl->nlong > 0 || pl->rows_cap > pl->threads / pl->lanes_per_row) return 0;
+    if (!fn || pl->nlong > 0 || pl->nmed > 0 || pl->rows_cap > pl->threads / pl->lanes_per_row) return 0;
     if (cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes) != cudaSuccess) return 0;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) fn, pl->threads, pl->smem_bytes) != cudaSuccess || per_sm < 1)

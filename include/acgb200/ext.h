@@ -44,6 +44,8 @@ struct acgb200_info {
     double last_blas_ms;        /* device time of the fused vector-update kernels of the last solve (profile=1) */
     int spmv_compressed_tiles;  /* tiles that carry no column indices (option "spmv_compress") */
     int64_t spmv_min_bytes;     /* bytes one SpMV launch must move at least, given the plan */
+    int spmv_nmedium;           /* rows handled one warp each (option "spmv_medium") */
+    int pad0;
 };
 ACG_API int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info);
 

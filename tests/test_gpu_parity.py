@@ -400,3 +400,30 @@ def test_fused_pipelined_iteration_matches_oracle(name, gen, compress, ab, oracl
     finally:
         ab.set_option("pcg_fused", 0)
     cg.free()
+
+
+@pytest.mark.skipif(os.environ.get("ACGB200_TEST_EXPERIMENTAL") != "1",
+                    reason="the warp-per-row kernel for medium rows is opt-in and not yet validated on hardware "
+                           "(set ACGB200_TEST_EXPERIMENTAL=1)")
+def test_medium_row_kernel_matches_oracle(ab, oracle):
+    """Option spmv_medium (spmv_medium_kernel): same product and same CG iterates on a power-law matrix."""
+    n, r, c, v = mg.rmat_spd(30000, 600000, seed=8)
+    ab.set_option("spmv_medium", 96)
+    try:
+        A, cg = _solver(ab, n, r, c, v)
+    finally:
+        ab.set_option("spmv_medium", 0)
+    assert cg.info()["spmv_nmedium"] > 0 and cg.info()["spmv_nlong"] > 0
+    csr = (A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy())
+    x = np.random.default_rng(1).standard_normal(n)
+    y, _ = cg.spmv(x)
+    want = oracle.dsymv(csr, 1.0, x, 0.0, np.zeros(n))
+    scale = oracle.dsymv((csr[0], csr[1], np.abs(csr[2])), 1.0, np.abs(x), 0.0, np.zeros(n))
+    assert np.all(np.abs(y - want) <= SPMV_RTOL * scale + 1e-300)
+    b = A.vector(); b.x[:] = np.random.default_rng(2).standard_normal(n)
+    for method, orc in (("solvempi", oracle.cg), ("solve_pipelined", oracle.cg_pipelined)):
+        ref = orc(csr, b.x, maxits=10, rtol=0.0)
+        xs = A.vector()
+        assert getattr(cg, method)(b, xs, maxits=10) == 0
+        assert np.abs(xs.x - ref["x"]).max() <= 1e-9 * np.abs(ref["x"]).max()
+    cg.free()

@@ -499,3 +499,32 @@ def test_rmat_generator(ab, oracle):
         assert out.returncode == 0, out.stderr[-2000:]
         seen.add(out.stdout.strip().splitlines()[-1])
     assert len(seen) == 1
+
+
+def test_medium_rows_leave_the_tiles(ab):
+    """Option spmv_medium = threshold: rows with threshold < length <= nnz_cap are planned for the
+    warp-per-row kernel; tiles, medium rows and long rows partition the rows, tiles keep their
+    bounds, and with the option off the plan is what it always was."""
+    A = ab.SymCsrMatrix.rmat_spd(60000, 600000, seed=3).dsymv_init(0.0)
+    lens = np.diff(A.frowptr)
+    base = ab.spmv_plan_host(A.frowptr)
+    assert base["nmedium"] == 0
+    for thr in (64, 200):
+        ab.set_option("spmv_medium", thr)
+        try:
+            pl = ab.spmv_plan_host(A.frowptr)
+        finally:
+            ab.set_option("spmv_medium", 0)
+        cap = pl["nnz_cap"]
+        assert pl["nmedium"] == int(((lens > thr) & (lens <= cap)).sum()) > 0
+        assert np.array_equal(pl["longrows"], np.nonzero(lens > cap)[0])
+        covered = np.zeros(len(lens), bool)
+        for row_begin, nrows, k_al, nnz_al in pl["tiles"]:
+            assert not covered[row_begin:row_begin + nrows].any()
+            covered[row_begin:row_begin + nrows] = True
+            assert lens[row_begin:row_begin + nrows].max() <= thr and nrows <= pl["rows_cap"]
+            assert lens[row_begin:row_begin + nrows].sum() <= cap
+        assert covered.sum() + pl["nmedium"] + len(pl["longrows"]) == len(lens)
+        assert not covered[lens > thr].any()
+    again = ab.spmv_plan_host(A.frowptr)
+    assert np.array_equal(again["tiles"], base["tiles"])
