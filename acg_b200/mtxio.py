@@ -47,3 +47,33 @@ def write_comm_matrix(path: str, counts) -> None:
         f.write(f"{counts.shape[0]} {counts.shape[1]} {len(p)}\n")
         for i, j in zip(p, q):
             f.write(f"{i + 1} {j + 1} {int(counts[i, j])}\n")
+
+
+def write_rowparts(path: str, rowparts) -> None:
+    """Row -> part map as the reference's mtxpartition writes it and its driver reads it
+    with --partition=FILE (cuda/acg-cuda.c:1542-1640): "vector array integer general",
+    one 1-based part number per row."""
+    rowparts = np.asarray(rowparts)
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket vector array integer general\n")
+        f.write(f"{len(rowparts)}\n")
+        f.write("\n".join(str(int(p) + 1) for p in rowparts))
+        f.write("\n")
+
+
+def read_rowparts(path: str) -> np.ndarray:
+    """Inverse of write_rowparts; also accepts "matrix array integer general" with one column."""
+    with open(path) as f:
+        head = f.readline().split()
+        if len(head) < 5 or head[0] != "%%MatrixMarket" or head[2] != "array" or head[1] not in ("vector", "matrix"):
+            raise ValueError(f"{path}: expected a Matrix Market vector in array format")
+        line = f.readline()
+        while line.startswith("%"):
+            line = f.readline()
+        dims = [int(t) for t in line.split()]
+        if head[1] == "matrix" and (len(dims) != 2 or dims[1] != 1):
+            raise ValueError(f"{path}: expected one column")
+        vals = np.array(f.read().split(), dtype=np.int64)
+    if len(vals) != dims[0]:
+        raise ValueError(f"{path}: {dims[0]} entries announced, {len(vals)} found")
+    return (vals - 1).astype(np.int32)
