@@ -24,7 +24,26 @@ def _cuda_device_count():
         return 0
 
 
+# Order of a run: the parity core first (ABI, oracle pins, host structures, GPU parity through
+# the C-ABI, multi-rank), then the callers around it (reference driver, example program, Python
+# command line).  Within a file, tests that have not had their first run on hardware yet go last,
+# so that under `-x` a problem in a new test cannot hide the verdict of the established ones.
+_FILE_ORDER = ["test_abi.py", "test_oracle_pin.py", "test_host_structs.py", "test_mtxfile.py", "test_gpu_parity.py",
+               "test_multirank.py", "test_reference_driver.py", "test_example_program.py", "test_driver_py.py"]
+_FIRST_RUN_PENDING = ("test_spmv_ragged_rows", "test_device_and_plain_entry_points", "test_power_law_properties",
+                      "test_stock_reference_gpu_solver_pins_the_oracle", "test_driver_manufactured_solution",
+                      "acg-device")
+
+
+def _order_key(item):
+    fname = os.path.basename(str(item.fspath))
+    rank = _FILE_ORDER.index(fname) if fname in _FILE_ORDER else len(_FILE_ORDER)
+    pending = any(tag in item.nodeid for tag in _FIRST_RUN_PENDING)
+    return (rank, pending)
+
+
 def pytest_collection_modifyitems(config, items):
+    items.sort(key=_order_key)          # stable: definition order is kept inside each group
     # `-m gpu` on a box without a device must fail loudly, not skip silently:
     # only skip when the run did not ask for gpu tests explicitly.
     if _cuda_device_count() > 0:
