@@ -37,7 +37,8 @@ def parse_args(argv=None):
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--epsilon", type=float, default=0.0, help="shift added to the diagonal (acgsymcsrmatrix_dsymv_init)")
     ap.add_argument("--partition", default="rows",
-                    help="rows (contiguous blocks), metis, or a Matrix Market vector file with 1-based part numbers "
+                    help="rows (contiguous blocks of equal row count), nnz (contiguous blocks of equal nonzero count; "
+                         "rank 0 reads the matrix once), metis, or a Matrix Market vector file with 1-based part numbers "
                          "(mtxpartition output, as the reference's --partition=FILE)")
     ap.add_argument("--manufactured-solution", action="store_true",
                     help="random unit x*, b = A x*, report ||x - x*|| (cuda/acg-cuda.c:1969-1979, :2376-2385)")
@@ -56,11 +57,12 @@ def row_partition(args, n, rank, world):
     from .api import SymCsrMatrix
     if args.partition == "rows":
         return abdist.contiguous_partition(n, world)
-    if args.partition == "metis":
+    if args.partition in ("metis", "nnz"):
         box = [None]
         if rank == 0:
             whole = SymCsrMatrix.read_mtx(args.A, binary=True)
-            box[0] = whole.partition_rows(world, kway=False, seed=args.seed)[0]
+            box[0] = (whole.partition_rows(world, kway=False, seed=args.seed)[0] if args.partition == "metis"
+                      else abdist.balanced_rows_partition(whole, world))
             whole.free()
         dist.broadcast_object_list(box, src=0)
         return np.ascontiguousarray(box[0], np.int32)

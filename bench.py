@@ -216,7 +216,7 @@ def main():
                           f"tolerances off", "n": w["N"] if w["kind"] == "rmat" else w["N"] ** 3,
               "solver": solver, "iters_per_step": args.iters,
               "partition": (f"{world} parts, " + ("METIS recursive" if args.partition == "metis" else
-                                                  ("contiguous row blocks" if w["kind"] == "rmat" else "geometric blocks")))
+                                                  ("contiguous row blocks of equal nonzero count" if w["kind"] == "rmat" else "geometric blocks")))
                            if world > 1 else "none",
               "l2": None}
     k = 27 if w["kind"] == "27pt" else 7
@@ -255,7 +255,8 @@ def main():
         # power-law graph: no geometry; every rank generates the (deterministic) matrix and keeps its part
         A = ab.SymCsrMatrix.rmat_spd(N, w["edges"], seed=42)
         if world > 1:
-            rowparts = A.partition_rows(world, seed=0)[0] if args.partition == "metis" else abdist.contiguous_partition(N, world)
+            rowparts = (A.partition_rows(world, seed=0)[0] if args.partition == "metis"
+                        else abdist.balanced_rows_partition(A, world))     # equal nonzeros, not equal rows
             parts = A.partition(world, rowparts)
             A.free()
             A = parts[rank]

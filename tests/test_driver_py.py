@@ -45,7 +45,7 @@ def test_rowparts_file_roundtrip(tmp_path):
     assert np.array_equal(mtxio.read_rowparts(path), rp)
 
 
-@pytest.mark.parametrize("partition", ["rows", "metis", "file"])
+@pytest.mark.parametrize("partition", ["rows", "nnz", "metis", "file"])
 def test_dry_run_decomposition(partition, ab, tmp_path):
     """Three processes read their parts from the binary file; the printed decomposition
     equals what partitioning the whole matrix gives, and the communication matrix file
@@ -56,6 +56,8 @@ def test_dry_run_decomposition(partition, ab, tmp_path):
     A = ab.SymCsrMatrix.init_real_double(n, r, c, v)
     if partition == "rows":
         rowparts, arg = abdist.contiguous_partition(n, 3), "rows"
+    elif partition == "nnz":
+        rowparts, arg = abdist.balanced_rows_partition(A, 3), "nnz"
     elif partition == "metis":
         rowparts, arg = A.partition_rows(3, kway=False, seed=1)[0], "metis"
     else:

@@ -528,3 +528,18 @@ def test_medium_rows_leave_the_tiles(ab):
         assert not covered[lens > thr].any()
     again = ab.spmv_plan_host(A.frowptr)
     assert np.array_equal(again["tiles"], base["tiles"])
+
+
+def test_balanced_rows_partition(ab):
+    """dist.balanced_rows_partition: contiguous blocks, every row assigned, nonzeros of the full
+    matrix per part within a few percent of each other even for a power-law matrix."""
+    from acg_b200 import dist as abdist
+    A = ab.SymCsrMatrix.rmat_spd(40000, 400000, seed=6)
+    rp = abdist.balanced_rows_partition(A, 5)
+    assert rp.min() == 0 and rp.max() == 4 and np.all(np.diff(rp) >= 0)
+    full = np.diff(A.dsymv_init(0.0).frowptr)
+    per = np.array([full[rp == p].sum() for p in range(5)])
+    assert per.sum() == A.c.fnpnzs
+    assert per.max() <= 1.05 * per.mean() + full.max()
+    rows = np.array([(rp == p).sum() for p in range(5)])
+    assert rows.max() > 3 * rows.min()                     # equal work is far from equal row counts here
