@@ -1418,41 +1418,7 @@ static inline int table_bytes(const acgb200_spmvplan *pl)
     return pl->compressed ? (((pl->npat + 1 + 3) & ~3) + ((pl->nentries + 3) & ~3)) * 4 : 0;
 }
 
-extern "C" int64_t acgb200_spmv_min_bytes(const acgb200_spmvplan *pl)
-{
-    /* values + (indices unless the tile is compressed) + per row: row pointer, y, x (+ pattern id) */
-    const double frac = pl->ntiles > 0 && pl->compressed ? (double) pl->ncompressed_tiles / pl->ntiles : 0.0;
-    return (int64_t) (pl->nnz * (8.0 + 4.0 * (1.0 - frac)) + pl->nrows * (20.0 + 2.0 * frac));
-}
-
-/*
- * Tile-plan heuristic, from sweeps on B200 (profiles/r01_spmv_sweep.md).  The
- * compute phase of a tile is a chain LDS(col) -> LDG(x) -> DFMA per nonzero and
- * ptxas keeps only ~2 gathers in flight per thread, so throughput comes from
- * resident warps: small stages (0.5-1k nonzeros, 6-11 KiB) let 10-18 CTAs of 128
- * threads share an SM.  Deeper TMA rings lower the CTA count and lose.
- *   lanes per row G : largest power of two with mean row length / G >= 4
- *   rows per tile   : T / G   (one pass per tile)
- *   nonzeros/tile   : rows * longest row for near-uniform rows (stencils),
- *                     else twice the mean -- rows longer than that take the
- *                     long-row path
- */
-extern "C" void acgb200_spmv_choose(acgb200_spmvplan *pl, int nrows, int64_t nnz, int64_t maxrowlen)
-{
-    const double avg = nrows > 0 ? (double) nnz / nrows : 0.0;
-    int G = 1;
-    while (G < 32 && avg / (2 * G) >= 4.0) G *= 2;
-    const int T = SPMV_THREADS;
-    const int rows_cap = T / G;
-    int64_t cap = (int64_t) (2.0 * avg * rows_cap) + 8;
-    if (maxrowlen > 0 && (double) maxrowlen <= 2.0 * avg + 8.0) cap = maxrowlen * rows_cap;
-    if (cap < 256) cap = 256;
-    if (cap > 6144) cap = 6144;
-    pl->nrows = nrows; pl->nnz = nnz;
-    pl->lanes_per_row = G; pl->rows_cap = rows_cap; pl->nnz_cap = (int) ((cap + 3) & ~(int64_t) 3);
-    pl->nstages = 2; pl->threads = T; pl->unroll = 8;
-    pl->long_chunks = 8;
-}
+/* acgb200_spmv_choose (tile-plan heuristic) and acgb200_spmv_min_bytes are host-only: plan.c */
 
 extern "C" int acgb200_spmv_configure(acgb200_spmvplan *pl)
 {

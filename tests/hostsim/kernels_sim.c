@@ -1,0 +1,361 @@
+/*
+ * kernels_sim.c -- TEST INFRASTRUCTURE ONLY.  Plain-C stand-ins for the launch
+ * interface of acg_b200/csrc/kernels.cu (internal.h), one thread, one GPU, no
+ * peer memory: each function does to the "device" arrays what the CUDA kernel
+ * of the same name does, including the iteration control (control words,
+ * parity-buffered scalars, accumulator housekeeping).  Together with
+ * cuda_mock.c this lets the CPU test-suite drive the real host code of the
+ * solver (cgcuda.c: set-up, warm-up, graph capture and replay, polling,
+ * convergence, reports) end to end and compare it with the oracle.  It says
+ * nothing about the CUDA kernels themselves -- those are tested on the B200.
+ *
+ * The SpMV walks the tile plan, the medium-row list and the long-row list the
+ * planner produced, so a row the plan forgot (or covered twice) shows up as a
+ * wrong product.
+ */
+#include "internal.h"
+#include "hostsim.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct gate { int iter, active; };
+
+static struct gate gate_read(const struct acgb200_ctrl *cin, const struct acgb200_devstate *st)
+{
+    struct gate g = { 0, 1 };
+    if (cin) { g.iter = cin->iter; g.active = cin->done == 0 && cin->iter < st->maxits; }
+    return g;
+}
+
+int acgb200_num_sms(void) { return 148; }
+void acgb200_blas1_set_ctas_per_sm(int v) { (void) v; }
+void acgb200_set_pdl(int v) { (void) v; }
+
+int acgb200_spmv_configure(struct acgb200_spmvplan *pl)
+{
+    pl->smem_bytes = 0;
+    pl->grid = pl->ntiles > 0 ? 1 : 1;
+    return 0;
+}
+
+/* ---- SpMV ------------------------------------------------------------------ */
+
+static double row_product(const struct acgb200_spmvargs *a, int row)
+{
+    double sum = 0.0;
+    for (int k = a->rowptr[row]; k < a->rowptr[row + 1]; k++) sum = fma(a->a[k], a->x[a->colidx[k]], sum);
+    return sum;
+}
+
+static void row_epilogue(const struct acgb200_spmvargs *a, int row, double sum, double *dot)
+{
+    if (a->mode == SPMV_R_B_AX) {
+        const double v = a->b[row] - sum;
+        a->y[row] = v;
+        if (row < a->dotrows) *dot = fma(v, v, *dot);
+    } else {
+        a->y[row] = sum;
+        if (a->mode == SPMV_Y_AX_DOT && row < a->dotrows) *dot = fma(a->x[row], sum, *dot);
+    }
+}
+
+static void spmv_exec(void *p)
+{
+    const struct acgb200_spmvargs *a = p;
+    const struct acgb200_spmvplan *pl = a->plan;
+    /* the tile kernel: control word forwarding and housekeeping, then the tiles */
+    if (pl->ntiles > 0 || a->ctrl_in) {
+        const struct gate g = gate_read(a->ctrl_in, a->st);
+        if (a->ctrl_in) {
+            *a->ctrl_out = *a->ctrl_in;
+            if (g.active) {
+                const int s = g.iter & 1;
+                if (a->housekeeping == 1) a->st->rr_loc[s ^ 1] = 0.0;
+                if (a->housekeeping == 2) { a->st->gd_loc[s ^ 1][0] = 0.0; a->st->gd_loc[s ^ 1][1] = 0.0; }
+            }
+        }
+        if (g.active) {
+            double dot = 0.0;
+            for (int t = 0; t < pl->ntiles; t++) {
+                const struct acgb200_tile tl = pl->d_tiles[t];
+                const int nrows = tl.nrows & ~ACGB200_TILE_COMPRESSED;
+                for (int r = tl.row_begin; r < tl.row_begin + nrows; r++) row_epilogue(a, r, row_product(a, r), &dot);
+            }
+            if (a->acc) *a->acc += dot;
+        }
+    }
+    /* medium and long rows: separate kernels, gated by the same incoming word */
+    for (int pass = 0; pass < 2; pass++) {
+        const int cnt = pass == 0 ? pl->nmed : pl->nlong;
+        const int *rows = pass == 0 ? pl->d_medrows : pl->d_longrows;
+        if (cnt <= 0) continue;
+        if (!gate_read(a->ctrl_in, a->st).active) continue;
+        double dot = 0.0;
+        for (int i = 0; i < cnt; i++) row_epilogue(a, rows[i], row_product(a, rows[i]), &dot);
+        if (a->acc) *a->acc += dot;
+    }
+}
+
+int acgb200_spmv_launch(const struct acgb200_spmvargs *a, cudaStream_t stream)
+{
+    (void) stream;
+    if (a->p2p) return 1;                       /* peer memory is not simulated */
+    if (a->plan->nlong > 0 && !a->plan->d_long_scratch) return 1;
+    return hostsim_run_or_record(spmv_exec, a, sizeof(*a));
+}
+
+int acgb200_offdiag_launch(const struct acgb200_offdiagargs *a, cudaStream_t stream)
+{
+    (void) stream;
+    return a->nrows <= 0 ? 0 : 1;               /* only distributed matrices have a border x ghost block */
+}
+
+int acgb200_comm_post(const struct acgb200_postargs *a, cudaStream_t stream) { (void) a; (void) stream; return 1; }
+
+/* ---- classic CG ------------------------------------------------------------- */
+
+struct upd_args {
+    int n; struct acgb200_devstate *st; int cin, cout, multi;
+    const double *q; double *z, *w, *t, *p, *r, *x;
+};
+
+static void update_r_exec(void *vp)
+{
+    const struct upd_args *a = vp;
+    struct acgb200_devstate *st = a->st;
+    const struct gate g = gate_read(&st->ctrl[a->cin], st);
+    if (a->cin != a->cout) st->ctrl[a->cout] = st->ctrl[a->cin];
+    if (!g.active) return;
+    const int s = g.iter & 1;
+    const double rr = a->multi ? st->rr[s] : st->rr_loc[s];
+    const double pap = a->multi ? st->pap[s] : st->pap_loc[s];
+    const double alpha = rr / pap;
+    double acc = 0.0;
+    for (int i = 0; i < a->n; i++) {
+        const double rv = fma(-alpha, a->t[i], a->r[i]);
+        a->r[i] = rv;
+        acc = fma(rv, rv, acc);
+    }
+    st->rr_loc[s ^ 1] += acc;
+}
+
+int acgb200_cg_update_r(int n, struct acgb200_devstate *st, int cin, int cout, int multi, struct acgb200_p2pdev *p2p,
+                        const double *t, double *r, cudaStream_t stream)
+{
+    (void) stream;
+    if (p2p) return 1;
+    struct upd_args a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.st = st; a.cin = cin; a.cout = cout; a.multi = multi; a.t = (double *) t; a.r = r;
+    return hostsim_run_or_record(update_r_exec, &a, sizeof(a));
+}
+
+static void update_xp_exec(void *vp)
+{
+    const struct upd_args *a = vp;
+    struct acgb200_devstate *st = a->st;
+    const struct gate g = gate_read(&st->ctrl[a->cin], st);
+    const int s = g.iter & 1;
+    const double rr = a->multi ? st->rr[s] : st->rr_loc[s];
+    const double rrn = a->multi ? st->rr[s ^ 1] : st->rr_loc[s ^ 1];
+    const double pap = a->multi ? st->pap[s] : st->pap_loc[s];
+    struct acgb200_ctrl c = st->ctrl[a->cin];
+    if (g.active) {
+        c.iter = g.iter + 1;
+        if (st->tol > 0.0 && sqrt(rrn) < st->tol) { c.done = 1; st->final_rr = rrn; }
+        st->pap_loc[s ^ 1] = 0.0;
+    }
+    st->ctrl[a->cout] = c;
+    if (!g.active) return;
+    const double alpha = rr / pap, beta = rrn / rr;
+    for (int i = 0; i < a->n; i++) {
+        const double pv = a->p[i];
+        a->x[i] = fma(alpha, pv, a->x[i]);
+        a->p[i] = fma(beta, pv, a->r[i]);
+    }
+}
+
+int acgb200_cg_update_xp(int n, struct acgb200_devstate *st, int cin, int cout, int multi, struct acgb200_p2pdev *p2p,
+                         const double *r, double *p, double *x, cudaStream_t stream)
+{
+    (void) stream;
+    if (p2p) return 1;
+    struct upd_args a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.st = st; a.cin = cin; a.cout = cout; a.multi = multi; a.r = (double *) r; a.p = p; a.x = x;
+    return hostsim_run_or_record(update_xp_exec, &a, sizeof(a));
+}
+
+/* ---- pipelined CG ------------------------------------------------------------ */
+
+static void pcg_update_exec(void *vp)
+{
+    const struct upd_args *a = vp;
+    struct acgb200_devstate *st = a->st;
+    const struct gate g = gate_read(&st->ctrl[a->cin], st);
+    const int s = g.iter & 1;
+    const double gamma = a->multi ? st->gd[s][0] : st->gd_loc[s][0];
+    const double delta = a->multi ? st->gd[s][1] : st->gd_loc[s][1];
+    const double gamma_prev = st->prev[s][0], alpha_prev = st->prev[s][1];
+    const int conv = st->tol > 0.0 && sqrt(gamma) < st->tol;
+    const double beta = gamma / gamma_prev;
+    const double alpha = gamma / (delta - beta * gamma / alpha_prev);
+    struct acgb200_ctrl c = st->ctrl[a->cin];
+    if (g.active) {
+        if (conv) { c.done = 1; st->final_rr = gamma; }
+        else { c.iter = g.iter + 1; st->prev[s ^ 1][0] = gamma; st->prev[s ^ 1][1] = alpha; }
+    }
+    st->ctrl[a->cout] = c;
+    if (!g.active || conv) return;
+    double g2 = 0.0, d2 = 0.0;
+    for (int i = 0; i < a->n; i++) {
+        const double zv = fma(beta, a->z[i], a->q[i]);
+        const double tv = fma(beta, a->t[i], a->w[i]);
+        const double pv = fma(beta, a->p[i], a->r[i]);
+        const double rv = fma(-alpha, tv, a->r[i]);
+        const double wv = fma(-alpha, zv, a->w[i]);
+        a->z[i] = zv; a->t[i] = tv; a->p[i] = pv;
+        a->x[i] = fma(alpha, pv, a->x[i]);
+        a->r[i] = rv; a->w[i] = wv;
+        g2 = fma(rv, rv, g2);
+        d2 = fma(wv, rv, d2);
+    }
+    st->gd_loc[s ^ 1][0] += g2;
+    st->gd_loc[s ^ 1][1] += d2;
+}
+
+int acgb200_pcg_update(int n, struct acgb200_devstate *st, int cin, int cout, int multi, struct acgb200_p2pdev *p2p,
+                       const double *q, double *z, double *w, double *t, double *p, double *r, double *x,
+                       cudaStream_t stream)
+{
+    (void) stream;
+    if (p2p) return 1;
+    struct upd_args a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.st = st; a.cin = cin; a.cout = cout; a.multi = multi;
+    a.q = q; a.z = z; a.w = w; a.t = t; a.p = p; a.r = r; a.x = x;
+    return hostsim_run_or_record(pcg_update_exec, &a, sizeof(a));
+}
+
+/* ---- pipelined CG, one kernel per iteration ----------------------------------- */
+
+struct fused_args {
+    struct acgb200_spmvargs sp;
+    int cin, multi;
+    double *z, *t, *p, *r, *x, *w0, *w1;
+};
+
+int acgb200_pcg_fused_grid(const struct acgb200_spmvplan *pl)
+{
+    if (pl->nlong > 0 || pl->nmed > 0 || pl->threads != 128 || pl->unroll != 8 ||
+        pl->rows_cap > pl->threads / pl->lanes_per_row) return 0;
+    return 1;
+}
+
+static void fused_exec(void *vp)
+{
+    const struct fused_args *a = vp;
+    const struct acgb200_spmvplan *pl = a->sp.plan;
+    struct acgb200_devstate *st = a->sp.st;
+    const struct gate g = gate_read(&st->ctrl[a->cin], st);
+    const int s = g.iter & 1;
+    const double gamma = a->multi ? st->gd[s][0] : st->gd_loc[s][0];
+    const double delta = a->multi ? st->gd[s][1] : st->gd_loc[s][1];
+    const double gamma_prev = st->prev[s][0], alpha_prev = st->prev[s][1];
+    const int conv = st->tol > 0.0 && sqrt(gamma) < st->tol;
+    const double beta = gamma / gamma_prev;
+    const double alpha = gamma / (delta - beta * gamma / alpha_prev);
+    struct acgb200_ctrl c = st->ctrl[a->cin];
+    if (g.active) {
+        st->gd[s][0] = gamma; st->gd[s][1] = delta;
+        if (conv) { c.done = 1; st->final_rr = gamma; }
+        else { c.iter = g.iter + 1; st->prev[s ^ 1][0] = gamma; st->prev[s ^ 1][1] = alpha; }
+    }
+    st->ctrl[a->cin ^ 1] = c;
+    if (!g.active || conv) return;
+    const double *wold = s ? a->w1 : a->w0;
+    double *wnew = s ? a->w0 : a->w1;
+    double g2 = 0.0, d2 = 0.0;
+    for (int t = 0; t < pl->ntiles; t++) {
+        const struct acgb200_tile tl = pl->d_tiles[t];
+        const int nrows = tl.nrows & ~ACGB200_TILE_COMPRESSED;
+        for (int row = tl.row_begin; row < tl.row_begin + nrows; row++) {
+            double qv = 0.0;
+            for (int k = a->sp.rowptr[row]; k < a->sp.rowptr[row + 1]; k++) qv = fma(a->sp.a[k], wold[a->sp.colidx[k]], qv);
+            const double wv0 = wold[row], rv0 = a->r[row];
+            const double zv = fma(beta, a->z[row], qv);
+            const double tv = fma(beta, a->t[row], wv0);
+            const double pv = fma(beta, a->p[row], rv0);
+            const double rv = fma(-alpha, tv, rv0);
+            const double wv = fma(-alpha, zv, wv0);
+            a->z[row] = zv; a->t[row] = tv; a->p[row] = pv;
+            a->x[row] = fma(alpha, pv, a->x[row]);
+            a->r[row] = rv; wnew[row] = wv;
+            g2 = fma(rv, rv, g2);
+            d2 = fma(wv, rv, d2);
+        }
+    }
+    st->gd_loc[s ^ 1][0] += g2;
+    st->gd_loc[s ^ 1][1] += d2;
+    /* last CTA: clear the slot this launch read */
+    st->gd_loc[s][0] = 0.0; st->gd_loc[s][1] = 0.0;
+}
+
+int acgb200_pcg_fused_launch(const struct acgb200_spmvargs *sp, int grid, int cin, int multi,
+                             double *z, double *t, double *p, double *r, double *x, double *w0, double *w1,
+                             cudaStream_t stream)
+{
+    (void) stream;
+    if (grid < 1 || sp->p2p) return 1;
+    struct fused_args a;
+    memset(&a, 0, sizeof(a));
+    a.sp = *sp; a.cin = cin; a.multi = multi;
+    a.z = z; a.t = t; a.p = p; a.r = r; a.x = x; a.w0 = w0; a.w1 = w1;
+    return hostsim_run_or_record(fused_exec, &a, sizeof(a));
+}
+
+/* ---- set-up helpers ------------------------------------------------------------ */
+
+struct dot_args { int n; const double *x, *y; double *acc; int two; };
+
+static void dot_exec(void *vp)
+{
+    const struct dot_args *a = vp;
+    double g = 0.0, d = 0.0;
+    for (int i = 0; i < a->n; i++) {
+        if (a->two) { g = fma(a->x[i], a->x[i], g); d = fma(a->y[i], a->x[i], d); }
+        else g = fma(a->x[i], a->y[i], g);
+    }
+    a->acc[0] += g;
+    if (a->two) a->acc[1] += d;
+}
+
+int acgb200_dot(int n, const double *x, const double *y, double *acc, cudaStream_t stream)
+{
+    (void) stream;
+    struct dot_args a = { n, x, y, acc, 0 };
+    return hostsim_run_or_record(dot_exec, &a, sizeof(a));
+}
+
+int acgb200_dot2(int n, const double *r, const double *w, double *acc2, cudaStream_t stream)
+{
+    (void) stream;
+    struct dot_args a = { n, r, w, acc2, 1 };
+    return hostsim_run_or_record(dot_exec, &a, sizeof(a));
+}
+
+int acgb200_gather(int n, double *dst, const double *src, const int *idx, cudaStream_t stream)
+{
+    (void) stream;
+    for (int i = 0; i < n; i++) dst[i] = src[idx[i]];
+    return 0;
+}
+
+int acgb200_scatter(int n, const double *src, double *dst, const int *idx, cudaStream_t stream)
+{
+    (void) stream;
+    for (int i = 0; i < n; i++) dst[idx[i]] = src[i];
+    return 0;
+}

@@ -1,0 +1,97 @@
+"""Host logic of the solver (acg_b200/csrc/cgcuda.c: set-up, warm-up, iteration
+control, CUDA-graph capture and replay, polling, convergence, return codes,
+reports) driven end to end on a device stand-in -- tests/hostsim/: the library's
+own C sources built against a mock of the CUDA runtime and plain-C stand-ins of
+the kernels' launch interface -- and compared with the oracle.  This checks the
+code around the kernels, not the kernels (those are checked on the B200 by
+test_gpu_parity.py).  The stand-in lives under tests/, is never loaded by the
+product package, and runs in a subprocess."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIM = os.path.join(ROOT, "tests", "hostsim")
+
+
+@pytest.fixture(scope="module")
+def simlib():
+    p = subprocess.run(["make", "-C", SIM], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "warning" not in p.stderr
+    return os.path.join(SIM, "libacgb200_hostsim.so")
+
+
+def _run(spec):
+    p = subprocess.run([sys.executable, os.path.join(SIM, "run_sim.py"), json.dumps(spec)], capture_output=True, text=True,
+                       timeout=600, env=dict(os.environ, OMP_NUM_THREADS="2"))
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    return json.loads(p.stdout.strip().splitlines()[-1])
+
+
+def _check(out, xtol=1e-10):
+    assert out["spmv_err"] < 1e-13 and out["report_ok"]
+    for i, r in enumerate(out["runs"]):
+        assert r["code"] == r["ref_code"], r
+        assert r["its"] == r["ref_its"], r
+        assert r["nsolves"] == i + 1
+        assert r["r0nrm2"] == pytest.approx(r["ref_r0nrm2"], rel=1e-13)
+        assert r["rnrm2"] == pytest.approx(r["ref_rnrm2"], rel=1e-6, abs=1e-12 * r["ref_r0nrm2"]), r
+        assert r["xerr"] < xtol, r
+
+
+RUNS = [{"method": "solvempi", "maxits": 200, "rtol": 1e-9, "warmup": 2},
+        {"method": "solve_pipelined", "maxits": 200, "rtol": 1e-9, "warmup": 1},
+        {"method": "solvempi", "maxits": 0}, {"method": "solvempi", "maxits": 1}, {"method": "solvempi", "maxits": 7},
+        {"method": "solve_pipelined", "maxits": 1}, {"method": "solve_pipelined", "maxits": 2},
+        {"method": "solve_pipelined", "maxits": 5}, {"method": "solve_pipelined", "maxits": 12},
+        {"method": "solvempi", "maxits": 3, "rtol": 1e-30}, {"method": "solve_pipelined", "maxits": 2, "rtol": 1e-30},
+        {"method": "solve_device", "maxits": 9}, {"method": "solve_device_pipelined", "maxits": 8}]
+
+
+@pytest.mark.parametrize("matrix", ["27pt", "7pt"])
+@pytest.mark.parametrize("graph", [1, 0], ids=["graph-replay", "direct"])
+def test_default_loops(matrix, graph, simlib):
+    """Classic and pipelined loops as shipped: tolerances on and off, odd and even iteration
+    counts (below and above the graph threshold), not-converged return code, warm-up, several
+    solves on one solver, with and without graph replay."""
+    out = _run({"matrix": matrix, "options": {"graph": graph}, "runs": RUNS})
+    _check(out)
+    launches = {(r["method"], r["maxits"]): r["launches"] for r in out["runs"]}
+    # 3 kernels per classic iteration, 2 per pipelined one, plus the set-up products (r0; r0 and w0)
+    assert launches[("solvempi", 7)] == 3 * 7 + 1 and launches[("solve_pipelined", 12)] == 2 * 12 + 2
+
+
+def test_one_kernel_pipelined_iteration(simlib):
+    """Option pcg_fused: the control words alternate, the accumulator slot is cleared by the
+    launch that read it, gamma of the last tested iterate is found where the host looks for it."""
+    out = _run({"matrix": "27pt", "options": {"pcg_fused": 1}, "runs": RUNS})
+    _check(out)
+    launches = {(r["method"], r["maxits"]): r["launches"] for r in out["runs"]}
+    assert launches[("solve_pipelined", 12)] == 12 + 2 and launches[("solve_pipelined", 1)] == 1 + 2
+    assert launches[("solvempi", 7)] == 3 * 7 + 1            # the classic loop is untouched by the option
+
+
+@pytest.mark.parametrize("options", [{}, {"spmv_medium": 64}, {"spmv_medium": 64, "pcg_fused": 1}],
+                         ids=["plain", "medium-rows", "medium-rows+fused-requested"])
+def test_power_law_rows(options, simlib):
+    """Long rows (and, on request, medium rows) leave the tiles; every row is still computed
+    exactly once; the one-kernel iteration steps aside when such rows exist."""
+    spec = {"matrix": "rmat", "options": options,
+            "runs": [{"method": "solvempi", "maxits": 10}, {"method": "solve_pipelined", "maxits": 11},
+                     {"method": "solve_pipelined", "maxits": 6, "warmup": 2}]}
+    out = _run(spec)
+    _check(out, xtol=1e-8)
+    assert out["nlong"] > 0
+    assert (out["nmedium"] > 0) == ("spmv_medium" in options)
+    two_kernel = [r["launches"] for r in out["runs"] if r["method"] == "solve_pipelined"]
+    assert two_kernel[0] > 2 * 11                             # SpMV (+ row-list kernels) + update per iteration
+
+
+def test_tiny_system(simlib):
+    out = _run({"matrix": "n3", "options": {"pcg_fused": 1},
+                "runs": [{"method": "solve_pipelined", "maxits": 2}, {"method": "solvempi", "maxits": 10, "rtol": 1e-12}]})
+    _check(out)
