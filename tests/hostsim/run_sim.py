@@ -51,8 +51,22 @@ def main():
             "rnrm2": float(cg.c.rnrm2), "ref_rnrm2": float(ref["rnrm2"]),
             "r0nrm2": float(cg.c.r0nrm2), "ref_r0nrm2": float(ref["r0nrm2"]), "bnrm2": float(cg.c.bnrm2),
             "xerr": float(np.abs(x.x - ref["x"]).max() / max(np.abs(ref["x"]).max(), 1e-300)),
-            "launches": int(cg.info()["last_launches"]), "nsolves": int(cg.c.nsolves)})
+            "launches": int(cg.info()["last_launches"]), "nsolves": int(cg.c.nsolves),
+            "spmv_count": int(cg.info()["last_spmv_count"]), "ngemv": int(cg.c.ngemv), "total_its": int(cg.c.ntotaliterations)})
     out["report_ok"] = "total solver time:" in cg.report()
+    # interface behaviour that needs no kernel at all
+    errs = {}
+    try:
+        cg.solvempi(b, A.vector(), maxits=5, diffatol=1e-3)
+    except ab.AcgError as e:
+        errs["diffatol"] = e.code
+    short = ab.Vector(max(n - 1, 1))
+    try:
+        cg.solvempi(short, A.vector(), maxits=5)
+    except ab.AcgError as e:
+        errs["short_b"] = e.code
+    out["errors"] = errs
+    out["nsolves_after_errors"] = int(cg.c.nsolves)
     cg.free()
     print(json.dumps(out))
 

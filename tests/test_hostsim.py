@@ -95,3 +95,33 @@ def test_tiny_system(simlib):
     out = _run({"matrix": "n3", "options": {"pcg_fused": 1},
                 "runs": [{"method": "solve_pipelined", "maxits": 2}, {"method": "solvempi", "maxits": 10, "rtol": 1e-12}]})
     _check(out)
+
+
+def test_profile_mode_and_poll_interval(simlib):
+    """profile=1 (what bench.py uses for the SpMV roofline): every SpMV of the solve window is
+    bracketed by events -- count = iterations + set-up products -- and graphs are not used;
+    the convergence poll interval does not change iteration counts or results."""
+    runs = [{"method": "solvempi", "maxits": 100, "rtol": 1e-9}, {"method": "solve_pipelined", "maxits": 100, "rtol": 1e-9},
+            {"method": "solve_pipelined", "maxits": 9}]
+    out = _run({"matrix": "7pt", "options": {"profile": 1}, "runs": runs})
+    _check(out)
+    for r in out["runs"]:
+        setup = 1 if r["method"] == "solvempi" else 2
+        if r["its"] == r["maxits"]:
+            assert r["spmv_count"] == r["its"] + setup       # tolerances off (bench.py's case): exact
+        else:
+            # the host enqueues ahead of the device-side stopping test: up to two poll intervals of
+            # launches that return at once are bracketed too
+            assert r["its"] + setup <= r["spmv_count"] <= r["its"] + setup + 16
+    base = [(r["its"], r["rnrm2"]) for r in out["runs"]]
+    for every in (1, 3, 64):
+        o = _run({"matrix": "7pt", "options": {"check_every": every}, "runs": runs})
+        _check(o)
+        assert [(r["its"], r["rnrm2"]) for r in o["runs"]] == base
+
+
+def test_rejected_calls_leave_the_counters_alone(simlib):
+    out = _run({"matrix": "7pt", "runs": [{"method": "solvempi", "maxits": 4}]})
+    assert out["errors"]["diffatol"] == 26                 # ACG_ERR_NOT_SUPPORTED (acg/cgcuda.c:424)
+    assert out["errors"]["short_b"] == 31                  # ACG_ERR_INDEX_OUT_OF_BOUNDS (acg/cgcuda.c:417-421)
+    assert out["nsolves_after_errors"] == 1
