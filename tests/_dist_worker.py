@@ -20,6 +20,11 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+if os.environ.get("ACGB200_TEST_HOSTSIM"):
+    # host-logic run on the device stand-in of tests/hostsim (CPU test-suite only): the binding
+    # is pointed at the stand-in before it loads anything
+    import acg_b200.api as _api                # noqa: E402
+    _api._LIBPATH = os.environ["ACGB200_TEST_HOSTSIM"]
 import acg_b200 as ab                      # noqa: E402
 from acg_b200 import dist as abdist        # noqa: E402
 from acg_b200 import matgen as mg          # noqa: E402
@@ -60,6 +65,12 @@ def local_matvec(m, h, xl):
     return y
 
 
+# exchange back-ends of the CG loop (options of acgb200_set_option on top of the defaults)
+BACKEND_OPTIONS = {"p2p-fused": {}, "p2p-unfused": {"p2p_fuse": 0}, "nccl": {"p2p": 0},
+                   "nccl-graph": {"p2p": 0, "graph": 2}, "nccl-serial-reduce": {"p2p": 0, "redstream": 0},
+                   "one-kernel": {"pcg_fused": 1}, "pdl": {"pdl": 1}, "one-kernel-pdl": {"pcg_fused": 1, "pdl": 1}}
+
+
 def allsum(v):
     t = torch.tensor([v], dtype=torch.float64)
     dist.all_reduce(t)
@@ -74,6 +85,9 @@ def main():
     ap.add_argument("--partition", default="block")
     ap.add_argument("--maxits", type=int, default=200)
     ap.add_argument("--rtol", type=float, default=1e-9)
+    ap.add_argument("--backends", default="",
+                    help="gpu mode: comma-separated loop back-ends to run one after the other in this launch "
+                         "(default: whatever the environment selects)")
     args = ap.parse_args()
     rank, world, _ = abdist.init_process(backend="gloo")
     N = args.size
@@ -136,20 +150,30 @@ def main():
     else:
         comm = abdist.nccl_comm(rank, world)
         assert comm.size() == world and comm.rank() == rank
-        cg = ab.SolverCuda(m, comm)
         b = m.vector(); b.x[:no] = bglob[m.nzrows[:no]]
         methods = []
-        for meth in ("solvempi", "solve_pipelined"):
+        defaults = {"p2p": 1, "p2p_fuse": 1, "graph": 1, "redstream": 1, "pcg_fused": 0, "pdl": 0}
+        for be in (args.backends.split(",") if args.backends else [""]):
+            if be:
+                for key, val in {**defaults, **BACKEND_OPTIONS[be]}.items():
+                    ab.set_option(key, val)
+            tag = f"{be}:" if be else ""
+            cg = ab.SolverCuda(m, comm)              # collective: the exchange is set up per solver
+            for meth in ("solvempi", "solve_pipelined"):
+                x = m.vector()
+                code = getattr(cg, meth)(b, x, maxits=maxits, residualrtol=rtol, warmup=2)
+                if code != 0:
+                    failures.append(f"{tag}{meth}: status {code}")
+                methods.append((tag + meth, x.x[:no].copy(), cg.c.niterations))
+            # fixed iteration counts, tolerances off
             x = m.vector()
-            code = getattr(cg, meth)(b, x, maxits=maxits, residualrtol=rtol, warmup=2)
-            if code != 0:
-                failures.append(f"{meth}: status {code}")
-            methods.append((meth, x.x[:no].copy(), cg.c.niterations))
-        # fixed iteration count, tolerances off
-        x = m.vector()
-        code = cg.solvempi(b, x, maxits=7)
-        methods.append(("solvempi-7its", x.x[:no].copy(), cg.c.niterations))
-        cg.free(); comm.destroy()
+            code = cg.solvempi(b, x, maxits=7)
+            methods.append((tag + "solvempi-7its", x.x[:no].copy(), cg.c.niterations))
+            x = m.vector()
+            code = cg.solve_pipelined(b, x, maxits=9)
+            methods.append((tag + "solve_pipelined-9its", x.x[:no].copy(), cg.c.niterations))
+            cg.free()
+        comm.destroy()
 
     # gather solutions on rank 0 and compare with the single-rank oracle
     gathered = [None] * world
@@ -165,7 +189,9 @@ def main():
                 its.add(ms[mi][2])
             if name.endswith("7its"):
                 want = O.cg(csr, bglob, maxits=7)
-            elif name == "solve_pipelined":
+            elif name.endswith("9its"):
+                want = O.cg_pipelined(csr, bglob, maxits=9)
+            elif name.endswith("solve_pipelined"):
                 want = O.cg_pipelined(csr, bglob, maxits=maxits, rtol=rtol)
             else:
                 want = O.cg(csr, bglob, maxits=maxits, rtol=rtol)

@@ -6,7 +6,9 @@
  * without a GPU.  "Device memory" is host memory, poisoned with NaN patterns
  * on allocation; streams and events are dummies (everything is synchronous);
  * a captured graph is a recorded list of the simulated kernel launches of
- * kernels_sim.c, replayed by cudaGraphLaunch.
+ * kernels_sim.c, replayed by cudaGraphLaunch.  Allocations are shared-memory
+ * objects so that multi-process tests can export and map them like CUDA IPC;
+ * the NCCL stand-in is nccl_mock.c.
  *
  * Built only into tests/hostsim/libacgb200_hostsim.so by tests/hostsim/Makefile.
  * Nothing under acg_b200/ refers to it: the product library links the real
@@ -15,9 +17,15 @@
 #include <cuda_runtime_api.h>
 #include <nccl.h>
 
+#include <fcntl.h>
+#include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "hostsim.h"
 
@@ -31,14 +39,117 @@ static double now_ms(void)
 }
 
 /* ---- memory ---------------------------------------------------------------- */
+/* Every "device" allocation is a POSIX shared-memory object, so that any of them
+ * can be exported with cudaIpcGetMemHandle and mapped by another process of a
+ * multi-rank test: the peer-memory exchange then really runs between processes. */
+struct simalloc { void *ptr; size_t size; char name[48]; int mapped_peer; };
+static struct simalloc allocs[1024];
+static int nallocs = 0;
+static pthread_mutex_t alloc_lock = PTHREAD_MUTEX_INITIALIZER;
+static unsigned long alloc_counter = 0;
+
+static void *shm_map(const char *name, size_t n, int create)
+{
+    const int fd = shm_open(name, create ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
+    if (fd < 0) return NULL;
+    if (create && ftruncate(fd, (off_t) n) != 0) { close(fd); shm_unlink(name); return NULL; }
+    void *p = mmap(NULL, n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    return p == MAP_FAILED ? NULL : p;
+}
+
+static void cleanup_allocs(void)
+{
+    for (int i = 0; i < nallocs; i++) if (allocs[i].ptr && !allocs[i].mapped_peer) shm_unlink(allocs[i].name);
+}
+
 cudaError_t cudaMalloc(void **p, size_t n)
 {
-    *p = malloc(n ? n : 1);
-    if (!*p) return cudaErrorMemoryAllocation;
-    memset(*p, 0xFF, n);                 /* NaN / -1: reading uninitialised "device" memory shows */
+    const size_t size = n ? n : 1;
+    pthread_mutex_lock(&alloc_lock);
+    if (nallocs == 0) atexit(cleanup_allocs);
+    int slot = -1;
+    for (int i = 0; i < nallocs; i++) if (!allocs[i].ptr) { slot = i; break; }
+    if (slot < 0 && nallocs < 1024) slot = nallocs++;
+    if (slot < 0) { pthread_mutex_unlock(&alloc_lock); return cudaErrorMemoryAllocation; }
+    snprintf(allocs[slot].name, sizeof(allocs[slot].name), "/acgb200sim_%d_%lu", (int) getpid(), alloc_counter++);
+    void *q = shm_map(allocs[slot].name, size, 1);
+    if (!q) { pthread_mutex_unlock(&alloc_lock); return cudaErrorMemoryAllocation; }
+    allocs[slot].ptr = q; allocs[slot].size = size; allocs[slot].mapped_peer = 0;
+    pthread_mutex_unlock(&alloc_lock);
+    memset(q, 0xFF, size);               /* NaN / -1: reading uninitialised "device" memory shows */
+    *p = q;
     return cudaSuccess;
 }
-cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+
+cudaError_t cudaFree(void *p)
+{
+    if (!p) return cudaSuccess;
+    pthread_mutex_lock(&alloc_lock);
+    for (int i = 0; i < nallocs; i++) {
+        if (allocs[i].ptr == p && !allocs[i].mapped_peer) {
+            munmap(p, allocs[i].size);
+            shm_unlink(allocs[i].name);
+            allocs[i].ptr = NULL;
+            pthread_mutex_unlock(&alloc_lock);
+            return cudaSuccess;
+        }
+    }
+    pthread_mutex_unlock(&alloc_lock);
+    return cudaErrorInvalidValue;
+}
+
+/* the handle carries the name and the size of the object */
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p)
+{
+    memset(h, 0, sizeof(*h));
+    pthread_mutex_lock(&alloc_lock);
+    for (int i = 0; i < nallocs; i++) {
+        if (allocs[i].ptr == p && !allocs[i].mapped_peer) {
+            memcpy(h->reserved, allocs[i].name, sizeof(allocs[i].name));
+            memcpy(h->reserved + 48, &allocs[i].size, sizeof(size_t));
+            pthread_mutex_unlock(&alloc_lock);
+            return cudaSuccess;
+        }
+    }
+    pthread_mutex_unlock(&alloc_lock);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned int f)
+{
+    (void) f;
+    char name[48];
+    size_t size = 0;
+    memcpy(name, h.reserved, sizeof(name)); name[47] = 0;
+    memcpy(&size, h.reserved + 48, sizeof(size_t));
+    void *q = shm_map(name, size, 0);
+    if (!q) return cudaErrorInvalidValue;
+    pthread_mutex_lock(&alloc_lock);
+    int slot = -1;
+    for (int i = 0; i < nallocs; i++) if (!allocs[i].ptr) { slot = i; break; }
+    if (slot < 0 && nallocs < 1024) slot = nallocs++;
+    if (slot >= 0) { allocs[slot].ptr = q; allocs[slot].size = size; allocs[slot].mapped_peer = 1; allocs[slot].name[0] = 0; }
+    pthread_mutex_unlock(&alloc_lock);
+    *p = q;
+    return cudaSuccess;
+}
+
+cudaError_t cudaIpcCloseMemHandle(void *p)
+{
+    pthread_mutex_lock(&alloc_lock);
+    for (int i = 0; i < nallocs; i++) {
+        if (allocs[i].ptr == p && allocs[i].mapped_peer) {
+            munmap(p, allocs[i].size);
+            allocs[i].ptr = NULL;
+            pthread_mutex_unlock(&alloc_lock);
+            return cudaSuccess;
+        }
+    }
+    pthread_mutex_unlock(&alloc_lock);
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t cudaMallocHost(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 cudaError_t cudaHostRegister(void *p, size_t n, unsigned int f) { (void) p; (void) n; (void) f; return cudaSuccess; }
@@ -149,30 +260,6 @@ int hostsim_run_or_record(void (*fn)(void *), const void *args, size_t size)
     return 0;
 }
 
-/* ---- inter-process pieces: not simulated (one process, null communicator) ---- */
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { (void) h; (void) p; return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned int f) { (void) p; (void) h; (void) f; return cudaErrorNotSupported; }
-cudaError_t cudaIpcCloseMemHandle(void *p) { (void) p; return cudaErrorNotSupported; }
-
-ncclResult_t ncclAllReduce(const void *s, void *r, size_t n, ncclDataType_t t, ncclRedOp_t o, ncclComm_t c, cudaStream_t st)
-{ (void) s; (void) r; (void) n; (void) t; (void) o; (void) c; (void) st; return ncclInvalidUsage; }
-ncclResult_t ncclAllGather(const void *s, void *r, size_t n, ncclDataType_t t, ncclComm_t c, cudaStream_t st)
-{ (void) s; (void) r; (void) n; (void) t; (void) c; (void) st; return ncclInvalidUsage; }
-ncclResult_t ncclSend(const void *s, size_t n, ncclDataType_t t, int peer, ncclComm_t c, cudaStream_t st)
-{ (void) s; (void) n; (void) t; (void) peer; (void) c; (void) st; return ncclInvalidUsage; }
-ncclResult_t ncclRecv(void *r, size_t n, ncclDataType_t t, int peer, ncclComm_t c, cudaStream_t st)
-{ (void) r; (void) n; (void) t; (void) peer; (void) c; (void) st; return ncclInvalidUsage; }
-ncclResult_t ncclGroupStart(void) { return ncclSuccess; }
-ncclResult_t ncclGroupEnd(void) { return ncclSuccess; }
-ncclResult_t ncclCommDestroy(ncclComm_t c) { (void) c; return ncclSuccess; }
-ncclResult_t ncclGetUniqueId(ncclUniqueId *id) { memset(id, 0, sizeof(*id)); return ncclInvalidUsage; }
-ncclResult_t ncclCommInitRank(ncclComm_t *c, int n, ncclUniqueId id, int r) { (void) c; (void) n; (void) id; (void) r; return ncclInvalidUsage; }
-ncclResult_t ncclCommCount(const ncclComm_t c, int *n) { (void) c; *n = 1; return ncclInvalidUsage; }
-ncclResult_t ncclCommUserRank(const ncclComm_t c, int *r) { (void) c; *r = 0; return ncclInvalidUsage; }
-ncclResult_t ncclCommSplit(ncclComm_t c, int color, int key, ncclComm_t *n, ncclConfig_t *cfg)
-{ (void) c; (void) color; (void) key; (void) n; (void) cfg; return ncclInvalidUsage; }
-
 /* ---- error strings ------------------------------------------------------------ */
 const char *cudaGetErrorString(cudaError_t e) { (void) e; return "host-simulation stand-in: no CUDA error strings"; }
 cudaError_t cudaPeekAtLastError(void) { return cudaSuccess; }
-const char *ncclGetErrorString(ncclResult_t r) { (void) r; return "host-simulation stand-in: no NCCL error strings"; }

@@ -17,8 +17,10 @@
 #include "hostsim.h"
 
 #include <math.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 struct gate { int iter, active; };
 
@@ -27,6 +29,74 @@ static struct gate gate_read(const struct acgb200_ctrl *cin, const struct acgb20
     struct gate g = { 0, 1 };
     if (cin) { g.iter = cin->iter; g.active = cin->done == 0 && cin->iter < st->maxits; }
     return g;
+}
+
+/* ---- peer-memory exchange (several processes, windows mapped through the IPC stand-in) ---- */
+
+#define RED_IDX(ch, parity, rank) ((((ch) * 2 + (parity)) * ACGB200_MAXR + (rank)) * 2)
+
+static double wall_ns(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e9 * (double) ts.tv_sec + (double) ts.tv_nsec;
+}
+
+/* as p2p_spin in kernels.cu: wait for *f >= seq, give up after timeout_ns and raise the sticky flag */
+static void p2p_spin(const unsigned long long *f, unsigned long long seq, struct acgb200_p2pdev *P)
+{
+    double t0 = 0.0;
+    unsigned polls = 0;
+    while (__atomic_load_n(f, __ATOMIC_ACQUIRE) < seq) {
+        if ((++polls & 255u) != 0) continue;
+        sched_yield();
+        if (__atomic_load_n(&P->timed_out, __ATOMIC_RELAXED)) return;
+        if (P->timeout_ns == 0) continue;
+        const double now = wall_ns();
+        if (t0 == 0.0) t0 = now;
+        else if (now - t0 > (double) P->timeout_ns) { __atomic_store_n(&P->timed_out, 1ull, __ATOMIC_RELEASE); return; }
+    }
+}
+
+static void p2p_wait_halo(struct acgb200_p2pdev *P, unsigned long long seq)
+{
+    for (int j = 0; j < P->nsenders; j++) p2p_spin(P->my_hflag + P->senders[j], seq, P);
+}
+
+static void p2p_reduce(struct acgb200_p2pdev *P, int ch, int parity, unsigned long long seq, double *out)
+{
+    for (int r = 0; r < P->nranks; r++) p2p_spin(P->my_rflag + ch * ACGB200_MAXR + r, seq, P);
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < P->nranks; r++) { const double *sl = P->my_red + RED_IDX(ch, parity, r); a += sl[0]; b += sl[1]; }
+    out[0] = a; out[1] = b;
+}
+
+static double p2p_sum_slot(const struct acgb200_p2pdev *P, int ch, int parity)
+{
+    double a = 0.0;
+    for (int r = 0; r < P->nranks; r++) a += P->my_red[RED_IDX(ch, parity, r)];
+    return a;
+}
+
+static void p2p_publish_red(struct acgb200_p2pdev *P, int ch, int parity, unsigned long long seq, const double *src, int count)
+{
+    for (int r = 0; r < P->nranks; r++) {
+        double *dst = P->peer_red[r] + RED_IDX(ch, parity, P->rank);
+        dst[0] = src[0];
+        dst[1] = count > 1 ? src[1] : 0.0;
+        __atomic_store_n(P->peer_rflag[r] + ch * ACGB200_MAXR + P->rank, seq, __ATOMIC_RELEASE);
+    }
+}
+
+static void p2p_publish_halo(struct acgb200_p2pdev *P, unsigned long long seq)
+{
+    for (int i = 0; i < P->nrecip; i++) __atomic_store_n(P->peer_hflag[i], seq, __ATOMIC_RELEASE);
+}
+
+static void p2p_push_row(const struct acgb200_p2pdev *P, int row, int parity, double v)
+{
+    const int b = row - P->borderoff;
+    for (int e = P->bptr[b]; e < P->bptr[b + 1]; e++) P->peer_ghost[P->bq[e]][parity][P->bdst[e]] = v;
 }
 
 int acgb200_num_sms(void) { return 148; }
@@ -42,10 +112,20 @@ int acgb200_spmv_configure(struct acgb200_spmvplan *pl)
 
 /* ---- SpMV ------------------------------------------------------------------ */
 
-static double row_product(const struct acgb200_spmvargs *a, int row)
+/* local block, plus -- fused peer-memory mode -- the border x ghost block with ghosts from the window */
+static double row_product(const struct acgb200_spmvargs *a, int row, const double **xg, int iter)
 {
     double sum = 0.0;
     for (int k = a->rowptr[row]; k < a->rowptr[row + 1]; k++) sum = fma(a->a[k], a->x[a->colidx[k]], sum);
+    if (a->p2p && row >= a->od_rowoffset) {
+        struct acgb200_p2pdev *P = (struct acgb200_p2pdev *) a->p2p;
+        if (!*xg) {
+            p2p_wait_halo(P, P->hbase + (unsigned long long) iter);
+            *xg = P->my_ghost[iter & 1] - a->od_nrows;
+        }
+        const int ob = row - a->od_rowoffset;
+        for (int k = a->orowptr[ob]; k < a->orowptr[ob + 1]; k++) sum = fma(a->oa[k], (*xg)[a->ocolidx[k]], sum);
+    }
     return sum;
 }
 
@@ -78,12 +158,17 @@ static void spmv_exec(void *p)
         }
         if (g.active) {
             double dot = 0.0;
+            const double *xg = NULL;
             for (int t = 0; t < pl->ntiles; t++) {
                 const struct acgb200_tile tl = pl->d_tiles[t];
                 const int nrows = tl.nrows & ~ACGB200_TILE_COMPRESSED;
-                for (int r = tl.row_begin; r < tl.row_begin + nrows; r++) row_epilogue(a, r, row_product(a, r), &dot);
+                for (int r = tl.row_begin; r < tl.row_begin + nrows; r++) row_epilogue(a, r, row_product(a, r, &xg, g.iter), &dot);
             }
             if (a->acc) *a->acc += dot;
+            if (a->p2p && a->pub_ch >= 0 && a->p2p->fuse) {
+                struct acgb200_p2pdev *P = (struct acgb200_p2pdev *) a->p2p;
+                p2p_publish_red(P, a->pub_ch, g.iter & 1, P->rbase + (unsigned long long) g.iter + 1ull, a->acc, 1);
+            }
         }
     }
     /* medium and long rows: separate kernels, gated by the same incoming word */
@@ -91,9 +176,11 @@ static void spmv_exec(void *p)
         const int cnt = pass == 0 ? pl->nmed : pl->nlong;
         const int *rows = pass == 0 ? pl->d_medrows : pl->d_longrows;
         if (cnt <= 0) continue;
-        if (!gate_read(a->ctrl_in, a->st).active) continue;
+        const struct gate g = gate_read(a->ctrl_in, a->st);
+        if (!g.active) continue;
         double dot = 0.0;
-        for (int i = 0; i < cnt; i++) row_epilogue(a, rows[i], row_product(a, rows[i]), &dot);
+        const double *xg = NULL;
+        for (int i = 0; i < cnt; i++) row_epilogue(a, rows[i], row_product(a, rows[i], &xg, g.iter), &dot);
         if (a->acc) *a->acc += dot;
     }
 }
@@ -101,23 +188,84 @@ static void spmv_exec(void *p)
 int acgb200_spmv_launch(const struct acgb200_spmvargs *a, cudaStream_t stream)
 {
     (void) stream;
-    if (a->p2p) return 1;                       /* peer memory is not simulated */
     if (a->plan->nlong > 0 && !a->plan->d_long_scratch) return 1;
     return hostsim_run_or_record(spmv_exec, a, sizeof(*a));
+}
+
+static void offdiag_exec(void *vp)
+{
+    const struct acgb200_offdiagargs *a = vp;
+    const struct gate g = gate_read(a->ctrl_in, a->st);
+    if (!g.active) return;
+    const double *xg = a->x + a->rowoffset;      /* ghost tail of x: ocolidx is rebased by -borderrowoffset */
+    if (a->p2p) {
+        struct acgb200_p2pdev *P = (struct acgb200_p2pdev *) a->p2p;
+        const int it = a->p2p_iter_override >= 0 ? a->p2p_iter_override : g.iter;
+        p2p_wait_halo(P, P->hbase + (unsigned long long) it);
+        xg = P->my_ghost[it & 1] - a->nrows;
+    }
+    double dot = 0.0;
+    for (int i = 0; i < a->nrows; i++) {
+        const int kb = a->orowptr[i], ke = a->orowptr[i + 1], row = a->rowoffset + i;
+        double sum = 0.0;
+        for (int k = kb; k < ke; k++) sum = fma(a->oa[k], xg[a->ocolidx[k]], sum);
+        double v = a->y[row];
+        if (kb != ke) { v = a->minus ? v - sum : v + sum; a->y[row] = v; }
+        if (a->dotkind == 1) dot = fma(a->x[row], v, dot);
+        else if (a->dotkind == 2) dot = fma(v, v, dot);
+    }
+    if (a->acc) *a->acc += dot;
 }
 
 int acgb200_offdiag_launch(const struct acgb200_offdiagargs *a, cudaStream_t stream)
 {
     (void) stream;
-    return a->nrows <= 0 ? 0 : 1;               /* only distributed matrices have a border x ghost block */
+    if (a->nrows <= 0) return 0;
+    return hostsim_run_or_record(offdiag_exec, a, sizeof(*a));
 }
 
-int acgb200_comm_post(const struct acgb200_postargs *a, cudaStream_t stream) { (void) a; (void) stream; return 1; }
+static void post_exec(void *vp)
+{
+    const struct acgb200_postargs *a = vp;
+    struct acgb200_p2pdev *P = a->p2p;
+    int iter = a->iter_override;
+    if (iter < 0) {
+        const struct gate g = gate_read(a->cin, a->st);
+        if (!g.active) return;
+        iter = g.iter;
+    }
+    if (a->vec) {
+        const int parity = iter & 1;
+        for (int q = 0; q < P->nrecip; q++)
+            for (int i = P->sdispls[q]; i < P->sdispls[q + 1]; i++)
+                P->peer_ghost[q][parity][P->peer_rdispl[q] + (i - P->sdispls[q])] = a->vec[a->sendbufidx[i]];
+    }
+    if (a->ch >= 0) {
+        const int parity = (iter + a->par_off) & 1;
+        const double *src = a->redbase + parity * a->redstride;
+        for (int r = 0; r < P->nranks; r++) {
+            double *dst = P->peer_red[r] + RED_IDX(a->ch, parity, P->rank);
+            dst[0] = src[0];
+            dst[1] = a->redcount > 1 ? src[1] : 0.0;
+        }
+    }
+    if (a->vec) p2p_publish_halo(P, P->hbase + (unsigned long long) iter);
+    if (a->ch >= 0)
+        for (int r = 0; r < P->nranks; r++)
+            __atomic_store_n(P->peer_rflag[r] + a->ch * ACGB200_MAXR + P->rank,
+                             P->rbase + (unsigned long long) (iter + a->seq_off), __ATOMIC_RELEASE);
+}
+
+int acgb200_comm_post(const struct acgb200_postargs *a, cudaStream_t stream)
+{
+    (void) stream;
+    return hostsim_run_or_record(post_exec, a, sizeof(*a));
+}
 
 /* ---- classic CG ------------------------------------------------------------- */
 
 struct upd_args {
-    int n; struct acgb200_devstate *st; int cin, cout, multi;
+    int n; struct acgb200_devstate *st; int cin, cout, multi; struct acgb200_p2pdev *P;
     const double *q; double *z, *w, *t, *p, *r, *x;
 };
 
@@ -129,8 +277,17 @@ static void update_r_exec(void *vp)
     if (a->cin != a->cout) st->ctrl[a->cout] = st->ctrl[a->cin];
     if (!g.active) return;
     const int s = g.iter & 1;
-    const double rr = a->multi ? st->rr[s] : st->rr_loc[s];
-    const double pap = a->multi ? st->pap[s] : st->pap_loc[s];
+    struct acgb200_p2pdev *P = a->P;
+    double rr, pap;
+    if (P) {
+        double glob[2];
+        p2p_reduce(P, 0, s, P->rbase + (unsigned long long) g.iter + 1ull, glob);
+        pap = glob[0];
+        rr = g.iter > 0 ? p2p_sum_slot(P, 1, s) : st->rr[0];
+    } else {
+        rr = a->multi ? st->rr[s] : st->rr_loc[s];
+        pap = a->multi ? st->pap[s] : st->pap_loc[s];
+    }
     const double alpha = rr / pap;
     double acc = 0.0;
     for (int i = 0; i < a->n; i++) {
@@ -139,16 +296,16 @@ static void update_r_exec(void *vp)
         acc = fma(rv, rv, acc);
     }
     st->rr_loc[s ^ 1] += acc;
+    if (P && P->fuse) p2p_publish_red(P, 1, s ^ 1, P->rbase + (unsigned long long) g.iter + 1ull, &st->rr_loc[s ^ 1], 1);
 }
 
 int acgb200_cg_update_r(int n, struct acgb200_devstate *st, int cin, int cout, int multi, struct acgb200_p2pdev *p2p,
                         const double *t, double *r, cudaStream_t stream)
 {
     (void) stream;
-    if (p2p) return 1;
     struct upd_args a;
     memset(&a, 0, sizeof(a));
-    a.n = n; a.st = st; a.cin = cin; a.cout = cout; a.multi = multi; a.t = (double *) t; a.r = r;
+    a.n = n; a.st = st; a.cin = cin; a.cout = cout; a.multi = multi; a.P = p2p; a.t = (double *) t; a.r = r;
     return hostsim_run_or_record(update_r_exec, &a, sizeof(a));
 }
 
@@ -158,12 +315,23 @@ static void update_xp_exec(void *vp)
     struct acgb200_devstate *st = a->st;
     const struct gate g = gate_read(&st->ctrl[a->cin], st);
     const int s = g.iter & 1;
-    const double rr = a->multi ? st->rr[s] : st->rr_loc[s];
-    const double rrn = a->multi ? st->rr[s ^ 1] : st->rr_loc[s ^ 1];
-    const double pap = a->multi ? st->pap[s] : st->pap_loc[s];
+    struct acgb200_p2pdev *P = a->P;
+    double rr, rrn, pap;
+    if (P && g.active) {
+        double glob[2];
+        p2p_reduce(P, 1, s ^ 1, P->rbase + (unsigned long long) g.iter + 1ull, glob);
+        rrn = glob[0];
+        rr = g.iter > 0 ? p2p_sum_slot(P, 1, s) : st->rr[0];
+        pap = p2p_sum_slot(P, 0, s);
+    } else {
+        rr = a->multi ? st->rr[s] : st->rr_loc[s];
+        rrn = a->multi ? st->rr[s ^ 1] : st->rr_loc[s ^ 1];
+        pap = a->multi ? st->pap[s] : st->pap_loc[s];
+    }
     struct acgb200_ctrl c = st->ctrl[a->cin];
     if (g.active) {
         c.iter = g.iter + 1;
+        if (P) st->rr[s ^ 1] = rrn;
         if (st->tol > 0.0 && sqrt(rrn) < st->tol) { c.done = 1; st->final_rr = rrn; }
         st->pap_loc[s ^ 1] = 0.0;
     }
@@ -173,18 +341,20 @@ static void update_xp_exec(void *vp)
     for (int i = 0; i < a->n; i++) {
         const double pv = a->p[i];
         a->x[i] = fma(alpha, pv, a->x[i]);
-        a->p[i] = fma(beta, pv, a->r[i]);
+        const double pn = fma(beta, pv, a->r[i]);
+        a->p[i] = pn;
+        if (P && P->fuse && i >= P->borderoff) p2p_push_row(P, i, s ^ 1, pn);
     }
+    if (P && P->fuse) p2p_publish_halo(P, P->hbase + (unsigned long long) g.iter + 1ull);
 }
 
 int acgb200_cg_update_xp(int n, struct acgb200_devstate *st, int cin, int cout, int multi, struct acgb200_p2pdev *p2p,
                          const double *r, double *p, double *x, cudaStream_t stream)
 {
     (void) stream;
-    if (p2p) return 1;
     struct upd_args a;
     memset(&a, 0, sizeof(a));
-    a.n = n; a.st = st; a.cin = cin; a.cout = cout; a.multi = multi; a.r = (double *) r; a.p = p; a.x = x;
+    a.n = n; a.st = st; a.cin = cin; a.cout = cout; a.multi = multi; a.P = p2p; a.r = (double *) r; a.p = p; a.x = x;
     return hostsim_run_or_record(update_xp_exec, &a, sizeof(a));
 }
 
@@ -196,21 +366,33 @@ static void pcg_update_exec(void *vp)
     struct acgb200_devstate *st = a->st;
     const struct gate g = gate_read(&st->ctrl[a->cin], st);
     const int s = g.iter & 1;
-    const double gamma = a->multi ? st->gd[s][0] : st->gd_loc[s][0];
-    const double delta = a->multi ? st->gd[s][1] : st->gd_loc[s][1];
+    struct acgb200_p2pdev *P = a->P;
+    double gamma, delta;
+    if (P && g.active && g.iter > 0) {
+        double glob[2];
+        p2p_reduce(P, 0, s, P->rbase + (unsigned long long) g.iter, glob);
+        gamma = glob[0]; delta = glob[1];
+    } else {
+        gamma = a->multi ? st->gd[s][0] : st->gd_loc[s][0];
+        delta = a->multi ? st->gd[s][1] : st->gd_loc[s][1];
+    }
     const double gamma_prev = st->prev[s][0], alpha_prev = st->prev[s][1];
     const int conv = st->tol > 0.0 && sqrt(gamma) < st->tol;
     const double beta = gamma / gamma_prev;
     const double alpha = gamma / (delta - beta * gamma / alpha_prev);
     struct acgb200_ctrl c = st->ctrl[a->cin];
     if (g.active) {
+        if (P) { st->gd[s][0] = gamma; st->gd[s][1] = delta; }
         if (conv) { c.done = 1; st->final_rr = gamma; }
         else { c.iter = g.iter + 1; st->prev[s ^ 1][0] = gamma; st->prev[s ^ 1][1] = alpha; }
     }
     st->ctrl[a->cout] = c;
     if (!g.active || conv) return;
     double g2 = 0.0, d2 = 0.0;
-    for (int i = 0; i < a->n; i++) {
+    /* as the kernel: border rows first in fused peer-memory mode */
+    const int push = P && P->fuse, first = push ? P->borderoff : 0;
+    for (int ii = 0; ii < a->n; ii++) {
+        const int i = (first + ii) % (a->n > 0 ? a->n : 1);
         const double zv = fma(beta, a->z[i], a->q[i]);
         const double tv = fma(beta, a->t[i], a->w[i]);
         const double pv = fma(beta, a->p[i], a->r[i]);
@@ -221,9 +403,15 @@ static void pcg_update_exec(void *vp)
         a->r[i] = rv; a->w[i] = wv;
         g2 = fma(rv, rv, g2);
         d2 = fma(wv, rv, d2);
+        if (push && i >= first) p2p_push_row(P, i, s ^ 1, wv);
     }
     st->gd_loc[s ^ 1][0] += g2;
     st->gd_loc[s ^ 1][1] += d2;
+    if (push) {
+        const unsigned long long it1 = (unsigned long long) g.iter + 1ull;
+        p2p_publish_red(P, 0, s ^ 1, P->rbase + it1, &st->gd_loc[s ^ 1][0], 2);
+        p2p_publish_halo(P, P->hbase + it1);
+    }
 }
 
 int acgb200_pcg_update(int n, struct acgb200_devstate *st, int cin, int cout, int multi, struct acgb200_p2pdev *p2p,
@@ -231,10 +419,9 @@ int acgb200_pcg_update(int n, struct acgb200_devstate *st, int cin, int cout, in
                        cudaStream_t stream)
 {
     (void) stream;
-    if (p2p) return 1;
     struct upd_args a;
     memset(&a, 0, sizeof(a));
-    a.n = n; a.st = st; a.cin = cin; a.cout = cout; a.multi = multi;
+    a.n = n; a.st = st; a.cin = cin; a.cout = cout; a.multi = multi; a.P = p2p;
     a.q = q; a.z = z; a.w = w; a.t = t; a.p = p; a.r = r; a.x = x;
     return hostsim_run_or_record(pcg_update_exec, &a, sizeof(a));
 }
@@ -261,8 +448,16 @@ static void fused_exec(void *vp)
     struct acgb200_devstate *st = a->sp.st;
     const struct gate g = gate_read(&st->ctrl[a->cin], st);
     const int s = g.iter & 1;
-    const double gamma = a->multi ? st->gd[s][0] : st->gd_loc[s][0];
-    const double delta = a->multi ? st->gd[s][1] : st->gd_loc[s][1];
+    struct acgb200_p2pdev *P = (struct acgb200_p2pdev *) a->sp.p2p;
+    double gamma, delta;
+    if (P && g.active && g.iter > 0) {
+        double glob[2];
+        p2p_reduce(P, 0, s, P->rbase + (unsigned long long) g.iter, glob);
+        gamma = glob[0]; delta = glob[1];
+    } else {
+        gamma = a->multi ? st->gd[s][0] : st->gd_loc[s][0];
+        delta = a->multi ? st->gd[s][1] : st->gd_loc[s][1];
+    }
     const double gamma_prev = st->prev[s][0], alpha_prev = st->prev[s][1];
     const int conv = st->tol > 0.0 && sqrt(gamma) < st->tol;
     const double beta = gamma / gamma_prev;
@@ -278,12 +473,21 @@ static void fused_exec(void *vp)
     const double *wold = s ? a->w1 : a->w0;
     double *wnew = s ? a->w0 : a->w1;
     double g2 = 0.0, d2 = 0.0;
+    const double *xg = NULL;
     for (int t = 0; t < pl->ntiles; t++) {
         const struct acgb200_tile tl = pl->d_tiles[t];
         const int nrows = tl.nrows & ~ACGB200_TILE_COMPRESSED;
         for (int row = tl.row_begin; row < tl.row_begin + nrows; row++) {
             double qv = 0.0;
             for (int k = a->sp.rowptr[row]; k < a->sp.rowptr[row + 1]; k++) qv = fma(a->sp.a[k], wold[a->sp.colidx[k]], qv);
+            if (P && row >= a->sp.od_rowoffset) {
+                if (!xg) {
+                    p2p_wait_halo(P, P->hbase + (unsigned long long) g.iter);
+                    xg = P->my_ghost[s] - a->sp.od_nrows;
+                }
+                const int ob = row - a->sp.od_rowoffset;
+                for (int k = a->sp.orowptr[ob]; k < a->sp.orowptr[ob + 1]; k++) qv = fma(a->sp.oa[k], xg[a->sp.ocolidx[k]], qv);
+            }
             const double wv0 = wold[row], rv0 = a->r[row];
             const double zv = fma(beta, a->z[row], qv);
             const double tv = fma(beta, a->t[row], wv0);
@@ -295,10 +499,16 @@ static void fused_exec(void *vp)
             a->r[row] = rv; wnew[row] = wv;
             g2 = fma(rv, rv, g2);
             d2 = fma(wv, rv, d2);
+            if (P && row >= P->borderoff) p2p_push_row(P, row, s ^ 1, wv);
         }
     }
     st->gd_loc[s ^ 1][0] += g2;
     st->gd_loc[s ^ 1][1] += d2;
+    if (P) {
+        const unsigned long long it1 = (unsigned long long) g.iter + 1ull;
+        p2p_publish_red(P, 0, s ^ 1, P->rbase + it1, &st->gd_loc[s ^ 1][0], 2);
+        p2p_publish_halo(P, P->hbase + it1);
+    }
     /* last CTA: clear the slot this launch read */
     st->gd_loc[s][0] = 0.0; st->gd_loc[s][1] = 0.0;
 }
@@ -308,7 +518,7 @@ int acgb200_pcg_fused_launch(const struct acgb200_spmvargs *sp, int grid, int ci
                              cudaStream_t stream)
 {
     (void) stream;
-    if (grid < 1 || sp->p2p) return 1;
+    if (grid < 1) return 1;
     struct fused_args a;
     memset(&a, 0, sizeof(a));
     a.sp = *sp; a.cin = cin; a.multi = multi;
@@ -346,16 +556,27 @@ int acgb200_dot2(int n, const double *r, const double *w, double *acc2, cudaStre
     return hostsim_run_or_record(dot_exec, &a, sizeof(a));
 }
 
+struct gs_args { int n; double *dst; const double *src; const int *idx; int scatter; };
+
+static void gs_exec(void *vp)
+{
+    const struct gs_args *a = vp;
+    if (a->scatter) for (int i = 0; i < a->n; i++) a->dst[a->idx[i]] = a->src[i];
+    else for (int i = 0; i < a->n; i++) a->dst[i] = a->src[a->idx[i]];
+}
+
 int acgb200_gather(int n, double *dst, const double *src, const int *idx, cudaStream_t stream)
 {
     (void) stream;
-    for (int i = 0; i < n; i++) dst[i] = src[idx[i]];
-    return 0;
+    if (n <= 0) return 0;
+    struct gs_args a = { n, dst, src, idx, 0 };
+    return hostsim_run_or_record(gs_exec, &a, sizeof(a));
 }
 
 int acgb200_scatter(int n, const double *src, double *dst, const int *idx, cudaStream_t stream)
 {
     (void) stream;
-    for (int i = 0; i < n; i++) dst[idx[i]] = src[i];
-    return 0;
+    if (n <= 0) return 0;
+    struct gs_args a = { n, dst, src, idx, 1 };
+    return hostsim_run_or_record(gs_exec, &a, sizeof(a));
 }

@@ -125,3 +125,41 @@ def test_rejected_calls_leave_the_counters_alone(simlib):
     assert out["errors"]["diffatol"] == 26                 # ACG_ERR_NOT_SUPPORTED (acg/cgcuda.c:424)
     assert out["errors"]["short_b"] == 31                  # ACG_ERR_INDEX_OUT_OF_BOUNDS (acg/cgcuda.c:417-421)
     assert out["nsolves_after_errors"] == 1
+
+
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
+@pytest.mark.parametrize("nproc,matrix,size,partition,backends,extra", [
+    (2, "27pt", 8, "block", "p2p-fused,p2p-unfused,nccl,nccl-graph,nccl-serial-reduce,one-kernel", []),
+    (3, "7pt", 9, "slab", "p2p-fused,one-kernel,nccl", []),
+    (4, "rmat", 3000, "random", "p2p-fused,one-kernel", ["--maxits", "12", "--rtol", "0"]),
+], ids=["2-ranks-all-backends", "3-ranks", "4-ranks-power-law"])
+def test_multi_rank_loops(nproc, matrix, size, partition, backends, extra, simlib):
+    """The distributed solver, one process per rank: the library's host code on the stand-in,
+    "device" allocations in shared memory so that the CUDA-IPC windows of the peer-memory exchange
+    are really shared between the processes, NCCL replaced by a file-based stand-in, and the
+    simulated kernels speaking the exchange protocol of kernels.cu (sequence-numbered flags,
+    parity-buffered ghost values and reduction slots).  Every loop back-end -- peer memory with
+    and without the pushes fused into the kernels, the one-kernel pipelined iteration, NCCL with
+    and without graph replay and with the reduction on the main stream -- must reproduce the
+    single-rank oracle.  What this cannot see: anything inside the CUDA kernels, and stream-level
+    concurrency on a real device."""
+    worker = os.path.join(ROOT, "tests", "_dist_worker.py")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), worker, "--mode", "gpu",
+           "--matrix", matrix, "--size", str(size), "--partition", partition, "--backends", backends] + extra
+    env = dict(os.environ, OMP_NUM_THREADS="2", ACGB200_TEST_HOSTSIM=simlib, ACGB200_P2P_TIMEOUT_MS="20000")
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    sys.stdout.write(p.stdout[-3000:])
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "FAIL" not in p.stdout
+    assert p.stdout.count(" OK") == 4 * len(backends.split(","))
+    import glob
+    assert not glob.glob("/dev/shm/acgb200sim_*")            # every "device" allocation was released
+    for f in glob.glob("/dev/shm/acgb200nccl_*"):            # NCCL stand-in leftovers of killed runs, if any
+        os.remove(f)
