@@ -163,3 +163,43 @@ def test_multi_rank_loops(nproc, matrix, size, partition, backends, extra, simli
     assert not glob.glob("/dev/shm/acgb200sim_*")            # every "device" allocation was released
     for f in glob.glob("/dev/shm/acgb200nccl_*"):            # NCCL stand-in leftovers of killed runs, if any
         os.remove(f)
+
+
+CONTRACT_KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                 "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks")
+
+
+@pytest.mark.parametrize("nproc", [1, 2])
+def test_bench_main_runs_and_prints_the_contract_line(nproc, simlib):
+    """bench.py's main(), unchanged, on the stand-in (tests/hostsim/run_bench_sim.py patches
+    torch.cuda availability and the nvidia-smi sampler around it): matrix set-up for one and
+    several ranks, timed pass, profiled pass, one JSON line from rank 0 with every key of the
+    bench contract.  Shape only -- nothing it prints is a measurement."""
+    script = os.path.join(SIM, "run_bench_sim.py")
+    args = ["--gpus", str(nproc), "--workload", "27pt-64", "--steps", "2", "--warmup", "1", "--iters", "6", "--cpu-iters", "2"]
+    if nproc == 1:
+        cmd = [sys.executable, script] + args
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+               "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), script] + args
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, OMP_NUM_THREADS="2"), cwd=ROOT)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1                                   # rank 0 only, one line
+    d = json.loads(lines[0])
+    for k in CONTRACT_KEYS:
+        assert k in d, k
+    assert d["n_gpus"] == nproc and d["steps"] == 2 and d["warmup"] == 1 and d["unit"] == "iterations/s"
+    assert d["value"] > 0 and d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    if nproc == 1:
+        assert d["gpu_launches"] == 2 * (2 * 6 + 2)          # 2 steps x (2 kernels x 6 iterations + 2 set-up products)
+    else:
+        assert d["gpu_launches"] > 2 * (2 * 6 + 2)           # + halo exchange and border x ghost block of the set-up products
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["launches_timed"] == 2 * (6 + 2) and r["frac"] == pytest.approx(r["achieved"] / r["peak"])
+    assert d["config"]["workload"].startswith("27pt stencil 64^3") and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert ("cpu_baseline" in d) == (nproc == 1)
+    if nproc == 1:
+        assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] > 0
+    else:
+        assert d["config"]["partition"].startswith("2 parts")
