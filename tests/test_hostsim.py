@@ -203,3 +203,38 @@ def test_bench_main_runs_and_prints_the_contract_line(nproc, simlib):
         assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] > 0
     else:
         assert d["config"]["partition"].startswith("2 parts")
+
+
+def test_smoke_entry_point(simlib):
+    """__graft_entry__.smoke() unchanged, on the stand-in: both solvers against the oracle."""
+    p = subprocess.run([sys.executable, os.path.join(SIM, "run_module_sim.py"), "__graft_entry__:smoke"],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="2"), cwd=ROOT)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    assert p.stdout.count("status 0") == 2 and "smoke launches" in p.stdout
+
+
+@pytest.mark.parametrize("nproc,partition", [(1, "rows"), (2, "nnz"), (3, "rows")])   # METIS is not linked into the stand-in
+def test_python_driver_solves(nproc, partition, simlib, tmp_path):
+    """python -m acg_b200.driver through its whole flow (per-rank ingest, partition, solver,
+    report, manufactured-solution error, gathered solution file) on the stand-in."""
+    import numpy as np
+    from acg_b200 import matgen as mg, mtxio
+    n, r, c, v = mg.stencil3d_27pt(10, 9, 8)
+    path, sol = str(tmp_path / "A.mtx"), str(tmp_path / "x.mtx")
+    mtxio.write_symmetric(path, n, r, c, v, binary=True)
+    args = [path, "--binary", "--solver", "acg-pipelined", "--max-iterations", "300", "--residual-rtol", "1e-10",
+            "--manufactured-solution", "--seed", "3", "--partition", partition, "--output-solution", sol, "-v"]
+    script = os.path.join(SIM, "run_module_sim.py")
+    if nproc == 1:
+        cmd = [sys.executable, script, "acg_b200.driver"] + args
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+               "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), script, "acg_b200.driver"] + args
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="2"), cwd=ROOT)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    import re
+    e1 = float(re.search(r"^error 2-norm: (\S+)", p.stderr, re.M).group(1))
+    assert e1 < 1e-8 and "total solver time:" in p.stderr
+    xs = np.random.default_rng(3).uniform(-1.0, 1.0, n); xs /= np.linalg.norm(xs)
+    x = np.array([float(t) for t in open(sol).read().split("\n")[2:] if t])
+    assert len(x) == n and np.linalg.norm(x - xs) == pytest.approx(e1, rel=1e-6, abs=1e-14)
