@@ -238,3 +238,29 @@ def test_python_driver_solves(nproc, partition, simlib, tmp_path):
     xs = np.random.default_rng(3).uniform(-1.0, 1.0, n); xs /= np.linalg.norm(xs)
     x = np.array([float(t) for t in open(sol).read().split("\n")[2:] if t])
     assert len(x) == n and np.linalg.norm(x - xs) == pytest.approx(e1, rel=1e-6, abs=1e-14)
+
+
+def test_c_example_program(simlib, tmp_path):
+    """examples/acgb200_solve.c, unchanged, linked against the stand-in instead of the product
+    library: read a Matrix Market file, solve, print the report and the solution."""
+    import numpy as np
+    from acg_b200 import matgen as mg, mtxio
+    from oracle import Oracle
+    exe = str(tmp_path / "acgb200_solve_sim")
+    cc = subprocess.run(["/usr/bin/gcc", "-O2", "-std=gnu11", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+                         os.path.join(ROOT, "examples", "acgb200_solve.c"), "-o", exe, "-L" + SIM, "-lacgb200_hostsim",
+                         "-Wl,-rpath," + SIM], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr[-2000:]
+    n, r, c, v = mg.stencil3d_27pt(9)
+    for binary in (True, False):
+        path = str(tmp_path / ("A.bin.mtx" if binary else "A.txt.mtx"))
+        mtxio.write_symmetric(path, n, r, c, v, binary=binary)
+        p = subprocess.run([exe, path] + (["--binary"] if binary else []) +
+                           ["--solver", "acg-pipelined", "--residual-rtol", "1e-9", "--max-iterations", "200", "--print-solution"],
+                           capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        O = Oracle()
+        want = O.cg_pipelined(O.full_csr(n, r, c, v), np.ones(n), maxits=200, rtol=1e-9)
+        x = np.array([float(t) for t in p.stdout.splitlines()[2:]])
+        assert len(x) == n and np.abs(x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
+        assert f"iterations: {want['niterations']}" in p.stderr
