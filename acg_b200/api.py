@@ -33,6 +33,7 @@ ACG_ERR_NOT_CONVERGED = 39
 class AcgError(RuntimeError):
     def __init__(self, code, where, detail=0):
         self.code = code
+        self.errcode = detail          # third-party code behind ACG_ERR_CUDA / ACG_ERR_NCCL (cudaError_t, ncclResult_t)
         msg = lib().acgerrcodestr(code, detail).decode()
         super().__init__(f"{where}: {msg} (acgerrcode {code})")
 

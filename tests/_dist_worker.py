@@ -68,7 +68,8 @@ def local_matvec(m, h, xl):
 # exchange back-ends of the CG loop (options of acgb200_set_option on top of the defaults)
 BACKEND_OPTIONS = {"p2p-fused": {}, "p2p-unfused": {"p2p_fuse": 0}, "nccl": {"p2p": 0},
                    "nccl-graph": {"p2p": 0, "graph": 2}, "nccl-serial-reduce": {"p2p": 0, "redstream": 0},
-                   "one-kernel": {"pcg_fused": 1}, "pdl": {"pdl": 1}, "one-kernel-pdl": {"pcg_fused": 1, "pdl": 1}}
+                   "one-kernel": {"pcg_fused": 1}, "pdl": {"pdl": 1}, "one-kernel-pdl": {"pcg_fused": 1, "pdl": 1},
+                   "watchdog": {}}
 
 
 def allsum(v):
@@ -159,6 +160,21 @@ def main():
                     ab.set_option(key, val)
             tag = f"{be}:" if be else ""
             cg = ab.SolverCuda(m, comm)              # collective: the exchange is set up per solver
+            if be == "watchdog":
+                # rank 1 stops after 5 iterations and never publishes again: the other ranks' kernels
+                # must give up (ACGB200_P2P_TIMEOUT_MS) and the solve must return an error, not hang
+                x = m.vector()
+                try:
+                    code = cg.solvempi(b, x, maxits=5 if rank == 1 else 12)
+                    outcome = f"returned {code}"
+                except ab.AcgError as e:
+                    outcome = f"error {e.code}/{e.errcode}"
+                want = "returned 0" if rank == 1 else "error 4/702"      # ACG_ERR_CUDA / cudaErrorLaunchTimeout
+                print(f"[gpu world={world}] watchdog rank {rank}: {outcome} {'OK' if outcome == want else 'FAIL'}", flush=True)
+                if outcome != want:
+                    failures.append(f"watchdog rank {rank}: {outcome}")
+                cg.free()
+                continue
             for meth in ("solvempi", "solve_pipelined"):
                 x = m.vector()
                 code = getattr(cg, meth)(b, x, maxits=maxits, residualrtol=rtol, warmup=2)
