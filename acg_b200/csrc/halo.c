@@ -127,15 +127,12 @@ int acghalo_exchange_cuda_begin(
     double *rbase = inplace ? (double *) d_dstbuf + hx->putdispls[1] : (double *) hx->d_recvbuf;
     ncclResult_t r = ncclGroupStart();
     if (r != ncclSuccess) { if (errcode) *errcode = (int) r; return ACG_ERR_NCCL; }
-    for (int p = 0; p < halo->nsenders; p++) {
+    for (int p = 0; p < halo->nsenders && r == ncclSuccess; p++)
         r = ncclRecv(rbase + halo->rdispls[p], (size_t) halo->recvcounts[p], ncclDouble, halo->senders[p], comm->ncclcomm, stream);
-        if (r != ncclSuccess) { if (errcode) *errcode = (int) r; return ACG_ERR_NCCL; }
-    }
-    for (int p = 0; p < halo->nrecipients; p++) {
+    for (int p = 0; p < halo->nrecipients && r == ncclSuccess; p++)
         r = ncclSend((const double *) hx->d_sendbuf + halo->sdispls[p], (size_t) halo->sendcounts[p], ncclDouble, halo->recipients[p], comm->ncclcomm, stream);
-        if (r != ncclSuccess) { if (errcode) *errcode = (int) r; return ACG_ERR_NCCL; }
-    }
-    r = ncclGroupEnd();
+    const ncclResult_t rend = ncclGroupEnd();          /* always closed, also after a failed call inside */
+    if (r == ncclSuccess) r = rend;
     if (r != ncclSuccess) { if (errcode) *errcode = (int) r; return ACG_ERR_NCCL; }
     if (!warmup) {
         halo->nmpisend += halo->nrecipients; halo->Bmpisend += (int64_t) halo->sendsize * (int64_t) sizeof(double);
