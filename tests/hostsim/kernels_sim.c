@@ -112,11 +112,31 @@ int acgb200_spmv_configure(struct acgb200_spmvplan *pl)
 
 /* ---- SpMV ------------------------------------------------------------------ */
 
+/* column of entry k of `row`: from the index array, or -- index-free tile -- rebuilt from the row's
+ * pattern (row + offset), as spmv_ctiles_kernel does; returns -1 if the two disagree */
+static int entry_column(const struct acgb200_spmvargs *a, int row, int k, int compressed_tile)
+{
+    const struct acgb200_spmvplan *pl = a->plan;
+    if (!compressed_tile) return a->colidx[k];
+    const int id = pl->d_patid[row];
+    if (id == (int) ACGB200_NOPATTERN || id >= pl->npat) return -1;
+    const int j = k - a->rowptr[row];
+    if (pl->d_patptr[id] + j >= pl->d_patptr[id + 1]) return -1;
+    const int col = row + pl->d_patoff[pl->d_patptr[id] + j];
+    return col == a->colidx[k] ? col : -1;
+}
+
+static int hostsim_bad_pattern = 0;
+
 /* local block, plus -- fused peer-memory mode -- the border x ghost block with ghosts from the window */
-static double row_product(const struct acgb200_spmvargs *a, int row, const double **xg, int iter)
+static double row_product_t(const struct acgb200_spmvargs *a, int row, const double **xg, int iter, int compressed_tile)
 {
     double sum = 0.0;
-    for (int k = a->rowptr[row]; k < a->rowptr[row + 1]; k++) sum = fma(a->a[k], a->x[a->colidx[k]], sum);
+    for (int k = a->rowptr[row]; k < a->rowptr[row + 1]; k++) {
+        const int col = entry_column(a, row, k, compressed_tile);
+        if (col < 0) { hostsim_bad_pattern = 1; return NAN; }
+        sum = fma(a->a[k], a->x[col], sum);
+    }
     if (a->p2p && row >= a->od_rowoffset) {
         struct acgb200_p2pdev *P = (struct acgb200_p2pdev *) a->p2p;
         if (!*xg) {
@@ -127,6 +147,11 @@ static double row_product(const struct acgb200_spmvargs *a, int row, const doubl
         for (int k = a->orowptr[ob]; k < a->orowptr[ob + 1]; k++) sum = fma(a->oa[k], (*xg)[a->ocolidx[k]], sum);
     }
     return sum;
+}
+
+static double row_product(const struct acgb200_spmvargs *a, int row, const double **xg, int iter)
+{
+    return row_product_t(a, row, xg, iter, 0);
 }
 
 static void row_epilogue(const struct acgb200_spmvargs *a, int row, double sum, double *dot)
@@ -162,7 +187,9 @@ static void spmv_exec(void *p)
             for (int t = 0; t < pl->ntiles; t++) {
                 const struct acgb200_tile tl = pl->d_tiles[t];
                 const int nrows = tl.nrows & ~ACGB200_TILE_COMPRESSED;
-                for (int r = tl.row_begin; r < tl.row_begin + nrows; r++) row_epilogue(a, r, row_product(a, r, &xg, g.iter), &dot);
+                const int cmp = pl->compressed && (tl.nrows & ACGB200_TILE_COMPRESSED) != 0;
+                for (int r = tl.row_begin; r < tl.row_begin + nrows; r++)
+                    row_epilogue(a, r, row_product_t(a, r, &xg, g.iter, cmp), &dot);
             }
             if (a->acc) *a->acc += dot;
             if (a->p2p && a->pub_ch >= 0 && a->p2p->fuse) {

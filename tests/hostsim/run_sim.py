@@ -35,7 +35,7 @@ def main():
     cg = ab.SolverCuda(A)
     inf = cg.info()
     b = A.vector(); b.x[:] = np.random.default_rng(5).standard_normal(n)
-    out = {"nlong": inf["spmv_nlong"], "nmedium": inf["spmv_nmedium"], "ntiles": inf["spmv_ntiles"], "runs": []}
+    out = {"nlong": inf["spmv_nlong"], "nmedium": inf["spmv_nmedium"], "ntiles": inf["spmv_ntiles"], "compressed_tiles": inf["spmv_compressed_tiles"], "runs": []}
     y, _ = cg.spmv(b.x)
     want = O.dsymv(csr, 1.0, b.x, 0.0, np.zeros(n))
     out["spmv_err"] = float(np.abs(y - want).max() / np.abs(want).max())

@@ -268,3 +268,15 @@ def test_c_example_program(simlib, tmp_path):
         x = np.array([float(t) for t in p.stdout.splitlines()[2:]])
         assert len(x) == n and np.abs(x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
         assert f"iterations: {want['niterations']}" in p.stderr
+
+
+@pytest.mark.parametrize("fused", [0, 1], ids=["two-kernel", "one-kernel"])
+def test_index_free_tile_plan_in_the_solver(fused, simlib):
+    """Option spmv_compress through acgsolvercuda_init: dictionary, pattern ids and tile flags reach
+    the "device"; the stand-in SpMV rebuilds the columns of compressed tiles from them (row + offset)
+    and refuses any entry that disagrees with the index array."""
+    out = _run({"matrix": "27pt", "options": {"spmv_compress": 1, "pcg_fused": fused},
+                "runs": [{"method": "solvempi", "maxits": 9}, {"method": "solve_pipelined", "maxits": 200, "rtol": 1e-9},
+                         {"method": "solve_pipelined", "maxits": 7}]})
+    _check(out)
+    assert out["compressed_tiles"] > 0.5 * out["ntiles"]
