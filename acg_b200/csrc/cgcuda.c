@@ -56,8 +56,9 @@ static struct {
     int pdl;            /* 1: programmatic dependent launch along the iteration chain (opt-in) */
     int pcg_fused;      /* 1: pipelined CG as one kernel per iteration (SpMV + update fused, opt-in) */
     int spmv_medium;    /* > 0: rows longer than this (and shorter than a tile) get a warp each (opt-in) */
+    int p2p_unified;    /* one-kernel iteration between GPUs: one CSR over [owned | ghost], vectors in the window */
     int loaded;
-} cfg = { .check_every = 8, .graph = 1, .redstream = 1, .p2p = 1, .p2p_fuse = 1 };
+} cfg = { .check_every = 8, .graph = 1, .redstream = 1, .p2p = 1, .p2p_fuse = 1, .p2p_unified = 1 };
 
 static void cfg_load(void)
 {
@@ -83,6 +84,7 @@ static void cfg_load(void)
     if ((s = getenv("ACGB200_PDL"))) cfg.pdl = atoi(s);
     if ((s = getenv("ACGB200_PCG_FUSED"))) cfg.pcg_fused = atoi(s);
     if ((s = getenv("ACGB200_SPMV_MEDIUM"))) cfg.spmv_medium = atoi(s);
+    if ((s = getenv("ACGB200_P2P_UNIFIED"))) cfg.p2p_unified = atoi(s);
     acgb200_blas1_set_ctas_per_sm(cfg.blas1_ctas);
     acgb200_set_pdl(cfg.pdl);
 }
@@ -108,6 +110,7 @@ int acgb200_set_option(const char *key, int value)
     else if (!strcmp(key, "pdl")) { cfg.pdl = value; acgb200_set_pdl(value); }
     else if (!strcmp(key, "pcg_fused")) cfg.pcg_fused = value;
     else if (!strcmp(key, "spmv_medium")) cfg.spmv_medium = value < 0 ? 0 : value;
+    else if (!strcmp(key, "p2p_unified")) cfg.p2p_unified = value;
     else return ACG_ERR_INVALID_VALUE;
     return ACG_SUCCESS;
 }
@@ -139,6 +142,12 @@ struct priv {
     int graph_launches[3];              /* kernel/NCCL launches inside one replay */
     double *d_w2;                       /* second w buffer of the one-kernel pipelined iteration */
     int fused_grid;                     /* its grid (0: not available for this plan) */
+    /* the same between GPUs with one CSR over [owned | pad | ghost] columns (ensure_unified) */
+    struct acgb200_spmvplan uplan;
+    int *d_urowptr, *d_ucolidx, *d_uzero;
+    double *d_ua;
+    int ufused_grid, unified;           /* unified: 0 not tried, 1 in use, -1 not possible for this matrix */
+    int graph2_unified;                 /* layout the cached one-kernel graph was captured with */
     double last_h2d_ms, last_d2h_ms;    /* host time spent before / after the solve window */
     cudaEvent_t ev_t0, ev_t1;           /* device-side bracket of the solve window */
     double last_solve_ms;
@@ -225,11 +234,14 @@ void acgsolvercuda_free(struct acgsolvercuda *cg)
             acgb200_p2p_free(&pv->p2p);
             if (pv->have_redcomm) { acgcomm_barrier(pv->stream, &pv->redcomm, NULL); cudaStreamSynchronize(pv->stream); }
             cudaFree(pv->p2p.window);
-            pv->p2p.window = NULL;
+            cudaFree(pv->p2p.vwindow);
+            pv->p2p.window = pv->p2p.vwindow = NULL;
         }
         if (pv->have_redcomm && pv->redcomm.ncclcomm) ncclCommDestroy(pv->redcomm.ncclcomm);
         for (int i = 0; i < 3; i++) if (pv->graph[i]) cudaGraphExecDestroy(pv->graph[i]);
         cudaFree(pv->d_w2);
+        cudaFree(pv->d_urowptr); cudaFree(pv->d_ucolidx); cudaFree(pv->d_ua); cudaFree(pv->d_uzero);
+        cudaFree(pv->uplan.d_tiles); cudaFree(pv->uplan.d_longrows); cudaFree(pv->uplan.d_long_scratch); cudaFree(pv->uplan.d_medrows);
         cudaFree(pv->plan.d_tiles); cudaFree(pv->plan.d_longrows); cudaFree(pv->plan.d_long_scratch); cudaFree(pv->plan.d_medrows);
         cudaFree(pv->plan.d_patptr); cudaFree(pv->plan.d_patoff); cudaFree(pv->plan.d_patid);
         cudaFree(pv->d_st);
@@ -615,6 +627,7 @@ struct solvectx {
     int launches;
     int capturing;            /* inside cudaStreamBeginCapture: no profiling marks */
     int p2p;                  /* loop exchanges go through peer memory */
+    struct acgb200_p2pdev *postdesc;   /* descriptor comm_post pushes through (NULL: the ordinary one) */
 };
 
 static int evpool_reserve(struct evpool *p, int n)
@@ -721,7 +734,7 @@ static int post(struct solvectx *c, int ctrl_slot, int iter_override, const doub
     int *errcode = c->errcode;
     struct acgb200_postargs a;
     memset(&a, 0, sizeof(a));
-    a.p2p = pv->p2p.d_desc;
+    a.p2p = c->postdesc ? c->postdesc : pv->p2p.d_desc;
     a.cin = &pv->d_st->ctrl[ctrl_slot]; a.st = pv->d_st;
     a.iter_override = iter_override;
     a.vec = vec; a.sendbufidx = (const int *) c->cg->haloexchange->d_sendbufidx;
@@ -1121,6 +1134,84 @@ static int pipelined_iteration(struct solvectx *c, int k)
     return ACG_SUCCESS;
 }
 
+/*
+ * One CSR over [owned | pad | ghost] columns for the one-kernel iteration between GPUs.  The
+ * reference's split into a local block and a border x ghost block (acg/symcsrmatrix.c:760-851)
+ * is kept for everything else; here the two are merged row by row (ghost column g becomes
+ * goff + g, goff = owned count rounded up to 16) so that border rows are TMA-staged like interior
+ * ones, and the SpMV input vectors are placed in an exported allocation whose ghost tail the
+ * neighbours write (p2p.c, acgb200_p2p_unify).  Collective (all ranks solve with the same options).
+ * Sets pv->unified to 1, or to -1 when the merged plan has no fused variant (long rows).
+ */
+static int ensure_unified(struct solvectx *c, const struct acgsymcsrmatrix *A)
+{
+    struct priv *pv = c->pv;
+    int *errcode = c->errcode;
+    if (pv->unified) return ACG_SUCCESS;
+    const int no = pv->nowned, nb = pv->nborder, boff = pv->borderoff, base = A->rowidxbase;
+    const int goff = (no + 15) & ~15;
+    int64_t *rp = malloc(((size_t) no + 1) * sizeof(*rp));
+    if (!rp) return ACG_ERR_ERRNO;
+    rp[0] = 0;
+    int64_t maxlen = 0;
+    for (int i = 0; i < no; i++) {
+        int64_t len = A->frowptr[i + 1] - A->frowptr[i];
+        if (i >= boff && i < boff + nb) len += A->orowptr[i - boff + 1] - A->orowptr[i - boff];
+        rp[i + 1] = rp[i] + len;
+        if (len > maxlen) maxlen = len;
+    }
+    const int64_t nnz = rp[no];
+    acgidx_t *ci = malloc((size_t) (nnz > 0 ? nnz : 1) * sizeof(*ci));
+    double *va = malloc((size_t) (nnz > 0 ? nnz : 1) * sizeof(*va));
+    if (!ci || !va) { free(rp); free(ci); free(va); return ACG_ERR_ERRNO; }
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < no; i++) {
+        int64_t l = rp[i];
+        for (int64_t k = A->frowptr[i]; k < A->frowptr[i + 1]; k++, l++) { ci[l] = A->fcolidx[k] - base; va[l] = A->fa[k]; }
+        if (i >= boff && i < boff + nb) {
+            /* columns of the border x ghost block are rebased by -borderrowoffset: ghost number = column - nborder */
+            for (int64_t k = A->orowptr[i - boff]; k < A->orowptr[i - boff + 1]; k++, l++) {
+                ci[l] = goff + (A->ocolidx[k] - base - nb); va[l] = A->oa[k];
+            }
+        }
+    }
+    int err = ACG_SUCCESS;
+    acgb200_spmv_choose(&pv->uplan, no, nnz, maxlen);
+    if (cfg.spmv_lanes > 0) pv->uplan.lanes_per_row = cfg.spmv_lanes;
+    if (cfg.spmv_nnz_cap > 0) pv->uplan.nnz_cap = cfg.spmv_nnz_cap;
+    if (cfg.spmv_rows_cap > 0) pv->uplan.rows_cap = cfg.spmv_rows_cap;
+    if (cfg.spmv_stages > 0) pv->uplan.nstages = cfg.spmv_stages > 8 ? 8 : cfg.spmv_stages;
+    pv->uplan.max_ctas_per_sm = cfg.spmv_max_ctas;
+    err = build_tiles(&pv->uplan, rp, NULL, errcode);
+    if (!err && acgb200_spmv_configure(&pv->uplan)) err = ACG_ERR_CUDA;
+    if (!err) pv->ufused_grid = acgb200_pcg_fused_grid(&pv->uplan);
+    if (!err && pv->ufused_grid > 0) {
+        err = upload_rowptr(&pv->d_urowptr, rp, no, 8, errcode);
+        if (!err) err = upload_block(&pv->d_ucolidx, &pv->d_ua, ci, va, nnz, 0, 16, errcode);
+        if (!err) {
+            cudaError_t e = cudaMalloc((void **) &pv->d_uzero, ((size_t) nb + 1 + 8) * sizeof(int));
+            if (!e) e = cudaMemset(pv->d_uzero, 0, ((size_t) nb + 1 + 8) * sizeof(int));
+            if (e) { *errcode = (int) e; err = ACG_ERR_CUDA; }
+        }
+    }
+    free(rp); free(ci); free(va);
+    if (err) return err;
+    /* every rank must take the same branch: agree on whether the merged plan is usable */
+    int ok = pv->ufused_grid > 0, allok = 0, *d_ok = NULL;
+    CU(cudaMalloc((void **) &d_ok, sizeof(int)));
+    CU(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    ncclResult_t r = ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c->comm->ncclcomm, pv->stream);
+    cudaError_t ce = r == ncclSuccess ? cudaMemcpyAsync(&allok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, pv->stream) : cudaSuccess;
+    if (!ce) ce = cudaStreamSynchronize(pv->stream);
+    cudaFree(d_ok);
+    if (r != ncclSuccess) { *errcode = (int) r; return ACG_ERR_NCCL; }
+    CU(ce);
+    if (!allok) { pv->unified = -1; return ACG_SUCCESS; }
+    OK(acgb200_p2p_unify(&pv->p2p, c->cg->halo, no, pv->nghost, c->comm, pv->stream, errcode));
+    pv->unified = 1;
+    return ACG_SUCCESS;
+}
+
 /* One launch per iteration: q = A w fused with the update (kernels.cu,
  * pcg_fused_kernel).  Iteration k reads control word k&1 and w buffer k&1. */
 static int fused_iteration(struct solvectx *c, int k)
@@ -1129,19 +1220,34 @@ static int fused_iteration(struct solvectx *c, int k)
     struct priv *pv = c->pv;
     int *errcode = c->errcode;
     const int peer = c->multi && c->p2p;
+    const int unified = peer && pv->unified == 1;
     struct acgb200_spmvargs a;
     memset(&a, 0, sizeof(a));
-    a.plan = &pv->plan;
-    a.rowptr = cg->d_rowptr; a.colidx = cg->d_colidx; a.a = cg->d_a;
     a.st = pv->d_st;
-    if (peer) {
-        a.p2p = pv->p2p.d_desc;
+    double *w0 = cg->d_w, *w1 = pv->d_w2;
+    int grid = pv->fused_grid;
+    if (unified) {
+        /* merged CSR, vectors in the exported allocation, ghost values arrive in their tails; the
+         * kernel's border x ghost loop sees empty rows (d_uzero) */
+        a.plan = &pv->uplan;
+        a.rowptr = pv->d_urowptr; a.colidx = pv->d_ucolidx; a.a = pv->d_ua;
+        a.p2p = pv->p2p.d_desc_u;
         a.od_rowoffset = pv->borderoff; a.od_nrows = pv->nborder;
-        a.orowptr = cg->d_orowptr; a.ocolidx = cg->d_ocolidx; a.oa = cg->d_oa;
+        a.orowptr = pv->d_uzero; a.ocolidx = pv->d_uzero; a.oa = pv->d_ua;
+        w0 = acgb200_p2p_uvec(&pv->p2p, 0); w1 = acgb200_p2p_uvec(&pv->p2p, 1);
+        grid = pv->ufused_grid;
+    } else {
+        a.plan = &pv->plan;
+        a.rowptr = cg->d_rowptr; a.colidx = cg->d_colidx; a.a = cg->d_a;
+        if (peer) {
+            a.p2p = pv->p2p.d_desc;
+            a.od_rowoffset = pv->borderoff; a.od_nrows = pv->nborder;
+            a.orowptr = cg->d_orowptr; a.ocolidx = cg->d_ocolidx; a.oa = cg->d_oa;
+        }
     }
     prof_mark(c, &pv->gemv);
-    KL(acgb200_pcg_fused_launch(&a, pv->fused_grid, k & 1, c->multi, cg->d_z, cg->d_t, cg->d_p, cg->d_r, c->d_x,
-                                cg->d_w, pv->d_w2, pv->stream));
+    KL(acgb200_pcg_fused_launch(&a, grid, k & 1, c->multi, cg->d_z, cg->d_t, cg->d_p, cg->d_r, c->d_x,
+                                w0, w1, pv->stream));
     prof_mark(c, &pv->gemv);
     c->launches += 1;
     return ACG_SUCCESS;
@@ -1173,7 +1279,13 @@ int acgsolvercuda_solve_pipelined(
     c.p2p = c.multi && pv->p2p.enabled && cfg.p2p;
     /* one kernel per iteration: on one GPU, or with the fused peer-memory exchange */
     int fused = 0;
-    if (cfg.pcg_fused && (!c.multi || (c.p2p && pv->p2p.h_desc.fuse))) {
+    if (cfg.pcg_fused && c.multi && c.p2p && pv->p2p.h_desc.fuse && cfg.p2p_unified) OK(ensure_unified(&c, A));
+    const int unified = c.multi && c.p2p && pv->unified == 1 && cfg.pcg_fused && cfg.p2p_unified;
+    if (unified) {
+        fused = 1;
+        c.postdesc = pv->p2p.d_desc_u;
+    } else if (cfg.pcg_fused && (!c.multi || (c.p2p && pv->p2p.h_desc.fuse))) {
+        if (pv->unified == 1) pv->unified = -1;       /* set up earlier but switched off now: use the split layout */
         if (!pv->fused_grid) pv->fused_grid = acgb200_pcg_fused_grid(&pv->plan);
         if (pv->fused_grid > 0) {
             if (!pv->d_w2) {
@@ -1183,6 +1295,11 @@ int acgsolvercuda_solve_pipelined(
             fused = 1;
         }
     }
+    if (pv->graph[2] && pv->graph2_unified != unified) {
+        /* the cached replay addresses the other layout's arrays */
+        cudaGraphExecDestroy(pv->graph[2]); pv->graph[2] = NULL;
+    }
+    pv->graph2_unified = unified;
     int (*const iteration)(struct solvectx *, int) = fused ? fused_iteration : pipelined_iteration;
     if (warmup > 0) {
         memset(&h, 0, sizeof(h));
@@ -1190,6 +1307,7 @@ int acgsolvercuda_solve_pipelined(
         for (int s = 0; s < 2; s++) { h.gd_loc[s][0] = h.gd[s][0] = 1; h.gd_loc[s][1] = h.gd[s][1] = 1; h.prev[s][0] = h.prev[s][1] = INFINITY; }
         OK(push_state(&c, &h));
         double *xsave = c.d_x; c.d_x = cg->d_r;
+        if (unified) CU(cudaMemcpyAsync(acgb200_p2p_uvec(&pv->p2p, 0), cg->d_w, obytes, cudaMemcpyDeviceToDevice, pv->stream));
         if (c.p2p) {
             OK(acgb200_p2p_begin(&pv->p2p, warmup, pv->stream));
             OK(post(&c, 0, 0, cg->d_w, -1, NULL, 0, 0, 0, 0));
@@ -1248,6 +1366,7 @@ int acgsolvercuda_solve_pipelined(
         h.gd_loc[0][1] = h.gd[0][1] = gd0[1];
         h.prev[0][0] = h.prev[0][1] = INFINITY;                    /* acg/cgcuda.c:1513-1514 */
         OK(push_state(&c, &h));
+        if (unified) CU(cudaMemcpyAsync(acgb200_p2p_uvec(&pv->p2p, 0), cg->d_w, obytes, cudaMemcpyDeviceToDevice, pv->stream));
         if (c.p2p) {
             /* w_0 goes to the neighbours' windows as exchange number 0 */
             OK(acgb200_p2p_begin(&pv->p2p, maxits, pv->stream));

@@ -68,7 +68,8 @@ def local_matvec(m, h, xl):
 # exchange back-ends of the CG loop (options of acgb200_set_option on top of the defaults)
 BACKEND_OPTIONS = {"p2p-fused": {}, "p2p-unfused": {"p2p_fuse": 0}, "nccl": {"p2p": 0},
                    "nccl-graph": {"p2p": 0, "graph": 2}, "nccl-serial-reduce": {"p2p": 0, "redstream": 0},
-                   "one-kernel": {"pcg_fused": 1}, "pdl": {"pdl": 1}, "one-kernel-pdl": {"pcg_fused": 1, "pdl": 1},
+                   "one-kernel": {"pcg_fused": 1}, "one-kernel-split": {"pcg_fused": 1, "p2p_unified": 0},
+                   "pdl": {"pdl": 1}, "one-kernel-pdl": {"pcg_fused": 1, "pdl": 1},
                    "watchdog": {}}
 
 
@@ -153,7 +154,7 @@ def main():
         assert comm.size() == world and comm.rank() == rank
         b = m.vector(); b.x[:no] = bglob[m.nzrows[:no]]
         methods = []
-        defaults = {"p2p": 1, "p2p_fuse": 1, "graph": 1, "redstream": 1, "pcg_fused": 0, "pdl": 0}
+        defaults = {"p2p": 1, "p2p_fuse": 1, "graph": 1, "redstream": 1, "pcg_fused": 0, "pdl": 0, "p2p_unified": 1}
         for be in (args.backends.split(",") if args.backends else [""]):
             if be:
                 for key, val in {**defaults, **BACKEND_OPTIONS[be]}.items():

@@ -504,14 +504,17 @@ static void fused_exec(void *vp)
     for (int t = 0; t < pl->ntiles; t++) {
         const struct acgb200_tile tl = pl->d_tiles[t];
         const int nrows = tl.nrows & ~ACGB200_TILE_COMPRESSED;
+        if (P && !xg && tl.row_begin + nrows > a->sp.od_rowoffset) {
+            /* as in the kernel: the first tile that reaches the border rows waits for the neighbours'
+             * values BEFORE any of its gathers -- with the unified layout the ghost values are read
+             * through the ordinary column indices */
+            p2p_wait_halo(P, P->hbase + (unsigned long long) g.iter);
+            xg = P->my_ghost[s] - a->sp.od_nrows;
+        }
         for (int row = tl.row_begin; row < tl.row_begin + nrows; row++) {
             double qv = 0.0;
             for (int k = a->sp.rowptr[row]; k < a->sp.rowptr[row + 1]; k++) qv = fma(a->sp.a[k], wold[a->sp.colidx[k]], qv);
             if (P && row >= a->sp.od_rowoffset) {
-                if (!xg) {
-                    p2p_wait_halo(P, P->hbase + (unsigned long long) g.iter);
-                    xg = P->my_ghost[s] - a->sp.od_nrows;
-                }
                 const int ob = row - a->sp.od_rowoffset;
                 for (int k = a->sp.orowptr[ob]; k < a->sp.orowptr[ob + 1]; k++) qv = fma(a->sp.oa[k], xg[a->sp.ocolidx[k]], qv);
             }

@@ -135,7 +135,7 @@ def _free_port():
 
 
 @pytest.mark.parametrize("nproc,matrix,size,partition,backends,extra", [
-    (2, "27pt", 8, "block", "p2p-fused,p2p-unfused,nccl,nccl-graph,nccl-serial-reduce,one-kernel", []),
+    (2, "27pt", 8, "block", "p2p-fused,p2p-unfused,nccl,nccl-graph,nccl-serial-reduce,one-kernel,one-kernel-split", []),
     (3, "7pt", 9, "slab", "watchdog,p2p-fused,one-kernel,nccl", []),
     (4, "rmat", 3000, "random", "p2p-fused,one-kernel", ["--maxits", "12", "--rtol", "0"]),
 ], ids=["2-ranks-all-backends", "3-ranks", "4-ranks-power-law"])
@@ -145,7 +145,8 @@ def test_multi_rank_loops(nproc, matrix, size, partition, backends, extra, simli
     are really shared between the processes, NCCL replaced by a file-based stand-in, and the
     simulated kernels speaking the exchange protocol of kernels.cu (sequence-numbered flags,
     parity-buffered ghost values and reduction slots).  Every loop back-end -- peer memory with
-    and without the pushes fused into the kernels, the one-kernel pipelined iteration, NCCL with
+    and without the pushes fused into the kernels, the one-kernel pipelined iteration (with the unified
+    [owned | ghost] layout and with the split one), NCCL with
     and without graph replay and with the reduction on the main stream -- must reproduce the
     single-rank oracle.  What this cannot see: anything inside the CUDA kernels, and stream-level
     concurrency on a real device."""
