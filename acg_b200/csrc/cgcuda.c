@@ -1177,10 +1177,12 @@ static int ensure_unified(struct solvectx *c, const struct acgsymcsrmatrix *A)
     }
     int err = ACG_SUCCESS;
     acgb200_spmv_choose(&pv->uplan, no, nnz, maxlen);
-    if (cfg.spmv_lanes > 0) pv->uplan.lanes_per_row = cfg.spmv_lanes;
-    if (cfg.spmv_nnz_cap > 0) pv->uplan.nnz_cap = cfg.spmv_nnz_cap;
-    if (cfg.spmv_rows_cap > 0) pv->uplan.rows_cap = cfg.spmv_rows_cap;
-    if (cfg.spmv_stages > 0) pv->uplan.nstages = cfg.spmv_stages > 8 ? 8 : cfg.spmv_stages;
+    /* same tile shape as the local block's plan: the few longer border rows must not enlarge the
+     * stages (shared memory per CTA decides how many CTAs an SM holds) -- border tiles simply end
+     * after fewer rows */
+    pv->uplan.lanes_per_row = pv->plan.lanes_per_row; pv->uplan.rows_cap = pv->plan.rows_cap;
+    pv->uplan.nnz_cap = pv->plan.nnz_cap; pv->uplan.nstages = pv->plan.nstages;
+    pv->uplan.threads = pv->plan.threads; pv->uplan.unroll = pv->plan.unroll;
     pv->uplan.max_ctas_per_sm = cfg.spmv_max_ctas;
     err = build_tiles(&pv->uplan, rp, NULL, errcode);
     if (!err && acgb200_spmv_configure(&pv->uplan)) err = ACG_ERR_CUDA;
