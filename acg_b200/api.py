@@ -116,7 +116,7 @@ class acgb200_info(C.Structure):
                                                                                   ("spmv_compressed_tiles", C.c_int),
                                                                                   ("spmv_min_bytes", C.c_int64),
                                                                                   ("spmv_nmedium", C.c_int),
-                                                                                  ("pad0", C.c_int)]
+                                                                                  ("last_layout", C.c_int)]
 
 
 class acgb200_mtxinfo(C.Structure):

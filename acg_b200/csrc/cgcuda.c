@@ -56,7 +56,8 @@ static struct {
     int pdl;            /* 1: programmatic dependent launch along the iteration chain (opt-in) */
     int pcg_fused;      /* 1: pipelined CG as one kernel per iteration (SpMV + update fused, opt-in) */
     int spmv_medium;    /* > 0: rows longer than this (and shorter than a tile) get a warp each (opt-in) */
-    int p2p_unified;    /* one-kernel iteration between GPUs: one CSR over [owned | ghost], vectors in the window */
+    int p2p_unified;    /* one CSR over [owned | ghost], vectors in the exported allocation: 1 for the one-kernel
+                         * pipelined iteration (default), 2 also for the classic loop (opt-in) */
     int loaded;
 } cfg = { .check_every = 8, .graph = 1, .redstream = 1, .p2p = 1, .p2p_fuse = 1, .p2p_unified = 1 };
 
@@ -147,7 +148,8 @@ struct priv {
     int *d_urowptr, *d_ucolidx, *d_uzero;
     double *d_ua;
     int ufused_grid, unified;           /* unified: 0 not tried, 1 in use, -1 not possible for this matrix */
-    int graph2_unified;                 /* layout the cached one-kernel graph was captured with */
+    int graph2_unified, graph0_unified; /* layout the cached one-kernel / classic graphs were captured with */
+    int last_layout;                    /* see struct acgb200_info */
     double last_h2d_ms, last_d2h_ms;    /* host time spent before / after the solve window */
     cudaEvent_t ev_t0, ev_t1;           /* device-side bracket of the solve window */
     double last_solve_ms;
@@ -627,7 +629,8 @@ struct solvectx {
     int launches;
     int capturing;            /* inside cudaStreamBeginCapture: no profiling marks */
     int p2p;                  /* loop exchanges go through peer memory */
-    struct acgb200_p2pdev *postdesc;   /* descriptor comm_post pushes through (NULL: the ordinary one) */
+    struct acgb200_p2pdev *postdesc;   /* descriptor the loop's kernels and posts use (NULL: the ordinary one) */
+    int unified;              /* this solve runs on the merged [owned | ghost] CSR with vectors in the exported allocation */
 };
 
 static int evpool_reserve(struct evpool *p, int n)
@@ -696,11 +699,19 @@ static int apply_A(struct solvectx *c, const double *x_ro, double *x_halo, doubl
         a.p2p = pv->p2p.d_desc;
         a.od_rowoffset = pv->borderoff; a.od_nrows = pv->nborder;
         a.orowptr = cg->d_orowptr; a.ocolidx = cg->d_ocolidx; a.oa = cg->d_oa;
-        if (pub_ch >= 0 && pv->plan.nlong == 0 && pv->plan.nmed == 0) a.pub_ch = pub_ch;
+        if (c->unified) {
+            /* merged CSR: ghost values are gathered through the ordinary column indices from the
+             * tail of x (which lives in the exported allocation); the border x ghost loop is empty */
+            a.plan = &pv->uplan;
+            a.rowptr = pv->d_urowptr; a.colidx = pv->d_ucolidx; a.a = pv->d_ua;
+            a.p2p = c->postdesc;
+            a.orowptr = pv->d_uzero; a.ocolidx = pv->d_uzero; a.oa = pv->d_ua;
+        }
+        if (pub_ch >= 0 && a.plan->nlong == 0 && a.plan->nmed == 0) a.pub_ch = pub_ch;
     }
     prof_mark(c, &pv->gemv);
     KL(acgb200_spmv_launch(&a, pv->stream));
-    c->launches += 1 + (pv->plan.nlong > 0 ? 2 : 0) + (pv->plan.nmed > 0 ? 1 : 0);
+    c->launches += 1 + (a.plan->nlong > 0 ? 2 : 0) + (a.plan->nmed > 0 ? 1 : 0);
     if (c->multi && !fused) {
         if (!peer) {
             OK(acghalo_exchange_cuda_end(cg->halo, cg->haloexchange, pv->nvec, x_halo, ACG_DOUBLE,
@@ -916,6 +927,8 @@ static int iterate(struct solvectx *c, int maxits, int poll, int kind, int (*iss
 /* classic CG                                                                */
 /* ------------------------------------------------------------------------ */
 
+static int ensure_unified(struct solvectx *c, const struct acgsymcsrmatrix *A);
+
 static int classic_iteration(struct solvectx *c, int k)
 {
     struct acgsolvercuda *cg = c->cg;
@@ -924,19 +937,23 @@ static int classic_iteration(struct solvectx *c, int k)
     int *errcode = c->errcode;
     const int s = k & 1, n = pv->nowned;
     const int peer = c->multi && c->p2p;
-    OK(apply_A(c, cg->d_p, cg->d_p, cg->d_t, NULL, SPMV_Y_AX_DOT, &st->pap_loc[s], 1, 1, 0, 0));
+    /* the search direction: the solver's own vector, or -- unified layout -- vector 0 of the exported allocation */
+    double *pvec = c->unified ? acgb200_p2p_uvec(&pv->p2p, 0) : cg->d_p;
+    struct acgb200_p2pdev *desc = !peer ? NULL : (c->postdesc ? c->postdesc : pv->p2p.d_desc);
+    const struct acgb200_spmvplan *pl = c->unified ? &pv->uplan : &pv->plan;
+    OK(apply_A(c, pvec, pvec, cg->d_t, NULL, SPMV_Y_AX_DOT, &st->pap_loc[s], 1, 1, 0, 0));
     if (peer) {
         /* (p,Ap) is published by the SpMV's last CTA; with long rows the dot is
          * only complete after the finishing kernel, so a separate post does it */
-        if (pv->plan.nlong > 0 || pv->plan.nmed > 0 || !pv->p2p.h_desc.fuse) OK(post(c, 1, -1, NULL, 0, &st->pap_loc[0], 1, 1, 0, 1));
+        if (pl->nlong > 0 || pl->nmed > 0 || !pv->p2p.h_desc.fuse) OK(post(c, 1, -1, NULL, 0, &st->pap_loc[0], 1, 1, 0, 1));
     } else OK(allreduce(c, &st->pap_loc[s], &st->pap[s], 1));
     prof_mark(c, &pv->blas);
-    KL(acgb200_cg_update_r(n, st, 1, 1, c->multi, pv->p2p.d_desc && peer ? pv->p2p.d_desc : NULL, cg->d_t, cg->d_r, pv->stream));
+    KL(acgb200_cg_update_r(n, st, 1, 1, c->multi, desc, cg->d_t, cg->d_r, pv->stream));
     if (!peer) OK(allreduce(c, &st->rr_loc[s ^ 1], &st->rr[s ^ 1], 1));
     else if (!pv->p2p.h_desc.fuse) OK(post(c, 1, -1, NULL, 1, &st->rr_loc[0], 1, 1, 1, 1));
-    KL(acgb200_cg_update_xp(n, st, 1, 0, c->multi, peer ? pv->p2p.d_desc : NULL, cg->d_r, cg->d_p, c->d_x, pv->stream));
+    KL(acgb200_cg_update_xp(n, st, 1, 0, c->multi, desc, cg->d_r, pvec, c->d_x, pv->stream));
     prof_mark(c, &pv->blas);
-    if (peer && !pv->p2p.h_desc.fuse) OK(post(c, 0, -1, cg->d_p, -1, NULL, 0, 0, 0, 0));     /* p for the next SpMV */
+    if (peer && !pv->p2p.h_desc.fuse) OK(post(c, 0, -1, pvec, -1, NULL, 0, 0, 0, 0));     /* p for the next SpMV */
     c->launches += 2 + (c->multi && !peer ? 2 : 0);
     return ACG_SUCCESS;
 }
@@ -976,6 +993,15 @@ int acgsolvercuda_solvempi(
     struct acgb200_devstate h;
 
     c.p2p = c.multi && pv->p2p.enabled && cfg.p2p;
+    /* opt-in: the loop on the merged [owned | ghost] CSR, p in the exported allocation */
+    if (c.p2p && pv->p2p.h_desc.fuse && cfg.p2p_unified >= 2) {
+        OK(ensure_unified(&c, A));
+        if (pv->unified == 1) { c.unified = 1; c.postdesc = pv->p2p.d_desc_c; }
+    }
+    if (pv->graph[0] && pv->graph0_unified != c.unified) { cudaGraphExecDestroy(pv->graph[0]); pv->graph[0] = NULL; }
+    pv->graph0_unified = c.unified;
+    pv->last_layout = c.unified ? 1 : 0;
+    double *const pvec = c.unified ? acgb200_p2p_uvec(&pv->p2p, 0) : cg->d_p;
     /* warm-up: `warmup` full iterations (every kernel, every communication path)
      * on state that is overwritten below (acg/cgcuda.c:607-705); d_r stands in
      * for x so the initial guess is untouched */
@@ -986,7 +1012,7 @@ int acgsolvercuda_solvempi(
         double *xsave = c.d_x; c.d_x = cg->d_r;
         if (c.p2p) {
             OK(acgb200_p2p_begin(&pv->p2p, warmup, pv->stream));
-            OK(post(&c, 0, 0, cg->d_p, -1, NULL, 0, 0, 0, 0));
+            OK(post(&c, 0, 0, pvec, -1, NULL, 0, 0, 0, 0));
         }
         for (int i = 0; i < warmup; i++) OK(classic_iteration(&c, i));
         c.d_x = xsave;
@@ -1020,7 +1046,7 @@ int acgsolvercuda_solvempi(
 
     /* r0 = b - A x0 with (r0,r0) folded in (acg/cgcuda.c:761-799,:819-832); p = r0 */
     OK(apply_A(&c, c.d_x, c.d_x, cg->d_r, c.d_b, SPMV_R_B_AX, &st->rr_loc[0], 0, 0, 0, -1));
-    CU(cudaMemcpyAsync(cg->d_p, cg->d_r, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, pv->stream));
+    CU(cudaMemcpyAsync(pvec, cg->d_r, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, pv->stream));
     OK(reduce_to_host(&c, &st->rr_loc[0], &st->rr[0], 1, &rr0));
     cg->rnrm2 = cg->r0nrm2 = sqrt(rr0);
     cg->ngemv++; cg->ncopy += 2; cg->nnrm2++;
@@ -1036,7 +1062,7 @@ int acgsolvercuda_solvempi(
         if (c.p2p) {
             /* p_0 = r_0 goes to the neighbours' windows as exchange number 0 */
             OK(acgb200_p2p_begin(&pv->p2p, maxits, pv->stream));
-            OK(post(&c, 0, 0, cg->d_p, -1, NULL, 0, 0, 0, 0));
+            OK(post(&c, 0, 0, pvec, -1, NULL, 0, 0, 0, 0));
         }
         OK(iterate(&c, maxits, tol > 0, 0, classic_iteration));
         OK(pull_state(&c, &h));
@@ -1222,7 +1248,7 @@ static int fused_iteration(struct solvectx *c, int k)
     struct priv *pv = c->pv;
     int *errcode = c->errcode;
     const int peer = c->multi && c->p2p;
-    const int unified = peer && pv->unified == 1;
+    const int unified = peer && c->unified;
     struct acgb200_spmvargs a;
     memset(&a, 0, sizeof(a));
     a.st = pv->d_st;
@@ -1285,9 +1311,9 @@ int acgsolvercuda_solve_pipelined(
     const int unified = c.multi && c.p2p && pv->unified == 1 && cfg.pcg_fused && cfg.p2p_unified;
     if (unified) {
         fused = 1;
+        c.unified = 1;
         c.postdesc = pv->p2p.d_desc_u;
     } else if (cfg.pcg_fused && (!c.multi || (c.p2p && pv->p2p.h_desc.fuse))) {
-        if (pv->unified == 1) pv->unified = -1;       /* set up earlier but switched off now: use the split layout */
         if (!pv->fused_grid) pv->fused_grid = acgb200_pcg_fused_grid(&pv->plan);
         if (pv->fused_grid > 0) {
             if (!pv->d_w2) {
@@ -1302,6 +1328,7 @@ int acgsolvercuda_solve_pipelined(
         cudaGraphExecDestroy(pv->graph[2]); pv->graph[2] = NULL;
     }
     pv->graph2_unified = unified;
+    pv->last_layout = (unified ? 1 : 0) + (fused ? 2 : 0);
     int (*const iteration)(struct solvectx *, int) = fused ? fused_iteration : pipelined_iteration;
     if (warmup > 0) {
         memset(&h, 0, sizeof(h));
@@ -1600,6 +1627,7 @@ int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info
     info->num_sms = acgb200_num_sms();
     info->spmv_compressed_tiles = pv->plan.ncompressed_tiles;
     info->spmv_nmedium = pv->plan.nmed;
+    info->last_layout = pv->last_layout;
     info->spmv_min_bytes = acgb200_spmv_min_bytes(&pv->plan);
     return ACG_SUCCESS;
 }

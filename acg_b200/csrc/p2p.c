@@ -64,7 +64,7 @@ void acgb200_p2p_free(struct acgb200_p2p *p)
         if (r != p->rank && p->peer_base[r]) cudaIpcCloseMemHandle(p->peer_base[r]);
     for (int r = 0; r < p->nranks; r++)
         if (r != p->rank && p->peer_vbase[r]) cudaIpcCloseMemHandle(p->peer_vbase[r]);
-    cudaFree(p->d_desc_u);
+    cudaFree(p->d_desc_u); cudaFree(p->d_desc_c);
     /* like the window, the vector allocation is freed by the caller after a barrier */
     cudaFree((void *) p->h_desc.bptr); cudaFree((void *) p->h_desc.bq); cudaFree((void *) p->h_desc.bdst);
     cudaFree(p->d_desc);
@@ -234,6 +234,12 @@ int acgb200_p2p_unify(struct acgb200_p2p *p, const struct acghalo *halo, int now
     free(all);
     CUP(cudaMalloc((void **) &p->d_desc_u, sizeof(u)));
     CUP(cudaMemcpy(p->d_desc_u, &u, sizeof(u), cudaMemcpyHostToDevice));
+    /* classic CG: p is updated in place and a rank cannot be a whole iteration ahead of a
+     * neighbour still reading it (two reductions per iteration), so one vector serves both parities */
+    for (int i = 0; i < halo->nrecipients; i++) u.peer_ghost[i][1] = u.peer_ghost[i][0];
+    u.my_ghost[1] = u.my_ghost[0];
+    CUP(cudaMalloc((void **) &p->d_desc_c, sizeof(u)));
+    CUP(cudaMemcpy(p->d_desc_c, &u, sizeof(u), cudaMemcpyHostToDevice));
     return ACG_SUCCESS;
 #undef CUP
 }
@@ -252,6 +258,9 @@ int acgb200_p2p_begin(struct acgb200_p2p *p, int maxits, cudaStream_t stream)
     if (e == cudaSuccess && p->d_desc_u)
         e = cudaMemcpyAsync(&p->d_desc_u->hbase, &p->h_desc.hbase, 3 * sizeof(unsigned long long),
                             cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess && p->d_desc_c)
+        e = cudaMemcpyAsync(&p->d_desc_c->hbase, &p->h_desc.hbase, 3 * sizeof(unsigned long long),
+                            cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     return e == cudaSuccess ? ACG_SUCCESS : ACG_ERR_CUDA;
 }
@@ -259,11 +268,13 @@ int acgb200_p2p_begin(struct acgb200_p2p *p, int maxits, cudaStream_t stream)
 /* after a solve: did any wait for a peer time out? */
 int acgb200_p2p_timed_out(struct acgb200_p2p *p, cudaStream_t stream, int *flag)
 {
-    unsigned long long v = 0, vu = 0;
+    unsigned long long v = 0, vu = 0, vc = 0;
     cudaError_t e = cudaMemcpyAsync(&v, &p->d_desc->timed_out, sizeof(v), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess && p->d_desc_u)
         e = cudaMemcpyAsync(&vu, &p->d_desc_u->timed_out, sizeof(vu), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && p->d_desc_c)
+        e = cudaMemcpyAsync(&vc, &p->d_desc_c->timed_out, sizeof(vc), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    *flag = v != 0 || vu != 0;
+    *flag = v != 0 || vu != 0 || vc != 0;
     return e == cudaSuccess ? ACG_SUCCESS : ACG_ERR_CUDA;
 }

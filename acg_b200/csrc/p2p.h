@@ -23,6 +23,7 @@ struct acgb200_p2p {
     int goff;                           /* index of the first ghost entry (owned count rounded up to 16) */
     void *peer_vbase[ACGB200_MAXR];
     struct acgb200_p2pdev *d_desc_u;    /* descriptor whose ghost pointers address the vector tails */
+    struct acgb200_p2pdev *d_desc_c;    /* the same with both parities on vector 0 (classic CG keeps one p) */
 };
 
 int acgb200_p2p_init(struct acgb200_p2p *p, const struct acghalo *halo, int borderoff, int nborder,

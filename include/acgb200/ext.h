@@ -45,7 +45,8 @@ struct acgb200_info {
     int spmv_compressed_tiles;  /* tiles that carry no column indices (option "spmv_compress") */
     int64_t spmv_min_bytes;     /* bytes one SpMV launch must move at least, given the plan */
     int spmv_nmedium;           /* rows handled one warp each (option "spmv_medium") */
-    int pad0;
+    int last_layout;            /* last solve's loop: 0 split local / border x ghost blocks, 1 one CSR over [owned | ghost];
+                                   +2 if the pipelined iteration ran as one kernel */
 };
 ACG_API int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info);
 

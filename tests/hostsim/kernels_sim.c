@@ -188,6 +188,13 @@ static void spmv_exec(void *p)
                 const struct acgb200_tile tl = pl->d_tiles[t];
                 const int nrows = tl.nrows & ~ACGB200_TILE_COMPRESSED;
                 const int cmp = pl->compressed && (tl.nrows & ACGB200_TILE_COMPRESSED) != 0;
+                if (a->p2p && !xg && tl.row_begin + nrows > a->od_rowoffset) {
+                    /* as in the kernel: wait for the neighbours before the first tile that reaches the
+                     * border rows touches anything (unified layout: ghosts come through the column indices) */
+                    struct acgb200_p2pdev *P = (struct acgb200_p2pdev *) a->p2p;
+                    p2p_wait_halo(P, P->hbase + (unsigned long long) g.iter);
+                    xg = P->my_ghost[g.iter & 1] - a->od_nrows;
+                }
                 for (int r = tl.row_begin; r < tl.row_begin + nrows; r++)
                     row_epilogue(a, r, row_product_t(a, r, &xg, g.iter, cmp), &dot);
             }
@@ -207,6 +214,11 @@ static void spmv_exec(void *p)
         if (!g.active) continue;
         double dot = 0.0;
         const double *xg = NULL;
+        if (a->p2p) {                            /* the row-list kernels wait at their start */
+            struct acgb200_p2pdev *P = (struct acgb200_p2pdev *) a->p2p;
+            p2p_wait_halo(P, P->hbase + (unsigned long long) g.iter);
+            xg = P->my_ghost[g.iter & 1] - a->od_nrows;
+        }
         for (int i = 0; i < cnt; i++) row_epilogue(a, rows[i], row_product(a, rows[i], &xg, g.iter), &dot);
         if (a->acc) *a->acc += dot;
     }

@@ -135,8 +135,8 @@ def _free_port():
 
 
 @pytest.mark.parametrize("nproc,matrix,size,partition,backends,extra", [
-    (2, "27pt", 8, "block", "p2p-fused,p2p-unfused,nccl,nccl-graph,nccl-serial-reduce,one-kernel,one-kernel-split", []),
-    (3, "7pt", 9, "slab", "watchdog,p2p-fused,one-kernel,nccl", []),
+    (2, "27pt", 8, "block", "p2p-fused,p2p-unfused,nccl,nccl-graph,nccl-serial-reduce,one-kernel,one-kernel-split,all-unified", []),
+    (3, "7pt", 9, "slab", "watchdog,p2p-fused,one-kernel,all-unified,nccl", []),
     (4, "rmat", 3000, "random", "p2p-fused,one-kernel", ["--maxits", "12", "--rtol", "0"]),
 ], ids=["2-ranks-all-backends", "3-ranks", "4-ranks-power-law"])
 def test_multi_rank_loops(nproc, matrix, size, partition, backends, extra, simlib):
