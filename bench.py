@@ -205,6 +205,15 @@ def main():
     ap.add_argument("--partition", default="block", choices=["block", "metis"],
                     help="row partition for N>1: geometric blocks or METIS (acgsymcsrmatrix_partition_rows)")
     args = ap.parse_args()
+    # torchrun exports OMP_NUM_THREADS=1 to every rank unless the caller set it.  The host-side set-up
+    # (matrix generator, full-storage expansion) and, above all, the reference's CPU solver are OpenMP
+    # code: give the reference arm all host cores (only rank 0 works there) and a rank of the GPU arm
+    # its share.  Must happen before anything loads libgomp (it reads the variable once).
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS") == "1" \
+            and not os.environ.get("BENCH_KEEP_OMP_NUM_THREADS"):
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        share = ncpu if args.impl == "reference" else max(1, ncpu // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"])))
+        os.environ["OMP_NUM_THREADS"] = str(share)
     w = WORKLOADS[args.workload]
     solver = args.solver or os.environ.get("BENCH_SOLVER") or w["solver"]
     rank = int(os.environ.get("RANK", "0"))
