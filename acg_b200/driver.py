@@ -99,6 +99,11 @@ def local_rhs(args, A, n):
 
 def main(argv=None):
     args = parse_args(argv)
+    # torchrun exports OMP_NUM_THREADS=1 unless the caller set it; the ingest and the full-storage
+    # expansion are OpenMP code -- give every rank its share of the cores (before libgomp loads)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        os.environ["OMP_NUM_THREADS"] = str(max(1, ncpu // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
     import torch
     import torch.distributed as dist
     from . import dist as abdist, mtxio
