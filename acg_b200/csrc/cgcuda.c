@@ -57,7 +57,7 @@ static struct {
     int pcg_fused;      /* 1: pipelined CG as one kernel per iteration (SpMV + update fused, opt-in) */
     int spmv_medium;    /* > 0: rows longer than this (and shorter than a tile) get a warp each (opt-in) */
     int p2p_unified;    /* one CSR over [owned | ghost], vectors in the exported allocation: 1 for the one-kernel
-                         * pipelined iteration (default), 2 also for the classic loop (opt-in) */
+                         * pipelined iteration (default), 2 also for the classic and the two-kernel pipelined loop */
     int loaded;
 } cfg = { .check_every = 8, .graph = 1, .redstream = 1, .p2p = 1, .p2p_fuse = 1, .p2p_unified = 1 };
 
@@ -148,7 +148,7 @@ struct priv {
     int *d_urowptr, *d_ucolidx, *d_uzero;
     double *d_ua;
     int ufused_grid, unified;           /* unified: 0 not tried, 1 in use, -1 not possible for this matrix */
-    int graph2_unified, graph0_unified; /* layout the cached one-kernel / classic graphs were captured with */
+    int graph2_unified, graph1_unified, graph0_unified;   /* layout each cached graph was captured with */
     int last_layout;                    /* see struct acgb200_info */
     double last_h2d_ms, last_d2h_ms;    /* host time spent before / after the solve window */
     cudaEvent_t ev_t0, ev_t1;           /* device-side bracket of the solve window */
@@ -1146,6 +1146,18 @@ static int pipelined_iteration(struct solvectx *c, int k)
             OK(allreduce(c, &st->gd_loc[s][0], &st->gd[s][0], 2));
         }
     }
+    if (c->unified) {
+        /* unified layout: w of iteration k lives in vector k&1 of the exported allocation; the
+         * update writes the next one (and the neighbours' tails of it) instead of updating in place */
+        double *win = acgb200_p2p_uvec(&pv->p2p, s), *wout = acgb200_p2p_uvec(&pv->p2p, s ^ 1);
+        OK(apply_A(c, win, win, cg->d_q, NULL, SPMV_Y_AX, NULL, 1, 2, 0, -1));
+        prof_mark(c, &pv->blas);
+        KL(acgb200_pcg_update_db(n, st, 1, 0, c->multi, c->postdesc, cg->d_q, cg->d_z, win, wout,
+                                 cg->d_t, cg->d_p, cg->d_r, c->d_x, pv->stream));
+        prof_mark(c, &pv->blas);
+        c->launches += 1;
+        return ACG_SUCCESS;
+    }
     OK(apply_A(c, cg->d_w, cg->d_w, cg->d_q, NULL, SPMV_Y_AX, NULL, 1, 2, 0, -1));
     if (k > 0 && side) CU(cudaStreamWaitEvent(pv->stream, pv->ev_red, 0));
     prof_mark(c, &pv->blas);
@@ -1323,12 +1335,19 @@ int acgsolvercuda_solve_pipelined(
             fused = 1;
         }
     }
+    if (!fused && c.p2p && pv->p2p.h_desc.fuse && cfg.p2p_unified >= 2) {
+        /* opt-in: the two-kernel loop on the merged CSR, w double-buffered in the exported allocation */
+        OK(ensure_unified(&c, A));
+        if (pv->unified == 1) { c.unified = 1; c.postdesc = pv->p2p.d_desc_u; }
+    }
     if (pv->graph[2] && pv->graph2_unified != unified) {
         /* the cached replay addresses the other layout's arrays */
         cudaGraphExecDestroy(pv->graph[2]); pv->graph[2] = NULL;
     }
+    if (pv->graph[1] && pv->graph1_unified != c.unified) { cudaGraphExecDestroy(pv->graph[1]); pv->graph[1] = NULL; }
     pv->graph2_unified = unified;
-    pv->last_layout = (unified ? 1 : 0) + (fused ? 2 : 0);
+    pv->graph1_unified = c.unified;
+    pv->last_layout = (c.unified ? 1 : 0) + (fused ? 2 : 0);
     int (*const iteration)(struct solvectx *, int) = fused ? fused_iteration : pipelined_iteration;
     if (warmup > 0) {
         memset(&h, 0, sizeof(h));
@@ -1336,7 +1355,7 @@ int acgsolvercuda_solve_pipelined(
         for (int s = 0; s < 2; s++) { h.gd_loc[s][0] = h.gd[s][0] = 1; h.gd_loc[s][1] = h.gd[s][1] = 1; h.prev[s][0] = h.prev[s][1] = INFINITY; }
         OK(push_state(&c, &h));
         double *xsave = c.d_x; c.d_x = cg->d_r;
-        if (unified) CU(cudaMemcpyAsync(acgb200_p2p_uvec(&pv->p2p, 0), cg->d_w, obytes, cudaMemcpyDeviceToDevice, pv->stream));
+        if (c.unified) CU(cudaMemcpyAsync(acgb200_p2p_uvec(&pv->p2p, 0), cg->d_w, obytes, cudaMemcpyDeviceToDevice, pv->stream));
         if (c.p2p) {
             OK(acgb200_p2p_begin(&pv->p2p, warmup, pv->stream));
             OK(post(&c, 0, 0, cg->d_w, -1, NULL, 0, 0, 0, 0));
@@ -1395,7 +1414,7 @@ int acgsolvercuda_solve_pipelined(
         h.gd_loc[0][1] = h.gd[0][1] = gd0[1];
         h.prev[0][0] = h.prev[0][1] = INFINITY;                    /* acg/cgcuda.c:1513-1514 */
         OK(push_state(&c, &h));
-        if (unified) CU(cudaMemcpyAsync(acgb200_p2p_uvec(&pv->p2p, 0), cg->d_w, obytes, cudaMemcpyDeviceToDevice, pv->stream));
+        if (c.unified) CU(cudaMemcpyAsync(acgb200_p2p_uvec(&pv->p2p, 0), cg->d_w, obytes, cudaMemcpyDeviceToDevice, pv->stream));
         if (c.p2p) {
             /* w_0 goes to the neighbours' windows as exchange number 0 */
             OK(acgb200_p2p_begin(&pv->p2p, maxits, pv->stream));

@@ -241,6 +241,13 @@ int acgb200_pcg_update(int n, struct acgb200_devstate *st, int cin, int cout, in
                        const double *q, double *z, double *w, double *t, double *p,
                        double *r, double *x, cudaStream_t stream);
 
+/* the same update with w double-buffered (reads w_in, writes w_out): the two-kernel pipelined loop on
+ * the unified [owned | ghost] layout */
+int acgb200_pcg_update_db(int n, struct acgb200_devstate *st, int cin, int cout, int multi,
+                          struct acgb200_p2pdev *p2p,
+                          const double *q, double *z, double *w_in, double *w_out, double *t, double *p,
+                          double *r, double *x, cudaStream_t stream);
+
 /* one kernel per pipelined iteration (opt-in): q = A w fused with the update;
  * w is double-buffered (w0: parity 0).  grid from acgb200_pcg_fused_grid (0: the
  * plan has no fused variant). */

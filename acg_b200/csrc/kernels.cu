@@ -1197,11 +1197,14 @@ cg_update_xp_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, a
 /* Pipelined CG: z=q+beta z; t=w+beta t; p=r+beta p; x+=alpha p; r-=alpha t;
  * w-=alpha z (acg/cg-kernels-cuda.cu:201-214), plus gamma'=(r,r), delta'=(w,r)
  * of the updated vectors for the next iteration. */
+/* DB: w is double-buffered -- read from w, written to wout (the unified [owned | ghost] layout keeps the
+ * two SpMV input vectors of consecutive iterations in the exported allocation); otherwise in place. */
+template <bool DB>
 __global__ void __launch_bounds__(BLAS1_THREADS)
 pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acgb200_p2pdev *P,
                   const double *__restrict__ q, double *__restrict__ z, double *__restrict__ w,
                   double *__restrict__ t, double *__restrict__ p, double *__restrict__ r,
-                  double *__restrict__ x)
+                  double *__restrict__ x, double *__restrict__ wout)
 {
     __shared__ double red[BLAS1_THREADS / 32];
     __shared__ double glob[2];
@@ -1251,7 +1254,8 @@ pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acg
             const double wv = fma(-alpha, zv, w[i]);
             z[i] = zv; t[i] = tv; p[i] = pv;
             x[i] = fma(alpha, pv, x[i]);
-            r[i] = rv; w[i] = wv;
+            r[i] = rv;
+            if (DB) wout[i] = wv; else w[i] = wv;
             g2 = fma(rv, rv, g2);
             d2 = fma(wv, rv, d2);
             if (push && pass == 0) p2p_push_row(P, i, s ^ 1, wv);
@@ -1579,8 +1583,19 @@ extern "C" int acgb200_pcg_update(int n, acgb200_devstate *st, int cin, int cout
                                   double *r, double *x, cudaStream_t stream)
 {
     static int occ = 0;
-    return (int) launch_chain(pcg_update_kernel, blas1_grid(n, (const void *) pcg_update_kernel, &occ), BLAS1_THREADS, 0, stream,
-                              n, st, cin, cout, multi, p2p, q, z, w, t, p, r, x);
+    return (int) launch_chain(pcg_update_kernel<false>, blas1_grid(n, (const void *) pcg_update_kernel<false>, &occ), BLAS1_THREADS, 0, stream,
+                              n, st, cin, cout, multi, p2p, q, z, w, t, p, r, x, (double *) NULL);
+}
+
+/* the same with w double-buffered: reads w_in, writes w_out */
+extern "C" int acgb200_pcg_update_db(int n, acgb200_devstate *st, int cin, int cout, int multi,
+                                     acgb200_p2pdev *p2p,
+                                     const double *q, double *z, double *w_in, double *w_out, double *t, double *p,
+                                     double *r, double *x, cudaStream_t stream)
+{
+    static int occ = 0;
+    return (int) launch_chain(pcg_update_kernel<true>, blas1_grid(n, (const void *) pcg_update_kernel<true>, &occ), BLAS1_THREADS, 0, stream,
+                              n, st, cin, cout, multi, p2p, q, z, w_in, t, p, r, x, w_out);
 }
 
 extern "C" int acgb200_comm_post(const acgb200_postargs *a, cudaStream_t stream)

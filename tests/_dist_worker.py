@@ -69,14 +69,15 @@ def local_matvec(m, h, xl):
 BACKEND_OPTIONS = {"p2p-fused": {}, "p2p-unfused": {"p2p_fuse": 0}, "nccl": {"p2p": 0},
                    "nccl-graph": {"p2p": 0, "graph": 2}, "nccl-serial-reduce": {"p2p": 0, "redstream": 0},
                    "one-kernel": {"pcg_fused": 1}, "one-kernel-split": {"pcg_fused": 1, "p2p_unified": 0},
-                   "all-unified": {"pcg_fused": 1, "p2p_unified": 2},
+                   "all-unified": {"pcg_fused": 1, "p2p_unified": 2}, "two-kernel-unified": {"p2p_unified": 2},
                    "pdl": {"pdl": 1}, "one-kernel-pdl": {"pcg_fused": 1, "pdl": 1},
                    "watchdog": {}}
 
 
 # struct acgb200_info.last_layout the back-end must report (matrices without long rows)
 EXPECTED_LAYOUT = {"p2p-fused": {"solvempi": 0, "solve_pipelined": 0}, "one-kernel": {"solvempi": 0, "solve_pipelined": 3},
-                   "one-kernel-split": {"solvempi": 0, "solve_pipelined": 2}, "all-unified": {"solvempi": 1, "solve_pipelined": 3}}
+                   "one-kernel-split": {"solvempi": 0, "solve_pipelined": 2}, "all-unified": {"solvempi": 1, "solve_pipelined": 3},
+                   "two-kernel-unified": {"solvempi": 1, "solve_pipelined": 1}}
 
 
 def allsum(v):

@@ -304,7 +304,7 @@ int acgb200_comm_post(const struct acgb200_postargs *a, cudaStream_t stream)
 /* ---- classic CG ------------------------------------------------------------- */
 
 struct upd_args {
-    int n; struct acgb200_devstate *st; int cin, cout, multi; struct acgb200_p2pdev *P;
+    int n; struct acgb200_devstate *st; int cin, cout, multi; struct acgb200_p2pdev *P; double *wout;
     const double *q; double *z, *w, *t, *p, *r, *x;
 };
 
@@ -439,7 +439,8 @@ static void pcg_update_exec(void *vp)
         const double wv = fma(-alpha, zv, a->w[i]);
         a->z[i] = zv; a->t[i] = tv; a->p[i] = pv;
         a->x[i] = fma(alpha, pv, a->x[i]);
-        a->r[i] = rv; a->w[i] = wv;
+        a->r[i] = rv;
+        if (a->wout) a->wout[i] = wv; else a->w[i] = wv;
         g2 = fma(rv, rv, g2);
         d2 = fma(wv, rv, d2);
         if (push && i >= first) p2p_push_row(P, i, s ^ 1, wv);
@@ -462,6 +463,18 @@ int acgb200_pcg_update(int n, struct acgb200_devstate *st, int cin, int cout, in
     memset(&a, 0, sizeof(a));
     a.n = n; a.st = st; a.cin = cin; a.cout = cout; a.multi = multi; a.P = p2p;
     a.q = q; a.z = z; a.w = w; a.t = t; a.p = p; a.r = r; a.x = x;
+    return hostsim_run_or_record(pcg_update_exec, &a, sizeof(a));
+}
+
+int acgb200_pcg_update_db(int n, struct acgb200_devstate *st, int cin, int cout, int multi, struct acgb200_p2pdev *p2p,
+                          const double *q, double *z, double *w_in, double *w_out, double *t, double *p, double *r, double *x,
+                          cudaStream_t stream)
+{
+    (void) stream;
+    struct upd_args a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.st = st; a.cin = cin; a.cout = cout; a.multi = multi; a.P = p2p;
+    a.q = q; a.z = z; a.w = w_in; a.wout = w_out; a.t = t; a.p = p; a.r = r; a.x = x;
     return hostsim_run_or_record(pcg_update_exec, &a, sizeof(a));
 }
 

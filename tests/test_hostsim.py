@@ -135,7 +135,7 @@ def _free_port():
 
 
 @pytest.mark.parametrize("nproc,matrix,size,partition,backends,extra", [
-    (2, "27pt", 8, "block", "p2p-fused,p2p-unfused,nccl,nccl-graph,nccl-serial-reduce,one-kernel,one-kernel-split,all-unified", []),
+    (2, "27pt", 8, "block", "p2p-fused,p2p-unfused,nccl,nccl-graph,nccl-serial-reduce,one-kernel,one-kernel-split,all-unified,two-kernel-unified", []),
     (3, "7pt", 9, "slab", "watchdog,p2p-fused,one-kernel,all-unified,nccl", []),
     (4, "rmat", 3000, "random", "p2p-fused,one-kernel", ["--maxits", "12", "--rtol", "0"]),
 ], ids=["2-ranks-all-backends", "3-ranks", "4-ranks-power-law"])
