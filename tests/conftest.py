@@ -72,6 +72,11 @@ def ref():
 
 @pytest.fixture(scope="session")
 def ab():
+    if os.environ.get("ACGB200_TEST_LIB"):
+        # development aid: run the host-structure tests against another build of the same sources
+        # (e.g. tests/hostsim built with -fsanitize=address,undefined, under LD_PRELOAD=libasan.so)
+        import acg_b200.api as api
+        api._LIBPATH = os.environ["ACGB200_TEST_LIB"]
     import acg_b200
     acg_b200.lib()
     return acg_b200
