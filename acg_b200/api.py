@@ -610,15 +610,29 @@ class SolverCuda:
                 "tsolve", "tgemv", "taxpy", "ngemv", "Bgemv", "naxpy", "Baxpy", "nallreduce", "nhalo", "Bhalo"]
         return {k: getattr(self.c, k) for k in keys}
 
-    def report(self) -> str:
-        """acgsolvercuda_fwrite into a string."""
+    TIMES = ("tsolve", "tgemv", "tdot", "tnrm2", "taxpy", "tcopy", "tallreduce", "thalo")
+    COUNTERS = ("nflops", "Bgemv", "Bdot", "Bnrm2", "Baxpy", "Bcopy", "Ballreduce", "Bhalo", "nhalomsgs")
+
+    def report(self, aggregate=None) -> str:
+        """acgsolvercuda_fwrite into a string.  ``aggregate``: dict of field values to print instead of
+        this rank's (times as the maximum, flop/byte/message counters as the sum over the ranks: what
+        acgsolvercuda_fwritempi reduces with MPI, acg/cgcuda.c:1990-2012)."""
+        src = self.c
+        if aggregate:
+            src = acgsolvercuda()
+            C.memmove(C.byref(src), C.byref(self.c), C.sizeof(acgsolvercuda))
+            for k, v in aggregate.items():
+                setattr(src, k, v)
+        return self._fwrite(src)
+
+    def _fwrite(self, struct) -> str:
         libc = C.CDLL(None)
         libc.fopen.restype = C.c_void_p
         libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
         libc.fclose.argtypes = [C.c_void_p]
         with tempfile.NamedTemporaryFile("r", suffix=".txt") as tf:
             f = libc.fopen(tf.name.encode(), b"w")
-            _check(lib().acgsolvercuda_fwrite(f, C.byref(self.c), 0), "acgsolvercuda_fwrite")
+            _check(lib().acgsolvercuda_fwrite(f, C.byref(struct), 0), "acgsolvercuda_fwrite")
             libc.fclose(f)
             return tf.read()
 

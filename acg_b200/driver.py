@@ -155,9 +155,18 @@ def main(argv=None):
     b.x[:no] = bo
     code = getattr(cg, SOLVERS[args.solver])(b, x, maxits=args.max_iterations, residualatol=args.residual_atol,
                                              residualrtol=args.residual_rtol, warmup=args.warmup)
-    log(cg.report())
     if world > 1:
+        # the report of acgsolvercuda_fwritempi (acg/cgcuda.c:1948-2216): times as the maximum,
+        # flop / byte / message counters as the sum over the ranks, printed by rank 0
+        mine = {k: getattr(cg.c, k) for k in SolverCuda.TIMES + SolverCuda.COUNTERS}
+        every = [None] * world
+        dist.all_gather_object(every, mine)
+        agg = {k: max(e[k] for e in every) for k in SolverCuda.TIMES}
+        agg.update({k: sum(e[k] for e in every) for k in SolverCuda.COUNTERS})
+        log(cg.report(aggregate=agg))
         log(f"processes: {world}")
+    else:
+        log(cg.report())
     if args.manufactured_solution:
         e2 = np.array([np.sum(xstar ** 2), np.sum((x.x[:no] - xstar) ** 2)])
         if world > 1:

@@ -240,6 +240,12 @@ def test_python_driver_solves(nproc, partition, simlib, tmp_path):
     import re
     e1 = float(re.search(r"^error 2-norm: (\S+)", p.stderr, re.M).group(1))
     assert e1 < 1e-8 and "total solver time:" in p.stderr
+    # the report is the aggregate over the ranks (as acgsolvercuda_fwritempi): the SpMV bytes of the whole
+    # matrix whatever the number of parts -- 12 B per nonzero plus vector terms per SpMV
+    gemv = re.search(r"gemv: \S+ seconds (\d+) times (\d+) B", p.stderr)
+    nspmv, nbytes = int(gemv.group(1)), int(gemv.group(2))
+    nnz_full = 2 * len(v) - n
+    assert nspmv * 12 * nnz_full <= nbytes <= nspmv * (12 * nnz_full + 60 * n)
     xs = np.random.default_rng(3).uniform(-1.0, 1.0, n); xs /= np.linalg.norm(xs)
     x = np.array([float(t) for t in open(sol).read().split("\n")[2:] if t])
     assert len(x) == n and np.linalg.norm(x - xs) == pytest.approx(e1, rel=1e-6, abs=1e-14)
