@@ -287,3 +287,43 @@ def test_index_free_tile_plan_in_the_solver(fused, simlib):
                          {"method": "solve_pipelined", "maxits": 7}]})
     _check(out)
     assert out["compressed_tiles"] > 0.5 * out["ntiles"]
+
+
+@pytest.mark.parametrize("solver,method", [("acg", "cg"), ("acg-pipelined", "cg_pipelined"),
+                                           ("acg-device", "cg"), ("acg-device-pipelined", "cg_pipelined")])
+def test_unmodified_reference_driver(solver, method, simlib, tmp_path):
+    """The objects of the UNMODIFIED cuda/acg-cuda.c and of the reference's host layer
+    (tools/build_driver.sh, compiled from where they lie) linked against the stand-in build of the
+    MPI flavour of the library: the whole drop-in boundary -- the reference's own Matrix Market
+    reader, acgsolvercuda_init, the solver dispatch of cuda/acg-cuda.c:2242-2262,
+    acgsolvercuda_fwritempi, the solution on stdout -- on the CPU, against the oracle."""
+    import re
+    import numpy as np
+    from acg_b200 import matgen as mg, mtxio
+    from oracle import Oracle
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "driver", "acg-cuda.o")):
+        pytest.skip("driver objects not built (needs the reference tree: tools/build_driver.sh)")
+    p = subprocess.run(["make", "-C", SIM, "driver"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    exe = os.path.join(SIM, "acg-cuda-sim")
+    n, r, c, v = mg.stencil3d_27pt(12, 10, 11)
+    path = str(tmp_path / "A.mtx")
+    mtxio.write_symmetric(path, n, r, c, v, binary=True)
+    p = subprocess.run([exe, path, "--binary", "--solver", solver, "--max-iterations", "200", "--residual-rtol", "1e-9",
+                        "--warmup", "2", "--numfmt", "%.17g"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-3000:]
+    O = Oracle()
+    want = getattr(O, method)(O.full_csr(n, r, c, v), np.ones(n), maxits=200, rtol=1e-9)
+    its = int(re.search(r"^\s*iterations: ([\d,]+)", p.stderr, re.M).group(1).replace(",", ""))
+    r0 = float(re.search(r"^\s*initial residual 2-norm: (\S+)", p.stderr, re.M).group(1))
+    assert its == want["niterations"] and r0 == pytest.approx(want["r0nrm2"], rel=1e-13)
+    lines = [ln for ln in p.stdout.splitlines() if ln and not ln.startswith("%")]
+    x = np.array([float(t) for t in lines[1:]])
+    assert int(lines[0].split()[0]) == n and np.abs(x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
+    if solver == "acg":
+        q = subprocess.run([exe, path, "--binary", "--solver", solver, "--max-iterations", "300", "--residual-rtol", "1e-10",
+                            "--manufactured-solution", "--seed", "7", "-q"], capture_output=True, text=True, timeout=300)
+        assert q.returncode == 0, q.stderr[-3000:]
+        e0 = float(re.search(r"^initial error 2-norm: (\S+)", q.stderr, re.M).group(1))
+        e1 = float(re.search(r"^error 2-norm: (\S+)", q.stderr, re.M).group(1))
+        assert e0 == pytest.approx(1.0, rel=1e-12) and e1 < 1e-7
