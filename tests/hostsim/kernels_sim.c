@@ -128,6 +128,52 @@ static int entry_column(const struct acgb200_spmvargs *a, int row, int k, int co
 
 static int hostsim_bad_pattern = 0;
 
+/* What spmv_issue / cspmv_issue stage for one tile: the 16-byte aligned slices of values, column
+ * indices and row pointers (pattern ids for index-free tiles), copied with the lengths the TMA
+ * copies use -- so a slice that runs past the padded device arrays is a real out-of-bounds read
+ * here (AddressSanitizer run, tools/asan_hostsim.sh) -- and checked against the stage capacity
+ * the kernel reserves in shared memory.  Returns 0 if the tile does not fit. */
+static int stage_tile(const struct acgb200_spmvargs *a, const struct acgb200_tile *tl, int compressed_tile,
+                      double *vals, int *cols, int *rp, unsigned short *pid)
+{
+    const struct acgb200_spmvplan *pl = a->plan;
+    const int nrows = tl->nrows & ~ACGB200_TILE_COMPRESSED;
+    const int sc = (pl->nnz_cap + 8 + 3) & ~3, rc = (pl->rows_cap + 1 + 8 + 3) & ~3, pc = (pl->rows_cap + 16 + 7) & ~7;
+    const int row_al = tl->row_begin & ~3;
+    const int nrp = (tl->row_begin + nrows + 1 - row_al + 3) & ~3;
+    if (tl->nnz_al > sc || nrp > rc || (tl->k_al & 3) || (tl->nnz_al & 3)) return 0;
+    memcpy(vals, a->a + tl->k_al, (size_t) tl->nnz_al * sizeof(double));
+    if (!compressed_tile) memcpy(cols, a->colidx + tl->k_al, (size_t) tl->nnz_al * sizeof(int));
+    memcpy(rp, a->rowptr + row_al, (size_t) nrp * sizeof(int));
+    if (compressed_tile) {
+        const int row_al8 = tl->row_begin & ~7;
+        const int npid = (tl->row_begin + nrows - row_al8 + 7) & ~7;
+        if (npid > pc) return 0;
+        memcpy(pid, pl->d_patid + row_al8, (size_t) npid * sizeof(unsigned short));
+    }
+    return 1;
+}
+
+/* one row of a staged tile, indexed as the kernel indexes shared memory */
+static double staged_row(const struct acgb200_spmvargs *a, const struct acgb200_tile *tl, int lr, int compressed_tile,
+                         const double *vals, const int *cols, const int *rp, const unsigned short *pid, const double *x)
+{
+    const struct acgb200_spmvplan *pl = a->plan;
+    const int *rps = rp + (tl->row_begin & 3);
+    const int kb = rps[lr] - tl->k_al, ke = rps[lr + 1] - tl->k_al, row = tl->row_begin + lr;
+    double sum = 0.0;
+    for (int k = kb; k < ke; k++) {
+        int col;
+        if (compressed_tile) {
+            const int id = (pid + (tl->row_begin & 7))[lr];
+            if (id >= pl->npat || pl->d_patptr[id] + (k - kb) >= pl->d_patptr[id + 1]) { hostsim_bad_pattern = 1; return NAN; }
+            col = row + pl->d_patoff[pl->d_patptr[id] + (k - kb)];
+        } else col = cols[k];
+        sum = fma(vals[k], x[col], sum);
+    }
+    return sum;
+}
+
 /* local block, plus -- fused peer-memory mode -- the border x ghost block with ghosts from the window */
 static double row_product_t(const struct acgb200_spmvargs *a, int row, const double **xg, int iter, int compressed_tile)
 {
@@ -184,10 +230,15 @@ static void spmv_exec(void *p)
         if (g.active) {
             double dot = 0.0;
             const double *xg = NULL;
+            const int sc = (pl->nnz_cap + 8 + 3) & ~3, rc = (pl->rows_cap + 1 + 8 + 3) & ~3, pc = (pl->rows_cap + 16 + 7) & ~7;
+            double *svals = malloc((size_t) sc * sizeof(double));
+            int *scols = malloc((size_t) sc * sizeof(int)), *srp = malloc((size_t) rc * sizeof(int));
+            unsigned short *spid = malloc((size_t) pc * sizeof(unsigned short));
             for (int t = 0; t < pl->ntiles; t++) {
                 const struct acgb200_tile tl = pl->d_tiles[t];
                 const int nrows = tl.nrows & ~ACGB200_TILE_COMPRESSED;
                 const int cmp = pl->compressed && (tl.nrows & ACGB200_TILE_COMPRESSED) != 0;
+                const int staged = stage_tile(a, &tl, cmp, svals, scols, srp, spid);
                 if (a->p2p && !xg && tl.row_begin + nrows > a->od_rowoffset) {
                     /* as in the kernel: wait for the neighbours before the first tile that reaches the
                      * border rows touches anything (unified layout: ghosts come through the column indices) */
@@ -195,9 +246,18 @@ static void spmv_exec(void *p)
                     p2p_wait_halo(P, P->hbase + (unsigned long long) g.iter);
                     xg = P->my_ghost[g.iter & 1] - a->od_nrows;
                 }
-                for (int r = tl.row_begin; r < tl.row_begin + nrows; r++)
-                    row_epilogue(a, r, row_product_t(a, r, &xg, g.iter, cmp), &dot);
+                for (int r = tl.row_begin; r < tl.row_begin + nrows; r++) {
+                    /* the product through the staged slices must be the product through the arrays */
+                    const double direct = row_product_t(a, r, &xg, g.iter, cmp);
+                    double via_stage = staged ? staged_row(a, &tl, r - tl.row_begin, cmp, svals, scols, srp, spid, a->x) : NAN;
+                    if (staged && a->p2p && r >= a->od_rowoffset && xg) {
+                        const int ob = r - a->od_rowoffset;
+                        for (int k = a->orowptr[ob]; k < a->orowptr[ob + 1]; k++) via_stage = fma(a->oa[k], xg[a->ocolidx[k]], via_stage);
+                    }
+                    row_epilogue(a, r, (staged && via_stage == direct) ? direct : NAN, &dot);
+                }
             }
+            free(svals); free(scols); free(srp); free(spid);
             if (a->acc) *a->acc += dot;
             if (a->p2p && a->pub_ch >= 0 && a->p2p->fuse) {
                 struct acgb200_p2pdev *P = (struct acgb200_p2pdev *) a->p2p;
