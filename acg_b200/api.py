@@ -140,6 +140,8 @@ EXPORTS = [
     "acghalo_exchange_cuda",
     "acgsolvercuda_free", "acgsolvercuda_init", "acgsolvercuda_solvempi", "acgsolvercuda_solve_pipelined",
     "acgsolvercuda_solve", "acgsolvercuda_solve_device", "acgsolvercuda_solve_device_pipelined",
+    "acgsolvercuda_init_constants", "acgsolvercuda_alpha", "acgsolvercuda_beta", "acgsolvercuda_daxpy_alpha",
+    "acgsolvercuda_daxpy_minus_alpha", "acgsolvercuda_daypx_beta", "acgsolvercuda_pipelined_daxpy_fused",
     "acgsolvercuda_fwrite",
     "acgb200_set_option", "acgsolvercuda_spmv", "acgsolvercuda_info", "acgb200_sizeof", "acgb200_have_mpi",
     "acgb200_nccl_unique_id", "acgb200_comm_init_rank", "acgb200_comm_destroy",
@@ -205,6 +207,15 @@ def lib() -> C.CDLL:
     L.acgsolvercuda_solve_pipelined.argtypes = common + [P(acgcomm), C.c_int, P(C.c_int), C.c_void_p, C.c_void_p]
     L.acgsolvercuda_solve.argtypes = common
     L.acgsolvercuda_solve_device.argtypes = common + [P(acgcomm), P(C.c_int)]
+    # acg/cg-kernels-cuda.h:45-97: device pointers as plain addresses
+    vp = C.c_void_p
+    L.acgsolvercuda_init_constants.argtypes = [P(vp), P(vp), P(vp)]
+    L.acgsolvercuda_alpha.argtypes = [vp, vp, vp, vp]
+    L.acgsolvercuda_beta.argtypes = [vp, vp, vp]
+    L.acgsolvercuda_daxpy_alpha.argtypes = [C.c_int, vp, vp, vp, vp]
+    L.acgsolvercuda_daxpy_minus_alpha.argtypes = [C.c_int, vp, vp, vp, vp]
+    L.acgsolvercuda_daypx_beta.argtypes = [C.c_int, vp, vp, vp, vp]
+    L.acgsolvercuda_pipelined_daxpy_fused.argtypes = [C.c_int] + [vp] * 11 + [vp]
     L.acgsolvercuda_solve_device_pipelined.argtypes = common + [P(acgcomm), P(C.c_int)]
     L.acgsolvercuda_fwrite.argtypes = [C.c_void_p, P(acgsolvercuda), C.c_int]
     L.acgsolvercuda_spmv.argtypes = [P(acgsolvercuda), f64p, f64p, C.c_int, P(C.c_double)]

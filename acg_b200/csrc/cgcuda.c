@@ -1510,6 +1510,57 @@ int acgsolvercuda_solve_device_pipelined(
 }
 
 /* ------------------------------------------------------------------------ */
+/* acg/cg-kernels-cuda.h:45-97: public BLAS-1 building blocks                 */
+/* ------------------------------------------------------------------------ */
+
+static double *d_constants = NULL;      /* {-1, 1, 0}: lives as long as the process, like the reference's __constant__ symbols */
+
+int acgsolvercuda_init_constants(double **d_minus_one, double **d_one, double **d_zero)
+{
+    if (!d_constants) {
+        const double h[3] = { -1.0, 1.0, 0.0 };
+        if (cudaMalloc((void **) &d_constants, sizeof(h)) != cudaSuccess) return ACG_ERR_CUDA;
+        if (cudaMemcpy(d_constants, h, sizeof(h), cudaMemcpyHostToDevice) != cudaSuccess) return ACG_ERR_CUDA;
+    }
+    *d_minus_one = d_constants; *d_one = d_constants + 1; *d_zero = d_constants + 2;
+    return ACG_SUCCESS;
+}
+
+int acgsolvercuda_alpha(double *d_alpha, double *d_minus_alpha, const double *d_rnrm2sqr, const double *d_pdott)
+{
+    return acgb200_helper_scalars(0, d_alpha, d_minus_alpha, d_rnrm2sqr, d_pdott, 0) ? ACG_ERR_CUDA : ACG_SUCCESS;
+}
+
+int acgsolvercuda_beta(double *d_beta, const double *d_rnrm2sqr, const double *d_rnrm2sqr_prev)
+{
+    return acgb200_helper_scalars(1, d_beta, NULL, d_rnrm2sqr, d_rnrm2sqr_prev, 0) ? ACG_ERR_CUDA : ACG_SUCCESS;
+}
+
+int acgsolvercuda_daxpy_alpha(int n, const double *d_rnrm2sqr, const double *d_pdott, const double *d_x, double *d_y)
+{
+    return acgb200_helper_axpy(0, n, d_rnrm2sqr, d_pdott, d_x, d_y, 0) ? ACG_ERR_CUDA : ACG_SUCCESS;
+}
+
+int acgsolvercuda_daxpy_minus_alpha(int n, const double *d_rnrm2sqr, const double *d_pdott, const double *d_x, double *d_y)
+{
+    return acgb200_helper_axpy(1, n, d_rnrm2sqr, d_pdott, d_x, d_y, 0) ? ACG_ERR_CUDA : ACG_SUCCESS;
+}
+
+int acgsolvercuda_daypx_beta(int n, const double *d_rnrm2sqr, const double *d_rnrm2sqr_prev, double *d_y, const double *d_x)
+{
+    return acgb200_helper_axpy(2, n, d_rnrm2sqr, d_rnrm2sqr_prev, d_x, d_y, 0) ? ACG_ERR_CUDA : ACG_SUCCESS;
+}
+
+int acgsolvercuda_pipelined_daxpy_fused(
+    int n, const double *d_gamma, double *d_gamma_prev, const double *d_delta, const double *d_q,
+    double *d_p, double *d_r, double *d_t, double *d_x, double *d_z, double *d_w, double *d_alpha_prev,
+    cudaStream_t stream)
+{
+    return acgb200_helper_pipelined(n, d_gamma, d_gamma_prev, d_delta, d_q, d_p, d_r, d_t, d_x, d_z, d_w, d_alpha_prev, stream)
+        ? ACG_ERR_CUDA : ACG_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------ */
 /* report                                                                    */
 /* ------------------------------------------------------------------------ */
 

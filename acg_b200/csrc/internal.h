@@ -256,6 +256,13 @@ int acgb200_pcg_fused_launch(const struct acgb200_spmvargs *args, int grid, int 
                              double *z, double *t, double *p, double *r, double *x,
                              double *w0, double *w1, cudaStream_t stream);
 
+/* the reference's public BLAS-1 building blocks (acg/cg-kernels-cuda.h:45-97; cgcuda.c wraps them) */
+int acgb200_helper_axpy(int op, int n, const double *num, const double *den, const double *x, double *y, cudaStream_t stream);
+int acgb200_helper_scalars(int op, double *out0, double *out1, const double *num, const double *den, cudaStream_t stream);
+int acgb200_helper_pipelined(int n, const double *gamma, double *gamma_prev, const double *delta, const double *q,
+                             double *p, double *r, double *t, double *x, double *z, double *w, double *alpha_prev,
+                             cudaStream_t stream);
+
 /* setup-time helpers */
 int acgb200_dot(int n, const double *x, const double *y, double *acc, cudaStream_t stream); /* acc += x.y */
 int acgb200_dot2(int n, const double *r, const double *w, double *acc2, cudaStream_t stream); /* acc2[0]+=r.r, acc2[1]+=w.r */

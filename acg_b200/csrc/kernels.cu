@@ -1634,3 +1634,84 @@ extern "C" int acgb200_scatter(int n, const double *src, double *dst, const int 
     scatter_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, src, dst, idx);
     return (int) cudaGetLastError();
 }
+
+/* ------------------------------------------------------------------------ */
+/* BLAS-1 building blocks of acg/cg-kernels-cuda.h:45-97 (public, unused by   */
+/* this library's own loops)                                                  */
+/* ------------------------------------------------------------------------ */
+
+enum { HELP_AXPY_QUOT = 0, HELP_AXMY_QUOT = 1, HELP_AYPX_QUOT = 2 };
+
+/* y = (num/den) x + y | y = -(num/den) x + y | y = (num/den) y + x, the quotient read on the device */
+template <int OP>
+__global__ void __launch_bounds__(BLAS1_THREADS)
+helper_axpy_kernel(int n, const double *num, const double *den, const double *__restrict__ x, double *__restrict__ y)
+{
+    const double a = OP == HELP_AXMY_QUOT ? -(*num) / (*den) : (*num) / (*den);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        y[i] = OP == HELP_AYPX_QUOT ? fma(a, y[i], x[i]) : fma(a, x[i], y[i]);
+}
+
+__global__ void helper_scalars_kernel(double *out0, double *out1, const double *num, const double *den, int op)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double q = (*num) / (*den);
+    if (op == 0) { *out0 = q; *out1 = -q; }        /* alpha, -alpha */
+    else *out0 = q;                                /* beta */
+}
+
+/* the recurrences of acg/cg-kernels-cuda.cu:201-214; the scalars gamma_prev, alpha_prev are updated by
+ * the single-thread kernel launched behind it (stream order replaces the reference's grid sync) */
+__global__ void __launch_bounds__(BLAS1_THREADS)
+helper_pipelined_kernel(int n, const double *gamma, const double *gamma_prev, const double *delta, const double *alpha_prev,
+                        const double *__restrict__ q, double *__restrict__ p, double *__restrict__ r, double *__restrict__ t,
+                        double *__restrict__ x, double *__restrict__ z, double *__restrict__ w)
+{
+    const double beta = (*gamma) / (*gamma_prev);
+    const double alpha = (*gamma) / ((*delta) - beta * (*gamma) / (*alpha_prev));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double zv = fma(beta, z[i], q[i]);
+        const double tv = fma(beta, t[i], w[i]);
+        const double pv = fma(beta, p[i], r[i]);
+        z[i] = zv; t[i] = tv; p[i] = pv;
+        x[i] = fma(alpha, pv, x[i]);
+        r[i] = fma(-alpha, tv, r[i]);
+        w[i] = fma(-alpha, zv, w[i]);
+    }
+}
+
+__global__ void helper_pipelined_scalars_kernel(const double *gamma, double *gamma_prev, const double *delta, double *alpha_prev)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double beta = (*gamma) / (*gamma_prev);
+    const double alpha = (*gamma) / ((*delta) - beta * (*gamma) / (*alpha_prev));
+    *gamma_prev = *gamma;
+    *alpha_prev = alpha;
+}
+
+extern "C" int acgb200_helper_axpy(int op, int n, const double *num, const double *den, const double *x, double *y, cudaStream_t stream)
+{
+    static int occ = 0;
+    const int grid = blas1_grid(n, (const void *) helper_axpy_kernel<HELP_AXPY_QUOT>, &occ);
+    if (op == HELP_AXPY_QUOT) helper_axpy_kernel<HELP_AXPY_QUOT><<<grid, BLAS1_THREADS, 0, stream>>>(n, num, den, x, y);
+    else if (op == HELP_AXMY_QUOT) helper_axpy_kernel<HELP_AXMY_QUOT><<<grid, BLAS1_THREADS, 0, stream>>>(n, num, den, x, y);
+    else helper_axpy_kernel<HELP_AYPX_QUOT><<<grid, BLAS1_THREADS, 0, stream>>>(n, num, den, x, y);
+    return (int) cudaGetLastError();
+}
+
+extern "C" int acgb200_helper_scalars(int op, double *out0, double *out1, const double *num, const double *den, cudaStream_t stream)
+{
+    helper_scalars_kernel<<<1, 32, 0, stream>>>(out0, out1, num, den, op);
+    return (int) cudaGetLastError();
+}
+
+extern "C" int acgb200_helper_pipelined(int n, const double *gamma, double *gamma_prev, const double *delta, const double *q,
+                                        double *p, double *r, double *t, double *x, double *z, double *w, double *alpha_prev,
+                                        cudaStream_t stream)
+{
+    static int occ = 0;
+    const int grid = blas1_grid(n, (const void *) helper_pipelined_kernel, &occ);
+    helper_pipelined_kernel<<<grid, BLAS1_THREADS, 0, stream>>>(n, gamma, gamma_prev, delta, alpha_prev, q, p, r, t, x, z, w);
+    helper_pipelined_scalars_kernel<<<1, 32, 0, stream>>>(gamma, gamma_prev, delta, alpha_prev);
+    return (int) cudaGetLastError();
+}

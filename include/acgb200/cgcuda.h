@@ -106,10 +106,27 @@ ACG_API int acgsolvercuda_solve(
     int maxits, double diffatol, double diffrtol, double residualatol, double residualrtol,
     int warmup);
 
-/* acg/cg-kernels-cuda.h:124, :163 -- device-resident solvers.  The reference
- * implements them on NVSHMEM only and otherwise returns
- * ACG_ERR_NVSHMEM_NOT_SUPPORTED (acg/cg-kernels-cuda.cu:1012, :1727); this
- * build has no NVSHMEM (north-star: NCCL only) and returns the same code. */
+/* acg/cg-kernels-cuda.h:45-97 -- the BLAS-1 building blocks of the reference's loops, operating on
+ * device scalars and vectors (acg/cg-kernels-cuda.cu:54-303).  The solvers of this library do not
+ * use them (their updates are fused, kernels.cu); they are kept for callers written against the
+ * reference's header.  Same semantics: alpha = rr/(p,Ap), beta = rr/rr_prev read on the device,
+ * launches on the legacy default stream except where a stream is passed. */
+ACG_API int acgsolvercuda_init_constants(double **d_minus_one, double **d_one, double **d_zero);      /* :45 */
+ACG_API int acgsolvercuda_alpha(double *d_alpha, double *d_minus_alpha, const double *d_rnrm2sqr, const double *d_pdott);   /* :50 */
+ACG_API int acgsolvercuda_beta(double *d_beta, const double *d_rnrm2sqr, const double *d_rnrm2sqr_prev);                  /* :56 */
+ACG_API int acgsolvercuda_daxpy_alpha(int n, const double *d_rnrm2sqr, const double *d_pdott, const double *d_x, double *d_y);        /* :61  y += (rr/pAp) x */
+ACG_API int acgsolvercuda_daxpy_minus_alpha(int n, const double *d_rnrm2sqr, const double *d_pdott, const double *d_x, double *d_y);  /* :68  y -= (rr/pAp) x */
+ACG_API int acgsolvercuda_pipelined_daxpy_fused(                                                       /* :76 */
+    int n, const double *d_gamma, double *d_gamma_prev, const double *d_delta, const double *d_q,
+    double *d_p, double *d_r, double *d_t, double *d_x, double *d_z, double *d_w, double *d_alpha_prev,
+    cudaStream_t stream);
+ACG_API int acgsolvercuda_daypx_beta(int n, const double *d_rnrm2sqr, const double *d_rnrm2sqr_prev, double *d_y, const double *d_x); /* :91  y = (rr/rr_prev) y + x */
+
+/* acg/cg-kernels-cuda.h:124, :163 -- device-resident solvers.  The reference implements them on
+ * NVSHMEM only (one cooperative kernel per solve) and otherwise returns
+ * ACG_ERR_NVSHMEM_NOT_SUPPORTED (acg/cg-kernels-cuda.cu:1012, :1727).  Here: with a null or NCCL
+ * communicator they run the classic / pipelined loop, whose control and inter-GPU communication are
+ * device-resident already (cgcuda.c); an NVSHMEM communicator gets ACG_ERR_NVSHMEM_NOT_SUPPORTED. */
 ACG_API int acgsolvercuda_solve_device(
     struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A,
     const struct acgvector *b, struct acgvector *x,

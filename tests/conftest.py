@@ -32,7 +32,7 @@ _FILE_ORDER = ["test_abi.py", "test_oracle_pin.py", "test_host_structs.py", "tes
                "test_multirank.py", "test_reference_driver.py", "test_example_program.py", "test_driver_py.py"]
 _FIRST_RUN_PENDING = ("test_spmv_ragged_rows", "test_device_and_plain_entry_points", "test_power_law_properties",
                       "test_stock_reference_gpu_solver_pins_the_oracle", "test_driver_manufactured_solution",
-                      "acg-device")
+                      "acg-device", "test_public_blas1_building_blocks")
 
 
 def _order_key(item):

@@ -695,3 +695,40 @@ int acgb200_scatter(int n, const double *src, double *dst, const int *idx, cudaS
     struct gs_args a = { n, dst, src, idx, 1 };
     return hostsim_run_or_record(gs_exec, &a, sizeof(a));
 }
+
+/* ---- the reference's public BLAS-1 building blocks (immediate: they are not part of any captured loop) ---- */
+
+int acgb200_helper_axpy(int op, int n, const double *num, const double *den, const double *x, double *y, cudaStream_t stream)
+{
+    (void) stream;
+    const double a = op == 1 ? -(*num) / (*den) : (*num) / (*den);
+    for (int i = 0; i < n; i++) y[i] = op == 2 ? fma(a, y[i], x[i]) : fma(a, x[i], y[i]);
+    return 0;
+}
+
+int acgb200_helper_scalars(int op, double *out0, double *out1, const double *num, const double *den, cudaStream_t stream)
+{
+    (void) stream;
+    const double q = (*num) / (*den);
+    *out0 = q;
+    if (op == 0) *out1 = -q;
+    return 0;
+}
+
+int acgb200_helper_pipelined(int n, const double *gamma, double *gamma_prev, const double *delta, const double *q,
+                             double *p, double *r, double *t, double *x, double *z, double *w, double *alpha_prev,
+                             cudaStream_t stream)
+{
+    (void) stream;
+    const double beta = (*gamma) / (*gamma_prev);
+    const double alpha = (*gamma) / ((*delta) - beta * (*gamma) / (*alpha_prev));
+    for (int i = 0; i < n; i++) {
+        const double zv = fma(beta, z[i], q[i]), tv = fma(beta, t[i], w[i]), pv = fma(beta, p[i], r[i]);
+        z[i] = zv; t[i] = tv; p[i] = pv;
+        x[i] = fma(alpha, pv, x[i]);
+        r[i] = fma(-alpha, tv, r[i]);
+        w[i] = fma(-alpha, zv, w[i]);
+    }
+    *gamma_prev = *gamma; *alpha_prev = alpha;
+    return 0;
+}

@@ -24,6 +24,42 @@ def case(name):
             "rmat": lambda: mg.rmat_spd(30000, 600000, seed=8), "n3": lambda: mg.poisson1d_3pt(3)}[name]()
 
 
+def blas1_blocks():
+    """acg/cg-kernels-cuda.h:45-97 through the C-ABI; on the stand-in "device" pointers are host addresses."""
+    import ctypes as C
+    L = ab.lib()
+    rng = np.random.default_rng(2)
+    n = 1001
+    ptr = lambda a: a.ctypes.data                                    # noqa: E731
+    out = {}
+    rr, pap, rrp = np.array([3.5]), np.array([1.25]), np.array([7.0])
+    al, mal, be = np.zeros(1), np.zeros(1), np.zeros(1)
+    assert L.acgsolvercuda_alpha(ptr(al), ptr(mal), ptr(rr), ptr(pap)) == 0
+    assert L.acgsolvercuda_beta(ptr(be), ptr(rr), ptr(rrp)) == 0
+    out["scalars"] = bool(al[0] == 2.8 and mal[0] == -2.8 and be[0] == 0.5)
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    y1 = y.copy(); assert L.acgsolvercuda_daxpy_alpha(n, ptr(rr), ptr(pap), ptr(x), ptr(y1)) == 0
+    y2 = y.copy(); assert L.acgsolvercuda_daxpy_minus_alpha(n, ptr(rr), ptr(pap), ptr(x), ptr(y2)) == 0
+    y3 = y.copy(); assert L.acgsolvercuda_daypx_beta(n, ptr(rr), ptr(rrp), ptr(y3), ptr(x)) == 0
+    out["axpy"] = bool(np.allclose(y1, y + 2.8 * x, rtol=1e-15, atol=1e-15) and np.allclose(y2, y - 2.8 * x, rtol=1e-15, atol=1e-15)
+                       and np.allclose(y3, 0.5 * y + x, rtol=1e-15, atol=1e-15))
+    g, gp, d, ap = np.array([2.0]), np.array([4.0]), np.array([3.0]), np.array([0.5])
+    v = {k: rng.standard_normal(n) for k in "qprtxzw"}
+    w0 = {k: a.copy() for k, a in v.items()}
+    assert L.acgsolvercuda_pipelined_daxpy_fused(n, ptr(g), ptr(gp), ptr(d), ptr(v["q"]), ptr(v["p"]), ptr(v["r"]), ptr(v["t"]),
+                                                 ptr(v["x"]), ptr(v["z"]), ptr(v["w"]), ptr(ap), None) == 0
+    beta = 2.0 / 4.0; alpha = 2.0 / (3.0 - beta * 2.0 / 0.5)
+    z = w0["q"] + beta * w0["z"]; t = w0["w"] + beta * w0["t"]; p = w0["r"] + beta * w0["p"]
+    ok = (np.allclose(v["z"], z) and np.allclose(v["t"], t) and np.allclose(v["p"], p) and np.allclose(v["x"], w0["x"] + alpha * p)
+          and np.allclose(v["r"], w0["r"] - alpha * t) and np.allclose(v["w"], w0["w"] - alpha * z))
+    out["pipelined"] = bool(ok and gp[0] == 2.0 and ap[0] == alpha)
+    m1, p1, z0 = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    assert L.acgsolvercuda_init_constants(C.byref(m1), C.byref(p1), C.byref(z0)) == 0
+    vals = [C.cast(q.value, C.POINTER(C.c_double))[0] for q in (m1, p1, z0)]
+    out["constants"] = vals == [-1.0, 1.0, 0.0]
+    return out
+
+
 def main():
     spec = json.loads(sys.argv[1])
     for k, v in spec.get("options", {}).items():
@@ -54,6 +90,8 @@ def main():
             "launches": int(cg.info()["last_launches"]), "nsolves": int(cg.c.nsolves),
             "spmv_count": int(cg.info()["last_spmv_count"]), "ngemv": int(cg.c.ngemv), "total_its": int(cg.c.ntotaliterations)})
     out["report_ok"] = "total solver time:" in cg.report()
+    if spec.get("blas1_blocks"):
+        out["blas1_blocks"] = blas1_blocks()
     # interface behaviour that needs no kernel at all
     errs = {}
     try:

@@ -427,3 +427,49 @@ def test_medium_row_kernel_matches_oracle(ab, oracle):
         assert getattr(cg, method)(b, xs, maxits=10) == 0
         assert np.abs(xs.x - ref["x"]).max() <= 1e-9 * np.abs(ref["x"]).max()
     cg.free()
+
+
+def test_public_blas1_building_blocks(ab):
+    """acg/cg-kernels-cuda.h:45-97 on the device (torch only provides the device arrays)."""
+    import ctypes as C
+    import torch
+    L = ab.lib()
+    dev = lambda a: torch.tensor(np.atleast_1d(a), dtype=torch.float64, device="cuda")       # noqa: E731
+    rng = np.random.default_rng(2)
+    n = 100003
+    rr, pap, rrp = dev(3.5), dev(1.25), dev(7.0)
+    al, mal, be = dev(0.0), dev(0.0), dev(0.0)
+    assert L.acgsolvercuda_alpha(al.data_ptr(), mal.data_ptr(), rr.data_ptr(), pap.data_ptr()) == 0
+    assert L.acgsolvercuda_beta(be.data_ptr(), rr.data_ptr(), rrp.data_ptr()) == 0
+    torch.cuda.synchronize()
+    assert (al.item(), mal.item(), be.item()) == (2.8, -2.8, 0.5)
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    dx = dev(x)
+    for fn, want in ((L.acgsolvercuda_daxpy_alpha, y + 2.8 * x), (L.acgsolvercuda_daxpy_minus_alpha, y - 2.8 * x)):
+        dy = dev(y)
+        assert fn(n, rr.data_ptr(), pap.data_ptr(), dx.data_ptr(), dy.data_ptr()) == 0
+        torch.cuda.synchronize()
+        assert np.allclose(dy.cpu().numpy(), want, rtol=1e-15, atol=1e-15)
+    dy = dev(y)
+    assert L.acgsolvercuda_daypx_beta(n, rr.data_ptr(), rrp.data_ptr(), dy.data_ptr(), dx.data_ptr()) == 0
+    torch.cuda.synchronize()
+    assert np.allclose(dy.cpu().numpy(), 0.5 * y + x, rtol=1e-15, atol=1e-15)
+    g, gp, d, ap = dev(2.0), dev(4.0), dev(3.0), dev(0.5)
+    h = {k: rng.standard_normal(n) for k in "qprtxzw"}
+    v = {k: dev(a) for k, a in h.items()}
+    assert L.acgsolvercuda_pipelined_daxpy_fused(n, g.data_ptr(), gp.data_ptr(), d.data_ptr(), v["q"].data_ptr(), v["p"].data_ptr(),
+                                                 v["r"].data_ptr(), v["t"].data_ptr(), v["x"].data_ptr(), v["z"].data_ptr(),
+                                                 v["w"].data_ptr(), ap.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    beta = 0.5; alpha = 2.0 / (3.0 - beta * 2.0 / 0.5)
+    z = h["q"] + beta * h["z"]; t = h["w"] + beta * h["t"]; p = h["r"] + beta * h["p"]
+    for k, want in (("z", z), ("t", t), ("p", p), ("x", h["x"] + alpha * p), ("r", h["r"] - alpha * t), ("w", h["w"] - alpha * z)):
+        assert np.allclose(v[k].cpu().numpy(), want, rtol=1e-14, atol=1e-14), k
+    assert gp.item() == 2.0 and ap.item() == alpha
+    m1, p1, z0 = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    assert L.acgsolvercuda_init_constants(C.byref(m1), C.byref(p1), C.byref(z0)) == 0
+    got = torch.zeros(3, dtype=torch.float64, device="cuda")
+    for i, q in enumerate((m1, p1, z0)):
+        assert L.acgsolvercuda_daxpy_alpha(1, q.value, p1.value, p1.value, got[i:i + 1].data_ptr()) == 0    # got[i] += (q/1)*1
+    torch.cuda.synchronize()
+    assert got.cpu().tolist() == [-1.0, 1.0, 0.0]

@@ -327,3 +327,10 @@ def test_unmodified_reference_driver(solver, method, simlib, tmp_path):
         e0 = float(re.search(r"^initial error 2-norm: (\S+)", q.stderr, re.M).group(1))
         e1 = float(re.search(r"^error 2-norm: (\S+)", q.stderr, re.M).group(1))
         assert e0 == pytest.approx(1.0, rel=1e-12) and e1 < 1e-7
+
+
+def test_public_blas1_building_blocks(simlib):
+    """acg/cg-kernels-cuda.h:45-97 (alpha, beta, daxpy_alpha, daxpy_minus_alpha, daypx_beta,
+    pipelined_daxpy_fused, init_constants): entry points, argument order and semantics."""
+    out = _run({"matrix": "n3", "blas1_blocks": 1, "runs": []})
+    assert out["blas1_blocks"] == {"scalars": True, "axpy": True, "pipelined": True, "constants": True}
