@@ -63,9 +63,14 @@ static void cleanup_allocs(void)
     for (int i = 0; i < nallocs; i++) if (allocs[i].ptr && !allocs[i].mapped_peer) shm_unlink(allocs[i].name);
 }
 
+/* fault injection for the clean-up paths: HOSTSIM_FAIL_MALLOC_AT=k makes the k-th device allocation fail */
+static long malloc_calls = 0;
+
 cudaError_t cudaMalloc(void **p, size_t n)
 {
     const size_t size = n ? n : 1;
+    const char *failat = getenv("HOSTSIM_FAIL_MALLOC_AT");
+    if (failat && ++malloc_calls == atol(failat)) { *p = NULL; return cudaErrorMemoryAllocation; }
     pthread_mutex_lock(&alloc_lock);
     if (nallocs == 0) atexit(cleanup_allocs);
     int slot = -1;

@@ -334,3 +334,19 @@ def test_public_blas1_building_blocks(simlib):
     pipelined_daxpy_fused, init_constants): entry points, argument order and semantics."""
     out = _run({"matrix": "n3", "blas1_blocks": 1, "runs": []})
     assert out["blas1_blocks"] == {"scalars": True, "axpy": True, "pipelined": True, "constants": True}
+
+
+def test_failing_device_allocations_are_survived(simlib):
+    """Fault injection (tests/hostsim/cuda_mock.c, HOSTSIM_FAIL_MALLOC_AT): whichever "device"
+    allocation of set-up or of the solves fails, the call returns ACG_ERR_CUDA, the process survives
+    and tears down what had been built (the AddressSanitizer run of tools/asan_hostsim.sh repeats
+    this on every allocation)."""
+    script = os.path.join(SIM, "run_fault.py")
+    seen = []
+    for k in list(range(1, 25, 3)) + [24, 1000]:
+        p = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=120,
+                           env=dict(os.environ, HOSTSIM_FAIL_MALLOC_AT=str(k), OMP_NUM_THREADS="2"))
+        assert p.returncode == 0, (k, p.stderr[-2000:])
+        seen.append((k, p.stdout.strip().splitlines()[-1]))
+    assert all(out == "error 4" for k, out in seen if k <= 24), seen          # ACG_ERR_CUDA
+    assert seen[-1] == (1000, "ok")
