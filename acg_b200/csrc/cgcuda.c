@@ -335,7 +335,7 @@ static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr, const
             pl->ncompressed_tiles = 0;
         }
     }
-    if (nt > 0) {
+    if (!e && nt > 0) {
         e = cudaMalloc((void **) &pl->d_tiles, (size_t) nt * sizeof(*tiles));
         if (!e) e = cudaMemcpy(pl->d_tiles, tiles, (size_t) nt * sizeof(*tiles), cudaMemcpyHostToDevice);
     }
