@@ -63,11 +63,19 @@ static void cleanup_allocs(void)
     for (int i = 0; i < nallocs; i++) if (allocs[i].ptr && !allocs[i].mapped_peer) shm_unlink(allocs[i].name);
 }
 
-/* fault injection for the clean-up paths: HOSTSIM_FAIL_MALLOC_AT=k makes the k-th device allocation fail */
-static long malloc_calls = 0;
+/* fault injection for the clean-up paths: HOSTSIM_FAIL_MALLOC_AT=k makes the k-th device allocation
+ * fail, HOSTSIM_FAIL_CALL_AT=k the k-th call of any runtime entry point that can fail */
+static long malloc_calls = 0, api_calls = 0;
+
+static int failpoint(void)
+{
+    const char *at = getenv("HOSTSIM_FAIL_CALL_AT");
+    return at && ++api_calls == atol(at);
+}
+#define FAILPOINT(err) do { if (failpoint()) return (err); } while (0)
 
 cudaError_t cudaMalloc(void **p, size_t n)
-{
+{ FAILPOINT(cudaErrorUnknown);
     const size_t size = n ? n : 1;
     const char *failat = getenv("HOSTSIM_FAIL_MALLOC_AT");
     if (failat && ++malloc_calls == atol(failat)) { *p = NULL; return cudaErrorMemoryAllocation; }
@@ -155,21 +163,21 @@ cudaError_t cudaIpcCloseMemHandle(void *p)
     return cudaErrorInvalidValue;
 }
 
-cudaError_t cudaMallocHost(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaMallocHost(void **p, size_t n) { FAILPOINT(cudaErrorUnknown); *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 cudaError_t cudaHostRegister(void *p, size_t n, unsigned int f) { (void) p; (void) n; (void) f; return cudaSuccess; }
 cudaError_t cudaHostUnregister(void *p) { (void) p; return cudaSuccess; }
-cudaError_t cudaMemcpy(void *d, const void *s, size_t n, enum cudaMemcpyKind k) { (void) k; if (n) memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, enum cudaMemcpyKind k) { FAILPOINT(cudaErrorUnknown); (void) k; if (n) memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, enum cudaMemcpyKind k, cudaStream_t st)
-{
+{ FAILPOINT(cudaErrorUnknown);
     (void) k; (void) st;
     if (hostsim_capturing) return cudaErrorStreamCaptureUnsupported;     /* the iteration bodies contain kernels only */
     if (n) memmove(d, s, n);
     return cudaSuccess;
 }
-cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemset(void *d, int v, size_t n) { FAILPOINT(cudaErrorUnknown); if (n) memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st)
-{
+{ FAILPOINT(cudaErrorUnknown);
     (void) st;
     if (hostsim_capturing) return cudaErrorStreamCaptureUnsupported;
     if (n) memset(d, v, n);
@@ -179,22 +187,22 @@ cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st)
 /* ---- device, streams, events ----------------------------------------------- */
 cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
-cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = -1; return cudaSuccess; }
+cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { FAILPOINT(cudaErrorUnknown); *lo = 0; *hi = -1; return cudaSuccess; }
 cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned int f, int p)
-{
+{ FAILPOINT(cudaErrorUnknown);
     (void) f; (void) p;
     *s = (cudaStream_t) malloc(8);
     return *s ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t s) { (void) s; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t s) { FAILPOINT(cudaErrorUnknown); (void) s; return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned int f) { (void) s; (void) e; (void) f; return cudaSuccess; }
 
 struct simevent { double t; };
-cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = (cudaEvent_t) calloc(1, sizeof(struct simevent)); return *e ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaEventCreate(cudaEvent_t *e) { FAILPOINT(cudaErrorUnknown); *e = (cudaEvent_t) calloc(1, sizeof(struct simevent)); return *e ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned int f) { (void) f; return cudaEventCreate(e); }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) { (void) s; ((struct simevent *) e)->t = now_ms(); return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) { FAILPOINT(cudaErrorUnknown); (void) s; ((struct simevent *) e)->t = now_ms(); return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t e) { (void) e; return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b)
 {
@@ -204,14 +212,14 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b)
 
 /* ---- graphs: a recorded list of simulated launches --------------------------- */
 cudaError_t cudaStreamBeginCapture(cudaStream_t s, enum cudaStreamCaptureMode m)
-{
+{ FAILPOINT(cudaErrorUnknown);
     (void) s; (void) m;
     if (hostsim_capturing) return cudaErrorIllegalState;
     hostsim_capturing = calloc(1, sizeof(*hostsim_capturing));
     return hostsim_capturing ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t *g)
-{
+{ FAILPOINT(cudaErrorUnknown);
     (void) s;
     *g = (cudaGraph_t) hostsim_capturing;
     hostsim_capturing = NULL;
@@ -225,7 +233,7 @@ static void graph_free(struct simgraph *g)
 }
 cudaError_t cudaGraphDestroy(cudaGraph_t g) { graph_free((struct simgraph *) g); return cudaSuccess; }
 cudaError_t cudaGraphInstantiate(cudaGraphExec_t *e, cudaGraph_t g, unsigned long long flags)
-{
+{ FAILPOINT(cudaErrorUnknown);
     (void) flags;
     const struct simgraph *src = (const struct simgraph *) g;
     struct simgraph *c = calloc(1, sizeof(*c));
@@ -242,7 +250,7 @@ cudaError_t cudaGraphInstantiate(cudaGraphExec_t *e, cudaGraph_t g, unsigned lon
 }
 cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { graph_free((struct simgraph *) e); return cudaSuccess; }
 cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t s)
-{
+{ FAILPOINT(cudaErrorUnknown);
     (void) s;
     const struct simgraph *g = (const struct simgraph *) e;
     for (int i = 0; i < g->n; i++) g->ops[i].fn(g->ops[i].args);

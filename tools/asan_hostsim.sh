@@ -21,6 +21,6 @@ ACGB200_TEST_HOSTSIM=$PWD/$D/libacgb200_hostsim.so python -m torch.distributed.r
     --master-addr 127.0.0.1 --master-port 31114 tests/_dist_worker.py --mode gpu --matrix 27pt --size 8 --partition block \
     --backends p2p-fused,p2p-unfused,one-kernel,all-unified,two-kernel-unified,nccl,nccl-graph 2>&1 \
     | grep -c " OK$\|FAIL\|runtime error\|AddressSanitizer" 
-echo "== every device allocation failing in turn"
-for k in $(seq 1 26); do ACGB200_TEST_LIB=$PWD/$D/libacgb200_hostsim.so HOSTSIM_FAIL_MALLOC_AT=$k python tests/hostsim/run_fault.py 2>&1 | grep -i "Sanitizer\|runtime error\|^ok\|^error"; done | sort | uniq -c
+echo "== every runtime call of set-up and solves failing in turn (159 at the end of round 1)"
+for k in $(seq 1 165); do ACGB200_TEST_LIB=$PWD/$D/libacgb200_hostsim.so HOSTSIM_FAIL_CALL_AT=$k python tests/hostsim/run_fault.py 2>&1 | grep -i "Sanitizer\|runtime error\|^ok\|^error"; done | sort | uniq -c
 rm -f /dev/shm/acgb200nccl_* /dev/shm/acgb200sim_*
