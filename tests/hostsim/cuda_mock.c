@@ -259,6 +259,11 @@ cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t s)
 
 int hostsim_run_or_record(void (*fn)(void *), const void *args, size_t size)
 {
+    {   /* HOSTSIM_FAIL_LAUNCH_AT=k: the k-th kernel launch (or NCCL call) reports an error */
+        static long launches = 0;
+        const char *at = getenv("HOSTSIM_FAIL_LAUNCH_AT");
+        if (at && ++launches == atol(at)) return (int) cudaErrorLaunchFailure;
+    }
     if (!hostsim_capturing) { fn((void *) args); return 0; }
     struct simgraph *g = hostsim_capturing;
     if (g->n == g->cap) {
