@@ -338,6 +338,15 @@ def main():
     tw1 = time.time()
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     resid = cg.c.rnrm2 / cg.c.r0nrm2
+    check = None
+    if world == 1:
+        # outside every timed region: the residual recomputed from the returned x with one more
+        # SpMV, next to the recurrence residual the solver reports (pipelined CG reports the last
+        # tested iterate, one step behind)
+        ax, _ = cg.spmv(x.x[:A.c.nownedrows])
+        true_rel = float(np.linalg.norm(b.x[:A.c.nownedrows] - ax) / cg.c.r0nrm2)
+        check = {"true_residual_rel": true_rel, "reported_residual_rel": float(resid),
+                 "what": "||b - A x|| / ||r0|| from the x of the last step vs the solver's own figure"}
 
     t = torch.tensor([dev_ms, host_s], dtype=torch.float64)
     if world > 1:
@@ -377,6 +386,7 @@ def main():
                          "note": "16*nnz contract bytes (BASELINE.md); rank 0's local block"},
             "clocks": clocks,
             "residual_after_step": resid,
+            "check": check,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(w, 1, 0, args.cpu_iters,
