@@ -156,6 +156,8 @@ def test_multi_rank_loops(nproc, matrix, size, partition, backends, extra, simli
            "--matrix", matrix, "--size", str(size), "--partition", partition, "--backends", backends] + extra
     # "watchdog": one rank stops publishing mid-solve; the others must give up after the timeout,
     # report ACG_ERR_CUDA / cudaErrorLaunchTimeout, and the next solver on the same ranks must work
+    import glob
+    before = set(glob.glob("/dev/shm/acgb200sim_*"))          # leftovers of killed processes are not this run's
     env = dict(os.environ, OMP_NUM_THREADS="2", ACGB200_TEST_HOSTSIM=simlib,
                ACGB200_P2P_TIMEOUT_MS="1500" if "watchdog" in backends else "20000")
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
@@ -164,8 +166,7 @@ def test_multi_rank_loops(nproc, matrix, size, partition, backends, extra, simli
     assert "FAIL" not in p.stdout
     names = backends.split(",")
     assert p.stdout.count(" OK") == 4 * len([b for b in names if b != "watchdog"]) + (nproc if "watchdog" in names else 0)
-    import glob
-    assert not glob.glob("/dev/shm/acgb200sim_*")            # every "device" allocation was released
+    assert not set(glob.glob("/dev/shm/acgb200sim_*")) - before      # every "device" allocation was released
     for f in glob.glob("/dev/shm/acgb200nccl_*"):            # NCCL stand-in leftovers of killed runs, if any
         os.remove(f)
 
