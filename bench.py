@@ -59,8 +59,9 @@ WORKLOADS = {
 
 
 def make_matrix(w):
-    """Upper-triangle COO of the whole stencil matrix (for the reference arms): the
-    one-part output of the threaded generator, the same entries as acg_b200.matgen's."""
+    """Upper-triangle COO of the whole matrix as the product's host generators build it (GPU arm only:
+    METIS runs, the file handed to the stock reference GPU solver, and the R-MAT matrix, which is
+    defined by the counter-based generator of acg_b200/csrc/rmat.c)."""
     import acg_b200 as ab
     N = w["N"]
     if w["kind"] == "rmat":
@@ -73,6 +74,38 @@ def make_matrix(w):
     n = int(A.c.nprows)
     A.free()
     return n, rows, cols, vals
+
+
+def build_local_matrix(w, partition, rank, world):
+    """This rank's part of the workload matrix with full storage initialised (GPU arm only)."""
+    import acg_b200 as ab
+    from acg_b200 import dist as abdist
+    N = w["N"]
+    if w["kind"] == "rmat":
+        # power-law graph: no geometry; every rank generates the (deterministic) matrix and keeps its part
+        A = ab.SymCsrMatrix.rmat_spd(N, w["edges"], seed=42)
+        if world > 1:
+            rowparts = (A.partition_rows(world, seed=0)[0] if partition == "metis"
+                        else abdist.balanced_rows_partition(A, world))     # equal nonzeros, not equal rows
+            parts = A.partition(world, rowparts)
+            A.free()
+            A = parts[rank]
+            for p, m in enumerate(parts):
+                if p != rank:
+                    m.free()
+        return A.dsymv_init(0.0)
+    k = 27 if w["kind"] == "27pt" else 7
+    if partition == "block" or world == 1:
+        # every rank builds only its own block (no global matrix anywhere); one rank = the whole box
+        if (N ** 3 * k) // world >= 2 ** 31:
+            raise SystemExit(f"bench.py: {w['kind']} {N}^3 does not fit 32-bit indices on {world} GPU(s)")
+        return abdist.local_stencil_part(k, N, N, N, rank, world)
+    if N ** 3 * k >= 2 ** 31:
+        raise SystemExit(f"bench.py: {w['kind']} {N}^3 is too large for a global METIS partition in one process")
+    n, r, c, v = make_matrix(w)
+    A = abdist.local_part(n, r, c, v, "metis", rank, world)
+    del r, c, v
+    return A
 
 
 def rhs(w, gidx):
@@ -129,38 +162,50 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
 
 
-def cpu_reference(w, steps, warmup, iters, solver_note):
-    """Time the reference's CPU CG (acg/cg.c) on the host cores; falls back to the
-    oracle port when oracle/_ref was not built."""
-    from oracle import Oracle, Ref, ref_available
-    n, r, c, v = make_matrix(w)
-    b = rhs(w, np.arange(n))
-    out = []
-    if ref_available():
-        R = Ref()
-        kind, cores = "reference", R.num_threads()
-        h = R.setup(n, r, c, v)
-        for s in range(warmup + steps):
-            res = R.solve(h, b, maxits=iters)
-            if s >= warmup:
-                out.append(res["tsolve"])
-        R.free(h)
+def cpu_arm(w, iters, steps, warmup, save_x=None):
+    """Run oracle/cpu_arm.py in a fresh process (threads pinned one per physical core, nothing of
+    the product in it) and return its JSON.  Stencil matrices are generated inside that process;
+    the R-MAT matrix is defined by the product's generator, so it is handed over as a file."""
+    import tempfile
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "cpu_arm.py"), "--iters", str(iters),
+           "--steps", str(steps), "--warmup", str(warmup)]
+    tmp = None
+    if w["kind"] == "rmat":
+        n, r, c, v = make_matrix(w)
+        tmp = tempfile.NamedTemporaryFile(suffix=".npz", dir="/dev/shm" if os.path.isdir("/dev/shm") else None, delete=False)
+        np.savez(tmp, n=n, rows=r, cols=c, vals=v, b=rhs(w, np.arange(n)))
+        tmp.close()
+        del r, c, v
+        cmd += ["--matrix", tmp.name]
     else:
-        O = Oracle()
-        kind, cores = "port", O.num_threads()
-        csr = O.full_csr(n, r, c, v)
-        for s in range(warmup + steps):
-            t0 = time.perf_counter()
-            O.cg(csr, b, maxits=iters)
-            if s >= warmup:
-                out.append(time.perf_counter() - t0)
-    tot = sum(out)
-    return dict(value=len(out) * iters / tot, unit="iterations/s", cores=cores, kind=kind,
-                sample=f"{len(out)} x {iters} classic CG iterations (acgsolver_solve) on the full "
-                       + (f"R-MAT n={w['N']}" if w["kind"] == "rmat" else f"{w['kind']} {w['N']}^3")
-                       + f" matrix, {rhs_name(w)}, x0=0; OpenMP dsymv on {cores} threads, BLAS-1 serial as in the reference"
-                       f"{solver_note}",
-                seconds=tot)
+        cmd += ["--kind", w["kind"], "--N", str(w["N"])]
+    if save_x:
+        cmd += ["--save-x", save_x]
+    env = {k: v for k, v in os.environ.items() if not k.startswith(("OMP_", "GOMP_", "KMP_"))}
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    finally:
+        if tmp:
+            os.unlink(tmp.name)
+    if p.returncode != 0:
+        raise RuntimeError("oracle/cpu_arm.py failed: " + p.stderr[-2000:])
+    return json.loads(p.stdout.strip().splitlines()[-1])
+
+
+def cpu_reference(w, steps, warmup, iters, solver_note, save_x=None):
+    """Time the reference's CPU CG (acg/cg.c through oracle/_ref; the oracle port when that build
+    is absent) on the host's physical cores."""
+    r = cpu_arm(w, iters, steps, warmup, save_x)
+    times = r["times"]
+    tot = sum(times)
+    what = f"R-MAT n={w['N']}" if w["kind"] == "rmat" else f"{w['kind']} {w['N']}^3"
+    return dict(value=len(times) * iters / tot, unit="iterations/s", cores=r["cores"], kind=r["kind"],
+                sample=f"{len(times)} x {iters} classic CG iterations (acgsolver_solve, acg/cg.c:198) on the full {what} "
+                       f"matrix, {rhs_name(w)}, x0=0; OpenMP dsymv on {r['cores']} threads pinned one per physical core, "
+                       f"BLAS-1 serial as in the reference{solver_note}",
+                seconds=tot, best_its_per_s=iters / min(times), median_its_per_s=iters / statistics.median(times),
+                numa_interleave_nodes=r["numa_interleave_nodes"], matrix_placed_by_threads=r["matrix_placed_by_threads"],
+                setup_s=r["setup_s"], rnrm2=r["rnrm2"], r0nrm2=r["r0nrm2"], niterations=r["niterations"])
 
 
 def reference_gpu(w, iters, solver):
@@ -198,7 +243,9 @@ def main():
     ap.add_argument("--workload", default="27pt-224", choices=sorted(WORKLOADS))
     ap.add_argument("--solver", default=None, choices=["pipelined", "classic"])
     ap.add_argument("--iters", type=int, default=100, help="CG iterations per step (reference default --max-iterations 100)")
-    ap.add_argument("--cpu-iters", type=int, default=5, help="iterations per CPU-baseline step")
+    ap.add_argument("--cpu-iters", type=int, default=None,
+                    help="classic iterations per CPU step (default: 5 for --impl reference; --iters for the GPU arm's "
+                         "cpu_baseline leg, whose x is also the full-size parity check)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--with-reference-gpu", action="store_true",
                     help="also run the stock reference GPU solver (cuSPARSE/cuBLAS) on the same matrix (1 GPU, adds minutes)")
@@ -206,14 +253,13 @@ def main():
                     help="row partition for N>1: geometric blocks or METIS (acgsymcsrmatrix_partition_rows)")
     args = ap.parse_args()
     # torchrun exports OMP_NUM_THREADS=1 to every rank unless the caller set it.  The host-side set-up
-    # (matrix generator, full-storage expansion) and, above all, the reference's CPU solver are OpenMP
-    # code: give the reference arm all host cores (only rank 0 works there) and a rank of the GPU arm
-    # its share.  Must happen before anything loads libgomp (it reads the variable once).
+    # (matrix generator, full-storage expansion) is OpenMP code: give a rank of the GPU arm its share of
+    # the host cores.  (The CPU arm sets its own OpenMP environment in its own process, oracle/cpu_arm.py.)
+    # Must happen before anything loads libgomp (it reads the variable once).
     if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS") == "1" \
             and not os.environ.get("BENCH_KEEP_OMP_NUM_THREADS"):
         ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        share = ncpu if args.impl == "reference" else max(1, ncpu // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"])))
-        os.environ["OMP_NUM_THREADS"] = str(share)
+        os.environ["OMP_NUM_THREADS"] = str(max(1, ncpu // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
     w = WORKLOADS[args.workload]
     solver = args.solver or os.environ.get("BENCH_SOLVER") or w["solver"]
     rank = int(os.environ.get("RANK", "0"))
@@ -227,6 +273,9 @@ def main():
               "partition": (f"{world} parts, " + ("METIS recursive" if args.partition == "metis" else
                                                   ("contiguous row blocks of equal nonzero count" if w["kind"] == "rmat" else "geometric blocks")))
                            if world > 1 else "none",
+              "reference_arm": {"solver": "classic", "iters_per_step": args.cpu_iters or 5,
+                                "what": "--impl reference: the reference's CPU path is classic CG (acg/cg.c:198; it has no CPU "
+                                        "pipelined CG); a step = this many of its iterations on the same matrix, b and x0"},
               "l2": None}
     k = 27 if w["kind"] == "27pt" else 7
     if w["kind"] == "rmat":
@@ -239,8 +288,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        note = "" if solver == "classic" else "; the reference has no CPU pipelined CG, classic CG is its CPU path"
-        cb = cpu_reference(w, args.steps, args.warmup, args.cpu_iters, note)
+        # The reference has no CPU pipelined CG: its CPU path is classic CG (acg/cg.c); a step of this
+        # arm is config.reference_arm.iters_per_step of those iterations on the same matrix and
+        # right-hand side (the metric, iterations/s, is per iteration either way).  Both arms print
+        # the same config, which states what each of them runs.
+        cpu_iters = config["reference_arm"]["iters_per_step"]
+        cb = cpu_reference(w, args.steps, args.warmup, cpu_iters, "")
         line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "iterations/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * cb["seconds"] / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
@@ -259,31 +312,7 @@ def main():
     import torch.distributed as dist
     comm = abdist.nccl_comm(rank, world)
 
-    N = w["N"]
-    if w["kind"] == "rmat":
-        # power-law graph: no geometry; every rank generates the (deterministic) matrix and keeps its part
-        A = ab.SymCsrMatrix.rmat_spd(N, w["edges"], seed=42)
-        if world > 1:
-            rowparts = (A.partition_rows(world, seed=0)[0] if args.partition == "metis"
-                        else abdist.balanced_rows_partition(A, world))     # equal nonzeros, not equal rows
-            parts = A.partition(world, rowparts)
-            A.free()
-            A = parts[rank]
-            for p, m in enumerate(parts):
-                if p != rank:
-                    m.free()
-        A.dsymv_init(0.0)
-    elif args.partition == "block":
-        # every rank builds only its own block (no global matrix anywhere); one rank = the whole box
-        if (N ** 3 * (27 if w["kind"] == "27pt" else 7)) // world >= 2 ** 31:
-            raise SystemExit(f"bench.py: {args.workload} does not fit 32-bit indices on {world} GPU(s)")
-        A = abdist.local_stencil_part(27 if w["kind"] == "27pt" else 7, N, N, N, rank, world)
-    else:
-        if N ** 3 * (27 if w["kind"] == "27pt" else 7) >= 2 ** 31:
-            raise SystemExit(f"bench.py: {args.workload} does not fit 32-bit indices on {world} GPU(s)")
-        n, r, c, v = make_matrix(w)
-        A = abdist.local_part(n, r, c, v, "metis" if world > 1 else None, rank, world)
-        del r, c, v
+    A = build_local_matrix(w, args.partition, rank, world)
     nnz_local = int(A.c.fnpnzs + A.c.onpnzs)
     cg = ab.SolverCuda(A, comm)
     b = A.vector()
@@ -297,13 +326,13 @@ def main():
     d2h = x.c.num_nonzeros * 8
     solve = cg.solve_pipelined if solver == "pipelined" else cg.solvempi
 
-    def step():
+    def step(fn=None):
         x.x[:] = 0.0
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        code = solve(b, x, maxits=args.iters)
+        code = (fn or solve)(b, x, maxits=args.iters)
         t1 = time.perf_counter()
         assert code == 0 and cg.c.niterations == args.iters
         return t1 - t0
@@ -337,14 +366,16 @@ def main():
     torch.cuda.synchronize()
     tw1 = time.time()
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
+    info = cg.info()
     resid = cg.c.rnrm2 / cg.c.r0nrm2
+    x_main = x.x[:nown].copy()
     check = None
     if world == 1:
         # outside every timed region: the residual recomputed from the returned x with one more
         # SpMV, next to the recurrence residual the solver reports (pipelined CG reports the last
         # tested iterate, one step behind)
-        ax, _ = cg.spmv(x.x[:A.c.nownedrows])
-        true_rel = float(np.linalg.norm(b.x[:A.c.nownedrows] - ax) / cg.c.r0nrm2)
+        ax, _ = cg.spmv(x_main)
+        true_rel = float(np.linalg.norm(b.x[:nown] - ax) / cg.c.r0nrm2)
         check = {"true_residual_rel": true_rel, "reported_residual_rel": float(resid),
                  "what": "||b - A x|| / ||r0|| from the x of the last step vs the solver's own figure"}
 
@@ -354,18 +385,54 @@ def main():
     dev_ms_max, host_s_max = float(t[0]), float(t[1])
     total_iters = args.steps * args.iters
 
+    # ---- full-size parity against the reference's CPU solver (1 GPU, outside the timed regions):
+    # the same args.iters classic iterations of acg/cg.c on the same matrix; its timing is the
+    # cpu_baseline, its x and residual the parity figures (north_star: 1e-10 relative)
+    cpu_baseline = parity = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        import tempfile
+        cpu_iters = args.cpu_iters or args.iters
+        xs = None
+        with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
+            xfile = os.path.join(td, "x_cpu.npy") if cpu_iters == args.iters else None
+            cpu_baseline = cpu_reference(w, 1, 0, cpu_iters, "" if solver == "classic" else "; GPU arm runs pipelined CG", xfile)
+            if xfile and os.path.exists(xfile):
+                xs = np.load(xfile)
+        if xs is not None:
+            step(cg.solvempi)                                   # GPU classic CG, same iterations
+            x_classic = x.x[:nown].copy()
+            r0 = cpu_baseline["r0nrm2"]
+            scale = float(np.abs(xs).max())
+            parity = {"iterations": args.iters, "cpu": "acgsolver_solve (acg/cg.c:198), oracle/_ref" if cpu_baseline["kind"] == "reference" else "oracle port",
+                      "gpu_classic_vs_cpu": {
+                          "rel_residual_diff": abs(cg.c.rnrm2 - cpu_baseline["rnrm2"]) / r0,
+                          "residual_ratio_minus_1": cg.c.rnrm2 / cpu_baseline["rnrm2"] - 1.0,
+                          "max_rel_x_diff": float(np.abs(x_classic - xs).max() / scale),
+                          "gpu_rnrm2": cg.c.rnrm2, "cpu_rnrm2": cpu_baseline["rnrm2"], "r0nrm2": r0},
+                      "tolerance": 1e-10}
+            if solver == "pipelined":
+                parity["gpu_pipelined_vs_gpu_classic"] = {
+                    "max_rel_x_diff": float(np.abs(x_main - x_classic).max() / scale),
+                    "note": "pipelined CG is a different recurrence (acg/cgcuda.c:1676-1788): same Krylov iterates in exact "
+                            "arithmetic, rounding differs; its reported residual is one iteration behind"}
+            parity["pass"] = bool(parity["gpu_classic_vs_cpu"]["rel_residual_diff"] <= 1e-10
+                                  and parity["gpu_classic_vs_cpu"]["max_rel_x_diff"] <= 1e-10)
+
     if rank == 0:
         peak, peak_src = peaks()
         t_spmv = spmv_ms / max(spmv_n, 1) * 1e-3
-        nloc = A.c.nownedrows
-        # opt-in experiment: the whole pipelined iteration is one kernel (SpMV + 12 vector streams)
-        one_kernel = solver == "pipelined" and os.environ.get("ACGB200_PCG_FUSED") == "1"
+        nloc = nown
+        one_kernel = bool(info["last_layout"] & 2)     # the whole pipelined iteration ran as one kernel (SpMV + 12 vector streams)
         extra = 96.0 * nloc if one_kernel else 0.0
         achieved = (16.0 * nnz_local + extra) / t_spmv / 1e9
-        prof = os.path.join(ROOT, "profiles", "r01_ncu_spmv.json")
-        traffic = None
+        min_bytes = float(info["spmv_min_bytes"]) + extra - (8.0 * nloc if one_kernel else 0.0)
+        prof = os.path.join(ROOT, "profiles", "r02_ncu_spmv.json")
+        traffic_source = None
         if os.path.exists(prof) and world == 1 and args.workload == "27pt-224":
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            pj = json.load(open(prof))
+            traffic_source = {"file": "profiles/r02_ncu_spmv.json", "kernel": pj.get("kernel"),
+                              "dram_bytes_per_launch": pj.get("dram_bytes_per_launch"),
+                              "note": "ncu --set full capture of the same kernel and workload, committed; not measured in this run"}
         line = {
             "metric": metric, "value": total_iters / (dev_ms_max * 1e-3), "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -375,22 +442,28 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "whole acgsolvercuda_solve* call with pinned host b, x: H2D of b and x0, set-up, iterations, D2H of x"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "pcg_fused_kernel" if one_kernel else "spmv_tiles_kernel",
+            "roofline": {"bound": "hbm", "kernel": "pcg_fused_kernel" if one_kernel else
+                         ("spmv_ctiles_kernel" if info["spmv_compressed_tiles"] > 0 else "spmv_tiles_kernel"),
                          "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None if one_kernel else traffic,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "traffic_source": traffic_source,
                          "bytes_per_launch": 16 * nnz_local + int(extra), "ms_per_launch": t_spmv * 1e3, "launches_timed": spmv_n,
                          "peak_source": peak_src,
-                         "achieved_min_traffic_gbs": (12.0 * nnz_local + (12.0 if one_kernel else 20.0) * nloc + extra) / t_spmv / 1e9,
+                         "min_bytes_per_launch": min_bytes,
+                         "achieved_min_traffic_gbs": min_bytes / t_spmv / 1e9,
+                         "frac_min_traffic": min_bytes / t_spmv / 1e9 / peak,
                          "spmv_gflops": 2.0 * nnz_local / t_spmv / 1e9,
                          "update_ms_per_iteration": blas_ms / max(args.steps * args.iters, 1),
-                         "note": "16*nnz contract bytes (BASELINE.md); rank 0's local block"},
+                         "note": "achieved/frac: 16*nnz contract bytes (BASELINE.md, SURVEY 8d); *_min_traffic: the bytes the "
+                                 "kernel's data layout must move at least (values, indices or pattern ids, row pointers, x, y); "
+                                 "rank 0's local block"},
             "clocks": clocks,
             "residual_after_step": resid,
             "check": check,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference(w, 1, 0, args.cpu_iters,
-                                                 "" if solver == "classic" else "; GPU arm runs pipelined CG")
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        if parity:
+            line["parity"] = parity
         if world == 1 and args.with_reference_gpu:
             cg.free(); b.free(); x.free(); A.free()          # give the memory back first
             line["reference_gpu"] = reference_gpu(w, args.iters, solver)

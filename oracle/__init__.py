@@ -135,6 +135,8 @@ class Ref:
         L.ref_solve.argtypes = [C.c_void_p, _f64, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, _f64]
         L.ref_free.restype = None
         L.ref_free.argtypes = [C.c_void_p]
+        if hasattr(L, "ref_place"):
+            L.ref_place.argtypes = [C.c_void_p]
         vp = C.c_void_p
         L.ref_partition_part.argtypes = [C.c_int, C.c_int64, _i32, _i32, _f64, C.c_int, _i32, C.c_int,
                                          _i64] + [vp] * 13
@@ -185,6 +187,10 @@ class Ref:
         status = self.lib.ref_solve(handle, b, None, x.ctypes.data if want_x else None, maxits, atol, rtol, out)
         return dict(status=status, niterations=int(out[0]), bnrm2=out[1], r0nrm2=out[2], rnrm2=out[3],
                     tsolve=out[4], tgemv=out[5], x=x)
+
+    def place(self, handle) -> int:
+        """First-touch the full-storage arrays by the threads that stream them (ref_shim.c, ref_place)."""
+        return int(self.lib.ref_place(handle)) if hasattr(self.lib, "ref_place") else 0
 
     def free(self, handle):
         self.lib.ref_free(handle)

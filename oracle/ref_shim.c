@@ -169,6 +169,40 @@ void *ref_setup(int n, int64_t nnz, const int *row, const int *col, const double
     return P;
 }
 
+
+/*
+ * NUMA placement of the full-storage arrays: acgsymcsrmatrix_dsymv_init fills them from one
+ * thread, so on a multi-socket host every page of the matrix lands on that thread's node and
+ * the OpenMP dsymv (acg/symcsrmatrix.c:902, static schedule over rows) streams most of it over
+ * the socket interconnect.  Here each thread of a loop with the same static schedule
+ * first-touches (and copies) the slice of frowptr / fcolidx / fa it will stream; the old
+ * arrays are freed and the pointers swapped.  Contents are bit-identical -- placement only.
+ * Returns 1 if the arrays were moved.
+ */
+int ref_place(void *handle)
+{
+    struct ref_problem *P = handle;
+    struct acgsymcsrmatrix *A = &P->A;
+    if (!A->frowptr || !A->fcolidx || !A->fa) return 0;
+    const acgidx_t m = A->nprows - A->nghostrows;
+    const int64_t nnz = A->fnpnzs;
+    int64_t *rp = malloc(((size_t) A->nprows + 1) * sizeof(*rp));
+    acgidx_t *ci = malloc((size_t) (nnz > 0 ? nnz : 1) * sizeof(*ci));
+    double *va = malloc((size_t) (nnz > 0 ? nnz : 1) * sizeof(*va));
+    if (!rp || !ci || !va) { free(rp); free(ci); free(va); return 0; }
+    const int64_t *orp = A->frowptr;
+    #pragma omp parallel for
+    for (acgidx_t i = 0; i < m - m % 4; i += 4) {
+        for (int r = 0; r < 4; r++) rp[i + r] = orp[i + r];
+        for (int64_t k = orp[i]; k < orp[i + 4]; k++) { ci[k] = A->fcolidx[k]; va[k] = A->fa[k]; }
+    }
+    for (acgidx_t i = m - m % 4; i <= A->nprows; i++) rp[i] = orp[i];
+    for (int64_t k = orp[m - m % 4]; k < nnz; k++) { ci[k] = A->fcolidx[k]; va[k] = A->fa[k]; }
+    free(A->frowptr); free(A->fcolidx); free(A->fa);
+    A->frowptr = rp; A->fcolidx = ci; A->fa = va;
+    return 1;
+}
+
 /* out[0..5] as in ref_cg; x0 may be NULL (zero initial guess) */
 int ref_solve(void *handle, const double *b, const double *x0, double *xout, int maxits,
               double residualatol, double residualrtol, double *out)
