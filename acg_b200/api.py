@@ -143,7 +143,7 @@ EXPORTS = [
     "acgsolvercuda_init_constants", "acgsolvercuda_alpha", "acgsolvercuda_beta", "acgsolvercuda_daxpy_alpha",
     "acgsolvercuda_daxpy_minus_alpha", "acgsolvercuda_daypx_beta", "acgsolvercuda_pipelined_daxpy_fused",
     "acgsolvercuda_fwrite",
-    "acgb200_set_option", "acgsolvercuda_spmv", "acgsolvercuda_info", "acgb200_sizeof", "acgb200_have_mpi",
+    "acgb200_set_option", "acgsolvercuda_spmv", "acgsolvercuda_spmv_ghost", "acgsolvercuda_info", "acgb200_sizeof", "acgb200_have_mpi",
     "acgb200_nccl_unique_id", "acgb200_comm_init_rank", "acgb200_comm_destroy",
     "acgb200_host_register", "acgb200_host_unregister", "acgb200_spmv_plan_host", "acgb200_spmv_plan_host2", "acgb200_p2p_inverse_map", "acgb200_patterns_host", "acgb200_stencil_part",
     "acgb200_mtx_info", "acgb200_mtx_read", "acgb200_mtx_read_part", "acgb200_comm_matrix_row", "acgb200_partition_rows_grid", "acgb200_grid_factors", "acgb200_rmat_spd",
@@ -219,6 +219,7 @@ def lib() -> C.CDLL:
     L.acgsolvercuda_solve_device_pipelined.argtypes = common + [P(acgcomm), P(C.c_int)]
     L.acgsolvercuda_fwrite.argtypes = [C.c_void_p, P(acgsolvercuda), C.c_int]
     L.acgsolvercuda_spmv.argtypes = [P(acgsolvercuda), f64p, f64p, C.c_int, P(C.c_double)]
+    L.acgsolvercuda_spmv_ghost.argtypes = [P(acgsolvercuda), f64p, f64p, C.c_int, P(C.c_double)]
     L.acgsolvercuda_info.argtypes = [P(acgsolvercuda), P(acgb200_info)]
     L.acgb200_set_option.argtypes = [C.c_char_p, C.c_int]
     L.acgb200_nccl_unique_id.argtypes = [C.c_void_p]
@@ -610,6 +611,16 @@ class SolverCuda:
         ms = C.c_double(0)
         _check(lib().acgsolvercuda_spmv(C.byref(self.c), x, y, nrep, C.byref(ms)), "acgsolvercuda_spmv")
         return y, ms.value
+
+    def spmv_ghost(self, x: np.ndarray, path: int):
+        """One part's share of y = A x with the ghost entries of x given (acgsolvercuda_spmv_ghost);
+        returns (y over the owned rows, fused dot x.y)."""
+        x = np.ascontiguousarray(x, np.float64)
+        assert len(x) == self.c.r.num_nonzeros
+        y = np.zeros(self.A.c.nownedrows, np.float64)
+        dot = C.c_double(0)
+        _check(lib().acgsolvercuda_spmv_ghost(C.byref(self.c), x, y, path, C.byref(dot)), "acgsolvercuda_spmv_ghost")
+        return y, dot.value
 
     def info(self) -> dict:
         inf = acgb200_info()

@@ -998,6 +998,9 @@ int acgsolvercuda_solvempi(
         OK(ensure_unified(&c, A));
         if (pv->unified == 1) { c.unified = 1; c.postdesc = pv->p2p.d_desc_c; }
     }
+    /* a rank that is ahead must not store into a peer's window while that peer's kernels of the
+     * previous solve are still reading it: order the first post of this solve behind every rank */
+    if (c.p2p) OK(acgcomm_barrier(pv->stream, comm, errcode));
     if (pv->graph[0] && pv->graph0_unified != c.unified) { cudaGraphExecDestroy(pv->graph[0]); pv->graph[0] = NULL; }
     pv->graph0_unified = c.unified;
     pv->last_layout = c.unified ? 1 : 0;
@@ -1340,6 +1343,7 @@ int acgsolvercuda_solve_pipelined(
         OK(ensure_unified(&c, A));
         if (pv->unified == 1) { c.unified = 1; c.postdesc = pv->p2p.d_desc_u; }
     }
+    if (c.p2p) OK(acgcomm_barrier(pv->stream, comm, errcode));     /* as in acgsolvercuda_solvempi */
     if (pv->graph[2] && pv->graph2_unified != unified) {
         /* the cached replay addresses the other layout's arrays */
         cudaGraphExecDestroy(pv->graph[2]); pv->graph[2] = NULL;
@@ -1677,6 +1681,84 @@ int acgsolvercuda_spmv(struct acgsolvercuda *cg, const double *x, double *y, int
     if (nrep > 0) CU(cudaEventElapsedTime(&ms, e0, e1));
     if (ms_per_spmv) *ms_per_spmv = nrep > 0 ? (double) ms / nrep : 0.0;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ACG_SUCCESS;
+}
+
+/*
+ * One part's share of y = A x on ONE device, ghost values supplied by the caller: x has the
+ * part's nvec = owned + ghost entries, y its owned rows.  path 0 is what the set-up products and
+ * the NCCL loop back-end run (local block through the tile kernel, then offdiag_kernel adding
+ * the border x ghost block from the ghost tail of x: acg/cgcuda.c:858 + :878); path 1 is the
+ * kernel of the peer-memory loop: border x ghost block inside the tile kernel, ghost values read
+ * from a window whose senders' flags are waited for (here a loop-back window in this device's
+ * memory, filled from x's tail, the flags already published).  *dot = sum_owned x_i y_i from the
+ * fused epilogue.  Needs no communicator -- it exists so that the border x ghost path of a
+ * partitioned matrix can be checked against the global product on a single GPU.
+ */
+int acgsolvercuda_spmv_ghost(struct acgsolvercuda *cg, const double *x, double *y, int path, double *dot)
+{
+    int errcode_ = 0, *errcode = &errcode_;
+    struct priv *pv = priv_of(cg);
+    if (!pv || (path != 0 && path != 1)) return ACG_ERR_INVALID_VALUE;
+    const int n = pv->nowned;
+    struct acgb200_devstate *st = pv->d_st;
+    CU(cudaMemcpyAsync(cg->d_p, x, (size_t) pv->nvec * sizeof(double), cudaMemcpyHostToDevice, pv->stream));
+    CU(cudaMemsetAsync(&st->tmp_loc[0], 0, sizeof(double), pv->stream));
+    struct acgb200_spmvargs a;
+    memset(&a, 0, sizeof(a));
+    a.plan = &pv->plan; a.rowptr = cg->d_rowptr; a.colidx = cg->d_colidx; a.a = cg->d_a;
+    a.x = cg->d_p; a.y = cg->d_t; a.mode = SPMV_Y_AX_DOT; a.acc = &st->tmp_loc[0]; a.dotrows = n; a.pub_ch = -1;
+    void *d_win = NULL;
+    if (path == 0) {
+        a.dotrows = pv->borderoff;                  /* the border rows' share of the dot comes from offdiag_kernel */
+        KL(acgb200_spmv_launch(&a, pv->stream));
+        struct acgb200_offdiagargs o;
+        memset(&o, 0, sizeof(o));
+        o.nrows = pv->nborder; o.rowoffset = pv->borderoff;
+        o.orowptr = cg->d_orowptr; o.ocolidx = cg->d_ocolidx; o.oa = cg->d_oa;
+        o.x = cg->d_p; o.y = cg->d_t; o.acc = &st->tmp_loc[0]; o.dotkind = 1; o.st = st; o.p2p_iter_override = -1;
+        KL(acgb200_offdiag_launch(&o, pv->stream));
+    } else {
+        /* loop-back window: [descriptor | flags (one per sender slot) | ghost values] */
+        const size_t goff = sizeof(struct acgb200_p2pdev) + ACGB200_MAXR * sizeof(unsigned long long);
+        const size_t bytes = goff + ((size_t) pv->nghost + 2) * sizeof(double);
+        struct acgb200_p2pdev *h = calloc(1, sizeof(*h));
+        if (!h) return ACG_ERR_ERRNO;
+        cudaError_t e = cudaMalloc(&d_win, bytes);
+        if (!e) e = cudaMemsetAsync(d_win, 0, bytes, pv->stream);
+        if (e) { free(h); cudaFree(d_win); *errcode = (int) e; return ACG_ERR_CUDA; }
+        unsigned long long *d_flags = (unsigned long long *) ((char *) d_win + sizeof(*h));
+        double *d_ghost = (double *) ((char *) d_win + goff);
+        h->nranks = 1; h->rank = 0;
+        h->nsenders = 3; h->senders[0] = 0; h->senders[1] = 5; h->senders[2] = ACGB200_MAXR - 1;
+        h->my_hflag = d_flags; h->my_ghost[0] = h->my_ghost[1] = d_ghost;
+        h->hbase = 41; h->timeout_ns = 2000000000ull;
+        h->borderoff = pv->borderoff; h->nborder = pv->nborder;
+        unsigned long long flags[ACGB200_MAXR];
+        for (int i = 0; i < ACGB200_MAXR; i++) flags[i] = 0;
+        flags[0] = 41; flags[5] = 42; flags[ACGB200_MAXR - 1] = 41;      /* published: sequence >= hbase + iteration 0 */
+        e = cudaMemcpyAsync(d_win, h, sizeof(*h), cudaMemcpyHostToDevice, pv->stream);
+        if (!e) e = cudaMemcpyAsync(d_flags, flags, sizeof(flags), cudaMemcpyHostToDevice, pv->stream);
+        if (!e && pv->nghost > 0)
+            e = cudaMemcpyAsync(d_ghost, cg->d_p + n, (size_t) pv->nghost * sizeof(double), cudaMemcpyDeviceToDevice, pv->stream);
+        /* the tail of x itself is poisoned: path 1 must take the ghosts from the window */
+        if (!e && pv->nghost > 0) e = cudaMemsetAsync(cg->d_p + n, 0xff, (size_t) pv->nghost * sizeof(double), pv->stream);
+        if (!e) e = cudaStreamSynchronize(pv->stream);
+        free(h);
+        if (e) { cudaFree(d_win); *errcode = (int) e; return ACG_ERR_CUDA; }
+        a.p2p = (const struct acgb200_p2pdev *) d_win;
+        a.od_rowoffset = pv->borderoff; a.od_nrows = pv->nborder;
+        a.orowptr = cg->d_orowptr; a.ocolidx = cg->d_ocolidx; a.oa = cg->d_oa;
+        int le = acgb200_spmv_launch(&a, pv->stream);
+        if (le) { cudaFree(d_win); *errcode = le; return ACG_ERR_CUDA; }
+    }
+    double hdot = 0;
+    cudaError_t e = cudaMemcpyAsync(y, cg->d_t, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, pv->stream);
+    if (!e) e = cudaMemcpyAsync(&hdot, &st->tmp_loc[0], sizeof(double), cudaMemcpyDeviceToHost, pv->stream);
+    if (!e) e = cudaStreamSynchronize(pv->stream);
+    cudaFree(d_win);
+    CU(e);
+    if (dot) *dot = hdot;
     return ACG_SUCCESS;
 }
 

@@ -8,6 +8,8 @@
 #include "acgb200/comm.h"
 #include "acgb200/error.h"
 
+#include <cuda_runtime_api.h>
+#include <pthread.h>
 #include <stddef.h>
 
 const char *acgcommtypestr(enum acgcommtype t)
@@ -119,12 +121,43 @@ int acgcomm_allreduce(const void *src, void *dst, int count, enum acgdatatype da
     return ACG_ERR_INVALID_VALUE;
 }
 
+/* one double per device for the barrier's allreduce (never read; zero + zero stays zero) */
+#define BARRIER_MAXDEV 64
+static double *barrier_scratch[BARRIER_MAXDEV];
+static pthread_mutex_t barrier_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static double *barrier_buffer(int *errcode)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (!e && (dev < 0 || dev >= BARRIER_MAXDEV)) e = cudaErrorInvalidDevice;
+    double *p = NULL;
+    if (!e) {
+        pthread_mutex_lock(&barrier_lock);
+        if (!barrier_scratch[dev]) {
+            e = cudaMalloc((void **) &barrier_scratch[dev], 2 * sizeof(double));
+            if (!e) e = cudaMemset(barrier_scratch[dev], 0, 2 * sizeof(double));
+            if (e) { cudaFree(barrier_scratch[dev]); barrier_scratch[dev] = NULL; }
+        }
+        p = barrier_scratch[dev];
+        pthread_mutex_unlock(&barrier_lock);
+    }
+    if (e && errcode) *errcode = (int) e;
+    return p;
+}
+
 int acgcomm_barrier(cudaStream_t stream, const struct acgcomm *comm, int *errcode)
 {
     if (!comm || comm->type == acgcomm_null) return ACG_SUCCESS;
     if (comm->type == acgcomm_nccl) {
-        /* acg/comm.c:331: a zero-length allreduce orders the stream behind every rank */
-        ncclResult_t r = ncclAllReduce(NULL, NULL, 0, ncclDouble, ncclSum, comm->ncclcomm, stream);
+        /* The reference enqueues a zero-length allreduce here (acg/comm.c:331).  NCCL drops empty
+         * collectives at enqueue without any rendezvous, so that orders nothing; a one-element
+         * allreduce does: work enqueued on `stream` behind it starts only after every rank has
+         * reached its own barrier call on its stream.  Callers that need the HOST ordered behind
+         * all ranks synchronise the stream afterwards. */
+        double *buf = barrier_buffer(errcode);
+        if (!buf) return ACG_ERR_CUDA;
+        ncclResult_t r = ncclAllReduce(buf, buf, 1, ncclDouble, ncclSum, comm->ncclcomm, stream);
         if (r != ncclSuccess) { if (errcode) *errcode = (int) r; return ACG_ERR_NCCL; }
         return ACG_SUCCESS;
     }

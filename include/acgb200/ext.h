@@ -30,6 +30,14 @@ ACG_API int acgb200_set_option(const char *key, int value);
  * stream and the mean duration is returned in milliseconds. */
 ACG_API int acgsolvercuda_spmv(struct acgsolvercuda *cg, const double *x, double *y, int nrep, double *ms_per_spmv);
 
+/* One part's share of y = A x on one device with the ghost entries of x supplied by the caller:
+ * x has num_nonzeros = owned + ghost entries (host), y the owned rows (host).  path 0: local block +
+ * offdiag_kernel on the ghost tail of x (set-up products / NCCL loop, acg/cgcuda.c:858,:878); path 1:
+ * the fused tile kernel of the peer-memory loop reading ghosts from a (loop-back) window after the
+ * flag wait.  *dot (may be NULL) = sum over owned rows of x_i*y_i from the fused epilogue.  For
+ * single-GPU parity tests of the border x ghost path of partitioned matrices. */
+ACG_API int acgsolvercuda_spmv_ghost(struct acgsolvercuda *cg, const double *x, double *y, int path, double *dot);
+
 struct acgb200_info {
     int spmv_lanes_per_row, spmv_rows_cap, spmv_nnz_cap, spmv_stages;
     int spmv_ntiles, spmv_nlong, spmv_grid, spmv_smem_bytes;

@@ -186,6 +186,7 @@ cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st)
 
 /* ---- device, streams, events ----------------------------------------------- */
 cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { FAILPOINT(cudaErrorUnknown); *lo = 0; *hi = -1; return cudaSuccess; }
 cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned int f, int p)
