@@ -113,10 +113,14 @@ class acgb200_info(C.Structure):
                                                                                   ("last_h2d_ms", C.c_double),
                                                                                   ("last_d2h_ms", C.c_double),
                                                                                   ("last_blas_ms", C.c_double),
-                                                                                  ("spmv_compressed_tiles", C.c_int),
+                                                                                  ("reserved0", C.c_int),
                                                                                   ("spmv_min_bytes", C.c_int64),
                                                                                   ("spmv_nmedium", C.c_int),
-                                                                                  ("last_layout", C.c_int)]
+                                                                                  ("reserved1", C.c_int),
+                                                                                  ("spmv_slices", C.c_int),
+                                                                                  ("spmv_slice_rows", C.c_int),
+                                                                                  ("spmv_slice_ub", C.c_int),
+                                                                                  ("spmv_slice_grid", C.c_int)]
 
 
 class acgb200_mtxinfo(C.Structure):
@@ -132,7 +136,7 @@ EXPORTS = [
     "acgvector_set_constant_real_double", "acgvector_copy", "acgvector_daxpy", "acgvector_dnrm2",
     "acgvector_usga", "acgvector_ussc",
     "acgsymcsrmatrix_init_real_double", "acgsymcsrmatrix_init_rowwise_real_double", "acgsymcsrmatrix_free",
-    "acgsymcsrmatrix_vector", "acgsymcsrmatrix_partition", "acgsymcsrmatrix_partition_rows", "acgsymcsrmatrix_halo", "acgsymcsrmatrix_dsymv_init",
+    "acgsymcsrmatrix_vector", "acgsymcsrmatrix_partition", "acgsymcsrmatrix_partition_rows", "acgsymcsrmatrix_halo", "acgsymcsrmatrix_dsymv_init", "acgsymcsrmatrix_dsymv_init_cuda",
     "acgcommtypestr", "acgcomm_init_nccl", "acgcomm_free", "acgcomm_size", "acgcomm_rank", "acgcomm_barrier",
     "acgcomm_allreduce",
     "acghalo_free", "acghaloexchange_init_cuda", "acghaloexchange_free", "acghaloexchange_profile",
@@ -145,7 +149,7 @@ EXPORTS = [
     "acgsolvercuda_fwrite",
     "acgb200_set_option", "acgsolvercuda_spmv", "acgsolvercuda_spmv_ghost", "acgsolvercuda_info", "acgb200_sizeof", "acgb200_have_mpi",
     "acgb200_nccl_unique_id", "acgb200_comm_init_rank", "acgb200_comm_destroy",
-    "acgb200_host_register", "acgb200_host_unregister", "acgb200_spmv_plan_host", "acgb200_spmv_plan_host2", "acgb200_p2p_inverse_map", "acgb200_patterns_host", "acgb200_stencil_part",
+    "acgb200_host_register", "acgb200_host_unregister", "acgb200_spmv_plan_host", "acgb200_spmv_plan_host2", "acgb200_slices_host", "acgb200_p2p_inverse_map", "acgb200_patterns_host", "acgb200_stencil_part",
     "acgb200_mtx_info", "acgb200_mtx_read", "acgb200_mtx_read_part", "acgb200_comm_matrix_row", "acgb200_partition_rows_grid", "acgb200_grid_factors", "acgb200_rmat_spd",
 ]
 
@@ -190,6 +194,7 @@ def lib() -> C.CDLL:
     L.acgb200_mtx_read_part.argtypes = [C.c_char_p, C.c_int, np.ctypeslib.ndpointer(np.int32, flags="C"), C.c_int,
                                         P(acgsymcsrmatrix)]
     L.acgsymcsrmatrix_dsymv_init.argtypes = [P(acgsymcsrmatrix), C.c_double]
+    L.acgsymcsrmatrix_dsymv_init_cuda.argtypes = [P(acgsymcsrmatrix), C.c_double, P(C.c_int)]
     L.acghalo_free.restype = None
     L.acghalo_free.argtypes = [P(acghalo)]
     L.acgvector_free.restype = None
@@ -229,6 +234,7 @@ def lib() -> C.CDLL:
     L.acgb200_patterns_host.argtypes = [C.c_int, i64p, i32p, C.c_int, P(C.c_int), P(C.c_int), i32p, i32p, u16p, P(C.c_int64)]
     L.acgb200_p2p_inverse_map.argtypes = [P(acghalo), C.c_int, C.c_int, i32p, i32p, i32p, i32p]
     L.acgb200_spmv_plan_host2.argtypes = [C.c_int, i64p, C.c_void_p, P(acgb200_info), i32p, C.c_int, i32p, C.c_int]
+    L.acgb200_slices_host.argtypes = [C.c_int, C.c_int, i64p, C.c_void_p, i32p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.acgb200_spmv_plan_host.argtypes = [C.c_int, i64p, P(acgb200_info), i32p, C.c_int, i32p, C.c_int]
     L.acgb200_comm_init_rank.argtypes = [P(acgcomm), C.c_int, C.c_void_p, C.c_int, P(C.c_int)]
     L.acgb200_comm_destroy.argtypes = [P(acgcomm)]
@@ -269,9 +275,30 @@ def patterns_host(rowptr, colidx, max_entries: int = 4096) -> dict:
                 patid=patid[:n].copy(), nmatched=nm.value)
 
 
+def slices_host(rowptr, colidx, cover_hi=None) -> dict:
+    """The pattern-slice plan acgsolvercuda_init would build (slices.c), computed on the host: the
+    covered 32-row slices as rows of (row0, nrows, len, vblk), the per-slice cover flags, and totals."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    colidx = np.ascontiguousarray(colidx, dtype=np.int32)
+    n = len(rowptr) - 1
+    nsl = (n + 31) // 32
+    slices4 = np.zeros(4 * max(nsl, 1), dtype=np.int32)
+    covered = np.zeros(max(nsl, 1), dtype=np.uint8)
+    totals = np.zeros(6, dtype=np.int64)
+    spatoff = np.zeros(8192, dtype=np.int32)
+    _check(lib().acgb200_slices_host(n, n if cover_hi is None else cover_hi, rowptr, colidx.ctypes.data_as(C.c_void_p),
+                                     slices4, nsl, covered.ctypes.data_as(C.c_void_p), totals.ctypes.data_as(C.c_void_p),
+                                     spatoff.ctypes.data_as(C.c_void_p)), "acgb200_slices_host")
+    ns = int(totals[0])
+    return dict(nslices=ns, slices=slices4[:4 * ns].reshape(ns, 4).copy(), covered=covered[:nsl].astype(bool),
+                blocks=int(totals[1]), nnz=int(totals[2]), rows=int(totals[3]), lpad=int(totals[4]), npat=int(totals[5]),
+                spatoff=spatoff)
+
+
 def spmv_plan_host(rowptr, colidx=None) -> dict:
     """Tile plan of the SpMV for a CSR row-pointer array (host only, no device).
-    With ``colidx`` the compression decision is included: ``compressed[t]``."""
+    With ``colidx`` the pattern slices are planned too and the tiles skip the rows they cover
+    (``slices``, ``slice_rows``; acg_b200.slices_host lists the slices themselves)."""
     rowptr = np.ascontiguousarray(rowptr, np.int64)
     n = len(rowptr) - 1
     tiles = np.zeros(4 * (n + 1), np.int32)
@@ -284,11 +311,9 @@ def spmv_plan_host(rowptr, colidx=None) -> dict:
     _check(lib().acgb200_spmv_plan_host2(n, rowptr, cptr, C.byref(inf), tiles, n + 1, longrows, n + 1), "acgb200_spmv_plan_host")
     nt, nl = inf.spmv_ntiles, inf.spmv_nlong
     t4 = tiles[:4 * nt].reshape(nt, 4).copy()
-    compressed = (t4[:, 1] & 0x40000000) != 0
-    t4[:, 1] &= ~np.int32(0x40000000)
     return dict(lanes=inf.spmv_lanes_per_row, rows_cap=inf.spmv_rows_cap, nnz_cap=inf.spmv_nnz_cap,
-                stages=inf.spmv_stages, tiles=t4, longrows=longrows[:nl].copy(), compressed=compressed,
-                nmedium=inf.spmv_nmedium)
+                stages=inf.spmv_stages, tiles=t4, longrows=longrows[:nl].copy(), nmedium=inf.spmv_nmedium,
+                slices=inf.spmv_slices, slice_rows=inf.spmv_slice_rows)
 
 
 def _view(ptr, n, dtype):
@@ -398,6 +423,14 @@ class SymCsrMatrix:
 
     def dsymv_init(self, eps: float = 0.0):
         _check(lib().acgsymcsrmatrix_dsymv_init(C.byref(self.c), eps), "acgsymcsrmatrix_dsymv_init")
+        return self
+
+    def dsymv_init_cuda(self, eps: float = 0.0):
+        """acgsymcsrmatrix_dsymv_init computed on the current CUDA device (expand.cu), copied back into the matrix."""
+        err = C.c_int(0)
+        code = lib().acgsymcsrmatrix_dsymv_init_cuda(C.byref(self.c), eps, C.byref(err))
+        if code != ACG_SUCCESS:
+            raise AcgError(code, "acgsymcsrmatrix_dsymv_init_cuda", err.value)
         return self
 
     def partition_rows(self, nparts: int, kway: bool = False, seed: int = 0):

@@ -51,15 +51,13 @@ static struct {
     int redstream;      /* pipelined CG: allreduce on its own stream + communicator */
     int p2p;            /* halo + reductions through peer memory (CUDA IPC) instead of NCCL */
     int p2p_fuse;       /* 1: border x ghost block inside the SpMV, pushes inside the update kernels */
-    int spmv_compress;  /* 1: index-free tiles where the rows' patterns repeat (opt-in, compress.c) */
     int blas1_ctas;     /* CTAs per SM of the fused BLAS-1 kernels (0 = one full wave, from the occupancy) */
     int pdl;            /* 1: programmatic dependent launch along the iteration chain (opt-in) */
-    int pcg_fused;      /* 1: pipelined CG as one kernel per iteration (SpMV + update fused, opt-in) */
     int spmv_medium;    /* > 0: rows longer than this (and shorter than a tile) get a warp each (opt-in) */
-    int p2p_unified;    /* one CSR over [owned | ghost], vectors in the exported allocation: 1 for the one-kernel
-                         * pipelined iteration (default), 2 also for the classic and the two-kernel pipelined loop */
+    int spmv_slices;    /* 1: pattern slices (slices.c) -- index-free slice-major storage of the rows that repeat a pattern */
+    int slice_ub, slice_threads, slice_pf, slice_max_ctas;   /* slice kernel shape overrides (0 / -1 = default) */
     int loaded;
-} cfg = { .check_every = 8, .graph = 1, .redstream = 1, .p2p = 1, .p2p_fuse = 1, .p2p_unified = 1 };
+} cfg = { .check_every = 8, .graph = 1, .redstream = 1, .p2p = 1, .p2p_fuse = 1, .spmv_slices = 1, .slice_pf = -1 };
 
 static void cfg_load(void)
 {
@@ -79,13 +77,15 @@ static void cfg_load(void)
     if ((s = getenv("ACGB200_REDSTREAM"))) cfg.redstream = atoi(s);
     if ((s = getenv("ACGB200_P2P"))) cfg.p2p = atoi(s);
     if ((s = getenv("ACGB200_P2P_FUSE"))) cfg.p2p_fuse = atoi(s);
-    if ((s = getenv("ACGB200_SPMV_COMPRESS"))) cfg.spmv_compress = atoi(s);
     if ((s = getenv("ACGB200_BLAS1_CTAS"))) cfg.blas1_ctas = atoi(s);
     if (cfg.check_every < 1) cfg.check_every = 1;
     if ((s = getenv("ACGB200_PDL"))) cfg.pdl = atoi(s);
-    if ((s = getenv("ACGB200_PCG_FUSED"))) cfg.pcg_fused = atoi(s);
     if ((s = getenv("ACGB200_SPMV_MEDIUM"))) cfg.spmv_medium = atoi(s);
-    if ((s = getenv("ACGB200_P2P_UNIFIED"))) cfg.p2p_unified = atoi(s);
+    if ((s = getenv("ACGB200_SPMV_SLICES"))) cfg.spmv_slices = atoi(s);
+    if ((s = getenv("ACGB200_SLICE_UB"))) cfg.slice_ub = atoi(s);
+    if ((s = getenv("ACGB200_SLICE_THREADS"))) cfg.slice_threads = atoi(s);
+    if ((s = getenv("ACGB200_SLICE_PF"))) cfg.slice_pf = atoi(s);
+    if ((s = getenv("ACGB200_SLICE_MAX_CTAS"))) cfg.slice_max_ctas = atoi(s);
     acgb200_blas1_set_ctas_per_sm(cfg.blas1_ctas);
     acgb200_set_pdl(cfg.pdl);
 }
@@ -106,12 +106,14 @@ int acgb200_set_option(const char *key, int value)
     else if (!strcmp(key, "redstream")) cfg.redstream = value;
     else if (!strcmp(key, "p2p")) cfg.p2p = value;
     else if (!strcmp(key, "p2p_fuse")) cfg.p2p_fuse = value;
-    else if (!strcmp(key, "spmv_compress")) cfg.spmv_compress = value;
     else if (!strcmp(key, "blas1_ctas")) { cfg.blas1_ctas = value; acgb200_blas1_set_ctas_per_sm(value); }
     else if (!strcmp(key, "pdl")) { cfg.pdl = value; acgb200_set_pdl(value); }
-    else if (!strcmp(key, "pcg_fused")) cfg.pcg_fused = value;
     else if (!strcmp(key, "spmv_medium")) cfg.spmv_medium = value < 0 ? 0 : value;
-    else if (!strcmp(key, "p2p_unified")) cfg.p2p_unified = value;
+    else if (!strcmp(key, "spmv_slices")) cfg.spmv_slices = value;
+    else if (!strcmp(key, "slice_ub")) cfg.slice_ub = value;
+    else if (!strcmp(key, "slice_threads")) cfg.slice_threads = value;
+    else if (!strcmp(key, "slice_pf")) cfg.slice_pf = value;
+    else if (!strcmp(key, "slice_max_ctas")) cfg.slice_max_ctas = value;
     else return ACG_ERR_INVALID_VALUE;
     return ACG_SUCCESS;
 }
@@ -131,6 +133,7 @@ struct priv {
     struct acgb200_devstate *h_st;      /* pinned scratch for state upload / readback */
     int nowned, ninner, nborder, nghost, borderoff, nvec;
     int64_t fnnz, onnz;
+    int device_expanded;                /* the full storage was built on the device (the host matrix has none) */
     cudaStream_t stream, commstream, redstream;
     cudaEvent_t ev_ready, ev_halo, ev_red, ev_poll[2];
     struct acgb200_p2p p2p;             /* peer-memory exchange (multi-GPU) */
@@ -141,15 +144,6 @@ struct priv {
                                          * two iterations each (parity 0 then 1) */
     int graph_multi[3];
     int graph_launches[3];              /* kernel/NCCL launches inside one replay */
-    double *d_w2;                       /* second w buffer of the one-kernel pipelined iteration */
-    int fused_grid;                     /* its grid (0: not available for this plan) */
-    /* the same between GPUs with one CSR over [owned | pad | ghost] columns (ensure_unified) */
-    struct acgb200_spmvplan uplan;
-    int *d_urowptr, *d_ucolidx, *d_uzero;
-    double *d_ua;
-    int ufused_grid, unified;           /* unified: 0 not tried, 1 in use, -1 not possible for this matrix */
-    int graph2_unified, graph1_unified, graph0_unified;   /* layout each cached graph was captured with */
-    int last_layout;                    /* see struct acgb200_info */
     double last_h2d_ms, last_d2h_ms;    /* host time spent before / after the solve window */
     cudaEvent_t ev_t0, ev_t1;           /* device-side bracket of the solve window */
     double last_solve_ms;
@@ -236,16 +230,12 @@ void acgsolvercuda_free(struct acgsolvercuda *cg)
             acgb200_p2p_free(&pv->p2p);
             if (pv->have_redcomm) { acgcomm_barrier(pv->stream, &pv->redcomm, NULL); cudaStreamSynchronize(pv->stream); }
             cudaFree(pv->p2p.window);
-            cudaFree(pv->p2p.vwindow);
-            pv->p2p.window = pv->p2p.vwindow = NULL;
+            pv->p2p.window = NULL;
         }
         if (pv->have_redcomm && pv->redcomm.ncclcomm) ncclCommDestroy(pv->redcomm.ncclcomm);
         for (int i = 0; i < 3; i++) if (pv->graph[i]) cudaGraphExecDestroy(pv->graph[i]);
-        cudaFree(pv->d_w2);
-        cudaFree(pv->d_urowptr); cudaFree(pv->d_ucolidx); cudaFree(pv->d_ua); cudaFree(pv->d_uzero);
-        cudaFree(pv->uplan.d_tiles); cudaFree(pv->uplan.d_longrows); cudaFree(pv->uplan.d_long_scratch); cudaFree(pv->uplan.d_medrows);
         cudaFree(pv->plan.d_tiles); cudaFree(pv->plan.d_longrows); cudaFree(pv->plan.d_long_scratch); cudaFree(pv->plan.d_medrows);
-        cudaFree(pv->plan.d_patptr); cudaFree(pv->plan.d_patoff); cudaFree(pv->plan.d_patid);
+        cudaFree(pv->plan.d_slices); cudaFree(pv->plan.d_sval); cudaFree(pv->plan.d_spatoff); cudaFree(pv->plan.d_spatid);
         cudaFree(pv->d_st);
         cudaFreeHost(pv->h_ctrl); cudaFreeHost(pv->h_st);
         if (pv->stream) cudaStreamDestroy(pv->stream);
@@ -268,7 +258,7 @@ void acgsolvercuda_free(struct acgsolvercuda *cg)
 /* Cut rows [0,nrows) into TMA tiles (see internal.h): greedy, row-aligned, at
  * most rows_cap rows and nnz_cap nonzeros per tile; rows longer than nnz_cap go
  * to the long-row list.  Host-only, no CUDA: testable without a device. */
-static int cut_tiles(const struct acgb200_spmvplan *pl, const int64_t *rowptr,
+static int cut_tiles(const struct acgb200_spmvplan *pl, const int64_t *rowptr, const unsigned char *covered,
                      struct acgb200_tile *tiles, int *ntiles, int *longrows, int *nlong, int *medrows, int *nmed)
 {
     const int n = pl->nrows;
@@ -276,12 +266,15 @@ static int cut_tiles(const struct acgb200_spmvplan *pl, const int64_t *rowptr,
     const int64_t out = pl->med_thr > 0 && pl->med_thr < pl->nnz_cap ? pl->med_thr : pl->nnz_cap;
     int nt = 0, nl = 0, nm = 0, r = 0;
     while (r < n) {
+        /* rows of a covered 32-row slice belong to the slice kernel (slices.c) */
+        if (covered && covered[r >> 5]) { r = (r | 31) + 1; continue; }
         int64_t len = rowptr[r + 1] - rowptr[r];
         if (len > pl->nnz_cap) { longrows[nl++] = r++; continue; }
         if (len > out) { medrows[nm++] = r++; continue; }
         const int start = r;
         int64_t cnt = 0;
         while (r < n && r - start < pl->rows_cap) {
+            if (covered && covered[r >> 5]) break;
             len = rowptr[r + 1] - rowptr[r];
             if (len > out || cnt + len > pl->nnz_cap) break;
             cnt += len; r++;
@@ -299,7 +292,8 @@ static int cut_tiles(const struct acgb200_spmvplan *pl, const int64_t *rowptr,
     return ACG_SUCCESS;
 }
 
-static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr, const struct acgb200_patterns *pat, int *errcode)
+static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr,
+                       const struct acgb200_sliceplan *sp, const unsigned short *patid, int *errcode)
 {
     const int n = pl->nrows;
     struct acgb200_tile *tiles = malloc(((size_t) n + 1) * sizeof(*tiles));
@@ -307,34 +301,11 @@ static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr, const
     int *medrows = malloc(((size_t) n + 1) * sizeof(*medrows));
     if (!tiles || !longrows || !medrows) { free(tiles); free(longrows); free(medrows); return ACG_ERR_ERRNO; }
     int nt = 0, nl = 0, nm = 0;
-    int err = cut_tiles(pl, rowptr, tiles, &nt, longrows, &nl, medrows, &nm);
+    int err = cut_tiles(pl, rowptr, sp && sp->nslices > 0 ? sp->covered : NULL, tiles, &nt, longrows, &nl, medrows, &nm);
     if (err) { free(tiles); free(longrows); free(medrows); return err; }
     pl->ntiles = nt; pl->nlong = nl; pl->nmed = nm;
     pl->d_tiles = NULL; pl->d_longrows = NULL; pl->d_long_scratch = NULL; pl->d_medrows = NULL;
     cudaError_t e = cudaSuccess;
-    pl->compressed = 0; pl->ncompressed_tiles = 0;
-    if (pat && pat->npat > 0) {
-        /* a tile drops its column indices if every one of its rows is in the dictionary */
-        for (int t = 0; t < nt; t++) {
-            int all = 1;
-            for (int r = tiles[t].row_begin; r < tiles[t].row_begin + tiles[t].nrows && all; r++)
-                all = pat->patid[r] != ACGB200_NOPATTERN;
-            if (all) { tiles[t].nrows |= ACGB200_TILE_COMPRESSED; pl->ncompressed_tiles++; }
-        }
-        if (2 * (int64_t) pl->ncompressed_tiles >= nt) {
-            pl->compressed = 1; pl->npat = pat->npat; pl->nentries = pat->nentries;
-            e = cudaMalloc((void **) &pl->d_patptr, ((size_t) pat->npat + 1) * sizeof(int));
-            if (!e) e = cudaMemcpy(pl->d_patptr, pat->patptr, ((size_t) pat->npat + 1) * sizeof(int), cudaMemcpyHostToDevice);
-            if (!e) e = cudaMalloc((void **) &pl->d_patoff, (size_t) (pat->nentries > 0 ? pat->nentries : 1) * sizeof(int));
-            if (!e) e = cudaMemcpy(pl->d_patoff, pat->patoff, (size_t) pat->nentries * sizeof(int), cudaMemcpyHostToDevice);
-            if (!e) e = cudaMalloc((void **) &pl->d_patid, ((size_t) n + 16) * sizeof(unsigned short));
-            if (!e) e = cudaMemset(pl->d_patid, 0, ((size_t) n + 16) * sizeof(unsigned short));
-            if (!e) e = cudaMemcpy(pl->d_patid, pat->patid, (size_t) n * sizeof(unsigned short), cudaMemcpyHostToDevice);
-        } else {
-            for (int t = 0; t < nt; t++) tiles[t].nrows &= ~ACGB200_TILE_COMPRESSED;
-            pl->ncompressed_tiles = 0;
-        }
-    }
     if (!e && nt > 0) {
         e = cudaMalloc((void **) &pl->d_tiles, (size_t) nt * sizeof(*tiles));
         if (!e) e = cudaMemcpy(pl->d_tiles, tiles, (size_t) nt * sizeof(*tiles), cudaMemcpyHostToDevice);
@@ -347,6 +318,21 @@ static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr, const
     if (!e && nm > 0) {
         e = cudaMalloc((void **) &pl->d_medrows, (size_t) nm * sizeof(int));
         if (!e) e = cudaMemcpy(pl->d_medrows, medrows, (size_t) nm * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    pl->nslices = 0;
+    if (!e && sp && sp->nslices > 0) {
+        pl->nslices = sp->nslices; pl->sval_blocks = sp->blocks; pl->slice_rows = sp->rows; pl->slice_nnz = sp->nnz;
+        pl->slice_lpad = sp->lpad; pl->slice_npat = sp->npat;
+        const size_t tab = (size_t) sp->npat * (size_t) sp->lpad;
+        e = cudaMalloc((void **) &pl->d_slices, (size_t) sp->nslices * sizeof(*sp->slices));
+        if (!e) e = cudaMemcpy(pl->d_slices, sp->slices, (size_t) sp->nslices * sizeof(*sp->slices), cudaMemcpyHostToDevice);
+        if (!e) e = cudaMalloc((void **) &pl->d_spatoff, (tab + 4) * sizeof(int));
+        if (!e) e = cudaMemset(pl->d_spatoff, 0, (tab + 4) * sizeof(int));
+        if (!e) e = cudaMemcpy(pl->d_spatoff, sp->spatoff, tab * sizeof(int), cudaMemcpyHostToDevice);
+        if (!e) e = cudaMalloc((void **) &pl->d_spatid, ((size_t) n + 32) * sizeof(unsigned short));
+        if (!e) e = cudaMemset(pl->d_spatid, 0, ((size_t) n + 32) * sizeof(unsigned short));
+        if (!e) e = cudaMemcpy(pl->d_spatid, patid, (size_t) n * sizeof(unsigned short), cudaMemcpyHostToDevice);
+        if (!e) e = cudaMalloc((void **) &pl->d_sval, (size_t) sp->blocks * 32 * sizeof(double));
     }
     free(tiles); free(longrows); free(medrows);
     CU(e);
@@ -368,11 +354,36 @@ int acgb200_patterns_host(int nrows, const int64_t *rowptr, const int *colidx, i
     return ACG_SUCCESS;
 }
 
+/* ext.h: the pattern-slice plan of a CSR matrix, host only (slices.c) */
+int acgb200_slices_host(int nrows, int cover_hi, const int64_t *rowptr, const int *colidx,
+                        int *slices4, int maxslices, unsigned char *covered, int64_t *totals6, int *spatoff)
+{
+    struct acgb200_patterns pat;
+    struct acgb200_sliceplan sp;
+    int err = acgb200_patterns_build(nrows, rowptr, colidx, 4096, &pat);
+    if (err) return err;
+    err = acgb200_slices_plan(nrows, cover_hi, rowptr, &pat, &sp);
+    if (!err && sp.nslices > maxslices) err = ACG_ERR_NO_BUFFER_SPACE;
+    if (!err) {
+        for (int i = 0; i < sp.nslices; i++) {
+            slices4[4 * i] = sp.slices[i].row0; slices4[4 * i + 1] = sp.slices[i].nrows;
+            slices4[4 * i + 2] = sp.slices[i].len; slices4[4 * i + 3] = sp.slices[i].vblk;
+        }
+        memcpy(covered, sp.covered, (size_t) ((nrows + 31) / 32));
+        totals6[0] = sp.nslices; totals6[1] = sp.blocks; totals6[2] = sp.nnz; totals6[3] = sp.rows;
+        totals6[4] = sp.lpad; totals6[5] = sp.npat;
+        if (sp.nslices > 0) memcpy(spatoff, sp.spatoff, (size_t) sp.npat * (size_t) sp.lpad * sizeof(int));
+    }
+    acgb200_sliceplan_free(&sp);
+    acgb200_patterns_free(&pat);
+    return err;
+}
+
 /* ext.h: the tile plan the solver would build for a CSR row-pointer array,
- * computed on the host without touching a device.  With colidx != NULL the
- * row-pattern dictionary is built too and tiles whose rows are all in it are
- * flagged ACGB200_TILE_COMPRESSED in their nrows field, exactly as
- * acgsolvercuda_init does under option "spmv_compress". */
+ * computed on the host without touching a device.  With colidx != NULL (0-based)
+ * the pattern slices are planned too, exactly as acgsolvercuda_init does under option
+ * "spmv_slices": the tiles then skip the rows of covered slices (acgb200_slices_host
+ * returns the slices themselves). */
 int acgb200_spmv_plan_host(int nrows, const int64_t *rowptr, struct acgb200_info *info,
                            int *tiles4, int maxtiles, int *longrows, int maxlong)
 {
@@ -396,23 +407,20 @@ int acgb200_spmv_plan_host2(int nrows, const int64_t *rowptr, const int *colidx,
     int *lr = malloc(((size_t) nrows + 1) * sizeof(*lr));
     int *mr = malloc(((size_t) nrows + 1) * sizeof(*mr));
     if (!tiles || !lr || !mr) { free(tiles); free(lr); free(mr); return ACG_ERR_ERRNO; }
-    int nt = 0, nl = 0, nm = 0, ncomp = 0;
-    int err = cut_tiles(&pl, rowptr, tiles, &nt, lr, &nl, mr, &nm);
-    if (!err && (nt > maxtiles || nl > maxlong)) err = ACG_ERR_NO_BUFFER_SPACE;
-    if (!err && colidx) {
-        struct acgb200_patterns pat;
+    int nt = 0, nl = 0, nm = 0, nsl = 0, slrows = 0;
+    int err = ACG_SUCCESS;
+    struct acgb200_patterns pat;
+    struct acgb200_sliceplan sp;
+    memset(&pat, 0, sizeof(pat)); memset(&sp, 0, sizeof(sp));
+    if (colidx && cfg.spmv_slices) {
         err = acgb200_patterns_build(nrows, rowptr, colidx, 4096, &pat);
-        if (!err) {
-            for (int t = 0; t < nt; t++) {
-                int all = pat.npat > 0;
-                for (int r = tiles[t].row_begin; r < tiles[t].row_begin + tiles[t].nrows && all; r++)
-                    all = pat.patid[r] != ACGB200_NOPATTERN;
-                if (all) { tiles[t].nrows |= ACGB200_TILE_COMPRESSED; ncomp++; }
-            }
-            if (2 * (int64_t) ncomp < nt) { for (int t = 0; t < nt; t++) tiles[t].nrows &= ~ACGB200_TILE_COMPRESSED; ncomp = 0; }
-            acgb200_patterns_free(&pat);
-        }
+        if (!err && pat.npat > 0) err = acgb200_slices_plan(nrows, nrows, rowptr, &pat, &sp);
+        nsl = sp.nslices; slrows = sp.rows;
     }
+    if (!err) err = cut_tiles(&pl, rowptr, sp.nslices > 0 ? sp.covered : NULL, tiles, &nt, lr, &nl, mr, &nm);
+    acgb200_sliceplan_free(&sp);
+    acgb200_patterns_free(&pat);
+    if (!err && (nt > maxtiles || nl > maxlong)) err = ACG_ERR_NO_BUFFER_SPACE;
     if (!err) {
         for (int t = 0; t < nt; t++) {
             tiles4[4 * t] = tiles[t].row_begin; tiles4[4 * t + 1] = tiles[t].nrows;
@@ -422,7 +430,7 @@ int acgb200_spmv_plan_host2(int nrows, const int64_t *rowptr, const int *colidx,
         memset(info, 0, sizeof(*info));
         info->spmv_lanes_per_row = pl.lanes_per_row; info->spmv_rows_cap = pl.rows_cap;
         info->spmv_nnz_cap = pl.nnz_cap; info->spmv_stages = pl.nstages;
-        info->spmv_ntiles = nt; info->spmv_nlong = nl; info->spmv_compressed_tiles = ncomp;
+        info->spmv_ntiles = nt; info->spmv_nlong = nl; info->spmv_slices = nsl; info->spmv_slice_rows = slrows;
         info->spmv_nmedium = nm;
     }
     free(tiles); free(lr); free(mr);
@@ -480,7 +488,9 @@ int acgsolvercuda_init(
     (void) cublas; (void) cusparse;
     memset(cg, 0, sizeof(*cg));
     cfg_load();
-    if (!A->frowptr || !A->fcolidx || !A->fa) return ACG_ERR_INVALID_VALUE;   /* needs acgsymcsrmatrix_dsymv_init */
+    /* without full storage (no acgsymcsrmatrix_dsymv_init call) the packed triangle is expanded on the device */
+    if (!A->frowptr && !A->rowptr) return ACG_ERR_INVALID_VALUE;
+    if (A->frowptr && (!A->fcolidx || !A->fa)) return ACG_ERR_INVALID_VALUE;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return ACG_ERR_CUDA;   /* no CPU fallback */
     int err = init_impl(cg, A, comm);
@@ -491,6 +501,7 @@ int acgsolvercuda_init(
 static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, const struct acgcomm *comm)
 {
     int errcode_ = 0, *errcode = &errcode_;
+    int commsize = 1;
     struct priv *pv = calloc(1, sizeof(*pv));
     if (!pv) return ACG_ERR_ERRNO;
     pv->key = cg;
@@ -527,7 +538,6 @@ static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, 
         /* a second communicator lets the pipelined allreduce run concurrently
          * with the halo exchange (operations on one NCCL communicator are
          * serialised).  Collective: every rank calls acgsolvercuda_init. */
-        int commsize = 1;
         OK(acgcomm_size(comm, &commsize));
         if (cfg.redstream && commsize > 1 && comm->type == acgcomm_nccl) {
             int rank = 0;
@@ -566,7 +576,6 @@ static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, 
     pv->nowned = A->nownedrows; pv->ninner = A->ninnerrows; pv->nborder = A->nborderrows;
     pv->nghost = A->nghostrows; pv->borderoff = A->borderrowoffset;
     pv->nvec = cg->r.num_nonzeros;
-    pv->fnnz = A->fnpnzs; pv->onnz = A->onpnzs;
 
     /* device scalars and control block */
     CU(cudaMalloc((void **) &pv->d_st, sizeof(*pv->d_st)));
@@ -580,20 +589,50 @@ static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, 
     CU(cudaMalloc((void **) &cg->d_p, vbytes)); CU(cudaMemset(cg->d_p, 0, vbytes));
     CU(cudaMalloc((void **) &cg->d_t, vbytes)); CU(cudaMemset(cg->d_t, 0, vbytes));
 
-    /* local block: rows [0,nowned) of the full storage */
-    OK(upload_rowptr(&cg->d_rowptr, A->frowptr, A->nprows, 8, errcode));
-    OK(upload_block(&cg->d_colidx, &cg->d_a, A->fcolidx, A->fa, A->fnpnzs, A->rowidxbase, 16, errcode));
-    /* border x ghost block */
-    OK(upload_rowptr(&cg->d_orowptr, A->orowptr, (int64_t) A->nborderrows + A->nghostrows, 8, errcode));
-    OK(upload_block(&cg->d_ocolidx, &cg->d_oa, A->ocolidx, A->oa, A->onpnzs, A->rowidxbase, 16, errcode));
+    /* local block (rows [0,nowned) of the full storage) and border x ghost block */
+    const int64_t *frp = A->frowptr;          /* host row pointers / columns of the local block, for the plans */
+    const acgidx_t *fcol = A->fcolidx;
+    int64_t *frp_tmp = NULL;
+    acgidx_t *fcol_tmp = NULL;
+    if (A->frowptr) {
+        OK(upload_rowptr(&cg->d_rowptr, A->frowptr, A->nprows, 8, errcode));
+        OK(upload_block(&cg->d_colidx, &cg->d_a, A->fcolidx, A->fa, A->fnpnzs, A->rowidxbase, 16, errcode));
+        OK(upload_rowptr(&cg->d_orowptr, A->orowptr, (int64_t) A->nborderrows + A->nghostrows, 8, errcode));
+        OK(upload_block(&cg->d_ocolidx, &cg->d_oa, A->ocolidx, A->oa, A->onpnzs, A->rowidxbase, 16, errcode));
+        pv->fnnz = A->fnpnzs; pv->onnz = A->onpnzs;
+    } else {
+        /* the caller did not build full storage: upload the packed triangle (half the bytes) and mirror it
+         * on the device (expand.cu) -- the arrays are those acgsymcsrmatrix_dsymv_init(A, 0) would have made */
+        struct acgb200_expanded ex;
+        OK(acgb200_expand_upload(A, 0.0, 8, 16, &ex, pv->stream, errcode));
+        cg->d_rowptr = ex.d_rowptr; cg->d_colidx = ex.d_colidx; cg->d_a = ex.d_a;
+        cg->d_orowptr = ex.d_orowptr; cg->d_ocolidx = ex.d_ocolidx; cg->d_oa = ex.d_oa;
+        pv->fnnz = ex.fnnz; pv->onnz = ex.onnz;
+        pv->device_expanded = 1;
+        /* the planners work on the host: row pointers always, columns only for the pattern dictionary */
+        int *t = malloc(((size_t) A->nprows + 1) * sizeof(*t));
+        frp_tmp = malloc(((size_t) A->nprows + 1) * sizeof(*frp_tmp));
+        if (!t || !frp_tmp) { free(t); free(frp_tmp); return ACG_ERR_ERRNO; }
+        cudaError_t ce = cudaMemcpy(t, cg->d_rowptr, ((size_t) A->nprows + 1) * sizeof(int), cudaMemcpyDeviceToHost);
+        for (int64_t i = 0; i <= A->nprows; i++) frp_tmp[i] = t[i];
+        free(t);
+        if (!ce && cfg.spmv_slices && ex.fnnz > 0) {
+            fcol_tmp = malloc((size_t) ex.fnnz * sizeof(*fcol_tmp));
+            if (!fcol_tmp) { free(frp_tmp); return ACG_ERR_ERRNO; }
+            ce = cudaMemcpy(fcol_tmp, cg->d_colidx, (size_t) ex.fnnz * sizeof(int), cudaMemcpyDeviceToHost);
+        }
+        if (ce) { free(frp_tmp); free(fcol_tmp); *errcode = (int) ce; return ACG_ERR_CUDA; }
+        frp = frp_tmp; fcol = fcol_tmp;
+    }
+    const int colbase = A->frowptr ? A->rowidxbase : 0;     /* device-expanded columns are 0-based */
 
     /* SpMV tile plan */
     int64_t maxlen = 0;
     for (acgidx_t i = 0; i < A->nownedrows; i++) {
-        const int64_t len = A->frowptr[i + 1] - A->frowptr[i];
+        const int64_t len = frp[i + 1] - frp[i];
         if (len > maxlen) maxlen = len;
     }
-    acgb200_spmv_choose(&pv->plan, A->nownedrows, A->frowptr[A->nownedrows], maxlen);
+    acgb200_spmv_choose(&pv->plan, A->nownedrows, frp[A->nownedrows], maxlen);
     if (cfg.spmv_lanes > 0) pv->plan.lanes_per_row = cfg.spmv_lanes;
     if (cfg.spmv_nnz_cap > 0) pv->plan.nnz_cap = cfg.spmv_nnz_cap;
     if (cfg.spmv_rows_cap > 0) pv->plan.rows_cap = cfg.spmv_rows_cap;
@@ -603,15 +642,37 @@ static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, 
     pv->plan.med_thr = cfg.spmv_medium;
     {
         struct acgb200_patterns pat;
+        struct acgb200_sliceplan sp;
         memset(&pat, 0, sizeof(pat));
-        if (cfg.spmv_compress && A->rowidxbase == 0)
-            OK(acgb200_patterns_build(A->nownedrows, A->frowptr, A->fcolidx, 4096, &pat));
-        int err = build_tiles(&pv->plan, A->frowptr, pat.npat > 0 ? &pat : NULL, errcode);
+        memset(&sp, 0, sizeof(sp));
+        int err = ACG_SUCCESS;
+        if (cfg.spmv_slices && colbase == 0 && fcol)
+            err = acgb200_patterns_build(A->nownedrows, frp, fcol, 4096, &pat);
+        if (!err && cfg.spmv_slices && pat.npat > 0) {
+            /* between GPUs the border rows stay with the tile kernel, which adds the border x ghost block */
+            const int cover_hi = (commsize > 1 || A->nghostrows > 0) ? A->borderrowoffset : A->nownedrows;
+            err = acgb200_slices_plan(A->nownedrows, cover_hi, frp, &pat, &sp);
+        }
+        if (!err) err = build_tiles(&pv->plan, frp, &sp, pat.patid, errcode);
+        if (!err && pv->plan.nslices > 0) {
+            const int d = sp.domlen;
+            pv->plan.slice_ub = cfg.slice_ub > 0 ? cfg.slice_ub : (d % 9 == 0 ? 9 : d % 7 == 0 ? 7 : d % 8 == 0 ? 8 : d % 5 == 0 ? 5 : 8);
+            pv->plan.slice_threads = cfg.slice_threads > 0 ? cfg.slice_threads : 128;
+            pv->plan.slice_pf = cfg.slice_pf >= 0 ? (cfg.slice_pf != 0) : 1;
+            pv->plan.slice_max_ctas = cfg.slice_max_ctas;
+        }
+        acgb200_sliceplan_free(&sp);
         acgb200_patterns_free(&pat);
+        free(frp_tmp); free(fcol_tmp);
         if (err) return err;
     }
     pv->plan.max_ctas_per_sm = cfg.spmv_max_ctas;
     KL(acgb200_spmv_configure(&pv->plan));
+    if (pv->plan.nslices > 0) {
+        /* slice-major copy of the covered rows' values, made on the device from the CSR values */
+        KL(acgb200_slices_fill(&pv->plan, cg->d_rowptr, cg->d_a, pv->stream));
+        CU(cudaStreamSynchronize(pv->stream));
+    }
     return ACG_SUCCESS;
 }
 
@@ -629,8 +690,6 @@ struct solvectx {
     int launches;
     int capturing;            /* inside cudaStreamBeginCapture: no profiling marks */
     int p2p;                  /* loop exchanges go through peer memory */
-    struct acgb200_p2pdev *postdesc;   /* descriptor the loop's kernels and posts use (NULL: the ordinary one) */
-    int unified;              /* this solve runs on the merged [owned | ghost] CSR with vectors in the exported allocation */
 };
 
 static int evpool_reserve(struct evpool *p, int n)
@@ -699,14 +758,6 @@ static int apply_A(struct solvectx *c, const double *x_ro, double *x_halo, doubl
         a.p2p = pv->p2p.d_desc;
         a.od_rowoffset = pv->borderoff; a.od_nrows = pv->nborder;
         a.orowptr = cg->d_orowptr; a.ocolidx = cg->d_ocolidx; a.oa = cg->d_oa;
-        if (c->unified) {
-            /* merged CSR: ghost values are gathered through the ordinary column indices from the
-             * tail of x (which lives in the exported allocation); the border x ghost loop is empty */
-            a.plan = &pv->uplan;
-            a.rowptr = pv->d_urowptr; a.colidx = pv->d_ucolidx; a.a = pv->d_ua;
-            a.p2p = c->postdesc;
-            a.orowptr = pv->d_uzero; a.ocolidx = pv->d_uzero; a.oa = pv->d_ua;
-        }
         if (pub_ch >= 0 && a.plan->nlong == 0 && a.plan->nmed == 0) a.pub_ch = pub_ch;
     }
     prof_mark(c, &pv->gemv);
@@ -745,7 +796,7 @@ static int post(struct solvectx *c, int ctrl_slot, int iter_override, const doub
     int *errcode = c->errcode;
     struct acgb200_postargs a;
     memset(&a, 0, sizeof(a));
-    a.p2p = c->postdesc ? c->postdesc : pv->p2p.d_desc;
+    a.p2p = pv->p2p.d_desc;
     a.cin = &pv->d_st->ctrl[ctrl_slot]; a.st = pv->d_st;
     a.iter_override = iter_override;
     a.vec = vec; a.sendbufidx = (const int *) c->cg->haloexchange->d_sendbufidx;
@@ -927,8 +978,6 @@ static int iterate(struct solvectx *c, int maxits, int poll, int kind, int (*iss
 /* classic CG                                                                */
 /* ------------------------------------------------------------------------ */
 
-static int ensure_unified(struct solvectx *c, const struct acgsymcsrmatrix *A);
-
 static int classic_iteration(struct solvectx *c, int k)
 {
     struct acgsolvercuda *cg = c->cg;
@@ -937,10 +986,9 @@ static int classic_iteration(struct solvectx *c, int k)
     int *errcode = c->errcode;
     const int s = k & 1, n = pv->nowned;
     const int peer = c->multi && c->p2p;
-    /* the search direction: the solver's own vector, or -- unified layout -- vector 0 of the exported allocation */
-    double *pvec = c->unified ? acgb200_p2p_uvec(&pv->p2p, 0) : cg->d_p;
-    struct acgb200_p2pdev *desc = !peer ? NULL : (c->postdesc ? c->postdesc : pv->p2p.d_desc);
-    const struct acgb200_spmvplan *pl = c->unified ? &pv->uplan : &pv->plan;
+    double *pvec = cg->d_p;
+    struct acgb200_p2pdev *desc = !peer ? NULL : pv->p2p.d_desc;
+    const struct acgb200_spmvplan *pl = &pv->plan;
     OK(apply_A(c, pvec, pvec, cg->d_t, NULL, SPMV_Y_AX_DOT, &st->pap_loc[s], 1, 1, 0, 0));
     if (peer) {
         /* (p,Ap) is published by the SpMV's last CTA; with long rows the dot is
@@ -993,18 +1041,10 @@ int acgsolvercuda_solvempi(
     struct acgb200_devstate h;
 
     c.p2p = c.multi && pv->p2p.enabled && cfg.p2p;
-    /* opt-in: the loop on the merged [owned | ghost] CSR, p in the exported allocation */
-    if (c.p2p && pv->p2p.h_desc.fuse && cfg.p2p_unified >= 2) {
-        OK(ensure_unified(&c, A));
-        if (pv->unified == 1) { c.unified = 1; c.postdesc = pv->p2p.d_desc_c; }
-    }
     /* a rank that is ahead must not store into a peer's window while that peer's kernels of the
      * previous solve are still reading it: order the first post of this solve behind every rank */
     if (c.p2p) OK(acgcomm_barrier(pv->stream, comm, errcode));
-    if (pv->graph[0] && pv->graph0_unified != c.unified) { cudaGraphExecDestroy(pv->graph[0]); pv->graph[0] = NULL; }
-    pv->graph0_unified = c.unified;
-    pv->last_layout = c.unified ? 1 : 0;
-    double *const pvec = c.unified ? acgb200_p2p_uvec(&pv->p2p, 0) : cg->d_p;
+    double *const pvec = cg->d_p;
     /* warm-up: `warmup` full iterations (every kernel, every communication path)
      * on state that is overwritten below (acg/cgcuda.c:607-705); d_r stands in
      * for x so the initial guess is untouched */
@@ -1149,18 +1189,6 @@ static int pipelined_iteration(struct solvectx *c, int k)
             OK(allreduce(c, &st->gd_loc[s][0], &st->gd[s][0], 2));
         }
     }
-    if (c->unified) {
-        /* unified layout: w of iteration k lives in vector k&1 of the exported allocation; the
-         * update writes the next one (and the neighbours' tails of it) instead of updating in place */
-        double *win = acgb200_p2p_uvec(&pv->p2p, s), *wout = acgb200_p2p_uvec(&pv->p2p, s ^ 1);
-        OK(apply_A(c, win, win, cg->d_q, NULL, SPMV_Y_AX, NULL, 1, 2, 0, -1));
-        prof_mark(c, &pv->blas);
-        KL(acgb200_pcg_update_db(n, st, 1, 0, c->multi, c->postdesc, cg->d_q, cg->d_z, win, wout,
-                                 cg->d_t, cg->d_p, cg->d_r, c->d_x, pv->stream));
-        prof_mark(c, &pv->blas);
-        c->launches += 1;
-        return ACG_SUCCESS;
-    }
     OK(apply_A(c, cg->d_w, cg->d_w, cg->d_q, NULL, SPMV_Y_AX, NULL, 1, 2, 0, -1));
     if (k > 0 && side) CU(cudaStreamWaitEvent(pv->stream, pv->ev_red, 0));
     prof_mark(c, &pv->blas);
@@ -1172,127 +1200,6 @@ static int pipelined_iteration(struct solvectx *c, int k)
      * is switched off */
     if (peer && !pv->p2p.h_desc.fuse) OK(post(c, 0, -1, cg->d_w, 0, &st->gd_loc[0][0], 2, 2, 0, 0));
     c->launches += 1 + (c->multi && !peer ? 1 : 0);
-    return ACG_SUCCESS;
-}
-
-/*
- * One CSR over [owned | pad | ghost] columns for the one-kernel iteration between GPUs.  The
- * reference's split into a local block and a border x ghost block (acg/symcsrmatrix.c:760-851)
- * is kept for everything else; here the two are merged row by row (ghost column g becomes
- * goff + g, goff = owned count rounded up to 16) so that border rows are TMA-staged like interior
- * ones, and the SpMV input vectors are placed in an exported allocation whose ghost tail the
- * neighbours write (p2p.c, acgb200_p2p_unify).  Collective (all ranks solve with the same options).
- * Sets pv->unified to 1, or to -1 when the merged plan has no fused variant (long rows).
- */
-static int ensure_unified(struct solvectx *c, const struct acgsymcsrmatrix *A)
-{
-    struct priv *pv = c->pv;
-    int *errcode = c->errcode;
-    if (pv->unified) return ACG_SUCCESS;
-    const int no = pv->nowned, nb = pv->nborder, boff = pv->borderoff, base = A->rowidxbase;
-    const int goff = (no + 15) & ~15;
-    int64_t *rp = malloc(((size_t) no + 1) * sizeof(*rp));
-    if (!rp) return ACG_ERR_ERRNO;
-    rp[0] = 0;
-    int64_t maxlen = 0;
-    for (int i = 0; i < no; i++) {
-        int64_t len = A->frowptr[i + 1] - A->frowptr[i];
-        if (i >= boff && i < boff + nb) len += A->orowptr[i - boff + 1] - A->orowptr[i - boff];
-        rp[i + 1] = rp[i] + len;
-        if (len > maxlen) maxlen = len;
-    }
-    const int64_t nnz = rp[no];
-    acgidx_t *ci = malloc((size_t) (nnz > 0 ? nnz : 1) * sizeof(*ci));
-    double *va = malloc((size_t) (nnz > 0 ? nnz : 1) * sizeof(*va));
-    if (!ci || !va) { free(rp); free(ci); free(va); return ACG_ERR_ERRNO; }
-#pragma omp parallel for schedule(static)
-    for (int i = 0; i < no; i++) {
-        int64_t l = rp[i];
-        for (int64_t k = A->frowptr[i]; k < A->frowptr[i + 1]; k++, l++) { ci[l] = A->fcolidx[k] - base; va[l] = A->fa[k]; }
-        if (i >= boff && i < boff + nb) {
-            /* columns of the border x ghost block are rebased by -borderrowoffset: ghost number = column - nborder */
-            for (int64_t k = A->orowptr[i - boff]; k < A->orowptr[i - boff + 1]; k++, l++) {
-                ci[l] = goff + (A->ocolidx[k] - base - nb); va[l] = A->oa[k];
-            }
-        }
-    }
-    int err = ACG_SUCCESS;
-    acgb200_spmv_choose(&pv->uplan, no, nnz, maxlen);
-    /* same tile shape as the local block's plan: the few longer border rows must not enlarge the
-     * stages (shared memory per CTA decides how many CTAs an SM holds) -- border tiles simply end
-     * after fewer rows */
-    pv->uplan.lanes_per_row = pv->plan.lanes_per_row; pv->uplan.rows_cap = pv->plan.rows_cap;
-    pv->uplan.nnz_cap = pv->plan.nnz_cap; pv->uplan.nstages = pv->plan.nstages;
-    pv->uplan.threads = pv->plan.threads; pv->uplan.unroll = pv->plan.unroll;
-    pv->uplan.max_ctas_per_sm = cfg.spmv_max_ctas;
-    err = build_tiles(&pv->uplan, rp, NULL, errcode);
-    if (!err && acgb200_spmv_configure(&pv->uplan)) err = ACG_ERR_CUDA;
-    if (!err) pv->ufused_grid = acgb200_pcg_fused_grid(&pv->uplan);
-    if (!err && pv->ufused_grid > 0) {
-        err = upload_rowptr(&pv->d_urowptr, rp, no, 8, errcode);
-        if (!err) err = upload_block(&pv->d_ucolidx, &pv->d_ua, ci, va, nnz, 0, 16, errcode);
-        if (!err) {
-            cudaError_t e = cudaMalloc((void **) &pv->d_uzero, ((size_t) nb + 1 + 8) * sizeof(int));
-            if (!e) e = cudaMemset(pv->d_uzero, 0, ((size_t) nb + 1 + 8) * sizeof(int));
-            if (e) { *errcode = (int) e; err = ACG_ERR_CUDA; }
-        }
-    }
-    free(rp); free(ci); free(va);
-    if (err) return err;
-    /* every rank must take the same branch: agree on whether the merged plan is usable */
-    int ok = pv->ufused_grid > 0, allok = 0, *d_ok = NULL;
-    CU(cudaMalloc((void **) &d_ok, sizeof(int)));
-    CU(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
-    ncclResult_t r = ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c->comm->ncclcomm, pv->stream);
-    cudaError_t ce = r == ncclSuccess ? cudaMemcpyAsync(&allok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, pv->stream) : cudaSuccess;
-    if (!ce) ce = cudaStreamSynchronize(pv->stream);
-    cudaFree(d_ok);
-    if (r != ncclSuccess) { *errcode = (int) r; return ACG_ERR_NCCL; }
-    CU(ce);
-    if (!allok) { pv->unified = -1; return ACG_SUCCESS; }
-    OK(acgb200_p2p_unify(&pv->p2p, c->cg->halo, no, pv->nghost, c->comm, pv->stream, errcode));
-    pv->unified = 1;
-    return ACG_SUCCESS;
-}
-
-/* One launch per iteration: q = A w fused with the update (kernels.cu,
- * pcg_fused_kernel).  Iteration k reads control word k&1 and w buffer k&1. */
-static int fused_iteration(struct solvectx *c, int k)
-{
-    struct acgsolvercuda *cg = c->cg;
-    struct priv *pv = c->pv;
-    int *errcode = c->errcode;
-    const int peer = c->multi && c->p2p;
-    const int unified = peer && c->unified;
-    struct acgb200_spmvargs a;
-    memset(&a, 0, sizeof(a));
-    a.st = pv->d_st;
-    double *w0 = cg->d_w, *w1 = pv->d_w2;
-    int grid = pv->fused_grid;
-    if (unified) {
-        /* merged CSR, vectors in the exported allocation, ghost values arrive in their tails; the
-         * kernel's border x ghost loop sees empty rows (d_uzero) */
-        a.plan = &pv->uplan;
-        a.rowptr = pv->d_urowptr; a.colidx = pv->d_ucolidx; a.a = pv->d_ua;
-        a.p2p = pv->p2p.d_desc_u;
-        a.od_rowoffset = pv->borderoff; a.od_nrows = pv->nborder;
-        a.orowptr = pv->d_uzero; a.ocolidx = pv->d_uzero; a.oa = pv->d_ua;
-        w0 = acgb200_p2p_uvec(&pv->p2p, 0); w1 = acgb200_p2p_uvec(&pv->p2p, 1);
-        grid = pv->ufused_grid;
-    } else {
-        a.plan = &pv->plan;
-        a.rowptr = cg->d_rowptr; a.colidx = cg->d_colidx; a.a = cg->d_a;
-        if (peer) {
-            a.p2p = pv->p2p.d_desc;
-            a.od_rowoffset = pv->borderoff; a.od_nrows = pv->nborder;
-            a.orowptr = cg->d_orowptr; a.ocolidx = cg->d_ocolidx; a.oa = cg->d_oa;
-        }
-    }
-    prof_mark(c, &pv->gemv);
-    KL(acgb200_pcg_fused_launch(&a, grid, k & 1, c->multi, cg->d_z, cg->d_t, cg->d_p, cg->d_r, c->d_x,
-                                w0, w1, pv->stream));
-    prof_mark(c, &pv->gemv);
-    c->launches += 1;
     return ACG_SUCCESS;
 }
 
@@ -1320,51 +1227,18 @@ int acgsolvercuda_solve_pipelined(
     OK(ensure_vec(&cg->z, &cg->d_z, A, pv->nvec, errcode));
 
     c.p2p = c.multi && pv->p2p.enabled && cfg.p2p;
-    /* one kernel per iteration: on one GPU, or with the fused peer-memory exchange */
-    int fused = 0;
-    if (cfg.pcg_fused && c.multi && c.p2p && pv->p2p.h_desc.fuse && cfg.p2p_unified) OK(ensure_unified(&c, A));
-    const int unified = c.multi && c.p2p && pv->unified == 1 && cfg.pcg_fused && cfg.p2p_unified;
-    if (unified) {
-        fused = 1;
-        c.unified = 1;
-        c.postdesc = pv->p2p.d_desc_u;
-    } else if (cfg.pcg_fused && (!c.multi || (c.p2p && pv->p2p.h_desc.fuse))) {
-        if (!pv->fused_grid) pv->fused_grid = acgb200_pcg_fused_grid(&pv->plan);
-        if (pv->fused_grid > 0) {
-            if (!pv->d_w2) {
-                CU(cudaMalloc((void **) &pv->d_w2, ((size_t) pv->nvec + 2) * sizeof(double)));
-                CU(cudaMemsetAsync(pv->d_w2, 0, ((size_t) pv->nvec + 2) * sizeof(double), pv->stream));
-            }
-            fused = 1;
-        }
-    }
-    if (!fused && c.p2p && pv->p2p.h_desc.fuse && cfg.p2p_unified >= 2) {
-        /* opt-in: the two-kernel loop on the merged CSR, w double-buffered in the exported allocation */
-        OK(ensure_unified(&c, A));
-        if (pv->unified == 1) { c.unified = 1; c.postdesc = pv->p2p.d_desc_u; }
-    }
     if (c.p2p) OK(acgcomm_barrier(pv->stream, comm, errcode));     /* as in acgsolvercuda_solvempi */
-    if (pv->graph[2] && pv->graph2_unified != unified) {
-        /* the cached replay addresses the other layout's arrays */
-        cudaGraphExecDestroy(pv->graph[2]); pv->graph[2] = NULL;
-    }
-    if (pv->graph[1] && pv->graph1_unified != c.unified) { cudaGraphExecDestroy(pv->graph[1]); pv->graph[1] = NULL; }
-    pv->graph2_unified = unified;
-    pv->graph1_unified = c.unified;
-    pv->last_layout = (c.unified ? 1 : 0) + (fused ? 2 : 0);
-    int (*const iteration)(struct solvectx *, int) = fused ? fused_iteration : pipelined_iteration;
     if (warmup > 0) {
         memset(&h, 0, sizeof(h));
         h.maxits = warmup;
         for (int s = 0; s < 2; s++) { h.gd_loc[s][0] = h.gd[s][0] = 1; h.gd_loc[s][1] = h.gd[s][1] = 1; h.prev[s][0] = h.prev[s][1] = INFINITY; }
         OK(push_state(&c, &h));
         double *xsave = c.d_x; c.d_x = cg->d_r;
-        if (c.unified) CU(cudaMemcpyAsync(acgb200_p2p_uvec(&pv->p2p, 0), cg->d_w, obytes, cudaMemcpyDeviceToDevice, pv->stream));
         if (c.p2p) {
             OK(acgb200_p2p_begin(&pv->p2p, warmup, pv->stream));
             OK(post(&c, 0, 0, cg->d_w, -1, NULL, 0, 0, 0, 0));
         }
-        for (int i = 0; i < warmup; i++) OK(iteration(&c, i));
+        for (int i = 0; i < warmup; i++) OK(pipelined_iteration(&c, i));
         c.d_x = xsave;
         KL(acgb200_dot(n, c.d_b, c.d_b, &st->tmp_loc[0], pv->stream));
         KL(acgb200_dot2(n, cg->d_r, cg->d_w, &st->tmp_loc[0], pv->stream));
@@ -1418,24 +1292,19 @@ int acgsolvercuda_solve_pipelined(
         h.gd_loc[0][1] = h.gd[0][1] = gd0[1];
         h.prev[0][0] = h.prev[0][1] = INFINITY;                    /* acg/cgcuda.c:1513-1514 */
         OK(push_state(&c, &h));
-        if (c.unified) CU(cudaMemcpyAsync(acgb200_p2p_uvec(&pv->p2p, 0), cg->d_w, obytes, cudaMemcpyDeviceToDevice, pv->stream));
         if (c.p2p) {
             /* w_0 goes to the neighbours' windows as exchange number 0 */
             OK(acgb200_p2p_begin(&pv->p2p, maxits, pv->stream));
             OK(post(&c, 0, 0, cg->d_w, -1, NULL, 0, 0, 0, 0));
         }
-        OK(iterate(&c, maxits, tol > 0, fused ? 2 : 1, iteration));
+        OK(iterate(&c, maxits, tol > 0, 1, pipelined_iteration));
         OK(pull_state(&c, &h));
-        /* the one-kernel iteration alternates between two control words: the
-         * later one counts */
-        const struct acgb200_ctrl *fc = &h.ctrl[0];
-        if (fused && (h.ctrl[1].done || h.ctrl[1].iter > h.ctrl[0].iter)) fc = &h.ctrl[1];
-        cg->niterations = fc->iter;
-        converged = fc->done;
+        cg->niterations = h.ctrl[0].iter;
+        converged = h.ctrl[0].done;
         /* the reference reports sqrt(gamma) of the last *tested* iterate
          * (acg/cgcuda.c:1760): gamma_k at convergence, gamma_{maxits-1} otherwise */
         const int kk = converged ? cg->niterations : (cg->niterations > 0 ? cg->niterations - 1 : 0);
-        const double g = converged ? h.final_rr : (kk == 0 ? gd0[0] : ((c.multi || fused) ? h.gd[kk & 1][0] : h.gd_loc[kk & 1][0]));
+        const double g = converged ? h.final_rr : (kk == 0 ? gd0[0] : (c.multi ? h.gd[kk & 1][0] : h.gd_loc[kk & 1][0]));
         cg->rnrm2 = sqrt(g);
         cg->ntotaliterations += cg->niterations;
     }
@@ -1777,9 +1646,9 @@ int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info
     info->last_h2d_ms = pv->last_h2d_ms; info->last_d2h_ms = pv->last_d2h_ms;
     info->last_blas_ms = pv->last_blas_ms;
     info->num_sms = acgb200_num_sms();
-    info->spmv_compressed_tiles = pv->plan.ncompressed_tiles;
+    info->spmv_slices = pv->plan.nslices; info->spmv_slice_rows = pv->plan.slice_rows;
+    info->spmv_slice_ub = pv->plan.slice_ub; info->spmv_slice_grid = pv->plan.slice_grid;
     info->spmv_nmedium = pv->plan.nmed;
-    info->last_layout = pv->last_layout;
     info->spmv_min_bytes = acgb200_spmv_min_bytes(&pv->plan);
     return ACG_SUCCESS;
 }

@@ -1,22 +1,23 @@
 /*
- * compress.c -- row-pattern dictionary for index-free SpMV tiles (host side).
+ * compress.c -- row-pattern dictionary (host side) of the SpMV's pattern slices.
  *
- * Column indices are a third of the CSR stream (4 of 12 bytes per nonzero).
  * Matrices from stencils and other structured discretisations repeat a small
  * number of row "patterns" -- the sequence of offsets col - row of a row's
  * nonzeros: 27 of them describe every row of the 27-point stencil on a box.
  * A row whose pattern is in the dictionary needs no column indices at all: a
- * 2-byte pattern id per row replaces 4 bytes per nonzero.  Rows with patterns
- * outside the dictionary (irregular matrices, rows next to a partition
- * boundary after the [interior|border] reordering) keep their indices; a tile
- * of the SpMV plan is "compressed" only if all of its rows are in the
- * dictionary.  Nothing here is specific to stencils: the dictionary is found
- * by hashing the rows of whatever matrix is given, and an unstructured matrix
- * simply ends up with no compressed tiles.
+ * 2-byte pattern id per row replaces 4 bytes per nonzero (and gives the row's
+ * length, so its row pointer goes too).  slices.c turns runs of 32 such rows
+ * into slice-major storage for spmv_slices_kernel; rows with patterns outside
+ * the dictionary (irregular matrices, rows next to a partition boundary after
+ * the [interior|border] reordering) keep the CSR tiles.  Nothing here is
+ * specific to stencils: the dictionary is found by hashing the rows of whatever
+ * matrix is given, and an unstructured matrix simply ends up with no slices.
  *
- * Status: opt-in (ACGB200_SPMV_COMPRESS=1 / option "spmv_compress"); the host
- * logic is tested on the CPU, the kernel that consumes it
- * (spmv_ctiles_kernel) has not been measured yet.
+ * History: round 1 used the dictionary for "index-free tiles" (the CSR tile
+ * kernel rebuilding columns from the pattern in shared memory).  Measured on
+ * the B200 in round 2 that kernel lost to the plain tiles (0.669 vs 0.631 ms at
+ * C3: fewer bytes, but the tile kernel is instruction-bound at that point) and
+ * was removed; the slice kernel is its successor.
  */
 #include "acgb200/error.h"
 #include "internal.h"

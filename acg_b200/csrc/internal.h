@@ -57,18 +57,47 @@ struct acgb200_spmvplan {
     int smem_bytes;                  /* dynamic shared memory per CTA */
     int long_chunks;                 /* CTAs per long row */
     int max_ctas_per_sm;             /* 0: occupancy limit */
-    /* index-free tiles (opt-in, see compress.c) */
-    int compressed;                  /* 1: tiles flagged ACGB200_TILE_COMPRESSED carry no column indices */
-    int npat, nentries;
-    int *d_patptr, *d_patoff;
-    unsigned short *d_patid;         /* [nrows] (+16 pad) */
-    int ncompressed_tiles;
+    /* pattern slices (slices.c): 32-row slices whose rows all repeat a dictionary pattern are stored
+     * slice-major (entry e of the 32 rows contiguous, rows padded to the slice's longest) and multiplied by
+     * spmv_slices_kernel -- 8 bytes per nonzero, no column indices, no row pointers, no shared-memory
+     * staging; their rows are left out of the tiles */
+    int nslices;
+    struct acgb200_slice *d_slices;  /* [nslices] */
+    double *d_sval;                  /* [sval_blocks * 32] */
+    int64_t sval_blocks;             /* value blocks of 32 doubles (one per slice and entry slot) */
+    int slice_rows;                  /* rows covered by slices */
+    int64_t slice_nnz;               /* nonzeros covered (without padding) */
+    int slice_lpad;                  /* row stride of the padded offset table */
+    int slice_npat;
+    int *d_spatoff;                  /* [slice_npat * slice_lpad] offsets col - row, zero beyond a pattern's length */
+    unsigned short *d_spatid;        /* [nrows] pattern id per row (valid for covered rows) */
+    int slice_ub, slice_threads, slice_pf, slice_grid, slice_smem, slice_max_ctas;
 };
+
+struct acgb200_patterns;
+
+/* one covered slice: rows [row0, row0+32), `len` entry slots, values at d_sval + 32 * vblk */
+struct acgb200_slice { int row0; int nrows; int len; int vblk; };
+
+/* host plan of the pattern slices (no CUDA): which full 32-row slices of rows [0,cover_hi) are
+ * covered, their descriptors, and the padded offset table.  Returns ACG_SUCCESS with *nslices == 0
+ * when slices do not pay (few covered rows).  Arrays are malloc'ed, the caller frees them. */
+struct acgb200_sliceplan {
+    int nslices; struct acgb200_slice *slices;
+    unsigned char *covered;          /* [(nrows+31)/32] 1: the slice's rows are handled by the slice kernel */
+    int64_t blocks, nnz;
+    int rows, lpad, npat, domlen;    /* domlen: most frequent row length among covered rows */
+    int *spatoff;                    /* [npat * lpad] */
+};
+int acgb200_slices_plan(int nrows, int cover_hi, const int64_t *rowptr, const struct acgb200_patterns *pat,
+                        struct acgb200_sliceplan *out);
+void acgb200_sliceplan_free(struct acgb200_sliceplan *sp);
+/* fill d_sval from the device CSR values (kernels.cu) */
+int acgb200_slices_fill(const struct acgb200_spmvplan *pl, const int *d_rowptr, const double *d_a, cudaStream_t stream);
 
 /* row-pattern dictionary (compress.c): rows whose pattern id is not
  * ACGB200_NOPATTERN need no column indices, col = row + patoff[patptr[id] + j] */
 #define ACGB200_NOPATTERN 0xFFFFu
-#define ACGB200_TILE_COMPRESSED 0x40000000      /* flag in acgb200_tile.nrows */
 struct acgb200_patterns {
     int npat, nentries;
     int *patptr;                 /* [npat+1] */
@@ -109,7 +138,7 @@ struct acgb200_devstate {
     double prev[2][2];               /* {gamma_{k-1}, alpha_{k-1}} read by update k from slot k&1 */
     /* setup-time reductions */
     double tmp_loc[2], tmp[2];
-    unsigned int ticket;             /* last-CTA detection of the one-kernel iteration (single GPU) */
+    unsigned int ticket;             /* spare (last-CTA detection on one GPU) */
     unsigned int pad1;
 };
 
@@ -241,27 +270,30 @@ int acgb200_pcg_update(int n, struct acgb200_devstate *st, int cin, int cout, in
                        const double *q, double *z, double *w, double *t, double *p,
                        double *r, double *x, cudaStream_t stream);
 
-/* the same update with w double-buffered (reads w_in, writes w_out): the two-kernel pipelined loop on
- * the unified [owned | ghost] layout */
-int acgb200_pcg_update_db(int n, struct acgb200_devstate *st, int cin, int cout, int multi,
-                          struct acgb200_p2pdev *p2p,
-                          const double *q, double *z, double *w_in, double *w_out, double *t, double *p,
-                          double *r, double *x, cudaStream_t stream);
-
-/* one kernel per pipelined iteration (opt-in): q = A w fused with the update;
- * w is double-buffered (w0: parity 0).  grid from acgb200_pcg_fused_grid (0: the
- * plan has no fused variant). */
-int acgb200_pcg_fused_grid(const struct acgb200_spmvplan *plan);
-int acgb200_pcg_fused_launch(const struct acgb200_spmvargs *args, int grid, int cin, int multi,
-                             double *z, double *t, double *p, double *r, double *x,
-                             double *w0, double *w1, cudaStream_t stream);
-
 /* the reference's public BLAS-1 building blocks (acg/cg-kernels-cuda.h:45-97; cgcuda.c wraps them) */
 int acgb200_helper_axpy(int op, int n, const double *num, const double *den, const double *x, double *y, cudaStream_t stream);
 int acgb200_helper_scalars(int op, double *out0, double *out1, const double *num, const double *den, cudaStream_t stream);
 int acgb200_helper_pipelined(int n, const double *gamma, double *gamma_prev, const double *delta, const double *q,
                              double *p, double *r, double *t, double *x, double *z, double *w, double *alpha_prev,
                              cudaStream_t stream);
+
+/* expand.cu: full-storage expansion of the packed symmetric CSR on the device
+ * (the GPU form of acgsymcsrmatrix_dsymv_init, acg/symcsrmatrix.c:760-851) */
+struct acgb200_expanded {
+    int *d_rowptr; int *d_colidx; double *d_a;          /* local block, 0-based columns */
+    int *d_orowptr; int *d_ocolidx; double *d_oa;       /* border x ghost block, columns rebased by -borderrowoffset */
+    int64_t fnnz, onnz;
+};
+int acgb200_expand_device(int n, int ghost0, int border0, int nob, int64_t pnnz,
+                          const int *d_prp, const int *d_pcol, const double *d_pa, double eps,
+                          int rp_pad, int blk_pad, struct acgb200_expanded *out, cudaStream_t stream);
+
+struct acgsymcsrmatrix;
+/* expand_host.c: upload the packed matrix and expand it on the device (rp_pad / blk_pad: trailing
+ * padding of the row-pointer / column+value arrays, as the TMA tile copies need) */
+int acgb200_expand_upload(const struct acgsymcsrmatrix *A, double eps, int rp_pad, int blk_pad,
+                          struct acgb200_expanded *out, cudaStream_t stream, int *errcode);
+void acgb200_expanded_free(struct acgb200_expanded *x);
 
 /* setup-time helpers */
 int acgb200_dot(int n, const double *x, const double *y, double *acc, cudaStream_t stream); /* acc += x.y */

@@ -105,6 +105,15 @@ __device__ __forceinline__ double ld_x(const double *p)
     return v;
 }
 
+/* coalesced read of matrix data that is used exactly once per SpMV: no L1 line, evict-first in L2,
+ * so the stream does not displace the x vector (which every row re-reads) from either cache */
+__device__ __forceinline__ double ld_stream(const double *p, uint64_t pol)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 /* Programmatic dependent launch (opt-in, ACGB200_PDL=1).  Every kernel of the
  * iteration chain starts with this: wait until the preceding kernel of the
  * stream has completed and flushed (nothing in global memory is touched before),
@@ -517,59 +526,80 @@ spmv_tiles_kernel(const SpmvParams P)
 }
 
 /* ------------------------------------------------------------------------ */
-/* SpMV over index-free ("compressed") tiles -- opt-in, see compress.c         */
+/* SpMV over pattern slices (slices.c): index-free, slice-major values         */
 /* ------------------------------------------------------------------------ */
 
-struct CmpParams {
-    const unsigned short *patid;   /* [nrows] pattern id per row */
-    const int *patptr;             /* [npat+1] */
-    const int *patoff;             /* [nentries] col - row */
-    int npat, nentries;
-    int pc;                        /* pattern-id slots per stage (multiple of 8) */
-    int rc;                        /* row-pointer slots per stage (multiple of 4) */
+struct SliceParams {
+    const acgb200_slice *slices;
+    int nslices;
+    const double *sval;
+    const unsigned short *patid;
+    const int *spatoff;            /* [npat * lpad], zero beyond a pattern's length */
+    int npat, lpad;
+    const double *x;
+    double *y;
+    const double *b;
+    double *acc;
+    int dotrows;
+    int mode;
+    const acgb200_ctrl *ctrl_in;
+    acgb200_ctrl *ctrl_out;        /* NULL: the tile kernel launched behind this one forwards the word */
+    acgb200_devstate *st;
+    int housekeeping;
 };
 
-/* stage layout: values [8*sc] | row pointers [4*rc] | pattern ids [2*pc] */
-__device__ __forceinline__ void cspmv_issue(
-    const SpmvParams &P, const CmpParams &C, const acgb200_tile &tl, unsigned char *stage, uint64_t *bar, uint64_t pol)
+/*
+ * One warp per slice, one row per lane.  Entry slot e of the slice's 32 rows is
+ * one coalesced 256-byte load (ld_stream); the column of lane's entry is
+ * row + offset[pattern of the row][e] from a zero-padded table in shared memory,
+ * so padded slots (value 0) gather x[row].  UB value loads and UB gathers are
+ * issued back to back before the UB FMAs; a row's products are added in CSR
+ * order into one accumulator.  No shared-memory staging of the matrix: residency
+ * is limited by registers only, the loads in flight per SM (warps x UB x 256 B
+ * of values) cover the HBM latency.
+ */
+template <int UB>
+__device__ __forceinline__ void slice_load(double (&vv)[UB], double (&xv)[UB], const double *v, const double *xr,
+                                           const int *offs, int e, uint64_t pol)
 {
-    const int nrows = tl.nrows & ~ACGB200_TILE_COMPRESSED;
-    const bool cmp = (tl.nrows & ACGB200_TILE_COMPRESSED) != 0;
-    const int row_al = tl.row_begin & ~3;
-    const int nrp = (tl.row_begin + nrows + 1 - row_al + 3) & ~3;
-    const int row_al8 = tl.row_begin & ~7;
-    const int npid = (tl.row_begin + nrows - row_al8 + 7) & ~7;
-    double *vals = reinterpret_cast<double *>(stage);
-    int *rptr = reinterpret_cast<int *>(stage + (size_t) P.sc * 8);
-    unsigned short *pid = reinterpret_cast<unsigned short *>(stage + (size_t) P.sc * 8 + (size_t) C.rc * 4);
-    mbar_arrive_expect_tx(bar, (uint32_t) tl.nnz_al * 8u + (uint32_t) nrp * 4u + (cmp ? (uint32_t) npid * 2u : 0u));
-    if (tl.nnz_al > 0) bulk_g2s(vals, P.a + tl.k_al, (uint32_t) tl.nnz_al * 8u, bar, pol);
-    bulk_g2s(rptr, P.rowptr + row_al, (uint32_t) nrp * 4u, bar, pol);
-    if (cmp) bulk_g2s(pid, C.patid + row_al8, (uint32_t) npid * 2u, bar, pol);
+#pragma unroll
+    for (int u = 0; u < UB; u++) vv[u] = ld_stream(v + (size_t) (e + u) * 32, pol);
+#pragma unroll
+    for (int u = 0; u < UB; u++) xv[u] = ld_x(xr + offs[e + u]);
 }
 
-/*
- * Same structure as spmv_tiles_kernel.  A compressed tile streams 8 B per
- * nonzero (values only) plus 6 B per row (row pointer, pattern id); column
- * indices are rebuilt as row + offset from the pattern table held in shared
- * memory.  Tiles that are not compressed (rows with patterns outside the
- * dictionary) read their column indices straight from global memory -- they
- * are rare by construction (the plan is only used when almost all tiles
- * compress).
- */
-template <int G, int T, int U>
-__global__ void __launch_bounds__(T, SPMV_MINB(T))
-spmv_ctiles_kernel(const SpmvParams P, const CmpParams C)
+template <int UB>
+__device__ __forceinline__ void slice_load_pred(double (&vv)[UB], double (&xv)[UB], const double *v, const double *xr,
+                                                const int *offs, int e, int L, uint64_t pol)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full_bar[SPMV_MAX_STAGES];
-    __shared__ double red[T / 32];
-    __shared__ int last_flag;
+#pragma unroll
+    for (int u = 0; u < UB; u++) vv[u] = e + u < L ? ld_stream(v + (size_t) (e + u) * 32, pol) : 0.0;
+#pragma unroll
+    for (int u = 0; u < UB; u++) xv[u] = e + u < L ? ld_x(xr + offs[e + u]) : 0.0;
+}
 
+template <int UB>
+__device__ __forceinline__ double slice_fma(const double (&vv)[UB], const double (&xv)[UB], double sum)
+{
+#pragma unroll
+    for (int u = 0; u < UB; u++) sum = fma(vv[u], xv[u], sum);
+    return sum;
+}
+
+/* PF: the loads of batch k+1 are issued before the products of batch k are added.  ptxas places a
+ * batch's FMAs as early as their operands allow, i.e. between the loads of the same batch, and a warp
+ * issues in order: without the prefetch a warp stalls on its first product with ~3 of its 2*UB loads in
+ * flight; with it the operands of the FMA it stalls on were requested a whole batch earlier. */
+template <int UB, int T, bool PF>
+__global__ void __launch_bounds__(T)
+spmv_slices_kernel(const SliceParams P)
+{
+    extern __shared__ __align__(16) int spat_s[];
+    __shared__ double red[T / 32];
     const int tid = threadIdx.x;
     pdl_prologue();
     const Gate gate = gate_read(P.ctrl_in, P.st);
-    if (blockIdx.x == 0 && tid == 0 && P.ctrl_in) {
+    if (P.ctrl_out && blockIdx.x == 0 && tid == 0 && P.ctrl_in) {
         *P.ctrl_out = *P.ctrl_in;
         if (gate.active) {
             const int s = gate.iter & 1;
@@ -578,336 +608,80 @@ spmv_ctiles_kernel(const SpmvParams P, const CmpParams C)
         }
     }
     if (!gate.active) return;
-
-    const int S = P.nstages;
-    /* pattern table behind the stage ring */
-    int *patptr_s = reinterpret_cast<int *>(smem + (size_t) S * P.stage_bytes);
-    int *patoff_s = patptr_s + ((C.npat + 1 + 3) & ~3);
-    for (int i = tid; i <= C.npat; i += T) patptr_s[i] = C.patptr[i];
-    for (int i = tid; i < C.nentries; i += T) patoff_s[i] = C.patoff[i];
-
-    uint64_t pol = 0;
-    if (tid == 0) {
-        pol = l2_policy_evict_first();
-        for (int s = 0; s < S; s++) mbar_init(&full_bar[s], 1);
-        mbar_init_fence();
-        for (int s = 0; s < S; s++) {
-            const int t = blockIdx.x + s * gridDim.x;
-            if (t < P.ntiles) cspmv_issue(P, C, P.tiles[t], smem + (size_t) s * P.stage_bytes, &full_bar[s], pol);
-        }
-    }
+    for (int i = tid; i < P.npat * P.lpad; i += T) spat_s[i] = P.spatoff[i];
     __syncthreads();
 
-    constexpr int RPP = T / G;
-    const int lane = tid % G;
-    const int grp = tid / G;
+    const uint64_t pol = l2_policy_evict_first();
+    const int lane = tid & 31;
+    const int warp = (blockIdx.x * T + tid) >> 5;
+    const int nwarps = (gridDim.x * T) >> 5;
     double dot = 0.0;
-    const double *xg = NULL;
-
-    int i = 0;
-    for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, i++) {
-        const int s = i % S;
-        const acgb200_tile tl = P.tiles[t];
-        const int nrows = tl.nrows & ~ACGB200_TILE_COMPRESSED;
-        const bool cmp = (tl.nrows & ACGB200_TILE_COMPRESSED) != 0;
-        if (P.p2p && !xg && tl.row_begin + nrows > P.od_rowoffset) {
-            p2p_wait_halo(P.p2p, P.p2p->hbase + (unsigned long long) gate.iter);
-            xg = P.p2p->my_ghost[gate.iter & 1] - P.od_nrows;
-        }
-        unsigned char *stage = smem + (size_t) s * P.stage_bytes;
-        const double *vals = reinterpret_cast<const double *>(stage);
-        const int *rp = reinterpret_cast<const int *>(stage + (size_t) P.sc * 8) + (tl.row_begin & 3);
-        const unsigned short *pid = reinterpret_cast<const unsigned short *>(stage + (size_t) P.sc * 8 + (size_t) C.rc * 4)
-                                    + (tl.row_begin & 7);
-
-        mbar_wait(&full_bar[s], (uint32_t) ((i / S) & 1));
-
-        for (int base = 0; base < nrows; base += RPP) {
-            const int lr = base + grp;
-            double sum = 0.0;
-            if (lr < nrows) {
-                const int row = tl.row_begin + lr;
-                const int kb = rp[lr] - tl.k_al;
-                const int ke = rp[lr + 1] - tl.k_al;
-                /* compressed: offsets of this row's pattern; raw: indices from global memory */
-                const int *offs = cmp ? patoff_s + patptr_s[pid[lr]] - kb : NULL;
-                const int *gcol = P.colidx + tl.k_al;
-                for (int k = kb + lane; k < ke; k += U * G) {
-                    int c[U];
-                    double v[U], xv[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const int kk = min(k + u * G, ke - 1);
-                        c[u] = cmp ? row + offs[kk] : __ldg(gcol + kk);
-                        v[u] = vals[kk];
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; u++) xv[u] = ld_x(P.x + c[u]);
-#pragma unroll
-                    for (int u = 0; u < U; u++) sum = fma((k + u * G < ke) ? v[u] : 0.0, xv[u], sum);
-                }
-                if (xg && row >= P.od_rowoffset) {
-                    const int ob = row - P.od_rowoffset;
-                    for (int k = P.orowptr[ob] + lane; k < P.orowptr[ob + 1]; k += G)
-                        sum = fma(P.oa[k], xg[P.ocolidx[k]], sum);
-                }
+    for (int s = warp; s < P.nslices; s += nwarps) {
+        const int4 sl = __ldg(reinterpret_cast<const int4 *>(P.slices) + s);     /* row0, nrows, len, vblk */
+        const int row = sl.x + lane;
+        const int *offs = spat_s + (int) P.patid[row] * P.lpad;
+        const double *v = P.sval + ((size_t) sl.w << 5) + lane;
+        const double *xr = P.x + row;
+        const int L = sl.z;
+        double sum = 0.0;
+        int e = 0;
+        if (PF) {
+            /* two register sets, straight-line body (predicated loads, no branch between a batch's loads
+             * and the previous batch's FMAs); slots past L load nothing and add 0 * 0 */
+            double va[UB], xa[UB], vb[UB], xb[UB];
+            slice_load_pred<UB>(va, xa, v, xr, offs, 0, L, pol);
+            for (; e < L; e += 2 * UB) {
+                slice_load_pred<UB>(vb, xb, v, xr, offs, e + UB, L, pol);
+                sum = slice_fma<UB>(va, xa, sum);
+                slice_load_pred<UB>(va, xa, v, xr, offs, e + 2 * UB, L, pol);
+                sum = slice_fma<UB>(vb, xb, sum);
             }
-            if (G > 1) sum = group_sum<G>(sum);
-            if (lr < nrows && lane == 0) {
-                const int row = tl.row_begin + lr;
-                if (P.mode == SPMV_R_B_AX) {
-                    const double v = P.b[row] - sum;
-                    P.y[row] = v;
-                    if (row < P.dotrows) dot = fma(v, v, dot);
-                } else {
-                    P.y[row] = sum;
-                    if (P.mode == SPMV_Y_AX_DOT && row < P.dotrows) dot = fma(__ldg(P.x + row), sum, dot);
-                }
+        } else {
+            for (; e + UB <= L; e += UB) {
+                double vv[UB], xv[UB];
+                slice_load<UB>(vv, xv, v, xr, offs, e, pol);
+                sum = slice_fma<UB>(vv, xv, sum);
             }
         }
-
-        __syncthreads();
-        if (tid == 0) {
-            const int tn = t + S * gridDim.x;
-            if (tn < P.ntiles) cspmv_issue(P, C, P.tiles[tn], stage, &full_bar[s], pol);
+        if (e < L) {
+            /* last, partial batch: slots past L are neither loaded nor added */
+            double vv[UB], xv[UB];
+#pragma unroll
+            for (int u = 0; u < UB; u++) vv[u] = e + u < L ? ld_stream(v + (size_t) (e + u) * 32, pol) : 0.0;
+#pragma unroll
+            for (int u = 0; u < UB; u++) xv[u] = e + u < L ? ld_x(xr + offs[e + u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < UB; u++) if (e + u < L) sum = fma(vv[u], xv[u], sum);
+        }
+        if (P.mode == SPMV_R_B_AX) {
+            const double r = P.b[row] - sum;
+            P.y[row] = r;
+            if (row < P.dotrows) dot = fma(r, r, dot);
+        } else {
+            P.y[row] = sum;
+            if (P.mode == SPMV_Y_AX_DOT && row < P.dotrows) dot = fma(__ldg(P.x + row), sum, dot);
         }
     }
-
     if (P.acc) {
         const double v = block_sum(dot, red);
         if (tid == 0 && v != 0.0) atomicAdd(P.acc, v);
     }
-    if (P.p2p && P.pub_ch >= 0 && P.p2p->fuse) {
-        __threadfence();
-        if (p2p_last_block(P.p2p, &last_flag))
-            p2p_publish_red(P.p2p, P.pub_ch, gate.iter & 1, P.p2p->rbase + (unsigned long long) gate.iter + 1ull, P.acc, 1);
-    }
 }
 
-/* ------------------------------------------------------------------------ */
-/* One kernel per pipelined-CG iteration (opt-in, option "pcg_fused")          */
-/* ------------------------------------------------------------------------ */
-
-/*
- * q = A w and the whole vector update of acg/cg-kernels-cuda.cu:201-214 in one
- * pass: a row's update needs only that row's q, so it runs as the epilogue of
- * the row's tile and q never goes to memory.  The SpMV gathers w at arbitrary
- * columns while w is being updated, hence w is double-buffered by iteration
- * parity (gathers read one buffer, the epilogue writes the other); z, t, p, x, r
- * are only touched at the tile's own rows.  Per row this moves 96 B of vectors
- * instead of 8 (q written) + 104 (update) B, and an iteration is one launch and
- * one grid-wide dependency instead of two -- which is what counts once a rank's
- * share of the matrix takes 0.1 ms.
- *
- * The scalars are those of the two-kernel path: {gamma,delta} of this iteration
- * were accumulated by the previous launch (peer-memory mode: published by its
- * last CTA to every rank and summed here in rank order), alpha and beta follow,
- * the stopping test precedes the update (acg/cgcuda.c:1764-1772).  Unlike that
- * path the reduction is needed at the *start* of the launch, so it no longer
- * overlaps the SpMV: algebraically the iteration is unchanged, the latency
- * hiding of pipelined CG is traded for the launch and the q traffic (between
- * GPUs of one NVSwitch domain the exposed latency is a few microseconds).
- *
- * Accumulators: slot s^1 of gd_loc collects {gamma,delta} of the next
- * iteration; slot s, read by every CTA at its start, is cleared by the last
- * CTA to finish, ready for the launch after this one.
- */
-struct FusedParams {
-    double *z, *t, *p, *r, *x;
-    double *w0, *w1;        /* w of even / odd iterations */
-    int cin;                /* control word read; cin^1 is written */
-    int multi;
-};
-
-template <int G, int T, int U, bool CMP>
-__global__ void __launch_bounds__(T, SPMV_MINB(T))
-pcg_fused_kernel(const SpmvParams P, const CmpParams C, const FusedParams F)
+/* slice-major copy of the covered rows' values out of the device CSR arrays (once, at init) */
+__global__ void __launch_bounds__(256)
+slices_fill_kernel(int nslices, const acgb200_slice *slices, const int *__restrict__ rowptr,
+                   const double *__restrict__ a, double *__restrict__ sval)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full_bar[SPMV_MAX_STAGES];
-    __shared__ double red[T / 32];
-    __shared__ double glob[2];
-    __shared__ double qs[2][T / G];          /* q of the current / previous tile (rows_cap <= T/G) */
-    __shared__ double ab[2];                 /* alpha, beta: kept out of the registers of the gather loop */
-    __shared__ int last_flag;
-
-    const int tid = threadIdx.x;
-    pdl_prologue();
-    acgb200_devstate *st = P.st;
-    acgb200_p2pdev *PP = P.p2p;
-    const Gate gate = gate_read(&st->ctrl[F.cin], st);
-    const int s = gate.iter & 1;
-    double gamma, delta;
-    if (PP && gate.active && gate.iter > 0) {
-        p2p_reduce(PP, 0, s, PP->rbase + (unsigned long long) gate.iter, glob);
-        gamma = glob[0]; delta = glob[1];
-    } else {
-        gamma = F.multi ? st->gd[s][0] : st->gd_loc[s][0];
-        delta = F.multi ? st->gd[s][1] : st->gd_loc[s][1];
-    }
-    const double gamma_prev = st->prev[s][0], alpha_prev = st->prev[s][1];
-    const bool conv = st->tol > 0.0 && sqrt(gamma) < st->tol;
-    if (tid == 0) {
-        const double beta = gamma / gamma_prev;
-        ab[1] = beta;
-        ab[0] = gamma / (delta - beta * gamma / alpha_prev);
-    }
-    if (blockIdx.x == 0 && tid == 0) {
-        const double alpha = ab[0];
-        acgb200_ctrl c = st->ctrl[F.cin];
-        if (gate.active) {
-            st->gd[s][0] = gamma; st->gd[s][1] = delta;      /* where the host finds the last tested gamma */
-            if (conv) { c.done = 1; st->final_rr = gamma; }
-            else { c.iter = gate.iter + 1; st->prev[s ^ 1][0] = gamma; st->prev[s ^ 1][1] = alpha; }
-        }
-        st->ctrl[F.cin ^ 1] = c;
-    }
-    if (!gate.active || conv) return;
-
-    const double *wold = s ? F.w1 : F.w0;
-    const int S = P.nstages;
-    /* index-free tiles (CMP): pattern table behind the stage ring, as in spmv_ctiles_kernel */
-    int *patptr_s = reinterpret_cast<int *>(smem + (size_t) S * P.stage_bytes);
-    int *patoff_s = patptr_s + ((C.npat + 1 + 3) & ~3);
-    if (CMP) {
-        for (int j = tid; j <= C.npat; j += T) patptr_s[j] = C.patptr[j];
-        for (int j = tid; j < C.nentries; j += T) patoff_s[j] = C.patoff[j];
-    }
-    if (tid == 0) {
-        const uint64_t pol = l2_policy_evict_first();
-        for (int i = 0; i < S; i++) mbar_init(&full_bar[i], 1);
-        mbar_init_fence();
-        for (int i = 0; i < S; i++) {
-            const int t = blockIdx.x + i * gridDim.x;
-            if (t < P.ntiles) {
-                if (CMP) cspmv_issue(P, C, P.tiles[t], smem + (size_t) i * P.stage_bytes, &full_bar[i], pol);
-                else spmv_issue(P, P.tiles[t], smem + (size_t) i * P.stage_bytes, &full_bar[i], pol);
-            }
-        }
-    }
-    __syncthreads();
-
-    constexpr int RPP = T / G;
-    const int lane = tid % G;
-    const int grp = tid / G;
-    const bool push = PP != NULL;            /* launched only with the fused exchange */
-    double g2 = 0.0, d2 = 0.0;
-    const double *xg = NULL;
-
-    int i = 0;
-    for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, i++) {
-        const int sidx = i % S;
-        acgb200_tile tl = P.tiles[t];
-        const bool cmp = CMP && (tl.nrows & ACGB200_TILE_COMPRESSED) != 0;
-        tl.nrows &= ~ACGB200_TILE_COMPRESSED;
-        if (PP && !xg && tl.row_begin + tl.nrows > P.od_rowoffset) {
-            p2p_wait_halo(PP, PP->hbase + (unsigned long long) gate.iter);
-            xg = PP->my_ghost[s] - P.od_nrows;
-        }
-        unsigned char *stage = smem + (size_t) sidx * P.stage_bytes;
-        const double *vals = reinterpret_cast<const double *>(stage);
-        /* stage layout: values | column indices | row pointers, or (CMP) values | row pointers | pattern ids */
-        const int *cols = reinterpret_cast<const int *>(stage + (size_t) P.sc * 8);
-        const int *rp = (CMP ? reinterpret_cast<const int *>(stage + (size_t) P.sc * 8)
-                             : reinterpret_cast<const int *>(stage + (size_t) P.sc * 12)) + (tl.row_begin & 3);
-        const unsigned short *pid = reinterpret_cast<const unsigned short *>(stage + (size_t) P.sc * 8 + (size_t) C.rc * 4)
-                                    + (tl.row_begin & 7);
-        const int *gcol = P.colidx + tl.k_al;
-        double *qt = qs[i & 1];
-
-        mbar_wait(&full_bar[sidx], (uint32_t) ((i / S) & 1));
-
-        for (int base = 0; base < tl.nrows; base += RPP) {
-            const int lr = base + grp;
-            double sum = 0.0;
-            if (lr < tl.nrows) {
-                const int row = tl.row_begin + lr;
-                const int kb = rp[lr] - tl.k_al;
-                const int ke = rp[lr + 1] - tl.k_al;
-                const int *offs = cmp ? patoff_s + patptr_s[pid[lr]] - kb : NULL;
-                for (int k = kb + lane; k < ke; k += U * G) {
-                    int c[U];
-                    double v[U], xv[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const int kk = min(k + u * G, ke - 1);
-                        if (CMP) c[u] = cmp ? row + offs[kk] : __ldg(gcol + kk);
-                        else c[u] = cols[kk];
-                        v[u] = vals[kk];
-                    }
-                    /* read-only path: the buffer being gathered is not written by this launch */
-#pragma unroll
-                    for (int u = 0; u < U; u++) xv[u] = ld_x(wold + c[u]);
-#pragma unroll
-                    for (int u = 0; u < U; u++) sum = fma((k + u * G < ke) ? v[u] : 0.0, xv[u], sum);
-                }
-                if (xg && row >= P.od_rowoffset) {
-                    const int ob = row - P.od_rowoffset;
-                    for (int k = P.orowptr[ob] + lane; k < P.orowptr[ob + 1]; k += G)
-                        sum = fma(P.oa[k], xg[P.ocolidx[k]], sum);
-                }
-            }
-            if (G > 1) sum = group_sum<G>(sum);
-            if (lr < tl.nrows && lane == 0) qt[lr] = sum;
-        }
-
-        __syncthreads();        /* q of the tile is in shared memory; stage sidx is free */
-        if (tid == 0) {
-            const int tn = t + S * gridDim.x;
-            if (tn < P.ntiles) {
-                if (CMP) cspmv_issue(P, C, P.tiles[tn], stage, &full_bar[sidx], l2_policy_evict_first());
-                else spmv_issue(P, P.tiles[tn], stage, &full_bar[sidx], l2_policy_evict_first());
-            }
-        }
-        /* update of the tile's rows, one thread per row, coalesced; the duty
-         * rotates over the warps so that no warp is the straggler of every tile.
-         * qs is double-buffered by tile parity: the next tile's q goes to the
-         * other half, and the barrier above of that tile orders this read
-         * before the half is written again. */
-        for (int lr = (tid + T - (i * 32) % T) % T; lr < tl.nrows; lr += T) {
-            const int row = tl.row_begin + lr;
-            const double alpha = ab[0], beta = ab[1];
-            double *wnew = s ? F.w0 : F.w1;
-            const double qv = qt[lr];
-            const double wv0 = wold[row], rv0 = F.r[row];
-            const double zv = fma(beta, F.z[row], qv);
-            const double tv = fma(beta, F.t[row], wv0);
-            const double pv = fma(beta, F.p[row], rv0);
-            const double rv = fma(-alpha, tv, rv0);
-            const double wv = fma(-alpha, zv, wv0);
-            F.z[row] = zv; F.t[row] = tv; F.p[row] = pv;
-            F.x[row] = fma(alpha, pv, F.x[row]);
-            F.r[row] = rv; wnew[row] = wv;
-            g2 = fma(rv, rv, g2);
-            d2 = fma(wv, rv, d2);
-            if (push && row >= PP->borderoff) p2p_push_row(PP, row, s ^ 1, wv);
-        }
-    }
-
-    g2 = block_sum(g2, red);
-    d2 = block_sum(d2, red);
-    if (tid == 0) {
-        atomicAdd(&st->gd_loc[s ^ 1][0], g2);
-        atomicAdd(&st->gd_loc[s ^ 1][1], d2);
-    }
-    if (PP) {
-        __threadfence_system();
-        if (p2p_last_block(PP, &last_flag)) {
-            const unsigned long long it1 = (unsigned long long) gate.iter + 1ull;
-            p2p_publish_red(PP, 0, s ^ 1, PP->rbase + it1, &st->gd_loc[s ^ 1][0], 2);
-            p2p_publish_halo(PP, PP->hbase + it1);
-            if (tid == 0) { st->gd_loc[s][0] = 0.0; st->gd_loc[s][1] = 0.0; }
-        }
-    } else {
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned int tk = atomicAdd(&st->ticket, 1u);
-            if (tk == gridDim.x - 1) {
-                st->ticket = 0;
-                st->gd_loc[s][0] = 0.0; st->gd_loc[s][1] = 0.0;
-            }
-        }
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int s = warp; s < nslices; s += nwarps) {
+        const acgb200_slice sl = slices[s];
+        const int row = sl.row0 + lane;
+        const int kb = rowptr[row], len = rowptr[row + 1] - kb;
+        double *v = sval + ((size_t) sl.vblk << 5) + lane;
+        for (int e = 0; e < sl.len; e++) v[(size_t) e * 32] = e < len ? a[kb + e] : 0.0;
     }
 }
 
@@ -1197,14 +971,11 @@ cg_update_xp_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, a
 /* Pipelined CG: z=q+beta z; t=w+beta t; p=r+beta p; x+=alpha p; r-=alpha t;
  * w-=alpha z (acg/cg-kernels-cuda.cu:201-214), plus gamma'=(r,r), delta'=(w,r)
  * of the updated vectors for the next iteration. */
-/* DB: w is double-buffered -- read from w, written to wout (the unified [owned | ghost] layout keeps the
- * two SpMV input vectors of consecutive iterations in the exported allocation); otherwise in place. */
-template <bool DB>
 __global__ void __launch_bounds__(BLAS1_THREADS)
 pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acgb200_p2pdev *P,
                   const double *__restrict__ q, double *__restrict__ z, double *__restrict__ w,
                   double *__restrict__ t, double *__restrict__ p, double *__restrict__ r,
-                  double *__restrict__ x, double *__restrict__ wout)
+                  double *__restrict__ x)
 {
     __shared__ double red[BLAS1_THREADS / 32];
     __shared__ double glob[2];
@@ -1255,7 +1026,7 @@ pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acg
             z[i] = zv; t[i] = tv; p[i] = pv;
             x[i] = fma(alpha, pv, x[i]);
             r[i] = rv;
-            if (DB) wout[i] = wv; else w[i] = wv;
+            w[i] = wv;
             g2 = fma(rv, rv, g2);
             d2 = fma(wv, rv, d2);
             if (push && pass == 0) p2p_push_row(P, i, s ^ 1, wv);
@@ -1396,40 +1167,33 @@ static spmv_fn spmv_variant(int G, int T, int U)
     return NULL;
 }
 
-typedef void (*cspmv_fn)(const SpmvParams, const CmpParams);
-
-static cspmv_fn cspmv_variant(int G, int T, int U)
-{
-    if (U != 8) return NULL;
-#define X(g, t) if (G == g && T == t) return spmv_ctiles_kernel<g, t, 8>;
-    X(1, 128) X(2, 128) X(4, 128) X(8, 128) X(16, 128) X(32, 128) X(4, 256) X(2, 256) X(1, 64)
-#undef X
-    return NULL;
-}
-
 static inline int stage_slots(const acgb200_spmvplan *pl) { return (pl->nnz_cap + 8 + 3) & ~3; }
 static inline int stage_rslots(const acgb200_spmvplan *pl) { return (pl->rows_cap + 1 + 8 + 3) & ~3; }
-static inline int stage_pslots(const acgb200_spmvplan *pl) { return (pl->rows_cap + 16 + 7) & ~7; }
 static inline int stage_bytes(const acgb200_spmvplan *pl)
 {
     const int sc = stage_slots(pl);
     const int rc = stage_rslots(pl);
-    if (pl->compressed) return (sc * 8 + rc * 4 + stage_pslots(pl) * 2 + 127) & ~127;
     return (sc * 12 + rc * 4 + 127) & ~127;
 }
-static inline int table_bytes(const acgb200_spmvplan *pl)
+
+typedef void (*slice_fn)(const SliceParams);
+
+/* (values + gathers in flight per lane, threads per CTA) of the slice kernel */
+static slice_fn slice_variant(int UB, int T, int PF)
 {
-    return pl->compressed ? (((pl->npat + 1 + 3) & ~3) + ((pl->nentries + 3) & ~3)) * 4 : 0;
+#define X(u, t) if (UB == u && T == t) return PF ? spmv_slices_kernel<u, t, true> : spmv_slices_kernel<u, t, false>;
+    X(3, 128) X(4, 128) X(5, 128) X(7, 128) X(8, 128) X(9, 128) X(14, 128) X(3, 256) X(4, 256) X(5, 256) X(7, 256) X(8, 256) X(9, 256) X(14, 256)
+#undef X
+    return NULL;
 }
 
 /* acgb200_spmv_choose (tile-plan heuristic) and acgb200_spmv_min_bytes are host-only: plan.c */
 
 extern "C" int acgb200_spmv_configure(acgb200_spmvplan *pl)
 {
-    const void *fn = pl->compressed ? (const void *) cspmv_variant(pl->lanes_per_row, pl->threads, pl->unroll)
-                                    : (const void *) spmv_variant(pl->lanes_per_row, pl->threads, pl->unroll);
+    const void *fn = (const void *) spmv_variant(pl->lanes_per_row, pl->threads, pl->unroll);
     if (!fn) return (int) cudaErrorInvalidConfiguration;
-    pl->smem_bytes = stage_bytes(pl) * pl->nstages + table_bytes(pl);
+    pl->smem_bytes = stage_bytes(pl) * pl->nstages;
     cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes);
     if (err) return (int) err;
     int per_sm = 0;
@@ -1441,13 +1205,53 @@ extern "C" int acgb200_spmv_configure(acgb200_spmvplan *pl)
     if (grid > pl->ntiles) grid = pl->ntiles;
     if (grid < 1) grid = 1;
     pl->grid = (int) grid;
+    if (pl->nslices > 0) {
+        slice_fn sfn = slice_variant(pl->slice_ub, pl->slice_threads, pl->slice_pf);
+        if (!sfn) return (int) cudaErrorInvalidConfiguration;
+        pl->slice_smem = ((pl->slice_npat * pl->slice_lpad + 3) & ~3) * (int) sizeof(int);
+        err = cudaFuncSetAttribute((const void *) sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->slice_smem);
+        if (err) return (int) err;
+        int sper = 0;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sper, (const void *) sfn, pl->slice_threads, pl->slice_smem);
+        if (err) return (int) err;
+        if (sper < 1) sper = 1;
+        if (pl->slice_max_ctas > 0 && sper > pl->slice_max_ctas) sper = pl->slice_max_ctas;
+        long long sgrid = (long long) acgb200_num_sms() * sper;
+        const long long need = ((long long) pl->nslices * 32 + pl->slice_threads - 1) / pl->slice_threads;
+        if (sgrid > need) sgrid = need;
+        pl->slice_grid = (int) (sgrid < 1 ? 1 : sgrid);
+    }
     return 0;
+}
+
+extern "C" int acgb200_slices_fill(const acgb200_spmvplan *pl, const int *d_rowptr, const double *d_a, cudaStream_t stream)
+{
+    if (pl->nslices <= 0) return 0;
+    long long grid = ((long long) pl->nslices * 32 + 255) / 256;
+    const long long cap = (long long) acgb200_num_sms() * 8;
+    if (grid > cap) grid = cap;
+    slices_fill_kernel<<<(int) grid, 256, 0, stream>>>(pl->nslices, pl->d_slices, d_rowptr, d_a, pl->d_sval);
+    return (int) cudaGetLastError();
 }
 
 extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t stream)
 {
     const acgb200_spmvplan *pl = a->plan;
-    if (pl->ntiles > 0 || a->ctrl_in) {   /* with no tiles the kernel still forwards the control word */
+    /* with neither tiles nor a peer-memory duty for the tile kernel, the slice kernel forwards the
+     * control word itself and the tile kernel is not launched */
+    const bool slices_forward = pl->nslices > 0 && pl->ntiles == 0 && !a->p2p;
+    if (pl->nslices > 0) {
+        /* first: the tile kernel's last CTA publishes the fused dot, which these rows add into */
+        SliceParams S;
+        S.slices = pl->d_slices; S.nslices = pl->nslices; S.sval = pl->d_sval;
+        S.patid = pl->d_spatid; S.spatoff = pl->d_spatoff; S.npat = pl->slice_npat; S.lpad = pl->slice_lpad;
+        S.x = a->x; S.y = a->y; S.b = a->b; S.acc = a->acc; S.dotrows = a->dotrows; S.mode = a->mode;
+        S.ctrl_in = a->ctrl_in; S.ctrl_out = slices_forward ? a->ctrl_out : NULL; S.st = a->st; S.housekeeping = a->housekeeping;
+        const cudaError_t le = launch_chain(slice_variant(pl->slice_ub, pl->slice_threads, pl->slice_pf), pl->slice_grid, pl->slice_threads,
+                                            (size_t) pl->slice_smem, stream, S);
+        if (le) return (int) le;
+    }
+    if (pl->ntiles > 0 || (a->ctrl_in && !slices_forward)) {   /* with no tiles the kernel still forwards the control word */
         SpmvParams P;
         P.tiles = pl->d_tiles; P.ntiles = pl->ntiles;
         P.sc = stage_slots(pl); P.stage_bytes = stage_bytes(pl); P.nstages = pl->nstages;
@@ -1456,17 +1260,9 @@ extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t strea
         P.ctrl_in = a->ctrl_in; P.ctrl_out = a->ctrl_out; P.st = a->st; P.housekeeping = a->housekeeping;
         P.p2p = (acgb200_p2pdev *) a->p2p; P.od_rowoffset = a->od_rowoffset; P.od_nrows = a->od_nrows;
         P.orowptr = a->orowptr; P.ocolidx = a->ocolidx; P.oa = a->oa; P.pub_ch = a->p2p ? a->pub_ch : -1;
-        if (pl->compressed) {
-            CmpParams C;
-            C.patid = pl->d_patid; C.patptr = pl->d_patptr; C.patoff = pl->d_patoff;
-            C.npat = pl->npat; C.nentries = pl->nentries;
-            C.pc = stage_pslots(pl); C.rc = stage_rslots(pl);
-            cspmv_variant(pl->lanes_per_row, pl->threads, pl->unroll)<<<pl->grid, pl->threads, pl->smem_bytes, stream>>>(P, C);
-        } else {
-            const cudaError_t le = launch_chain(spmv_variant(pl->lanes_per_row, pl->threads, pl->unroll),
-                                                pl->grid, pl->threads, (size_t) pl->smem_bytes, stream, P);
-            if (le) return (int) le;
-        }
+        const cudaError_t le = launch_chain(spmv_variant(pl->lanes_per_row, pl->threads, pl->unroll),
+                                            pl->grid, pl->threads, (size_t) pl->smem_bytes, stream, P);
+        if (le) return (int) le;
         cudaError_t err = cudaGetLastError();
         if (err) return (int) err;
     }
@@ -1494,59 +1290,6 @@ extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t strea
         if (err) return (int) err;
     }
     return 0;
-}
-
-typedef void (*fused_fn)(const SpmvParams, const CmpParams, const FusedParams);
-
-static fused_fn fused_variant(int G, int T, int U, int compressed)
-{
-    if (U != 8 || T != 128) return NULL;
-#define X(g) if (G == g) return compressed ? pcg_fused_kernel<g, 128, 8, true> : pcg_fused_kernel<g, 128, 8, false>;
-    X(1) X(2) X(4) X(8) X(16) X(32)
-#undef X
-    return NULL;
-}
-
-/* grid of the fused kernel for this plan (0: no variant / does not fit) */
-extern "C" int acgb200_pcg_fused_grid(const acgb200_spmvplan *pl)
-{
-    fused_fn fn = fused_variant(pl->lanes_per_row, pl->threads, pl->unroll, pl->compressed);
-    if (!fn || pl->nlong > 0 || pl->nmed > 0 || pl->rows_cap > pl->threads / pl->lanes_per_row) return 0;
-    if (cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes) != cudaSuccess) return 0;
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *) fn, pl->threads, pl->smem_bytes) != cudaSuccess || per_sm < 1)
-        return 0;
-    if (pl->max_ctas_per_sm > 0 && per_sm > pl->max_ctas_per_sm) per_sm = pl->max_ctas_per_sm;
-    long long grid = (long long) acgb200_num_sms() * per_sm;
-    if (grid > pl->ntiles) grid = pl->ntiles;
-    return grid < 1 ? 1 : (int) grid;
-}
-
-extern "C" int acgb200_pcg_fused_launch(const acgb200_spmvargs *a, int grid, int cin, int multi,
-                                        double *z, double *t, double *p, double *r, double *x,
-                                        double *w0, double *w1, cudaStream_t stream)
-{
-    const acgb200_spmvplan *pl = a->plan;
-    fused_fn fn = fused_variant(pl->lanes_per_row, pl->threads, pl->unroll, pl->compressed);
-    if (!fn || grid < 1) return (int) cudaErrorInvalidConfiguration;
-    SpmvParams P;
-    P.tiles = pl->d_tiles; P.ntiles = pl->ntiles;
-    P.sc = stage_slots(pl); P.stage_bytes = stage_bytes(pl); P.nstages = pl->nstages;
-    P.rowptr = a->rowptr; P.colidx = a->colidx; P.a = a->a; P.x = NULL; P.y = NULL; P.b = NULL;
-    P.acc = NULL; P.dotrows = 0; P.mode = SPMV_Y_AX;
-    P.ctrl_in = NULL; P.ctrl_out = NULL; P.st = a->st; P.housekeeping = 0;
-    P.p2p = (acgb200_p2pdev *) a->p2p; P.od_rowoffset = a->od_rowoffset; P.od_nrows = a->od_nrows;
-    P.orowptr = a->orowptr; P.ocolidx = a->ocolidx; P.oa = a->oa; P.pub_ch = -1;
-    CmpParams C;
-    memset(&C, 0, sizeof(C));
-    if (pl->compressed) {
-        C.patid = pl->d_patid; C.patptr = pl->d_patptr; C.patoff = pl->d_patoff;
-        C.npat = pl->npat; C.nentries = pl->nentries;
-        C.pc = stage_pslots(pl); C.rc = stage_rslots(pl);
-    }
-    FusedParams F;
-    F.z = z; F.t = t; F.p = p; F.r = r; F.x = x; F.w0 = w0; F.w1 = w1; F.cin = cin; F.multi = multi;
-    return (int) launch_chain(fn, grid, pl->threads, (size_t) pl->smem_bytes, stream, P, C, F);
 }
 
 extern "C" int acgb200_offdiag_launch(const acgb200_offdiagargs *a, cudaStream_t stream)
@@ -1583,19 +1326,8 @@ extern "C" int acgb200_pcg_update(int n, acgb200_devstate *st, int cin, int cout
                                   double *r, double *x, cudaStream_t stream)
 {
     static int occ = 0;
-    return (int) launch_chain(pcg_update_kernel<false>, blas1_grid(n, (const void *) pcg_update_kernel<false>, &occ), BLAS1_THREADS, 0, stream,
-                              n, st, cin, cout, multi, p2p, q, z, w, t, p, r, x, (double *) NULL);
-}
-
-/* the same with w double-buffered: reads w_in, writes w_out */
-extern "C" int acgb200_pcg_update_db(int n, acgb200_devstate *st, int cin, int cout, int multi,
-                                     acgb200_p2pdev *p2p,
-                                     const double *q, double *z, double *w_in, double *w_out, double *t, double *p,
-                                     double *r, double *x, cudaStream_t stream)
-{
-    static int occ = 0;
-    return (int) launch_chain(pcg_update_kernel<true>, blas1_grid(n, (const void *) pcg_update_kernel<true>, &occ), BLAS1_THREADS, 0, stream,
-                              n, st, cin, cout, multi, p2p, q, z, w_in, t, p, r, x, w_out);
+    return (int) launch_chain(pcg_update_kernel, blas1_grid(n, (const void *) pcg_update_kernel, &occ), BLAS1_THREADS, 0, stream,
+                              n, st, cin, cout, multi, p2p, q, z, w, t, p, r, x);
 }
 
 extern "C" int acgb200_comm_post(const acgb200_postargs *a, cudaStream_t stream)

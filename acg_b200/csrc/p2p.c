@@ -62,10 +62,6 @@ void acgb200_p2p_free(struct acgb200_p2p *p)
     if (!p) return;
     for (int r = 0; r < p->nranks; r++)
         if (r != p->rank && p->peer_base[r]) cudaIpcCloseMemHandle(p->peer_base[r]);
-    for (int r = 0; r < p->nranks; r++)
-        if (r != p->rank && p->peer_vbase[r]) cudaIpcCloseMemHandle(p->peer_vbase[r]);
-    cudaFree(p->d_desc_u); cudaFree(p->d_desc_c);
-    /* like the window, the vector allocation is freed by the caller after a barrier */
     cudaFree((void *) p->h_desc.bptr); cudaFree((void *) p->h_desc.bq); cudaFree((void *) p->h_desc.bdst);
     cudaFree(p->d_desc);
     /* the window itself is freed by the caller after a barrier (peers may still
@@ -180,70 +176,6 @@ int acgb200_p2p_init(struct acgb200_p2p *p, const struct acghalo *halo, int bord
 #undef CUP
 }
 
-struct vrecord { cudaIpcMemHandle_t handle; unsigned long long vstride; int goff; int pad; };
-
-/*
- * Unified layout for the one-kernel pipelined iteration: instead of separate ghost buffers the
- * window way, every rank exports two whole SpMV input vectors [owned | pad to 16 | ghost] (one per
- * iteration parity; the pad keeps owned and ghost entries in different cache lines, so that a line
- * fetched before the halo wait can never hold a stale ghost value).  The descriptor variant d_desc_u
- * is the ordinary one with the ghost pointers redirected to those tails -- flags, reduction slots
- * and the inverse send map are shared -- so the kernels need no second code path: they gather
- * through one CSR whose ghost columns are goff + ghost number.  Collective.
- */
-int acgb200_p2p_unify(struct acgb200_p2p *p, const struct acghalo *halo, int nowned, int nghost,
-                      const struct acgcomm *comm, cudaStream_t stream, int *errcode)
-{
-    if (!p->enabled) return ACG_ERR_INVALID_VALUE;
-    if (p->d_desc_u) return ACG_SUCCESS;
-#define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { if (errcode) *errcode = (int) e_; return ACG_ERR_CUDA; } } while (0)
-    p->goff = (nowned + 15) & ~15;
-    p->vstride = ((size_t) p->goff + (size_t) nghost + 2 + 15) & ~(size_t) 15;
-    const size_t bytes = 2 * p->vstride * sizeof(double);
-    CUP(cudaMalloc(&p->vwindow, bytes));
-    CUP(cudaMemset(p->vwindow, 0, bytes));
-    struct vrecord mine, *all = malloc((size_t) p->nranks * sizeof(*all));
-    if (!all) return ACG_ERR_ERRNO;
-    memset(&mine, 0, sizeof(mine));
-    CUP(cudaIpcGetMemHandle(&mine.handle, p->vwindow));
-    mine.vstride = p->vstride; mine.goff = p->goff;
-    void *d_mine = NULL, *d_all = NULL;
-    CUP(cudaMalloc(&d_mine, sizeof(mine)));
-    CUP(cudaMalloc(&d_all, (size_t) p->nranks * sizeof(mine)));
-    CUP(cudaMemcpyAsync(d_mine, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream));
-    ncclResult_t nr = ncclAllGather(d_mine, d_all, sizeof(mine), ncclChar, comm->ncclcomm, stream);
-    if (nr != ncclSuccess) { if (errcode) *errcode = (int) nr; free(all); return ACG_ERR_NCCL; }
-    CUP(cudaMemcpyAsync(all, d_all, (size_t) p->nranks * sizeof(mine), cudaMemcpyDeviceToHost, stream));
-    CUP(cudaStreamSynchronize(stream));
-    cudaFree(d_mine); cudaFree(d_all);
-    for (int r = 0; r < p->nranks; r++) {
-        if (r == p->rank) { p->peer_vbase[r] = p->vwindow; continue; }
-        cudaError_t e = cudaIpcOpenMemHandle(&p->peer_vbase[r], all[r].handle, cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) { if (errcode) *errcode = (int) e; free(all); return ACG_ERR_CUDA; }
-    }
-    struct acgb200_p2pdev u = p->h_desc;
-    for (int i = 0; i < halo->nrecipients; i++) {
-        const int q = halo->recipients[i];
-        double *base = p->peer_vbase[q];
-        u.peer_ghost[i][0] = base + all[q].goff;
-        u.peer_ghost[i][1] = base + all[q].vstride + all[q].goff;
-    }
-    u.my_ghost[0] = acgb200_p2p_uvec(p, 0) + p->goff;
-    u.my_ghost[1] = acgb200_p2p_uvec(p, 1) + p->goff;
-    u.ticket = 0;
-    free(all);
-    CUP(cudaMalloc((void **) &p->d_desc_u, sizeof(u)));
-    CUP(cudaMemcpy(p->d_desc_u, &u, sizeof(u), cudaMemcpyHostToDevice));
-    /* classic CG: p is updated in place and a rank cannot be a whole iteration ahead of a
-     * neighbour still reading it (two reductions per iteration), so one vector serves both parities */
-    for (int i = 0; i < halo->nrecipients; i++) u.peer_ghost[i][1] = u.peer_ghost[i][0];
-    u.my_ghost[1] = u.my_ghost[0];
-    CUP(cudaMalloc((void **) &p->d_desc_c, sizeof(u)));
-    CUP(cudaMemcpy(p->d_desc_c, &u, sizeof(u), cudaMemcpyHostToDevice));
-    return ACG_SUCCESS;
-#undef CUP
-}
-
 /* start a new solve: fresh sequence bases above everything published so far
  * (identical on all ranks, which make identical call sequences) */
 int acgb200_p2p_begin(struct acgb200_p2p *p, int maxits, cudaStream_t stream)
@@ -255,12 +187,6 @@ int acgb200_p2p_begin(struct acgb200_p2p *p, int maxits, cudaStream_t stream)
     p->h_desc.timed_out = 0;
     cudaError_t e = cudaMemcpyAsync(&p->d_desc->hbase, &p->h_desc.hbase, 3 * sizeof(unsigned long long),
                                     cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess && p->d_desc_u)
-        e = cudaMemcpyAsync(&p->d_desc_u->hbase, &p->h_desc.hbase, 3 * sizeof(unsigned long long),
-                            cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess && p->d_desc_c)
-        e = cudaMemcpyAsync(&p->d_desc_c->hbase, &p->h_desc.hbase, 3 * sizeof(unsigned long long),
-                            cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     return e == cudaSuccess ? ACG_SUCCESS : ACG_ERR_CUDA;
 }
@@ -268,13 +194,9 @@ int acgb200_p2p_begin(struct acgb200_p2p *p, int maxits, cudaStream_t stream)
 /* after a solve: did any wait for a peer time out? */
 int acgb200_p2p_timed_out(struct acgb200_p2p *p, cudaStream_t stream, int *flag)
 {
-    unsigned long long v = 0, vu = 0, vc = 0;
+    unsigned long long v = 0;
     cudaError_t e = cudaMemcpyAsync(&v, &p->d_desc->timed_out, sizeof(v), cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess && p->d_desc_u)
-        e = cudaMemcpyAsync(&vu, &p->d_desc_u->timed_out, sizeof(vu), cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess && p->d_desc_c)
-        e = cudaMemcpyAsync(&vc, &p->d_desc_c->timed_out, sizeof(vc), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    *flag = v != 0 || vu != 0 || vc != 0;
+    *flag = v != 0;
     return e == cudaSuccess ? ACG_SUCCESS : ACG_ERR_CUDA;
 }

@@ -15,27 +15,11 @@ struct acgb200_p2p {
     struct acgb200_p2pdev h_desc;       /* host mirror */
     struct acgb200_p2pdev *d_desc;      /* device descriptor the kernels read */
     unsigned long long seq;             /* next unused sequence number */
-    /* "unified" variant (acgb200_p2p_unify): the SpMV input vectors live in a second exported
-     * allocation, laid out [owned | pad | ghost], two of them (iteration parity); the peers store
-     * ghost values straight into the tail, so one CSR over owned and ghost columns serves the SpMV */
-    void *vwindow;                      /* this rank's two vectors */
-    size_t vstride;                     /* doubles per vector */
-    int goff;                           /* index of the first ghost entry (owned count rounded up to 16) */
-    void *peer_vbase[ACGB200_MAXR];
-    struct acgb200_p2pdev *d_desc_u;    /* descriptor whose ghost pointers address the vector tails */
-    struct acgb200_p2pdev *d_desc_c;    /* the same with both parities on vector 0 (classic CG keeps one p) */
 };
 
 int acgb200_p2p_init(struct acgb200_p2p *p, const struct acghalo *halo, int borderoff, int nborder,
                      const struct acgcomm *comm, cudaStream_t stream, int *errcode);
 int acgb200_p2p_begin(struct acgb200_p2p *p, int maxits, cudaStream_t stream);
-/* collective: export two [owned | pad | ghost] vectors per rank and build the descriptor variant */
-int acgb200_p2p_unify(struct acgb200_p2p *p, const struct acghalo *halo, int nowned, int nghost,
-                      const struct acgcomm *comm, cudaStream_t stream, int *errcode);
-static inline double *acgb200_p2p_uvec(const struct acgb200_p2p *p, int parity)
-{
-    return (double *) p->vwindow + (size_t) parity * p->vstride;
-}
 void acgb200_p2p_free(struct acgb200_p2p *p);
 /* after a solve: *flag = 1 if a device-side wait for a peer gave up (ACGB200_P2P_TIMEOUT_MS, default 30 s) */
 int acgb200_p2p_timed_out(struct acgb200_p2p *p, cudaStream_t stream, int *flag);

@@ -10,9 +10,9 @@
 
 int64_t acgb200_spmv_min_bytes(const struct acgb200_spmvplan *pl)
 {
-    /* values + (indices unless the tile is compressed) + per row: row pointer, y, x (+ pattern id) */
-    const double frac = pl->ntiles > 0 && pl->compressed ? (double) pl->ncompressed_tiles / pl->ntiles : 0.0;
-    return (int64_t) (pl->nnz * (8.0 + 4.0 * (1.0 - frac)) + pl->nrows * (20.0 + 2.0 * frac));
+    /* tiles: values + indices + per row: row pointer, y, x; slices: padded values + per row: pattern id, y, x */
+    const int64_t tnnz = pl->nnz - pl->slice_nnz, trows = pl->nrows - pl->slice_rows;
+    return tnnz * 12 + trows * 20 + pl->sval_blocks * 256 + (int64_t) pl->slice_rows * 18;
 }
 
 /*

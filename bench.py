@@ -422,10 +422,11 @@ def main():
         peak, peak_src = peaks()
         t_spmv = spmv_ms / max(spmv_n, 1) * 1e-3
         nloc = nown
-        one_kernel = bool(info["last_layout"] & 2)     # the whole pipelined iteration ran as one kernel (SpMV + 12 vector streams)
-        extra = 96.0 * nloc if one_kernel else 0.0
-        achieved = (16.0 * nnz_local + extra) / t_spmv / 1e9
-        min_bytes = float(info["spmv_min_bytes"]) + extra - (8.0 * nloc if one_kernel else 0.0)
+        achieved = 16.0 * nnz_local / t_spmv / 1e9
+        # the SpMV of one vector: rows that repeat a pattern through spmv_slices_kernel, the others through spmv_tiles_kernel
+        kernel_name = ("spmv_slices_kernel" if info["spmv_slice_rows"] == nloc else
+                       "spmv_tiles_kernel" if info["spmv_slices"] == 0 else "spmv_slices_kernel + spmv_tiles_kernel")
+        min_bytes = float(info["spmv_min_bytes"])
         prof = os.path.join(ROOT, "profiles", "r02_ncu_spmv.json")
         traffic_source = None
         if os.path.exists(prof) and world == 1 and args.workload == "27pt-224":
@@ -442,11 +443,11 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "whole acgsolvercuda_solve* call with pinned host b, x: H2D of b and x0, set-up, iterations, D2H of x"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "pcg_fused_kernel" if one_kernel else
-                         ("spmv_ctiles_kernel" if info["spmv_compressed_tiles"] > 0 else "spmv_tiles_kernel"),
+            "roofline": {"bound": "hbm", "kernel": kernel_name,
+                         "slice_rows": info["spmv_slice_rows"], "tile_rows": nloc - info["spmv_slice_rows"],
                          "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "traffic_source": traffic_source,
-                         "bytes_per_launch": 16 * nnz_local + int(extra), "ms_per_launch": t_spmv * 1e3, "launches_timed": spmv_n,
+                         "bytes_per_launch": 16 * nnz_local, "ms_per_launch": t_spmv * 1e3, "launches_timed": spmv_n,
                          "peak_source": peak_src,
                          "min_bytes_per_launch": min_bytes,
                          "achieved_min_traffic_gbs": min_bytes / t_spmv / 1e9,

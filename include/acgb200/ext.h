@@ -16,8 +16,9 @@ extern "C" {
  * tgemv/taxpy like the reference's -DACG_ENABLE_PROFILING, acg/cgcuda.c:69-73),
  * "check_every" (iterations between convergence polls), "spmv_lanes",
  * "spmv_nnz_cap", "spmv_rows_cap", "spmv_stages", "spmv_threads", "spmv_unroll",
- * "spmv_max_ctas" (SpMV tile plan overrides, read at acgsolvercuda_init), "spmv_compress"
- * (0/1, default 0: drop the column indices of tiles whose rows repeat a pattern, compress.c), "graph"
+ * "spmv_max_ctas" (SpMV tile plan overrides, read at acgsolvercuda_init), "spmv_slices"
+ * (0/1, default 1: index-free slice-major storage of the rows that repeat a pattern, slices.c; shape
+ * overrides "slice_ub", "slice_threads", "slice_pf", "slice_max_ctas"), "spmv_medium", "graph"
  * (0/1: replay iteration pairs as CUDA graphs), "redstream" (0/1: pipelined
  * allreduce on its own stream and communicator; read at acgsolvercuda_init).  Environment variables ACGB200_<KEY> set the
  * same values at first use. */
@@ -50,11 +51,13 @@ struct acgb200_info {
     double last_h2d_ms;         /* host time of the b, x0 upload of the last solve */
     double last_d2h_ms;         /* host time of the x download of the last solve */
     double last_blas_ms;        /* device time of the fused vector-update kernels of the last solve (profile=1) */
-    int spmv_compressed_tiles;  /* tiles that carry no column indices (option "spmv_compress") */
+    int reserved0;              /* (round 1: compressed tiles, removed) */
     int64_t spmv_min_bytes;     /* bytes one SpMV launch must move at least, given the plan */
     int spmv_nmedium;           /* rows handled one warp each (option "spmv_medium") */
-    int last_layout;            /* last solve's loop: 0 split local / border x ghost blocks, 1 one CSR over [owned | ghost];
-                                   +2 if the pipelined iteration ran as one kernel */
+    int reserved1;              /* (round 1: loop layout, the variants were removed) */
+    int spmv_slices;            /* 32-row pattern slices multiplied by spmv_slices_kernel (option "spmv_slices", slices.c) */
+    int spmv_slice_rows;        /* rows they cover; the other rows are in tiles */
+    int spmv_slice_ub, spmv_slice_grid;
 };
 ACG_API int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info);
 
@@ -64,10 +67,26 @@ ACG_API int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_in
  * tile; info->spmv_* describe the plan.  For tests of the host logic. */
 ACG_API int acgb200_spmv_plan_host(int nrows, const int64_t *rowptr, struct acgb200_info *info,
                                    int *tiles4, int maxtiles, int *longrows, int maxlong);
-/* same, and with colidx != NULL (0-based) also the compression decision: tiles whose
- * rows are all in the row-pattern dictionary have bit 30 set in their nrows field */
+/* same, and with colidx != NULL (0-based) also the pattern slices: the tiles then skip the rows of
+ * covered slices; info->spmv_slices / spmv_slice_rows count them (acgb200_slices_host lists them) */
 ACG_API int acgb200_spmv_plan_host2(int nrows, const int64_t *rowptr, const int *colidx, struct acgb200_info *info,
                                     int *tiles4, int maxtiles, int *longrows, int maxlong);
+
+/* The pattern-slice plan of a 0-based CSR matrix (slices.c), host only: slices4 gets {row0, nrows,
+ * len, vblk} per covered slice (at most maxslices), covered one byte per 32-row slice, totals
+ * {nslices, value blocks of 32 doubles, nonzeros covered, rows covered, row stride of the padded
+ * offset table, patterns}, spatoff (8192 ints) the zero-padded offset table.  Rows [0,cover_hi) are
+ * eligible. */
+ACG_API int acgb200_slices_host(int nrows, int cover_hi, const int64_t *rowptr, const int *colidx,
+                                int *slices4, int maxslices, unsigned char *covered, int64_t *totals6, int *spatoff);
+
+/* acgsymcsrmatrix_dsymv_init (acg/symcsrmatrix.c:760-851) computed on the current CUDA device
+ * (expand.cu): the packed triangle is uploaded, mirrored there into the full local block and the
+ * border x ghost block, and copied back into A -- arrays byte-identical to the host routine's.
+ * ACG_ERR_CUDA without a device (the host routine is the one to call then).  Programs that only
+ * want to solve need not call either: acgsolvercuda_init expands on the device by itself when the
+ * matrix has no full storage (diagonal shift 0), which also halves the matrix upload. */
+ACG_API int acgsymcsrmatrix_dsymv_init_cuda(struct acgsymcsrmatrix *A, double eps, int *cudaerrcode);
 
 /* One part of the block-partitioned 7- or 27-point stencil matrix on an
  * nx*ny*nz box (diag 6 / 26, neighbours -1, lexicographic numbering, px*py*pz
@@ -117,8 +136,8 @@ ACG_API int acgb200_mtx_read_part(const char *path, int nparts, const int *rowpa
  * exchange; nparts entries. */
 ACG_API int acgb200_comm_matrix_row(const struct acgsymcsrmatrix *A, int nparts, int64_t *row);
 
-/* Row-pattern dictionary of a 0-based CSR matrix (host logic of the index-free
- * SpMV tiles, compress.c).  patptr needs max_entries+1 ints (at most that many
+/* Row-pattern dictionary of a 0-based CSR matrix (host logic of the pattern
+ * slices, compress.c).  patptr needs max_entries+1 ints (at most that many
  * patterns), patoff max_entries ints, patid nrows entries; 0xFFFF in patid
  * marks a row whose pattern is not in the dictionary. */
 ACG_API int acgb200_patterns_host(int nrows, const int64_t *rowptr, const int *colidx, int max_entries,

@@ -68,16 +68,8 @@ def local_matvec(m, h, xl):
 # exchange back-ends of the CG loop (options of acgb200_set_option on top of the defaults)
 BACKEND_OPTIONS = {"p2p-fused": {}, "p2p-unfused": {"p2p_fuse": 0}, "nccl": {"p2p": 0},
                    "nccl-graph": {"p2p": 0, "graph": 2}, "nccl-serial-reduce": {"p2p": 0, "redstream": 0},
-                   "one-kernel": {"pcg_fused": 1}, "one-kernel-split": {"pcg_fused": 1, "p2p_unified": 0},
-                   "all-unified": {"pcg_fused": 1, "p2p_unified": 2}, "two-kernel-unified": {"p2p_unified": 2},
-                   "pdl": {"pdl": 1}, "one-kernel-pdl": {"pcg_fused": 1, "pdl": 1},
+                   "tiles-only": {"spmv_slices": 0}, "pdl": {"pdl": 1},
                    "watchdog": {}}
-
-
-# struct acgb200_info.last_layout the back-end must report (matrices without long rows)
-EXPECTED_LAYOUT = {"p2p-fused": {"solvempi": 0, "solve_pipelined": 0}, "one-kernel": {"solvempi": 0, "solve_pipelined": 3},
-                   "one-kernel-split": {"solvempi": 0, "solve_pipelined": 2}, "all-unified": {"solvempi": 1, "solve_pipelined": 3},
-                   "two-kernel-unified": {"solvempi": 1, "solve_pipelined": 1}}
 
 
 def allsum(v):
@@ -161,7 +153,7 @@ def main():
         assert comm.size() == world and comm.rank() == rank
         b = m.vector(); b.x[:no] = bglob[m.nzrows[:no]]
         methods = []
-        defaults = {"p2p": 1, "p2p_fuse": 1, "graph": 1, "redstream": 1, "pcg_fused": 0, "pdl": 0, "p2p_unified": 1}
+        defaults = {"p2p": 1, "p2p_fuse": 1, "graph": 1, "redstream": 1, "pdl": 0, "spmv_slices": 1}
         for be in (args.backends.split(",") if args.backends else [""]):
             if be:
                 for key, val in {**defaults, **BACKEND_OPTIONS[be]}.items():
@@ -189,10 +181,6 @@ def main():
                 if code != 0:
                     failures.append(f"{tag}{meth}: status {code}")
                 methods.append((tag + meth, x.x[:no].copy(), cg.c.niterations))
-                if be in EXPECTED_LAYOUT and cg.info()["spmv_nlong"] == 0:
-                    want_layout = EXPECTED_LAYOUT[be][meth]
-                    if cg.info()["last_layout"] != want_layout:
-                        failures.append(f"{tag}{meth}: loop layout {cg.info()['last_layout']}, expected {want_layout}")
             # fixed iteration counts, tolerances off
             x = m.vector()
             code = cg.solvempi(b, x, maxits=7)

@@ -110,79 +110,105 @@ int acgb200_spmv_configure(struct acgb200_spmvplan *pl)
     return 0;
 }
 
-/* ---- SpMV ------------------------------------------------------------------ */
-
-/* column of entry k of `row`: from the index array, or -- index-free tile -- rebuilt from the row's
- * pattern (row + offset), as spmv_ctiles_kernel does; returns -1 if the two disagree */
-static int entry_column(const struct acgb200_spmvargs *a, int row, int k, int compressed_tile)
+/* expand.cu stand-in: the reference's serial fill (acg/symcsrmatrix.c:760-851) on the "device" arrays */
+int acgb200_expand_device(int n, int ghost0, int border0, int nob, int64_t pnnz,
+                          const int *prp, const int *pcol, const double *pa, double eps,
+                          int rp_pad, int blk_pad, struct acgb200_expanded *out, cudaStream_t stream)
 {
-    const struct acgb200_spmvplan *pl = a->plan;
-    if (!compressed_tile) return a->colidx[k];
-    const int id = pl->d_patid[row];
-    if (id == (int) ACGB200_NOPATTERN || id >= pl->npat) return -1;
-    const int j = k - a->rowptr[row];
-    if (pl->d_patptr[id] + j >= pl->d_patptr[id + 1]) return -1;
-    const int col = row + pl->d_patoff[pl->d_patptr[id] + j];
-    return col == a->colidx[k] ? col : -1;
+    (void) stream; (void) pnnz;
+    memset(out, 0, sizeof(*out));
+    int *frp = NULL, *orp = NULL;
+    if (cudaMalloc((void **) &frp, ((size_t) n + 1 + (size_t) rp_pad) * sizeof(int))) return 2;
+    if (cudaMalloc((void **) &orp, ((size_t) nob + 1 + (size_t) rp_pad) * sizeof(int))) return 2;
+    memset(frp, 0, ((size_t) n + 1) * sizeof(int));
+    memset(orp, 0, ((size_t) nob + 1) * sizeof(int));
+    for (int i = 0; i < n; i++)
+        for (int k = prp[i]; k < prp[i + 1]; k++) {
+            const int j = pcol[k];
+            if (j < ghost0) { frp[i + 1]++; if (i != j) frp[j + 1]++; }
+            else if (i >= border0) orp[i - border0 + 1]++;
+        }
+    for (int i = 0; i < n; i++) frp[i + 1] += frp[i];
+    for (int i = 0; i < nob; i++) orp[i + 1] += orp[i];
+    const int fnnz = frp[n], onnz = orp[nob];
+    for (int i = 1; i <= rp_pad; i++) { frp[n + i] = fnnz; orp[nob + i] = onnz; }
+    int *fcol = NULL, *ocol = NULL, *cur = calloc((size_t) n + 1, sizeof(int)), *ocur = calloc((size_t) nob + 1, sizeof(int));
+    double *fa = NULL, *oa = NULL;
+    if (cudaMalloc((void **) &fcol, ((size_t) fnnz + (size_t) blk_pad + 1) * sizeof(int))) return 2;
+    if (cudaMalloc((void **) &fa, ((size_t) fnnz + (size_t) blk_pad + 1) * sizeof(double))) return 2;
+    if (cudaMalloc((void **) &ocol, ((size_t) onnz + (size_t) blk_pad + 1) * sizeof(int))) return 2;
+    if (cudaMalloc((void **) &oa, ((size_t) onnz + (size_t) blk_pad + 1) * sizeof(double))) return 2;
+    memset(fcol + fnnz, 0, ((size_t) blk_pad + 1) * sizeof(int)); memset(fa + fnnz, 0, ((size_t) blk_pad + 1) * sizeof(double));
+    memset(ocol + onnz, 0, ((size_t) blk_pad + 1) * sizeof(int)); memset(oa + onnz, 0, ((size_t) blk_pad + 1) * sizeof(double));
+    for (int i = 0; i < n; i++)
+        for (int k = prp[i]; k < prp[i + 1]; k++) {
+            const int j = pcol[k];
+            if (j < ghost0) {
+                int l = frp[i] + cur[i]++;
+                fcol[l] = j; fa[l] = pa[k] + (i == j ? eps : 0.0);
+                if (i != j) { l = frp[j] + cur[j]++; fcol[l] = i; fa[l] = pa[k]; }
+            } else if (i >= border0) {
+                const int l = orp[i - border0] + ocur[i - border0]++;
+                ocol[l] = j - border0; oa[l] = pa[k];
+            }
+        }
+    free(cur); free(ocur);
+    out->d_rowptr = frp; out->d_colidx = fcol; out->d_a = fa;
+    out->d_orowptr = orp; out->d_ocolidx = ocol; out->d_oa = oa;
+    out->fnnz = fnnz; out->onnz = onnz;
+    return 0;
 }
 
-static int hostsim_bad_pattern = 0;
+int acgb200_slices_fill(const struct acgb200_spmvplan *pl, const int *d_rowptr, const double *d_a, cudaStream_t stream)
+{
+    (void) stream;
+    for (int s = 0; s < pl->nslices; s++) {
+        const struct acgb200_slice sl = pl->d_slices[s];
+        for (int lane = 0; lane < 32; lane++) {
+            const int row = sl.row0 + lane, kb = d_rowptr[row], len = d_rowptr[row + 1] - kb;
+            for (int e = 0; e < sl.len; e++)
+                pl->d_sval[((size_t) sl.vblk << 5) + (size_t) e * 32 + lane] = e < len ? d_a[kb + e] : 0.0;
+        }
+    }
+    return 0;
+}
 
-/* What spmv_issue / cspmv_issue stage for one tile: the 16-byte aligned slices of values, column
- * indices and row pointers (pattern ids for index-free tiles), copied with the lengths the TMA
- * copies use -- so a slice that runs past the padded device arrays is a real out-of-bounds read
- * here (AddressSanitizer run, tools/asan_hostsim.sh) -- and checked against the stage capacity
- * the kernel reserves in shared memory.  Returns 0 if the tile does not fit. */
-static int stage_tile(const struct acgb200_spmvargs *a, const struct acgb200_tile *tl, int compressed_tile,
-                      double *vals, int *cols, int *rp, unsigned short *pid)
+/* ---- SpMV ------------------------------------------------------------------ */
+
+
+/* What spmv_issue stages for one tile: the 16-byte aligned slices of values, column indices and row
+ * pointers, copied with the lengths the TMA copies use -- so a slice that runs past the padded device
+ * arrays is a real out-of-bounds read here (AddressSanitizer run, tools/asan_hostsim.sh) -- and
+ * checked against the stage capacity the kernel reserves in shared memory.  Returns 0 if the tile
+ * does not fit. */
+static int stage_tile(const struct acgb200_spmvargs *a, const struct acgb200_tile *tl, double *vals, int *cols, int *rp)
 {
     const struct acgb200_spmvplan *pl = a->plan;
-    const int nrows = tl->nrows & ~ACGB200_TILE_COMPRESSED;
-    const int sc = (pl->nnz_cap + 8 + 3) & ~3, rc = (pl->rows_cap + 1 + 8 + 3) & ~3, pc = (pl->rows_cap + 16 + 7) & ~7;
+    const int sc = (pl->nnz_cap + 8 + 3) & ~3, rc = (pl->rows_cap + 1 + 8 + 3) & ~3;
     const int row_al = tl->row_begin & ~3;
-    const int nrp = (tl->row_begin + nrows + 1 - row_al + 3) & ~3;
+    const int nrp = (tl->row_begin + tl->nrows + 1 - row_al + 3) & ~3;
     if (tl->nnz_al > sc || nrp > rc || (tl->k_al & 3) || (tl->nnz_al & 3)) return 0;
     memcpy(vals, a->a + tl->k_al, (size_t) tl->nnz_al * sizeof(double));
-    if (!compressed_tile) memcpy(cols, a->colidx + tl->k_al, (size_t) tl->nnz_al * sizeof(int));
+    memcpy(cols, a->colidx + tl->k_al, (size_t) tl->nnz_al * sizeof(int));
     memcpy(rp, a->rowptr + row_al, (size_t) nrp * sizeof(int));
-    if (compressed_tile) {
-        const int row_al8 = tl->row_begin & ~7;
-        const int npid = (tl->row_begin + nrows - row_al8 + 7) & ~7;
-        if (npid > pc) return 0;
-        memcpy(pid, pl->d_patid + row_al8, (size_t) npid * sizeof(unsigned short));
-    }
     return 1;
 }
 
 /* one row of a staged tile, indexed as the kernel indexes shared memory */
-static double staged_row(const struct acgb200_spmvargs *a, const struct acgb200_tile *tl, int lr, int compressed_tile,
-                         const double *vals, const int *cols, const int *rp, const unsigned short *pid, const double *x)
+static double staged_row(const struct acgb200_tile *tl, int lr, const double *vals, const int *cols, const int *rp, const double *x)
 {
-    const struct acgb200_spmvplan *pl = a->plan;
     const int *rps = rp + (tl->row_begin & 3);
-    const int kb = rps[lr] - tl->k_al, ke = rps[lr + 1] - tl->k_al, row = tl->row_begin + lr;
+    const int kb = rps[lr] - tl->k_al, ke = rps[lr + 1] - tl->k_al;
     double sum = 0.0;
-    for (int k = kb; k < ke; k++) {
-        int col;
-        if (compressed_tile) {
-            const int id = (pid + (tl->row_begin & 7))[lr];
-            if (id >= pl->npat || pl->d_patptr[id] + (k - kb) >= pl->d_patptr[id + 1]) { hostsim_bad_pattern = 1; return NAN; }
-            col = row + pl->d_patoff[pl->d_patptr[id] + (k - kb)];
-        } else col = cols[k];
-        sum = fma(vals[k], x[col], sum);
-    }
+    for (int k = kb; k < ke; k++) sum = fma(vals[k], x[cols[k]], sum);
     return sum;
 }
 
 /* local block, plus -- fused peer-memory mode -- the border x ghost block with ghosts from the window */
-static double row_product_t(const struct acgb200_spmvargs *a, int row, const double **xg, int iter, int compressed_tile)
+static double row_product(const struct acgb200_spmvargs *a, int row, const double **xg, int iter)
 {
     double sum = 0.0;
-    for (int k = a->rowptr[row]; k < a->rowptr[row + 1]; k++) {
-        const int col = entry_column(a, row, k, compressed_tile);
-        if (col < 0) { hostsim_bad_pattern = 1; return NAN; }
-        sum = fma(a->a[k], a->x[col], sum);
-    }
+    for (int k = a->rowptr[row]; k < a->rowptr[row + 1]; k++) sum = fma(a->a[k], a->x[a->colidx[k]], sum);
     if (a->p2p && row >= a->od_rowoffset) {
         struct acgb200_p2pdev *P = (struct acgb200_p2pdev *) a->p2p;
         if (!*xg) {
@@ -193,11 +219,6 @@ static double row_product_t(const struct acgb200_spmvargs *a, int row, const dou
         for (int k = a->orowptr[ob]; k < a->orowptr[ob + 1]; k++) sum = fma(a->oa[k], (*xg)[a->ocolidx[k]], sum);
     }
     return sum;
-}
-
-static double row_product(const struct acgb200_spmvargs *a, int row, const double **xg, int iter)
-{
-    return row_product_t(a, row, xg, iter, 0);
 }
 
 static void row_epilogue(const struct acgb200_spmvargs *a, int row, double sum, double *dot)
@@ -212,12 +233,51 @@ static void row_epilogue(const struct acgb200_spmvargs *a, int row, double sum, 
     }
 }
 
+/* the slice kernel (spmv_slices_kernel): every covered row through the slice-major values and the
+ * zero-padded offset table, cross-checked against the row's product through the CSR arrays */
+static void slices_exec(const struct acgb200_spmvargs *a, int forward)
+{
+    const struct acgb200_spmvplan *pl = a->plan;
+    const struct gate g = gate_read(a->ctrl_in, a->st);
+    if (forward && a->ctrl_in) {
+        *a->ctrl_out = *a->ctrl_in;
+        if (g.active) {
+            const int s = g.iter & 1;
+            if (a->housekeeping == 1) a->st->rr_loc[s ^ 1] = 0.0;
+            if (a->housekeeping == 2) { a->st->gd_loc[s ^ 1][0] = 0.0; a->st->gd_loc[s ^ 1][1] = 0.0; }
+        }
+    }
+    if (!g.active) return;
+    double dot = 0.0;
+    for (int s = 0; s < pl->nslices; s++) {
+        const struct acgb200_slice sl = pl->d_slices[s];
+        for (int lane = 0; lane < 32; lane++) {
+            const int row = sl.row0 + lane;
+            const int id = pl->d_spatid[row];
+            double sum = 0.0;
+            int bad = id >= pl->slice_npat || sl.nrows != 32;
+            for (int e = 0; e < sl.len && !bad; e++) {
+                const double v = pl->d_sval[((size_t) sl.vblk << 5) + (size_t) e * 32 + lane];
+                const int col = row + pl->d_spatoff[(size_t) id * pl->slice_lpad + e];
+                sum = fma(v, a->x[col], sum);
+            }
+            /* the same row through the CSR arrays, same order */
+            double direct = 0.0;
+            for (int k = a->rowptr[row]; k < a->rowptr[row + 1]; k++) direct = fma(a->a[k], a->x[a->colidx[k]], direct);
+            row_epilogue(a, row, (!bad && sum == direct) ? sum : NAN, &dot);
+        }
+    }
+    if (a->acc) *a->acc += dot;
+}
+
 static void spmv_exec(void *p)
 {
     const struct acgb200_spmvargs *a = p;
     const struct acgb200_spmvplan *pl = a->plan;
+    const int slices_forward = pl->nslices > 0 && pl->ntiles == 0 && !a->p2p;
+    if (pl->nslices > 0) slices_exec(a, slices_forward);
     /* the tile kernel: control word forwarding and housekeeping, then the tiles */
-    if (pl->ntiles > 0 || a->ctrl_in) {
+    if (pl->ntiles > 0 || (a->ctrl_in && !slices_forward)) {
         const struct gate g = gate_read(a->ctrl_in, a->st);
         if (a->ctrl_in) {
             *a->ctrl_out = *a->ctrl_in;
@@ -230,26 +290,23 @@ static void spmv_exec(void *p)
         if (g.active) {
             double dot = 0.0;
             const double *xg = NULL;
-            const int sc = (pl->nnz_cap + 8 + 3) & ~3, rc = (pl->rows_cap + 1 + 8 + 3) & ~3, pc = (pl->rows_cap + 16 + 7) & ~7;
+            const int sc = (pl->nnz_cap + 8 + 3) & ~3, rc = (pl->rows_cap + 1 + 8 + 3) & ~3;
             double *svals = malloc((size_t) sc * sizeof(double));
             int *scols = malloc((size_t) sc * sizeof(int)), *srp = malloc((size_t) rc * sizeof(int));
-            unsigned short *spid = malloc((size_t) pc * sizeof(unsigned short));
             for (int t = 0; t < pl->ntiles; t++) {
                 const struct acgb200_tile tl = pl->d_tiles[t];
-                const int nrows = tl.nrows & ~ACGB200_TILE_COMPRESSED;
-                const int cmp = pl->compressed && (tl.nrows & ACGB200_TILE_COMPRESSED) != 0;
-                const int staged = stage_tile(a, &tl, cmp, svals, scols, srp, spid);
-                if (a->p2p && !xg && tl.row_begin + nrows > a->od_rowoffset) {
+                const int staged = stage_tile(a, &tl, svals, scols, srp);
+                if (a->p2p && !xg && tl.row_begin + tl.nrows > a->od_rowoffset) {
                     /* as in the kernel: wait for the neighbours before the first tile that reaches the
-                     * border rows touches anything (unified layout: ghosts come through the column indices) */
+                     * border rows touches anything */
                     struct acgb200_p2pdev *P = (struct acgb200_p2pdev *) a->p2p;
                     p2p_wait_halo(P, P->hbase + (unsigned long long) g.iter);
                     xg = P->my_ghost[g.iter & 1] - a->od_nrows;
                 }
-                for (int r = tl.row_begin; r < tl.row_begin + nrows; r++) {
+                for (int r = tl.row_begin; r < tl.row_begin + tl.nrows; r++) {
                     /* the product through the staged slices must be the product through the arrays */
-                    const double direct = row_product_t(a, r, &xg, g.iter, cmp);
-                    double via_stage = staged ? staged_row(a, &tl, r - tl.row_begin, cmp, svals, scols, srp, spid, a->x) : NAN;
+                    const double direct = row_product(a, r, &xg, g.iter);
+                    double via_stage = staged ? staged_row(&tl, r - tl.row_begin, svals, scols, srp, a->x) : NAN;
                     if (staged && a->p2p && r >= a->od_rowoffset && xg) {
                         const int ob = r - a->od_rowoffset;
                         for (int k = a->orowptr[ob]; k < a->orowptr[ob + 1]; k++) via_stage = fma(a->oa[k], xg[a->ocolidx[k]], via_stage);
@@ -257,7 +314,7 @@ static void spmv_exec(void *p)
                     row_epilogue(a, r, (staged && via_stage == direct) ? direct : NAN, &dot);
                 }
             }
-            free(svals); free(scols); free(srp); free(spid);
+            free(svals); free(scols); free(srp);
             if (a->acc) *a->acc += dot;
             if (a->p2p && a->pub_ch >= 0 && a->p2p->fuse) {
                 struct acgb200_p2pdev *P = (struct acgb200_p2pdev *) a->p2p;
@@ -500,7 +557,7 @@ static void pcg_update_exec(void *vp)
         a->z[i] = zv; a->t[i] = tv; a->p[i] = pv;
         a->x[i] = fma(alpha, pv, a->x[i]);
         a->r[i] = rv;
-        if (a->wout) a->wout[i] = wv; else a->w[i] = wv;
+        a->w[i] = wv;
         g2 = fma(rv, rv, g2);
         d2 = fma(wv, rv, d2);
         if (push && i >= first) p2p_push_row(P, i, s ^ 1, wv);
@@ -524,121 +581,6 @@ int acgb200_pcg_update(int n, struct acgb200_devstate *st, int cin, int cout, in
     a.n = n; a.st = st; a.cin = cin; a.cout = cout; a.multi = multi; a.P = p2p;
     a.q = q; a.z = z; a.w = w; a.t = t; a.p = p; a.r = r; a.x = x;
     return hostsim_run_or_record(pcg_update_exec, &a, sizeof(a));
-}
-
-int acgb200_pcg_update_db(int n, struct acgb200_devstate *st, int cin, int cout, int multi, struct acgb200_p2pdev *p2p,
-                          const double *q, double *z, double *w_in, double *w_out, double *t, double *p, double *r, double *x,
-                          cudaStream_t stream)
-{
-    (void) stream;
-    struct upd_args a;
-    memset(&a, 0, sizeof(a));
-    a.n = n; a.st = st; a.cin = cin; a.cout = cout; a.multi = multi; a.P = p2p;
-    a.q = q; a.z = z; a.w = w_in; a.wout = w_out; a.t = t; a.p = p; a.r = r; a.x = x;
-    return hostsim_run_or_record(pcg_update_exec, &a, sizeof(a));
-}
-
-/* ---- pipelined CG, one kernel per iteration ----------------------------------- */
-
-struct fused_args {
-    struct acgb200_spmvargs sp;
-    int cin, multi;
-    double *z, *t, *p, *r, *x, *w0, *w1;
-};
-
-int acgb200_pcg_fused_grid(const struct acgb200_spmvplan *pl)
-{
-    if (pl->nlong > 0 || pl->nmed > 0 || pl->threads != 128 || pl->unroll != 8 ||
-        pl->rows_cap > pl->threads / pl->lanes_per_row) return 0;
-    return 1;
-}
-
-static void fused_exec(void *vp)
-{
-    const struct fused_args *a = vp;
-    const struct acgb200_spmvplan *pl = a->sp.plan;
-    struct acgb200_devstate *st = a->sp.st;
-    const struct gate g = gate_read(&st->ctrl[a->cin], st);
-    const int s = g.iter & 1;
-    struct acgb200_p2pdev *P = (struct acgb200_p2pdev *) a->sp.p2p;
-    double gamma, delta;
-    if (P && g.active && g.iter > 0) {
-        double glob[2];
-        p2p_reduce(P, 0, s, P->rbase + (unsigned long long) g.iter, glob);
-        gamma = glob[0]; delta = glob[1];
-    } else {
-        gamma = a->multi ? st->gd[s][0] : st->gd_loc[s][0];
-        delta = a->multi ? st->gd[s][1] : st->gd_loc[s][1];
-    }
-    const double gamma_prev = st->prev[s][0], alpha_prev = st->prev[s][1];
-    const int conv = st->tol > 0.0 && sqrt(gamma) < st->tol;
-    const double beta = gamma / gamma_prev;
-    const double alpha = gamma / (delta - beta * gamma / alpha_prev);
-    struct acgb200_ctrl c = st->ctrl[a->cin];
-    if (g.active) {
-        st->gd[s][0] = gamma; st->gd[s][1] = delta;
-        if (conv) { c.done = 1; st->final_rr = gamma; }
-        else { c.iter = g.iter + 1; st->prev[s ^ 1][0] = gamma; st->prev[s ^ 1][1] = alpha; }
-    }
-    st->ctrl[a->cin ^ 1] = c;
-    if (!g.active || conv) return;
-    const double *wold = s ? a->w1 : a->w0;
-    double *wnew = s ? a->w0 : a->w1;
-    double g2 = 0.0, d2 = 0.0;
-    const double *xg = NULL;
-    for (int t = 0; t < pl->ntiles; t++) {
-        const struct acgb200_tile tl = pl->d_tiles[t];
-        const int nrows = tl.nrows & ~ACGB200_TILE_COMPRESSED;
-        if (P && !xg && tl.row_begin + nrows > a->sp.od_rowoffset) {
-            /* as in the kernel: the first tile that reaches the border rows waits for the neighbours'
-             * values BEFORE any of its gathers -- with the unified layout the ghost values are read
-             * through the ordinary column indices */
-            p2p_wait_halo(P, P->hbase + (unsigned long long) g.iter);
-            xg = P->my_ghost[s] - a->sp.od_nrows;
-        }
-        for (int row = tl.row_begin; row < tl.row_begin + nrows; row++) {
-            double qv = 0.0;
-            for (int k = a->sp.rowptr[row]; k < a->sp.rowptr[row + 1]; k++) qv = fma(a->sp.a[k], wold[a->sp.colidx[k]], qv);
-            if (P && row >= a->sp.od_rowoffset) {
-                const int ob = row - a->sp.od_rowoffset;
-                for (int k = a->sp.orowptr[ob]; k < a->sp.orowptr[ob + 1]; k++) qv = fma(a->sp.oa[k], xg[a->sp.ocolidx[k]], qv);
-            }
-            const double wv0 = wold[row], rv0 = a->r[row];
-            const double zv = fma(beta, a->z[row], qv);
-            const double tv = fma(beta, a->t[row], wv0);
-            const double pv = fma(beta, a->p[row], rv0);
-            const double rv = fma(-alpha, tv, rv0);
-            const double wv = fma(-alpha, zv, wv0);
-            a->z[row] = zv; a->t[row] = tv; a->p[row] = pv;
-            a->x[row] = fma(alpha, pv, a->x[row]);
-            a->r[row] = rv; wnew[row] = wv;
-            g2 = fma(rv, rv, g2);
-            d2 = fma(wv, rv, d2);
-            if (P && row >= P->borderoff) p2p_push_row(P, row, s ^ 1, wv);
-        }
-    }
-    st->gd_loc[s ^ 1][0] += g2;
-    st->gd_loc[s ^ 1][1] += d2;
-    if (P) {
-        const unsigned long long it1 = (unsigned long long) g.iter + 1ull;
-        p2p_publish_red(P, 0, s ^ 1, P->rbase + it1, &st->gd_loc[s ^ 1][0], 2);
-        p2p_publish_halo(P, P->hbase + it1);
-    }
-    /* last CTA: clear the slot this launch read */
-    st->gd_loc[s][0] = 0.0; st->gd_loc[s][1] = 0.0;
-}
-
-int acgb200_pcg_fused_launch(const struct acgb200_spmvargs *sp, int grid, int cin, int multi,
-                             double *z, double *t, double *p, double *r, double *x, double *w0, double *w1,
-                             cudaStream_t stream)
-{
-    (void) stream;
-    if (grid < 1) return 1;
-    struct fused_args a;
-    memset(&a, 0, sizeof(a));
-    a.sp = *sp; a.cin = cin; a.multi = multi;
-    a.z = z; a.t = t; a.p = p; a.r = r; a.x = x; a.w0 = w0; a.w1 = w1;
-    return hostsim_run_or_record(fused_exec, &a, sizeof(a));
 }
 
 /* ---- set-up helpers ------------------------------------------------------------ */

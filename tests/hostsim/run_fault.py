@@ -13,13 +13,13 @@ from acg_b200 import matgen as mg                    # noqa: E402
 
 n, r, c, v = mg.stencil3d_27pt(7)
 A = ab.SymCsrMatrix.init_real_double(n, r, c, v).dsymv_init(0.0)
-ab.set_option("spmv_compress", 1)
 try:
-    cg = ab.SolverCuda(A)
+    cg = ab.SolverCuda(A)                             # pattern slices + tiles (default)
     b = A.vector(); b.x[:] = 1.0; x = A.vector()
     cg.solvempi(b, x, maxits=8, warmup=1)
     cg.solve_pipelined(b, x, maxits=8, warmup=1)
-    ab.set_option("pcg_fused", 1)
+    cg.free()
+    cg = ab.SolverCuda(ab.SymCsrMatrix.init_real_double(n, r, c, v))      # no full storage: device-side expansion
     cg.solve_pipelined(b, x, maxits=8)
     cg.free()
     print("ok")

@@ -309,37 +309,46 @@ def test_power_law_properties(n, edges, ab):
     cg.free()
 
 
-@pytest.mark.skipif(os.environ.get("ACGB200_TEST_EXPERIMENTAL") != "1",
-                    reason="index-free SpMV tiles are opt-in and not yet validated on hardware "
-                           "(set ACGB200_TEST_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("name,gen", [CASES[0], CASES[1], CASES[2], CASES[5]], ids=[CASES[i][0] for i in (0, 1, 2, 5)])
-def test_compressed_tiles_match_oracle(name, gen, ab, oracle):
-    """Option spmv_compress=1 (compress.c, spmv_ctiles_kernel): same results."""
+SLICE_CASES = [CASES[0], CASES[1], CASES[2], CASES[3]]
+
+
+@pytest.mark.parametrize("ub,pf", [(0, 1), (9, 0), (4, 1), (7, 0), (14, 1), (3, 1)])
+@pytest.mark.parametrize("name,gen", SLICE_CASES, ids=[c[0] for c in SLICE_CASES])
+def test_pattern_slices_match_oracle(name, gen, ub, pf, ab, oracle):
+    """spmv_slices_kernel (slices.c): rows that repeat a pattern are multiplied from slice-major
+    values without indices; every batch width / prefetch variant gives the oracle's product, the
+    fused dots of both CG loops included, and agrees with the tile kernel (option off) to rounding."""
     n, r, c, v = gen()
-    ab.set_option("spmv_compress", 1)
+    ab.set_option("slice_ub", ub); ab.set_option("slice_pf", pf)
     try:
         A, cg = _solver(ab, n, r, c, v)
+        ab.set_option("spmv_slices", 0)
+        cg_tiles = ab.SolverCuda(A)
     finally:
-        ab.set_option("spmv_compress", 0)
+        ab.set_option("spmv_slices", 1); ab.set_option("slice_ub", 0); ab.set_option("slice_pf", -1)
+    inf = cg.info()
+    assert inf["spmv_slices"] > 0 and inf["spmv_slice_rows"] == 32 * inf["spmv_slices"]
+    assert cg_tiles.info()["spmv_slices"] == 0
     csr = (A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy())
     x = np.random.default_rng(1).standard_normal(n)
     y, _ = cg.spmv(x)
+    y2, _ = cg_tiles.spmv(x)
     want = oracle.dsymv(csr, 1.0, x, 0.0, np.zeros(n))
     scale = oracle.dsymv((csr[0], csr[1], np.abs(csr[2])), 1.0, np.abs(x), 0.0, np.zeros(n))
     assert np.all(np.abs(y - want) <= SPMV_RTOL * scale + 1e-300)
-    if name != "rmat-longrows":
-        assert cg.info()["spmv_compressed_tiles"] > 0
+    assert np.all(np.abs(y - y2) <= SPMV_RTOL * scale + 1e-300)
+    if name != "1d5pt":
         b = A.vector(); b.x[:] = 1.0
-        xs = A.vector()
-        ref = oracle.cg(csr, b.x, maxits=300, rtol=1e-9)
-        assert cg.solvempi(b, xs, maxits=300, residualrtol=1e-9) == 0 and cg.c.niterations == ref["niterations"]
-        assert np.abs(xs.x - ref["x"]).max() <= 1e-9 * np.abs(ref["x"]).max()
-    cg.free()
+        for method, oname in (("solvempi", "cg"), ("solve_pipelined", "cg_pipelined")):
+            xs = A.vector()
+            ref = getattr(oracle, oname)(csr, b.x, maxits=300, rtol=1e-9)
+            assert getattr(cg, method)(b, xs, maxits=300, residualrtol=1e-9) == 0
+            assert cg.c.niterations == ref["niterations"]
+            assert np.abs(xs.x - ref["x"]).max() <= 1e-9 * np.abs(ref["x"]).max()
+            assert abs(cg.c.rnrm2 - ref["rnrm2"]) <= RES_RTOL * ref["r0nrm2"]
+    cg.free(); cg_tiles.free()
 
 
-@pytest.mark.skipif(os.environ.get("ACGB200_TEST_EXPERIMENTAL") != "1",
-                    reason="programmatic dependent launch is opt-in and not yet validated on hardware "
-                           "(set ACGB200_TEST_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("method", ["solvempi", "solve_pipelined"])
 def test_pdl_matches_oracle(method, ab, oracle):
     """Option pdl=1 (griddepcontrol along the iteration chain, also inside the captured
@@ -360,49 +369,6 @@ def test_pdl_matches_oracle(method, ab, oracle):
     cg.free()
 
 
-@pytest.mark.skipif(os.environ.get("ACGB200_TEST_EXPERIMENTAL") != "1",
-                    reason="the one-kernel pipelined iteration is opt-in and not yet validated on hardware "
-                           "(set ACGB200_TEST_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("compress", [0, 1], ids=["csr-tiles", "index-free-tiles"])
-@pytest.mark.parametrize("name,gen", [CASES[0], CASES[1], CASES[2], CASES[4], CASES[7]],
-                         ids=[CASES[i][0] for i in (0, 1, 2, 4, 7)])
-def test_fused_pipelined_iteration_matches_oracle(name, gen, compress, ab, oracle):
-    """Option pcg_fused=1 (pcg_fused_kernel: q = A w and the vector update in one launch,
-    w double-buffered): same iterates, iteration count, norms and return codes as the
-    two-kernel pipelined loop, with and without tolerances, odd and even iteration counts."""
-    n, r, c, v = gen()
-    ab.set_option("spmv_compress", compress)
-    try:
-        A, cg = _solver(ab, n, r, c, v)
-    finally:
-        ab.set_option("spmv_compress", 0)
-    csr = (A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy())
-    b = A.vector(); b.x[:] = np.random.default_rng(5).standard_normal(n)
-    ab.set_option("pcg_fused", 1)
-    try:
-        want = oracle.cg_pipelined(csr, b.x, maxits=300, rtol=1e-9)
-        x = A.vector()
-        assert cg.solve_pipelined(b, x, maxits=300, residualrtol=1e-9, warmup=1) == 0
-        assert cg.c.niterations == want["niterations"]
-        assert cg.c.rnrm2 / cg.c.r0nrm2 == pytest.approx(want["rnrm2"] / want["r0nrm2"], rel=1e-6, abs=RES_RTOL)
-        assert np.abs(x.x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
-        for its in (1, 2, 7, 12):                                   # tolerances off: exactly `its` iterations
-            if n < 4 and its > 2:
-                continue
-            want = oracle.cg_pipelined(csr, b.x, maxits=its, rtol=0.0)
-            x = A.vector()
-            assert cg.solve_pipelined(b, x, maxits=its) == 0 and cg.c.niterations == its
-            assert cg.c.rnrm2 == pytest.approx(want["rnrm2"], rel=1e-8)
-            assert np.abs(x.x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
-        assert cg.solve_pipelined(b, x, maxits=2, residualrtol=1e-30) == 39     # ACG_ERR_NOT_CONVERGED
-    finally:
-        ab.set_option("pcg_fused", 0)
-    cg.free()
-
-
-@pytest.mark.skipif(os.environ.get("ACGB200_TEST_EXPERIMENTAL") != "1",
-                    reason="the warp-per-row kernel for medium rows is opt-in and not yet validated on hardware "
-                           "(set ACGB200_TEST_EXPERIMENTAL=1)")
 def test_medium_row_kernel_matches_oracle(ab, oracle):
     """Option spmv_medium (spmv_medium_kernel): same product and same CG iterates on a power-law matrix."""
     n, r, c, v = mg.rmat_spd(30000, 600000, seed=8)

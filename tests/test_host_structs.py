@@ -336,10 +336,11 @@ def test_stencil_part_large_is_cheap(ab):
 
 @pytest.mark.parametrize("name,gen", [("27pt", lambda: mg.stencil3d_27pt(10, 9, 11)), ("7pt", lambda: mg.laplace3d_7pt(12)),
                                       ("27pt-part", None)], ids=["27pt", "7pt", "27pt-part"])
-def test_compressed_tile_arithmetic_emulated(name, gen, ab, oracle):
-    """Emulation of the index arithmetic of spmv_ctiles_kernel on the CPU, from
-    exactly the arrays the device gets (tile descriptors with their aligned
-    slice starts, pattern ids, pattern table): y = A x tile by tile."""
+def test_slices_and_tiles_arithmetic_emulated(name, gen, ab, oracle):
+    """Emulation on the CPU of the index arithmetic of slices_fill_kernel + spmv_slices_kernel and of
+    spmv_tiles_kernel, from exactly the arrays the device gets (slice descriptors, zero-padded offset
+    table, pattern ids; tile descriptors with their aligned slice starts): every row is computed
+    exactly once and y = A x."""
     if gen is None:
         from acg_b200 import dist as abdist
         n, r, c, v = mg.stencil3d_27pt(12)
@@ -352,33 +353,47 @@ def test_compressed_tile_arithmetic_emulated(name, gen, ab, oracle):
         n, r, c, v = gen()
         rowptr, colidx, vals = oracle.full_csr(n, r, c, v)
         no = nvec = n
-    plan = ab.spmv_plan_host(rowptr, colidx)
+    plan = ab.spmv_plan_host(rowptr, colidx)          # tiles around the covered slices
+    sp = ab.slices_host(rowptr, colidx)
     pat = ab.patterns_host(rowptr, colidx)
-    assert plan["compressed"].sum() > 0.5 * len(plan["tiles"])
+    assert sp["nslices"] > 0 and plan["slices"] == sp["nslices"] and plan["slice_rows"] == sp["rows"]
     x = np.random.default_rng(3).standard_normal(nvec)
     y = np.zeros(no)
-    patid_dev = np.concatenate([pat["patid"], np.zeros(16, np.uint16)])         # device array is padded
-    for (row_begin, nrows, k_al, nnz_al), cmp in zip(plan["tiles"], plan["compressed"]):
-        # what cspmv_issue stages: values slice, row-pointer slice, pattern-id slice
+    count = np.zeros(no, dtype=int)
+    lpad, table = sp["lpad"], sp["spatoff"]
+    # slices_fill_kernel: slice-major values, rows padded with zeros
+    sval = np.full(32 * sp["blocks"], np.nan)
+    for row0, _, L, vblk in sp["slices"]:
+        for lane in range(32):
+            kb, ln = rowptr[row0 + lane], rowptr[row0 + lane + 1] - rowptr[row0 + lane]
+            for e in range(L):
+                sval[32 * vblk + 32 * e + lane] = vals[kb + e] if e < ln else 0.0
+    assert not np.isnan(sval).any()
+    # spmv_slices_kernel: lane = row, column = row + table[pattern][slot]
+    for row0, _, L, vblk in sp["slices"]:
+        for lane in range(32):
+            row = row0 + lane
+            offs = table[int(pat["patid"][row]) * lpad:][:lpad]
+            acc = 0.0
+            for e in range(L):
+                acc += sval[32 * vblk + 32 * e + lane] * x[row + offs[e]]
+            y[row] = acc
+            count[row] += 1
+    for row_begin, nrows, k_al, nnz_al in plan["tiles"]:
+        # what spmv_issue stages: values / indices slice, row-pointer slice
         vals_s = np.concatenate([vals, np.zeros(16)])[k_al:k_al + nnz_al]
+        cols_s = np.concatenate([colidx, np.zeros(16, colidx.dtype)])[k_al:k_al + nnz_al]
         row_al = row_begin & ~3
         nrp = (row_begin + nrows + 1 - row_al + 3) & ~3
         rptr_s = np.concatenate([rowptr, np.full(8, rowptr[-1])])[row_al:row_al + nrp]
-        row_al8 = row_begin & ~7
-        npid = (row_begin + nrows - row_al8 + 7) & ~7
-        pid_s = patid_dev[row_al8:row_al8 + npid]
         rp = rptr_s[row_begin & 3:]
-        pid = pid_s[row_begin & 7:]
         for lr in range(nrows):
             row = row_begin + lr
             kb, ke = rp[lr] - k_al, rp[lr + 1] - k_al
             assert 0 <= kb <= ke <= nnz_al
-            if cmp:
-                base = pat["patptr"][pid[lr]] - kb                 # offs = patoff_s + patptr_s[pid] - kb
-                cols = np.array([row + pat["patoff"][base + kk] for kk in range(kb, ke)], dtype=np.int64)
-            else:
-                cols = colidx[k_al + kb:k_al + ke]                 # gcol = colidx + k_al
-            y[row] = vals_s[kb:ke] @ x[cols] if ke > kb else 0.0
+            y[row] = vals_s[kb:ke] @ x[cols_s[kb:ke]] if ke > kb else 0.0
+            count[row] += 1
+    assert (count == 1).all()
     want = np.zeros(no)
     for i in range(no):
         want[i] = vals[rowptr[i]:rowptr[i + 1]] @ x[colidx[rowptr[i]:rowptr[i + 1]]]

@@ -52,6 +52,18 @@ RUNS = [{"method": "solvempi", "maxits": 200, "rtol": 1e-9, "warmup": 2},
         {"method": "solve_device", "maxits": 9}, {"method": "solve_device_pipelined", "maxits": 8}]
 
 
+@pytest.mark.parametrize("slices", [1, 0], ids=["slices", "tiles-only"])
+def test_pattern_slices_and_device_expansion(slices, simlib):
+    """The stencil's rows go to pattern slices (slices.c) and the rest to tiles -- the stand-in fails a row
+    the two plans forget or cover twice; and a matrix without full storage is expanded on the device by
+    acgsolvercuda_init (expand_host.c; here the stand-in's serial fill) with the same results."""
+    out = _run({"matrix": "27pt", "options": {"spmv_slices": slices}, "no_full_storage": 1, "runs": RUNS[:4] + RUNS[7:9]})
+    _check(out)
+    assert (out["slices"] > 0) == bool(slices) and out["slice_rows"] == 32 * out["slices"]
+    if slices:
+        assert out["slice_rows"] >= 600 and out["ntiles"] >= 1        # 720 rows: most of the 22 full slices; the ragged end and padding-heavy slices in tiles
+
+
 @pytest.mark.parametrize("matrix", ["27pt", "7pt"])
 @pytest.mark.parametrize("graph", [1, 0], ids=["graph-replay", "direct"])
 def test_default_loops(matrix, graph, simlib):
@@ -65,21 +77,10 @@ def test_default_loops(matrix, graph, simlib):
     assert launches[("solvempi", 7)] == 3 * 7 + 1 and launches[("solve_pipelined", 12)] == 2 * 12 + 2
 
 
-def test_one_kernel_pipelined_iteration(simlib):
-    """Option pcg_fused: the control words alternate, the accumulator slot is cleared by the
-    launch that read it, gamma of the last tested iterate is found where the host looks for it."""
-    out = _run({"matrix": "27pt", "options": {"pcg_fused": 1}, "runs": RUNS})
-    _check(out)
-    launches = {(r["method"], r["maxits"]): r["launches"] for r in out["runs"]}
-    assert launches[("solve_pipelined", 12)] == 12 + 2 and launches[("solve_pipelined", 1)] == 1 + 2
-    assert launches[("solvempi", 7)] == 3 * 7 + 1            # the classic loop is untouched by the option
-
-
-@pytest.mark.parametrize("options", [{}, {"spmv_medium": 64}, {"spmv_medium": 64, "pcg_fused": 1}],
-                         ids=["plain", "medium-rows", "medium-rows+fused-requested"])
+@pytest.mark.parametrize("options", [{}, {"spmv_medium": 64}], ids=["plain", "medium-rows"])
 def test_power_law_rows(options, simlib):
     """Long rows (and, on request, medium rows) leave the tiles; every row is still computed
-    exactly once; the one-kernel iteration steps aside when such rows exist."""
+    exactly once."""
     spec = {"matrix": "rmat", "options": options,
             "runs": [{"method": "solvempi", "maxits": 10}, {"method": "solve_pipelined", "maxits": 11},
                      {"method": "solve_pipelined", "maxits": 6, "warmup": 2}]}
@@ -92,7 +93,7 @@ def test_power_law_rows(options, simlib):
 
 
 def test_tiny_system(simlib):
-    out = _run({"matrix": "n3", "options": {"pcg_fused": 1},
+    out = _run({"matrix": "n3", "options": {},
                 "runs": [{"method": "solve_pipelined", "maxits": 2}, {"method": "solvempi", "maxits": 10, "rtol": 1e-12}]})
     _check(out)
 
@@ -135,9 +136,9 @@ def _free_port():
 
 
 @pytest.mark.parametrize("nproc,matrix,size,partition,backends,extra", [
-    (2, "27pt", 8, "block", "p2p-fused,p2p-unfused,nccl,nccl-graph,nccl-serial-reduce,one-kernel,one-kernel-split,all-unified,two-kernel-unified", []),
-    (3, "7pt", 9, "slab", "watchdog,p2p-fused,one-kernel,all-unified,nccl", []),
-    (4, "rmat", 3000, "random", "p2p-fused,one-kernel", ["--maxits", "12", "--rtol", "0"]),
+    (2, "27pt", 8, "block", "p2p-fused,p2p-unfused,nccl,nccl-graph,nccl-serial-reduce,tiles-only", []),
+    (3, "7pt", 9, "slab", "watchdog,p2p-fused,tiles-only,nccl", []),
+    (4, "rmat", 3000, "random", "p2p-fused,nccl", ["--maxits", "12", "--rtol", "0"]),
 ], ids=["2-ranks-all-backends", "3-ranks", "4-ranks-power-law"])
 def test_multi_rank_loops(nproc, matrix, size, partition, backends, extra, simlib):
     """The distributed solver, one process per rank: the library's host code on the stand-in,
@@ -145,9 +146,8 @@ def test_multi_rank_loops(nproc, matrix, size, partition, backends, extra, simli
     are really shared between the processes, NCCL replaced by a file-based stand-in, and the
     simulated kernels speaking the exchange protocol of kernels.cu (sequence-numbered flags,
     parity-buffered ghost values and reduction slots).  Every loop back-end -- peer memory with
-    and without the pushes fused into the kernels, the one-kernel pipelined iteration (with the unified
-    [owned | ghost] layout and with the split one), NCCL with
-    and without graph replay and with the reduction on the main stream -- must reproduce the
+    and without the pushes fused into the kernels, with and without pattern slices for the interior rows, NCCL
+    with and without graph replay and with the reduction on the main stream -- must reproduce the
     single-rank oracle.  What this cannot see: anything inside the CUDA kernels, and stream-level
     concurrency on a real device."""
     worker = os.path.join(ROOT, "tests", "_dist_worker.py")
@@ -276,18 +276,6 @@ def test_c_example_program(simlib, tmp_path):
         x = np.array([float(t) for t in p.stdout.splitlines()[2:]])
         assert len(x) == n and np.abs(x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
         assert f"iterations: {want['niterations']}" in p.stderr
-
-
-@pytest.mark.parametrize("fused", [0, 1], ids=["two-kernel", "one-kernel"])
-def test_index_free_tile_plan_in_the_solver(fused, simlib):
-    """Option spmv_compress through acgsolvercuda_init: dictionary, pattern ids and tile flags reach
-    the "device"; the stand-in SpMV rebuilds the columns of compressed tiles from them (row + offset)
-    and refuses any entry that disagrees with the index array."""
-    out = _run({"matrix": "27pt", "options": {"spmv_compress": 1, "pcg_fused": fused},
-                "runs": [{"method": "solvempi", "maxits": 9}, {"method": "solve_pipelined", "maxits": 200, "rtol": 1e-9},
-                         {"method": "solve_pipelined", "maxits": 7}]})
-    _check(out)
-    assert out["compressed_tiles"] > 0.5 * out["ntiles"]
 
 
 @pytest.mark.parametrize("solver,method", [("acg", "cg"), ("acg-pipelined", "cg_pipelined"),

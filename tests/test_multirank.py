@@ -60,7 +60,7 @@ def _ngpu():
 _ALL = os.environ.get("ACGB200_TEST_ALL_BACKENDS") == "1"
 _BACKENDS = "p2p-fused,p2p-unfused,nccl,nccl-graph" if _ALL else "p2p-fused"
 if os.environ.get("ACGB200_TEST_EXPERIMENTAL") == "1":
-    _BACKENDS += ",one-kernel,one-kernel-split,all-unified,two-kernel-unified,pdl,one-kernel-pdl"
+    _BACKENDS += ",tiles-only,pdl"
 
 
 @pytest.mark.gpu

@@ -21,28 +21,32 @@ sys.path.insert(0, ROOT)
 import numpy as np          # noqa: E402
 
 DEFAULTS = dict(profile=0, spmv_lanes=0, spmv_nnz_cap=0, spmv_rows_cap=0, spmv_stages=0, spmv_threads=0,
-                spmv_unroll=0, spmv_max_ctas=0, graph=1, redstream=1, p2p=1, p2p_fuse=1, spmv_compress=0,
-                blas1_ctas=0, pdl=0, pcg_fused=0, spmv_medium=0, p2p_unified=1)
+                spmv_unroll=0, spmv_max_ctas=0, graph=1, redstream=1, p2p=1, p2p_fuse=1, blas1_ctas=0, pdl=0,
+                spmv_medium=0, spmv_slices=1, slice_ub=0, slice_threads=0, slice_pf=-1, slice_max_ctas=0)
 
 VARIANTS = {
     "base": {},
+    "noslices": {"spmv_slices": 0},
     "oldgrid": {"blas1_ctas": 4},
     "pdl": {"pdl": 1},
-    "compress": {"spmv_compress": 1},
-    "onekernel": {"pcg_fused": 1},
-    "onekernel_pdl": {"pcg_fused": 1, "pdl": 1},
-    "onekernel_compress": {"pcg_fused": 1, "spmv_compress": 1},
-    "compress_pdl": {"spmv_compress": 1, "pdl": 1},
     "nograph": {"graph": 0},
     "med128": {"spmv_medium": 128},
     "med256": {"spmv_medium": 256},
     "med64": {"spmv_medium": 64},
+    "med32": {"spmv_medium": 32},
     "nccl": {"p2p": 0},
     "nccl_graph": {"p2p": 0, "graph": 2},
     "unfused": {"p2p_fuse": 0},
-    "onekernel_split": {"pcg_fused": 1, "p2p_unified": 0},
-    "unified2": {"p2p_unified": 2},
-    "merge": {"spmv_merge": 1},
+    # slice kernel shapes: s<ub>[p][_t<threads>][_c<max ctas>]  (p = prefetch the next batch)
+    "s9": {"slice_ub": 9, "slice_pf": 0}, "s9p": {"slice_ub": 9, "slice_pf": 1},
+    "s4": {"slice_ub": 4, "slice_pf": 0}, "s4p": {"slice_ub": 4, "slice_pf": 1},
+    "s3p": {"slice_ub": 3, "slice_pf": 1}, "s5p": {"slice_ub": 5, "slice_pf": 1}, "s5": {"slice_ub": 5, "slice_pf": 0},
+    "s7": {"slice_ub": 7, "slice_pf": 0}, "s7p": {"slice_ub": 7, "slice_pf": 1},
+    "s8p": {"slice_ub": 8, "slice_pf": 1}, "s14": {"slice_ub": 14, "slice_pf": 0}, "s14p": {"slice_ub": 14, "slice_pf": 1},
+    "s9p_t256": {"slice_ub": 9, "slice_pf": 1, "slice_threads": 256}, "s9_t256": {"slice_ub": 9, "slice_pf": 0, "slice_threads": 256},
+    "s5p_t256": {"slice_ub": 5, "slice_pf": 1, "slice_threads": 256},
+    "s9p_c4": {"slice_ub": 9, "slice_pf": 1, "slice_max_ctas": 4}, "s9p_c3": {"slice_ub": 9, "slice_pf": 1, "slice_max_ctas": 3},
+    "s9_c8": {"slice_ub": 9, "slice_pf": 0, "slice_max_ctas": 8},
 }
 
 
@@ -95,12 +99,14 @@ def main():
                 except Exception:
                     if v:
                         raise
+            t_init = time.time()
             try:
                 cg = ab.SolverCuda(A, comm)
             except Exception as e:
                 if rank == 0:
                     print(f"{solver}/{name}: init failed: {e}", flush=True)
                 continue
+            init_s = time.time() - t_init
             solve = cg.solve_pipelined if solver == "pipelined" else cg.solvempi
 
             def step():
@@ -152,15 +158,17 @@ def main():
                        ms_per_iter=float(tt[0]) / (args.steps * args.iters),
                        spmv_ms=spmv_ms / max(spmv_n, 1), update_ms_per_iter=blas_ms / (2 * args.iters),
                        launches_per_step=launches / args.steps, resid=cg.c.rnrm2 / cg.c.r0nrm2,
-                       max_rel_x_diff_vs_first=xdiff, layout=inf["last_layout"], ntiles=inf["spmv_ntiles"],
-                       nlong=inf["spmv_nlong"], nmedium=inf["spmv_nmedium"], compressed_tiles=inf["spmv_compressed_tiles"],
+                       max_rel_x_diff_vs_first=xdiff, ntiles=inf["spmv_ntiles"], slices=inf["spmv_slices"],
+                       slice_rows=inf["spmv_slice_rows"], slice_ub=inf["spmv_slice_ub"], slice_grid=inf["spmv_slice_grid"],
+                       nlong=inf["spmv_nlong"], nmedium=inf["spmv_nmedium"], init_s=init_s,
                        spmv_min_bytes=inf["spmv_min_bytes"], nnz_local=nnz_local, nown=nown,
                        spmv_gbs_min=inf["spmv_min_bytes"] / max(spmv_ms / max(spmv_n, 1), 1e-9) / 1e6)
             if rank == 0:
                 out.write(json.dumps(rec) + "\n"); out.flush()
                 print(f"{solver}/{name}: {rec['its_per_s']:.1f} it/s (e2e {rec['e2e_its_per_s']:.1f}) ms/iter {rec['ms_per_iter']:.4f} "
                       f"spmv {rec['spmv_ms']:.4f} ms ({rec['spmv_gbs_min']:.0f} GB/s min-bytes) upd {rec['update_ms_per_iter']:.4f} "
-                      f"launches/step {rec['launches_per_step']:.0f} resid {rec['resid']:.3e} xdiff {xdiff:.2e} layout {rec['layout']}",
+                      f"launches/step {rec['launches_per_step']:.0f} resid {rec['resid']:.3e} xdiff {xdiff:.2e} "
+                      f"slices {rec['slices']} (ub {rec['slice_ub']} grid {rec['slice_grid']}) tiles {rec['ntiles']} init {init_s:.1f} s",
                       flush=True)
             cg.free()
     for k, v in DEFAULTS.items():

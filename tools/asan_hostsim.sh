@@ -19,7 +19,7 @@ ACGB200_TEST_LIB=$PWD/$D/libacgb200_hostsim.so python -m pytest tests/test_host_
 echo "== solver, 3 ranks, every loop back-end"
 ACGB200_TEST_HOSTSIM=$PWD/$D/libacgb200_hostsim.so python -m torch.distributed.run --nnodes=1 --nproc-per-node=3 \
     --master-addr 127.0.0.1 --master-port 31114 tests/_dist_worker.py --mode gpu --matrix 27pt --size 8 --partition block \
-    --backends p2p-fused,p2p-unfused,one-kernel,all-unified,two-kernel-unified,nccl,nccl-graph 2>&1 \
+    --backends p2p-fused,p2p-unfused,tiles-only,nccl,nccl-graph 2>&1 \
     | grep -c " OK$\|FAIL\|runtime error\|AddressSanitizer" 
 echo "== every runtime call of set-up and solves failing in turn (159 at the end of round 1)"
 for k in $(seq 1 165); do ACGB200_TEST_LIB=$PWD/$D/libacgb200_hostsim.so HOSTSIM_FAIL_CALL_AT=$k python tests/hostsim/run_fault.py 2>&1 | grep -i "Sanitizer\|runtime error\|^ok\|^error"; done | sort | uniq -c

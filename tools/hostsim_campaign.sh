@@ -10,7 +10,7 @@ for cfg in "2 7pt 7 slab" "4 27pt 9 block" "3 rmat 2000 random" "4 7pt 10 random
   extra=""; [ "$2" = "rmat" ] && extra="--maxits 10 --rtol 0"
   out=$(timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$1 --master-addr 127.0.0.1 --master-port $((30000 + RANDOM % 2000)) \
         tests/_dist_worker.py --mode gpu --matrix $2 --size $3 --partition $4 \
-        --backends p2p-fused,p2p-unfused,one-kernel,one-kernel-split,all-unified,two-kernel-unified,nccl,nccl-graph $extra 2>&1)
+        --backends p2p-fused,p2p-unfused,tiles-only,nccl,nccl-graph $extra 2>&1)
   ok=$(echo "$out" | grep -c " OK$"); bad=$(echo "$out" | grep -c "FAIL\|Traceback")
   echo "$cfg: ok=$ok bad=$bad"
   [ "$bad" != "0" ] && { echo "$out" | grep "FAIL\|Error" | head -5; fail=1; }
