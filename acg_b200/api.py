@@ -120,7 +120,10 @@ class acgb200_info(C.Structure):
                                                                                   ("spmv_slices", C.c_int),
                                                                                   ("spmv_slice_rows", C.c_int),
                                                                                   ("spmv_slice_ub", C.c_int),
-                                                                                  ("spmv_slice_grid", C.c_int)]
+                                                                                  ("spmv_slice_grid", C.c_int),
+                                                                                  ("spmv_merge_tiles", C.c_int),
+                                                                                  ("spmv_merge_rows", C.c_int),
+                                                                                  ("spmv_merge_split", C.c_int)]
 
 
 class acgb200_mtxinfo(C.Structure):
@@ -149,7 +152,7 @@ EXPORTS = [
     "acgsolvercuda_fwrite",
     "acgb200_set_option", "acgsolvercuda_spmv", "acgsolvercuda_spmv_ghost", "acgsolvercuda_info", "acgb200_sizeof", "acgb200_have_mpi",
     "acgb200_nccl_unique_id", "acgb200_comm_init_rank", "acgb200_comm_destroy",
-    "acgb200_host_register", "acgb200_host_unregister", "acgb200_spmv_plan_host", "acgb200_spmv_plan_host2", "acgb200_slices_host", "acgb200_p2p_inverse_map", "acgb200_patterns_host", "acgb200_stencil_part",
+    "acgb200_host_register", "acgb200_host_unregister", "acgb200_spmv_plan_host", "acgb200_spmv_plan_host2", "acgb200_slices_host", "acgb200_merge_plan_host", "acgb200_p2p_inverse_map", "acgb200_patterns_host", "acgb200_stencil_part",
     "acgb200_mtx_info", "acgb200_mtx_read", "acgb200_mtx_read_part", "acgb200_comm_matrix_row", "acgb200_partition_rows_grid", "acgb200_grid_factors", "acgb200_rmat_spd",
 ]
 
@@ -234,6 +237,7 @@ def lib() -> C.CDLL:
     L.acgb200_patterns_host.argtypes = [C.c_int, i64p, i32p, C.c_int, P(C.c_int), P(C.c_int), i32p, i32p, u16p, P(C.c_int64)]
     L.acgb200_p2p_inverse_map.argtypes = [P(acghalo), C.c_int, C.c_int, i32p, i32p, i32p, i32p]
     L.acgb200_spmv_plan_host2.argtypes = [C.c_int, i64p, C.c_void_p, P(acgb200_info), i32p, C.c_int, i32p, C.c_int]
+    L.acgb200_merge_plan_host.argtypes = [C.c_int, i64p, C.c_int, i32p, C.c_int, i32p, P(C.c_int), P(C.c_int)]
     L.acgb200_slices_host.argtypes = [C.c_int, C.c_int, i64p, C.c_void_p, i32p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.acgb200_spmv_plan_host.argtypes = [C.c_int, i64p, P(acgb200_info), i32p, C.c_int, i32p, C.c_int]
     L.acgb200_comm_init_rank.argtypes = [P(acgcomm), C.c_int, C.c_void_p, C.c_int, P(C.c_int)]
@@ -273,6 +277,19 @@ def patterns_host(rowptr, colidx, max_entries: int = 4096) -> dict:
                                        patid, C.byref(nm)), "acgb200_patterns_host")
     return dict(npat=npat.value, patptr=patptr[:npat.value + 1].copy(), patoff=patoff[:nent.value].copy(),
                 patid=patid[:n].copy(), nmatched=nm.value)
+
+
+def merge_plan_host(rowptr, items: int = 1024, hi=None) -> dict:
+    """The merge-path tile plan of rows [0,hi) (mergeplan.c), computed on the host: tiles as rows of
+    (r0, nre, k0, nnz), split rows as rows of (row, ta, tb)."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    n = len(rowptr) - 1 if hi is None else hi
+    cap = int((n + rowptr[n]) // items + 2)
+    tiles = np.zeros(4 * cap, np.int32)
+    split = np.zeros(3 * cap, np.int32)
+    nt, ns = C.c_int(0), C.c_int(0)
+    _check(lib().acgb200_merge_plan_host(n, rowptr, items, tiles, cap, split, C.byref(nt), C.byref(ns)), "acgb200_merge_plan_host")
+    return dict(tiles=tiles[:4 * nt.value].reshape(nt.value, 4).copy(), split=split[:3 * ns.value].reshape(ns.value, 3).copy())
 
 
 def slices_host(rowptr, colidx, cover_hi=None) -> dict:

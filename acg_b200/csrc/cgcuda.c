@@ -54,10 +54,12 @@ static struct {
     int blas1_ctas;     /* CTAs per SM of the fused BLAS-1 kernels (0 = one full wave, from the occupancy) */
     int pdl;            /* 1: programmatic dependent launch along the iteration chain (opt-in) */
     int spmv_medium;    /* > 0: rows longer than this (and shorter than a tile) get a warp each (opt-in) */
+    int spmv_merge;     /* merge-path tiles for irregular rows (mergeplan.c): -1 decide from the row lengths, 0 off, 1 on */
+    int merge_items, merge_threads, merge_max_ctas;   /* their shape (0 = default) */
     int spmv_slices;    /* 1: pattern slices (slices.c) -- index-free slice-major storage of the rows that repeat a pattern */
-    int slice_ub, slice_threads, slice_pf, slice_max_ctas;   /* slice kernel shape overrides (0 / -1 = default) */
+    int slice_ub, slice_threads, slice_pf, slice_max_ctas, slice_minb;   /* slice kernel shape overrides (0 / -1 = default) */
     int loaded;
-} cfg = { .check_every = 8, .graph = 1, .redstream = 1, .p2p = 1, .p2p_fuse = 1, .spmv_slices = 1, .slice_pf = -1 };
+} cfg = { .check_every = 8, .graph = 1, .redstream = 1, .p2p = 1, .p2p_fuse = 1, .spmv_slices = 1, .slice_pf = -1, .spmv_merge = -1 };
 
 static void cfg_load(void)
 {
@@ -81,11 +83,16 @@ static void cfg_load(void)
     if (cfg.check_every < 1) cfg.check_every = 1;
     if ((s = getenv("ACGB200_PDL"))) cfg.pdl = atoi(s);
     if ((s = getenv("ACGB200_SPMV_MEDIUM"))) cfg.spmv_medium = atoi(s);
+    if ((s = getenv("ACGB200_SPMV_MERGE"))) cfg.spmv_merge = atoi(s);
+    if ((s = getenv("ACGB200_MERGE_ITEMS"))) cfg.merge_items = atoi(s);
+    if ((s = getenv("ACGB200_MERGE_THREADS"))) cfg.merge_threads = atoi(s);
+    if ((s = getenv("ACGB200_MERGE_MAX_CTAS"))) cfg.merge_max_ctas = atoi(s);
     if ((s = getenv("ACGB200_SPMV_SLICES"))) cfg.spmv_slices = atoi(s);
     if ((s = getenv("ACGB200_SLICE_UB"))) cfg.slice_ub = atoi(s);
     if ((s = getenv("ACGB200_SLICE_THREADS"))) cfg.slice_threads = atoi(s);
     if ((s = getenv("ACGB200_SLICE_PF"))) cfg.slice_pf = atoi(s);
     if ((s = getenv("ACGB200_SLICE_MAX_CTAS"))) cfg.slice_max_ctas = atoi(s);
+    if ((s = getenv("ACGB200_SLICE_MINB"))) cfg.slice_minb = atoi(s);
     acgb200_blas1_set_ctas_per_sm(cfg.blas1_ctas);
     acgb200_set_pdl(cfg.pdl);
 }
@@ -109,11 +116,16 @@ int acgb200_set_option(const char *key, int value)
     else if (!strcmp(key, "blas1_ctas")) { cfg.blas1_ctas = value; acgb200_blas1_set_ctas_per_sm(value); }
     else if (!strcmp(key, "pdl")) { cfg.pdl = value; acgb200_set_pdl(value); }
     else if (!strcmp(key, "spmv_medium")) cfg.spmv_medium = value < 0 ? 0 : value;
+    else if (!strcmp(key, "spmv_merge")) cfg.spmv_merge = value;
+    else if (!strcmp(key, "merge_items")) cfg.merge_items = value;
+    else if (!strcmp(key, "merge_threads")) cfg.merge_threads = value;
+    else if (!strcmp(key, "merge_max_ctas")) cfg.merge_max_ctas = value;
     else if (!strcmp(key, "spmv_slices")) cfg.spmv_slices = value;
     else if (!strcmp(key, "slice_ub")) cfg.slice_ub = value;
     else if (!strcmp(key, "slice_threads")) cfg.slice_threads = value;
     else if (!strcmp(key, "slice_pf")) cfg.slice_pf = value;
     else if (!strcmp(key, "slice_max_ctas")) cfg.slice_max_ctas = value;
+    else if (!strcmp(key, "slice_minb")) cfg.slice_minb = value;
     else return ACG_ERR_INVALID_VALUE;
     return ACG_SUCCESS;
 }
@@ -126,6 +138,7 @@ struct evpool { cudaEvent_t *ev; int n, cap; };
 
 struct priv {
     const struct acgsolvercuda *key;
+    const void *d_r_id;                 /* cg->d_r: identifies the solver if the caller moves the struct */
     struct priv *next;
     struct acgb200_spmvplan plan;
     struct acgb200_devstate *d_st;
@@ -142,7 +155,7 @@ struct priv {
     double *d_b, *d_x;                  /* right-hand side / solution on the device, kept between solves */
     cudaGraphExec_t graph[3];           /* [0] classic, [1] pipelined, [2] pipelined as one kernel per iteration:
                                          * two iterations each (parity 0 then 1) */
-    int graph_multi[3];
+    int graph_sig[3];                   /* loop configuration each cached graph was captured with (graph_signature) */
     int graph_launches[3];              /* kernel/NCCL launches inside one replay */
     double last_h2d_ms, last_d2h_ms;    /* host time spent before / after the solve window */
     cudaEvent_t ev_t0, ev_t1;           /* device-side bracket of the solve window */
@@ -166,6 +179,13 @@ static struct priv *priv_of(const struct acgsolvercuda *cg)
     struct priv *found = NULL;
     pthread_mutex_lock(&registry_lock);
     for (struct priv *p = registry; p; p = p->next) if (p->key == cg) { found = p; break; }
+    if (!found && cg->d_r) {
+        /* the caller copied or moved the struct (the reference allows that: it is plain data).  The device
+         * vector d_r is allocated by acgsolvercuda_init and belongs to exactly one solver: find the state
+         * through it and follow the struct to its new address. */
+        for (struct priv *p = registry; p; p = p->next)
+            if (p->d_r_id == (const void *) cg->d_r) { found = p; p->key = cg; break; }
+    }
     pthread_mutex_unlock(&registry_lock);
     return found;
 }
@@ -177,12 +197,12 @@ static void priv_add(struct priv *pv)
     pthread_mutex_unlock(&registry_lock);
 }
 
-static void priv_drop(const struct acgsolvercuda *cg)
+static void priv_drop(struct priv *pv)
 {
     struct priv *d = NULL;
     pthread_mutex_lock(&registry_lock);
     for (struct priv **pp = &registry; *pp; pp = &(*pp)->next) {
-        if ((*pp)->key == cg) { d = *pp; *pp = d->next; break; }
+        if (*pp == pv) { d = *pp; *pp = d->next; break; }
     }
     pthread_mutex_unlock(&registry_lock);
     free(d);
@@ -236,6 +256,7 @@ void acgsolvercuda_free(struct acgsolvercuda *cg)
         for (int i = 0; i < 3; i++) if (pv->graph[i]) cudaGraphExecDestroy(pv->graph[i]);
         cudaFree(pv->plan.d_tiles); cudaFree(pv->plan.d_longrows); cudaFree(pv->plan.d_long_scratch); cudaFree(pv->plan.d_medrows);
         cudaFree(pv->plan.d_slices); cudaFree(pv->plan.d_sval); cudaFree(pv->plan.d_spatoff); cudaFree(pv->plan.d_spatid);
+        cudaFree(pv->plan.d_mtiles); cudaFree(pv->plan.d_msplit); cudaFree(pv->plan.d_mpart);
         cudaFree(pv->d_st);
         cudaFreeHost(pv->h_ctrl); cudaFreeHost(pv->h_st);
         if (pv->stream) cudaStreamDestroy(pv->stream);
@@ -251,20 +272,20 @@ void acgsolvercuda_free(struct acgsolvercuda *cg)
         for (int i = 0; i < pv->gemv.cap; i++) cudaEventDestroy(pv->gemv.ev[i]);
         for (int i = 0; i < pv->blas.cap; i++) cudaEventDestroy(pv->blas.ev[i]);
         free(pv->gemv.ev); free(pv->blas.ev);
-        priv_drop(cg);
+        priv_drop(pv);
     }
 }
 
 /* Cut rows [0,nrows) into TMA tiles (see internal.h): greedy, row-aligned, at
  * most rows_cap rows and nnz_cap nonzeros per tile; rows longer than nnz_cap go
  * to the long-row list.  Host-only, no CUDA: testable without a device. */
-static int cut_tiles(const struct acgb200_spmvplan *pl, const int64_t *rowptr, const unsigned char *covered,
+static int cut_tiles(const struct acgb200_spmvplan *pl, const int64_t *rowptr, const unsigned char *covered, int row_lo,
                      struct acgb200_tile *tiles, int *ntiles, int *longrows, int *nlong, int *medrows, int *nmed)
 {
     const int n = pl->nrows;
     /* rows above `out` leave the tiles: the long ones (> nnz_cap) always, the medium ones on request */
     const int64_t out = pl->med_thr > 0 && pl->med_thr < pl->nnz_cap ? pl->med_thr : pl->nnz_cap;
-    int nt = 0, nl = 0, nm = 0, r = 0;
+    int nt = 0, nl = 0, nm = 0, r = row_lo;        /* rows below row_lo are in merge-path tiles (mergeplan.c) */
     while (r < n) {
         /* rows of a covered 32-row slice belong to the slice kernel (slices.c) */
         if (covered && covered[r >> 5]) { r = (r | 31) + 1; continue; }
@@ -293,7 +314,8 @@ static int cut_tiles(const struct acgb200_spmvplan *pl, const int64_t *rowptr, c
 }
 
 static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr,
-                       const struct acgb200_sliceplan *sp, const unsigned short *patid, int *errcode)
+                       const struct acgb200_sliceplan *sp, const unsigned short *patid,
+                       const struct acgb200_mergeplan *mp, int *errcode)
 {
     const int n = pl->nrows;
     struct acgb200_tile *tiles = malloc(((size_t) n + 1) * sizeof(*tiles));
@@ -301,7 +323,8 @@ static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr,
     int *medrows = malloc(((size_t) n + 1) * sizeof(*medrows));
     if (!tiles || !longrows || !medrows) { free(tiles); free(longrows); free(medrows); return ACG_ERR_ERRNO; }
     int nt = 0, nl = 0, nm = 0;
-    int err = cut_tiles(pl, rowptr, sp && sp->nslices > 0 ? sp->covered : NULL, tiles, &nt, longrows, &nl, medrows, &nm);
+    int err = cut_tiles(pl, rowptr, sp && sp->nslices > 0 ? sp->covered : NULL, mp && mp->ntiles > 0 ? mp->rows : 0,
+                        tiles, &nt, longrows, &nl, medrows, &nm);
     if (err) { free(tiles); free(longrows); free(medrows); return err; }
     pl->ntiles = nt; pl->nlong = nl; pl->nmed = nm;
     pl->d_tiles = NULL; pl->d_longrows = NULL; pl->d_long_scratch = NULL; pl->d_medrows = NULL;
@@ -334,6 +357,16 @@ static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr,
         if (!e) e = cudaMemcpy(pl->d_spatid, patid, (size_t) n * sizeof(unsigned short), cudaMemcpyHostToDevice);
         if (!e) e = cudaMalloc((void **) &pl->d_sval, (size_t) sp->blocks * 32 * sizeof(double));
     }
+    pl->nmtiles = 0;
+    if (!e && mp && mp->ntiles > 0) {
+        pl->nmtiles = mp->ntiles; pl->nsplit = mp->nsplit; pl->merge_items = mp->items; pl->merge_rows = mp->rows; pl->merge_nnz = mp->nnz;
+        e = cudaMalloc((void **) &pl->d_mtiles, (size_t) mp->ntiles * sizeof(*mp->tiles));
+        if (!e) e = cudaMemcpy(pl->d_mtiles, mp->tiles, (size_t) mp->ntiles * sizeof(*mp->tiles), cudaMemcpyHostToDevice);
+        if (!e) e = cudaMalloc((void **) &pl->d_msplit, (size_t) (mp->nsplit > 0 ? mp->nsplit : 1) * sizeof(*mp->split));
+        if (!e && mp->nsplit > 0) e = cudaMemcpy(pl->d_msplit, mp->split, (size_t) mp->nsplit * sizeof(*mp->split), cudaMemcpyHostToDevice);
+        if (!e) e = cudaMalloc((void **) &pl->d_mpart, 2 * (size_t) mp->ntiles * sizeof(double));
+        if (!e) e = cudaMemset(pl->d_mpart, 0, 2 * (size_t) mp->ntiles * sizeof(double));
+    }
     free(tiles); free(longrows); free(medrows);
     CU(e);
     return ACG_SUCCESS;
@@ -352,6 +385,27 @@ int acgb200_patterns_host(int nrows, const int64_t *rowptr, const int *colidx, i
     memcpy(patid, pat.patid, (size_t) nrows * sizeof(unsigned short));
     acgb200_patterns_free(&pat);
     return ACG_SUCCESS;
+}
+
+/* ext.h: the merge-path tile plan, host only (mergeplan.c) */
+int acgb200_merge_plan_host(int hi, const int64_t *rowptr, int items, int *tiles4, int maxtiles,
+                            int *split3, int *ntiles, int *nsplit)
+{
+    struct acgb200_mergeplan mp;
+    int err = acgb200_merge_plan(hi, rowptr, items, &mp);
+    if (!err && mp.ntiles > maxtiles) err = ACG_ERR_NO_BUFFER_SPACE;
+    if (!err) {
+        for (int t = 0; t < mp.ntiles; t++) {
+            tiles4[4 * t] = mp.tiles[t].r0; tiles4[4 * t + 1] = mp.tiles[t].nre;
+            tiles4[4 * t + 2] = mp.tiles[t].k0; tiles4[4 * t + 3] = mp.tiles[t].nnz;
+        }
+        for (int i = 0; i < mp.nsplit; i++) {
+            split3[3 * i] = mp.split[i].row; split3[3 * i + 1] = mp.split[i].ta; split3[3 * i + 2] = mp.split[i].tb;
+        }
+        *ntiles = mp.ntiles; *nsplit = mp.nsplit;
+    }
+    acgb200_mergeplan_free(&mp);
+    return err;
 }
 
 /* ext.h: the pattern-slice plan of a CSR matrix, host only (slices.c) */
@@ -417,7 +471,7 @@ int acgb200_spmv_plan_host2(int nrows, const int64_t *rowptr, const int *colidx,
         if (!err && pat.npat > 0) err = acgb200_slices_plan(nrows, nrows, rowptr, &pat, &sp);
         nsl = sp.nslices; slrows = sp.rows;
     }
-    if (!err) err = cut_tiles(&pl, rowptr, sp.nslices > 0 ? sp.covered : NULL, tiles, &nt, lr, &nl, mr, &nm);
+    if (!err) err = cut_tiles(&pl, rowptr, sp.nslices > 0 ? sp.covered : NULL, 0, tiles, &nt, lr, &nl, mr, &nm);
     acgb200_sliceplan_free(&sp);
     acgb200_patterns_free(&pat);
     if (!err && (nt > maxtiles || nl > maxlong)) err = ACG_ERR_NO_BUFFER_SPACE;
@@ -555,7 +609,7 @@ static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, 
             if (!ok) (void) cudaGetLastError();
             int *d_ok = NULL, allok = 0;
             CU(cudaMalloc((void **) &d_ok, sizeof(int)));
-            CU(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+            { cudaError_t ce0 = cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice); if (ce0) { cudaFree(d_ok); CU(ce0); } }
             ncclResult_t r = ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm->ncclcomm, pv->stream);
             if (r != ncclSuccess) { cudaFree(d_ok); *errcode = (int) r; return ACG_ERR_NCCL; }
             cudaError_t ce = cudaMemcpyAsync(&allok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, pv->stream);
@@ -586,6 +640,7 @@ static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, 
     /* device vectors: owned + ghost entries, padded to an even count */
     const size_t vbytes = ((size_t) pv->nvec + 2) * sizeof(double);
     CU(cudaMalloc((void **) &cg->d_r, vbytes)); CU(cudaMemset(cg->d_r, 0, vbytes));
+    pv->d_r_id = cg->d_r;
     CU(cudaMalloc((void **) &cg->d_p, vbytes)); CU(cudaMemset(cg->d_p, 0, vbytes));
     CU(cudaMalloc((void **) &cg->d_t, vbytes)); CU(cudaMemset(cg->d_t, 0, vbytes));
 
@@ -653,13 +708,34 @@ static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, 
             const int cover_hi = (commsize > 1 || A->nghostrows > 0) ? A->borderrowoffset : A->nownedrows;
             err = acgb200_slices_plan(A->nownedrows, cover_hi, frp, &pat, &sp);
         }
-        if (!err) err = build_tiles(&pv->plan, frp, &sp, pat.patid, errcode);
+        /* irregular row lengths (power-law matrices): merge-path tiles instead of row-aligned ones for the rows
+         * the slices did not take.  "Irregular": the longest row is far above the mean. */
+        struct acgb200_mergeplan mp;
+        memset(&mp, 0, sizeof(mp));
+        if (!err && sp.nslices == 0 && cfg.spmv_merge != 0) {
+            const int hi = (commsize > 1 || A->nghostrows > 0) ? A->borderrowoffset : A->nownedrows;
+            const double avg = hi > 0 ? (double) frp[hi] / hi : 0.0;
+            int64_t mx = 0;
+            for (int i = 0; i < hi; i++) if (frp[i + 1] - frp[i] > mx) mx = frp[i + 1] - frp[i];
+            if (hi >= 1024 && (cfg.spmv_merge > 0 || (double) mx > 8.0 * avg + 64.0))
+                err = acgb200_merge_plan(hi, frp, cfg.merge_items > 0 ? cfg.merge_items : 1024, &mp);
+        }
+        if (!err) err = build_tiles(&pv->plan, frp, &sp, pat.patid, &mp, errcode);
+        if (!err && pv->plan.nmtiles > 0) {
+            pv->plan.merge_threads = cfg.merge_threads > 0 ? cfg.merge_threads : 128;
+            pv->plan.merge_stages = 2;
+            pv->plan.merge_max_ctas = cfg.merge_max_ctas;
+        }
+        acgb200_mergeplan_free(&mp);
         if (!err && pv->plan.nslices > 0) {
             const int d = sp.domlen;
             pv->plan.slice_ub = cfg.slice_ub > 0 ? cfg.slice_ub : (d % 9 == 0 ? 9 : d % 7 == 0 ? 7 : d % 8 == 0 ? 8 : d % 5 == 0 ? 5 : 8);
             pv->plan.slice_threads = cfg.slice_threads > 0 ? cfg.slice_threads : 128;
-            pv->plan.slice_pf = cfg.slice_pf >= 0 ? (cfg.slice_pf != 0) : 1;
+            /* measured on the B200 (profiles/r02/b_ab_224.log): without prefetch the kernel needs 48 registers and ten
+             * CTAs of 128 threads share an SM -- 0.397 ms at C3 against 0.450 ms for the prefetching variant */
+            pv->plan.slice_pf = cfg.slice_pf >= 0 ? (cfg.slice_pf != 0) : 0;
             pv->plan.slice_max_ctas = cfg.slice_max_ctas;
+            pv->plan.slice_minb = cfg.slice_minb;
         }
         acgb200_sliceplan_free(&sp);
         acgb200_patterns_free(&pat);
@@ -762,7 +838,15 @@ static int apply_A(struct solvectx *c, const double *x_ro, double *x_halo, doubl
     }
     prof_mark(c, &pv->gemv);
     KL(acgb200_spmv_launch(&a, pv->stream));
-    c->launches += 1 + (a.plan->nlong > 0 ? 2 : 0) + (a.plan->nmed > 0 ? 1 : 0);
+    {
+        /* kernels acgb200_spmv_launch issues for this plan (kernels.cu): slices | merge tiles (+ fix-up), the tile
+         * kernel unless the first one forwards the control word itself, medium rows, long rows (two kernels) */
+        const struct acgb200_spmvplan *pl = a.plan;
+        const int first = pl->nslices > 0 || pl->nmtiles > 0;
+        const int tilek = pl->ntiles > 0 || (a.ctrl_in && !(first && pl->ntiles == 0 && !a.p2p));
+        c->launches += (pl->nslices > 0) + (pl->nmtiles > 0) + (pl->nmtiles > 0 && pl->nsplit > 0) + tilek
+                       + (pl->nlong > 0 ? 2 : 0) + (pl->nmed > 0 ? 1 : 0);
+    }
     if (c->multi && !fused) {
         if (!peer) {
             OK(acghalo_exchange_cuda_end(cg->halo, cg->haloexchange, pv->nvec, x_halo, ACG_DOUBLE,
@@ -850,8 +934,11 @@ static int solve_begin(struct solvectx *c, struct acgsolvercuda *cg, const struc
         CU(cudaMemsetAsync(pv->d_x, 0, vbytes, pv->stream));
     }
     c->d_b = pv->d_b; c->d_x = pv->d_x;
-    CU(cudaMemcpyAsync(c->d_b, b->x, (size_t) b->num_nonzeros * sizeof(double), cudaMemcpyHostToDevice, pv->stream));
-    CU(cudaMemcpyAsync(c->d_x, x->x, (size_t) x->num_nonzeros * sizeof(double), cudaMemcpyHostToDevice, pv->stream));
+    /* a caller may hand over longer vectors than this part's owned + ghost entries: only those are used */
+    const size_t nb = (size_t) (b->num_nonzeros < pv->nvec ? b->num_nonzeros : pv->nvec);
+    const size_t nx = (size_t) (x->num_nonzeros < pv->nvec ? x->num_nonzeros : pv->nvec);
+    CU(cudaMemcpyAsync(c->d_b, b->x, nb * sizeof(double), cudaMemcpyHostToDevice, pv->stream));
+    CU(cudaMemcpyAsync(c->d_x, x->x, nx * sizeof(double), cudaMemcpyHostToDevice, pv->stream));
     CU(cudaStreamSynchronize(pv->stream));
     pv->last_h2d_ms = 1e3 * (wall() - tb);
     return ACG_SUCCESS;
@@ -861,7 +948,8 @@ static int solve_end(struct solvectx *c, struct acgvector *x, int status)
 {
     int *errcode = c->errcode;
     const double te = wall();
-    CU(cudaMemcpyAsync(x->x, c->d_x, (size_t) x->num_nonzeros * sizeof(double), cudaMemcpyDeviceToHost, c->pv->stream));
+    const size_t nx = (size_t) (x->num_nonzeros < c->pv->nvec ? x->num_nonzeros : c->pv->nvec);
+    CU(cudaMemcpyAsync(x->x, c->d_x, nx * sizeof(double), cudaMemcpyDeviceToHost, c->pv->stream));
     CU(cudaStreamSynchronize(c->pv->stream));
     c->pv->last_d2h_ms = 1e3 * (wall() - te);
     CU(cudaGetLastError());
@@ -903,11 +991,20 @@ static double threshold(double atol, double rtol, double r0nrm2)
  * pointers the kernels and NCCL calls use are fixed for the life of the solver
  * and the iteration index only enters through its parity, so one two-iteration
  * graph serves the whole solve (and later solves). */
+/* everything besides the (fixed) pointers that decides which kernels and NCCL calls an iteration issues:
+ * a cached graph is only replayed for the configuration it was captured with (options can change between
+ * two solves on one solver) */
+static int graph_signature(const struct solvectx *c)
+{
+    return 1 | (c->multi ? 2 : 0) | (c->p2p ? 4 : 0) | (c->pv->p2p.h_desc.fuse ? 8 : 0) | (cfg.pdl ? 16 : 0)
+           | (cfg.redstream ? 32 : 0) | (c->pv->have_redcomm ? 64 : 0);
+}
+
 static int capture_pair(struct solvectx *c, int kind, int (*issue)(struct solvectx *, int))
 {
     struct priv *pv = c->pv;
     int *errcode = c->errcode;
-    if (pv->graph[kind] && pv->graph_multi[kind] == c->multi) return ACG_SUCCESS;
+    if (pv->graph[kind] && pv->graph_sig[kind] == graph_signature(c)) return ACG_SUCCESS;
     if (pv->graph[kind]) { cudaGraphExecDestroy(pv->graph[kind]); pv->graph[kind] = NULL; }
     const int before = c->launches;
     cudaGraph_t g = NULL;
@@ -924,7 +1021,7 @@ static int capture_pair(struct solvectx *c, int kind, int (*issue)(struct solvec
     e = cudaGraphInstantiate(&pv->graph[kind], g, 0);
     cudaGraphDestroy(g);
     CU(e);
-    pv->graph_multi[kind] = c->multi;
+    pv->graph_sig[kind] = graph_signature(c);
     return ACG_SUCCESS;
 }
 
@@ -944,7 +1041,7 @@ static int iterate(struct solvectx *c, int maxits, int poll, int kind, int (*iss
     const int use_graph = cfg.graph && !cfg.profile && maxits >= 6 && (!c->multi || c->p2p || cfg.graph >= 2);
     while (issued < maxits) {
         if (use_graph && issued >= 2 && maxits - issued >= 2) {
-            if (!pv->graph[kind] || pv->graph_multi[kind] != c->multi) OK(capture_pair(c, kind, issue));
+            if (!pv->graph[kind] || pv->graph_sig[kind] != graph_signature(c)) OK(capture_pair(c, kind, issue));
             CU(cudaGraphLaunch(pv->graph[kind], pv->stream));
             c->launches += pv->graph_launches[kind];
             issued += 2; since_poll += 2;
@@ -1646,6 +1743,7 @@ int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info
     info->last_h2d_ms = pv->last_h2d_ms; info->last_d2h_ms = pv->last_d2h_ms;
     info->last_blas_ms = pv->last_blas_ms;
     info->num_sms = acgb200_num_sms();
+    info->spmv_merge_tiles = pv->plan.nmtiles; info->spmv_merge_rows = pv->plan.merge_rows; info->spmv_merge_split = pv->plan.nsplit;
     info->spmv_slices = pv->plan.nslices; info->spmv_slice_rows = pv->plan.slice_rows;
     info->spmv_slice_ub = pv->plan.slice_ub; info->spmv_slice_grid = pv->plan.slice_grid;
     info->spmv_nmedium = pv->plan.nmed;

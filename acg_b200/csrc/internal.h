@@ -71,8 +71,30 @@ struct acgb200_spmvplan {
     int slice_npat;
     int *d_spatoff;                  /* [slice_npat * slice_lpad] offsets col - row, zero beyond a pattern's length */
     unsigned short *d_spatid;        /* [nrows] pattern id per row (valid for covered rows) */
-    int slice_ub, slice_threads, slice_pf, slice_grid, slice_smem, slice_max_ctas;
+    int slice_ub, slice_threads, slice_pf, slice_minb, slice_grid, slice_smem, slice_max_ctas;
+    /* merge-path tiles (mergeplan.c): rows [0, merge_rows) of an irregular (power-law) matrix, cut into tiles
+     * of merge_items merged items (row ends + nonzeros) and multiplied by spmv_merge_kernel; rows cut by tile
+     * boundaries are finished by spmv_merge_fix_kernel from the tiles' partial sums */
+    int nmtiles, nsplit, merge_items, merge_rows;
+    int64_t merge_nnz;
+    struct acgb200_mtile *d_mtiles;  /* [nmtiles] */
+    struct acgb200_msplit *d_msplit; /* [nsplit] */
+    double *d_mpart;                 /* [2 * nmtiles]: slot 0 head piece, slot 1 tail piece of each tile */
+    int merge_grid, merge_smem, merge_threads, merge_stages, merge_max_ctas;
 };
+
+/* one merge-path tile: row ends of rows [r0, r0+nre), nonzeros [k0, k0+nnz) */
+struct acgb200_mtile { int r0; int nre; int k0; int nnz; };
+/* a row cut by tile boundaries: its pieces are the tail pieces of tiles ta..tb-1 and the head piece of tile tb */
+struct acgb200_msplit { int row; int ta; int tb; int pad; };
+struct acgb200_mergeplan {
+    int ntiles, nsplit, items, rows;
+    int64_t nnz;
+    struct acgb200_mtile *tiles;
+    struct acgb200_msplit *split;
+};
+int acgb200_merge_plan(int hi, const int64_t *rowptr, int items, struct acgb200_mergeplan *out);
+void acgb200_mergeplan_free(struct acgb200_mergeplan *mp);
 
 struct acgb200_patterns;
 

@@ -558,24 +558,26 @@ struct SliceParams {
  * is limited by registers only, the loads in flight per SM (warps x UB x 256 B
  * of values) cover the HBM latency.
  */
+/* x entry of slot e+u: the column is formed in 32-bit arithmetic (row + offset), so the address costs one
+ * IADD and one IMAD.WIDE instead of a sign extension and a 64-bit add per gather */
 template <int UB>
-__device__ __forceinline__ void slice_load(double (&vv)[UB], double (&xv)[UB], const double *v, const double *xr,
+__device__ __forceinline__ void slice_load(double (&vv)[UB], double (&xv)[UB], const double *v, const double *x, int row,
                                            const int *offs, int e, uint64_t pol)
 {
 #pragma unroll
     for (int u = 0; u < UB; u++) vv[u] = ld_stream(v + (size_t) (e + u) * 32, pol);
 #pragma unroll
-    for (int u = 0; u < UB; u++) xv[u] = ld_x(xr + offs[e + u]);
+    for (int u = 0; u < UB; u++) xv[u] = ld_x(x + (row + offs[e + u]));
 }
 
 template <int UB>
-__device__ __forceinline__ void slice_load_pred(double (&vv)[UB], double (&xv)[UB], const double *v, const double *xr,
+__device__ __forceinline__ void slice_load_pred(double (&vv)[UB], double (&xv)[UB], const double *v, const double *x, int row,
                                                 const int *offs, int e, int L, uint64_t pol)
 {
 #pragma unroll
     for (int u = 0; u < UB; u++) vv[u] = e + u < L ? ld_stream(v + (size_t) (e + u) * 32, pol) : 0.0;
 #pragma unroll
-    for (int u = 0; u < UB; u++) xv[u] = e + u < L ? ld_x(xr + offs[e + u]) : 0.0;
+    for (int u = 0; u < UB; u++) xv[u] = e + u < L ? ld_x(x + (row + offs[e + u])) : 0.0;
 }
 
 template <int UB>
@@ -590,8 +592,8 @@ __device__ __forceinline__ double slice_fma(const double (&vv)[UB], const double
  * batch's FMAs as early as their operands allow, i.e. between the loads of the same batch, and a warp
  * issues in order: without the prefetch a warp stalls on its first product with ~3 of its 2*UB loads in
  * flight; with it the operands of the FMA it stalls on were requested a whole batch earlier. */
-template <int UB, int T, bool PF>
-__global__ void __launch_bounds__(T)
+template <int UB, int T, bool PF, int MB>
+__global__ void __launch_bounds__(T, MB)
 spmv_slices_kernel(const SliceParams P)
 {
     extern __shared__ __align__(16) int spat_s[];
@@ -621,7 +623,6 @@ spmv_slices_kernel(const SliceParams P)
         const int row = sl.x + lane;
         const int *offs = spat_s + (int) P.patid[row] * P.lpad;
         const double *v = P.sval + ((size_t) sl.w << 5) + lane;
-        const double *xr = P.x + row;
         const int L = sl.z;
         double sum = 0.0;
         int e = 0;
@@ -629,17 +630,17 @@ spmv_slices_kernel(const SliceParams P)
             /* two register sets, straight-line body (predicated loads, no branch between a batch's loads
              * and the previous batch's FMAs); slots past L load nothing and add 0 * 0 */
             double va[UB], xa[UB], vb[UB], xb[UB];
-            slice_load_pred<UB>(va, xa, v, xr, offs, 0, L, pol);
+            slice_load_pred<UB>(va, xa, v, P.x, row, offs, 0, L, pol);
             for (; e < L; e += 2 * UB) {
-                slice_load_pred<UB>(vb, xb, v, xr, offs, e + UB, L, pol);
+                slice_load_pred<UB>(vb, xb, v, P.x, row, offs, e + UB, L, pol);
                 sum = slice_fma<UB>(va, xa, sum);
-                slice_load_pred<UB>(va, xa, v, xr, offs, e + 2 * UB, L, pol);
+                slice_load_pred<UB>(va, xa, v, P.x, row, offs, e + 2 * UB, L, pol);
                 sum = slice_fma<UB>(vb, xb, sum);
             }
         } else {
             for (; e + UB <= L; e += UB) {
                 double vv[UB], xv[UB];
-                slice_load<UB>(vv, xv, v, xr, offs, e, pol);
+                slice_load<UB>(vv, xv, v, P.x, row, offs, e, pol);
                 sum = slice_fma<UB>(vv, xv, sum);
             }
         }
@@ -649,7 +650,7 @@ spmv_slices_kernel(const SliceParams P)
 #pragma unroll
             for (int u = 0; u < UB; u++) vv[u] = e + u < L ? ld_stream(v + (size_t) (e + u) * 32, pol) : 0.0;
 #pragma unroll
-            for (int u = 0; u < UB; u++) xv[u] = e + u < L ? ld_x(xr + offs[e + u]) : 0.0;
+            for (int u = 0; u < UB; u++) xv[u] = e + u < L ? ld_x(P.x + (row + offs[e + u])) : 0.0;
 #pragma unroll
             for (int u = 0; u < UB; u++) if (e + u < L) sum = fma(vv[u], xv[u], sum);
         }
@@ -682,6 +683,221 @@ slices_fill_kernel(int nslices, const acgb200_slice *slices, const int *__restri
         const int kb = rowptr[row], len = rowptr[row + 1] - kb;
         double *v = sval + ((size_t) sl.vblk << 5) + lane;
         for (int e = 0; e < sl.len; e++) v[(size_t) e * 32] = e < len ? a[kb + e] : 0.0;
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* SpMV over merge-path tiles (mergeplan.c): power-law row lengths             */
+/* ------------------------------------------------------------------------ */
+
+struct MergeParams {
+    const acgb200_mtile *tiles;
+    int ntiles;
+    int sc, rc;                    /* value/index slots and row-pointer slots per stage (multiples of 4) */
+    int stage_bytes, nstages;
+    const int *rowptr;
+    const int *colidx;
+    const double *a;
+    double *part;                  /* [2 * ntiles] */
+    const double *x;
+    double *y;
+    const double *b;
+    double *acc;
+    int dotrows;
+    int mode;
+    const acgb200_ctrl *ctrl_in;
+    acgb200_ctrl *ctrl_out;        /* NULL: the tile kernel launched behind this one forwards the word */
+    acgb200_devstate *st;
+    int housekeeping;
+};
+
+#define MERGE_LONGSEG 32           /* pieces longer than this are summed by a whole warp */
+#define MERGE_LISTCAP 128
+
+__device__ __forceinline__ void merge_issue(const MergeParams &P, const acgb200_mtile &tl, unsigned char *stage,
+                                            uint64_t *bar, uint64_t pol)
+{
+    const int k_al = tl.k0 & ~3;
+    const int nnz_al = (tl.k0 + tl.nnz - k_al + 3) & ~3;
+    const int row_al = tl.r0 & ~3;
+    const int nrp = (tl.r0 + tl.nre + 1 - row_al + 3) & ~3;
+    double *vals = reinterpret_cast<double *>(stage);
+    int *cols = reinterpret_cast<int *>(stage + (size_t) P.sc * 8);
+    int *rptr = reinterpret_cast<int *>(stage + (size_t) P.sc * 12);
+    mbar_arrive_expect_tx(bar, (uint32_t) nnz_al * 12u + (uint32_t) nrp * 4u);
+    if (nnz_al > 0) {
+        bulk_g2s(vals, P.a + k_al, (uint32_t) nnz_al * 8u, bar, pol);
+        bulk_g2s(cols, P.colidx + k_al, (uint32_t) nnz_al * 4u, bar, pol);
+    }
+    bulk_g2s(rptr, P.rowptr + row_al, (uint32_t) nrp * 4u, bar, pol);
+}
+
+/* what a finished row does with its sum (same epilogues as the tile kernel) */
+__device__ __forceinline__ void spmv_row_epilogue(int row, double sum, int mode, const double *x, double *y, const double *b,
+                                                  int dotrows, double &dot)
+{
+    if (mode == SPMV_R_B_AX) {
+        const double v = b[row] - sum;
+        y[row] = v;
+        if (row < dotrows) dot = fma(v, v, dot);
+    } else {
+        y[row] = sum;
+        if (mode == SPMV_Y_AX_DOT && row < dotrows) dot = fma(__ldg(x + row), sum, dot);
+    }
+}
+
+/*
+ * Per tile: (1) every thread multiplies a strided share of the tile's nonzeros -- U gathers in
+ * flight, equal work for all threads whatever the rows look like -- and leaves the products in
+ * shared memory; (2) the tile's units (one per row end, plus the piece behind the last row end) are
+ * summed from shared memory: a thread per unit, units longer than MERGE_LONGSEG by a warp.  A unit
+ * that is a whole row gets the epilogue; the piece of a split row goes to part[] for the fix-up
+ * kernel (slot 0: the row ends here but began in an earlier tile; slot 1: the row continues).
+ */
+template <int T, int U>
+__global__ void __launch_bounds__(T)
+spmv_merge_kernel(const MergeParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[SPMV_MAX_STAGES];
+    __shared__ double red[T / 32];
+    __shared__ int lst[MERGE_LISTCAP];
+    __shared__ int nlst;
+
+    const int tid = threadIdx.x;
+    pdl_prologue();
+    const Gate gate = gate_read(P.ctrl_in, P.st);
+    if (P.ctrl_out && blockIdx.x == 0 && tid == 0 && P.ctrl_in) {
+        *P.ctrl_out = *P.ctrl_in;
+        if (gate.active) {
+            const int s = gate.iter & 1;
+            if (P.housekeeping == 1) P.st->rr_loc[s ^ 1] = 0.0;
+            if (P.housekeeping == 2) { P.st->gd_loc[s ^ 1][0] = 0.0; P.st->gd_loc[s ^ 1][1] = 0.0; }
+        }
+    }
+    if (!gate.active) return;
+
+    const int S = P.nstages;
+    double *prod = reinterpret_cast<double *>(smem + (size_t) S * P.stage_bytes);     /* [sc] products of the current tile */
+    uint64_t pol = 0;
+    if (tid == 0) {
+        nlst = 0;
+        pol = l2_policy_evict_first();
+        for (int s = 0; s < S; s++) mbar_init(&full_bar[s], 1);
+        mbar_init_fence();
+        for (int s = 0; s < S; s++) {
+            const int t = blockIdx.x + s * gridDim.x;
+            if (t < P.ntiles) merge_issue(P, P.tiles[t], smem + (size_t) s * P.stage_bytes, &full_bar[s], pol);
+        }
+    }
+    __syncthreads();
+
+    double dot = 0.0;
+    int i = 0;
+    for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, i++) {
+        const int s = i % S;
+        const acgb200_mtile tl = P.tiles[t];
+        unsigned char *stage = smem + (size_t) s * P.stage_bytes;
+        const int koff = tl.k0 & 3;                    /* first own nonzero inside the 16-byte aligned slice */
+        const double *vals = reinterpret_cast<const double *>(stage) + koff;
+        const int *cols = reinterpret_cast<const int *>(stage + (size_t) P.sc * 8) + koff;
+        const int *rp = reinterpret_cast<const int *>(stage + (size_t) P.sc * 12) + (tl.r0 & 3);    /* rp[j] = rowptr[r0 + j] */
+
+        mbar_wait(&full_bar[s], (uint32_t) ((i / S) & 1));
+
+        /* (1) products */
+        for (int base = 0; base < tl.nnz; base += T * U) {
+            int c[U];
+            double v[U], xv[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int kk = min(base + u * T + tid, tl.nnz - 1);
+                c[u] = cols[kk];
+                v[u] = vals[kk];
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) xv[u] = ld_x(P.x + c[u]);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int kk = base + u * T + tid;
+                if (kk < tl.nnz) prod[kk] = v[u] * xv[u];
+            }
+        }
+        __syncthreads();
+
+        /* (2a) a thread per unit: j < nre is row r0 + j, j == nre the piece behind the last row end */
+        const int kend = tl.k0 + tl.nnz;
+        for (int j = tid; j <= tl.nre; j += T) {
+            const int a0 = max(rp[j], tl.k0) - tl.k0;
+            const int b0 = (j < tl.nre ? rp[j + 1] : kend) - tl.k0;
+            if (b0 - a0 > MERGE_LONGSEG) {
+                const int slot = atomicAdd(&nlst, 1);
+                if (slot < MERGE_LISTCAP) { lst[slot] = j; continue; }
+                /* (cannot happen: a tile holds fewer than MERGE_LISTCAP pieces of that length; summed here if it did) */
+            }
+            double sum = 0.0;
+            for (int k = a0; k < b0; k++) sum += prod[k];
+            if (j == tl.nre) P.part[2 * (size_t) t + 1] = sum;
+            else if (j == 0 && rp[0] < tl.k0) P.part[2 * (size_t) t] = sum;
+            else spmv_row_epilogue(tl.r0 + j, sum, P.mode, P.x, P.y, P.b, P.dotrows, dot);
+        }
+        if (tid == 0 && !(tl.nre > 0 && rp[0] < tl.k0)) P.part[2 * (size_t) t] = 0.0;      /* no head piece in this tile */
+        __syncthreads();
+
+        /* (2b) long units: a warp each, lanes stride over the piece, fixed shuffle tree */
+        const int nl = min(nlst, MERGE_LISTCAP);
+        for (int q = tid >> 5; q < nl; q += T / 32) {
+            const int j = lst[q];
+            const int a0 = max(rp[j], tl.k0) - tl.k0;
+            const int b0 = (j < tl.nre ? rp[j + 1] : kend) - tl.k0;
+            double sum = 0.0;
+            for (int k = a0 + (tid & 31); k < b0; k += 32) sum += prod[k];
+            sum = warp_sum(sum);
+            if ((tid & 31) == 0) {
+                if (j == tl.nre) P.part[2 * (size_t) t + 1] = sum;
+                else if (j == 0 && rp[0] < tl.k0) P.part[2 * (size_t) t] = sum;
+                else spmv_row_epilogue(tl.r0 + j, sum, P.mode, P.x, P.y, P.b, P.dotrows, dot);
+            }
+        }
+        __syncthreads();        /* stage s, prod[] and the list are free again */
+        if (tid == 0) {
+            nlst = 0;
+            const int tn = t + S * gridDim.x;
+            if (tn < P.ntiles) merge_issue(P, P.tiles[tn], stage, &full_bar[s], pol);
+        }
+    }
+
+    if (P.acc) {
+        const double v = block_sum(dot, red);
+        if (tid == 0 && v != 0.0) atomicAdd(P.acc, v);
+    }
+}
+
+/* split rows: add the pieces in tile order (a warp per row), then the row's epilogue */
+__global__ void __launch_bounds__(256)
+spmv_merge_fix_kernel(int nsplit, const acgb200_msplit *split, const double *part,
+                      const double *x, double *y, const double *b, double *acc, int dotrows, int mode,
+                      const acgb200_ctrl *cin, const acgb200_devstate *st)
+{
+    __shared__ double red[8];
+    if (!gate_read(cin, st).active) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    double dot = 0.0;
+    for (int i = warp; i < nsplit; i += nwarps) {
+        const acgb200_msplit sp = split[i];
+        double sum = 0.0;
+        for (int t = sp.ta + lane; t < sp.tb; t += 32) sum += part[2 * (size_t) t + 1];
+        sum = warp_sum(sum);
+        if (lane == 0) {
+            sum += part[2 * (size_t) sp.tb];
+            spmv_row_epilogue(sp.row, sum, mode, x, y, b, dotrows, dot);
+        }
+    }
+    if (acc) {
+        dot = block_sum(dot, red);
+        if (threadIdx.x == 0 && dot != 0.0) atomicAdd(acc, dot);
     }
 }
 
@@ -1179,13 +1395,31 @@ static inline int stage_bytes(const acgb200_spmvplan *pl)
 typedef void (*slice_fn)(const SliceParams);
 
 /* (values + gathers in flight per lane, threads per CTA) of the slice kernel */
-static slice_fn slice_variant(int UB, int T, int PF)
+/* MB: resident CTAs per SM the register allocator must leave room for (0: no constraint) */
+static slice_fn slice_variant(int UB, int T, int PF, int MB)
 {
-#define X(u, t) if (UB == u && T == t) return PF ? spmv_slices_kernel<u, t, true> : spmv_slices_kernel<u, t, false>;
-    X(3, 128) X(4, 128) X(5, 128) X(7, 128) X(8, 128) X(9, 128) X(14, 128) X(3, 256) X(4, 256) X(5, 256) X(7, 256) X(8, 256) X(9, 256) X(14, 256)
+#define X(u, t) if (UB == u && T == t && MB == 0) return PF ? spmv_slices_kernel<u, t, true, 0> : spmv_slices_kernel<u, t, false, 0>;
+    X(3, 128) X(4, 128) X(5, 128) X(7, 128) X(8, 128) X(9, 128) X(14, 128) X(4, 256) X(5, 256) X(7, 256) X(8, 256) X(9, 256) X(14, 256)
+    X(7, 64) X(9, 64)
+#undef X
+#define X(u, t, m) if (UB == u && T == t && MB == m && !PF) return spmv_slices_kernel<u, t, false, m>;
+    X(9, 128, 10) X(9, 128, 12) X(7, 128, 10) X(7, 128, 12) X(14, 128, 6) X(14, 128, 8) X(9, 256, 5) X(9, 64, 20)
 #undef X
     return NULL;
 }
+
+typedef void (*merge_fn)(const MergeParams);
+
+static merge_fn merge_variant(int T)
+{
+    if (T == 128) return spmv_merge_kernel<128, 8>;
+    if (T == 256) return spmv_merge_kernel<256, 4>;
+    return NULL;
+}
+
+static inline int merge_slots(const acgb200_spmvplan *pl) { return (pl->merge_items + 8 + 3) & ~3; }
+static inline int merge_rslots(const acgb200_spmvplan *pl) { return (pl->merge_items + 1 + 8 + 3) & ~3; }
+static inline int merge_stage_bytes(const acgb200_spmvplan *pl) { return (merge_slots(pl) * 12 + merge_rslots(pl) * 4 + 127) & ~127; }
 
 /* acgb200_spmv_choose (tile-plan heuristic) and acgb200_spmv_min_bytes are host-only: plan.c */
 
@@ -1205,8 +1439,23 @@ extern "C" int acgb200_spmv_configure(acgb200_spmvplan *pl)
     if (grid > pl->ntiles) grid = pl->ntiles;
     if (grid < 1) grid = 1;
     pl->grid = (int) grid;
+    if (pl->nmtiles > 0) {
+        merge_fn mfn = merge_variant(pl->merge_threads);
+        if (!mfn) return (int) cudaErrorInvalidConfiguration;
+        pl->merge_smem = merge_stage_bytes(pl) * pl->merge_stages + merge_slots(pl) * (int) sizeof(double);
+        err = cudaFuncSetAttribute((const void *) mfn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->merge_smem);
+        if (err) return (int) err;
+        int mper = 0;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mper, (const void *) mfn, pl->merge_threads, pl->merge_smem);
+        if (err) return (int) err;
+        if (mper < 1) mper = 1;
+        if (pl->merge_max_ctas > 0 && mper > pl->merge_max_ctas) mper = pl->merge_max_ctas;
+        long long mgrid = (long long) acgb200_num_sms() * mper;
+        if (mgrid > pl->nmtiles) mgrid = pl->nmtiles;
+        pl->merge_grid = (int) (mgrid < 1 ? 1 : mgrid);
+    }
     if (pl->nslices > 0) {
-        slice_fn sfn = slice_variant(pl->slice_ub, pl->slice_threads, pl->slice_pf);
+        slice_fn sfn = slice_variant(pl->slice_ub, pl->slice_threads, pl->slice_pf, pl->slice_minb);
         if (!sfn) return (int) cudaErrorInvalidConfiguration;
         pl->slice_smem = ((pl->slice_npat * pl->slice_lpad + 3) & ~3) * (int) sizeof(int);
         err = cudaFuncSetAttribute((const void *) sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->slice_smem);
@@ -1239,7 +1488,29 @@ extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t strea
     const acgb200_spmvplan *pl = a->plan;
     /* with neither tiles nor a peer-memory duty for the tile kernel, the slice kernel forwards the
      * control word itself and the tile kernel is not launched */
-    const bool slices_forward = pl->nslices > 0 && pl->ntiles == 0 && !a->p2p;
+    const bool slices_forward = (pl->nslices > 0 || pl->nmtiles > 0) && pl->ntiles == 0 && !a->p2p;
+    if (pl->nmtiles > 0) {
+        /* rows [0, merge_rows) of an irregular matrix: merge-path tiles, then the rows cut by tile boundaries */
+        MergeParams M;
+        M.tiles = pl->d_mtiles; M.ntiles = pl->nmtiles; M.sc = merge_slots(pl); M.rc = merge_rslots(pl);
+        M.stage_bytes = merge_stage_bytes(pl); M.nstages = pl->merge_stages;
+        M.rowptr = a->rowptr; M.colidx = a->colidx; M.a = a->a; M.part = pl->d_mpart;
+        M.x = a->x; M.y = a->y; M.b = a->b; M.acc = a->acc; M.dotrows = a->dotrows; M.mode = a->mode;
+        M.ctrl_in = a->ctrl_in; M.ctrl_out = slices_forward ? a->ctrl_out : NULL; M.st = a->st; M.housekeeping = a->housekeeping;
+        const cudaError_t le = launch_chain(merge_variant(pl->merge_threads), pl->merge_grid, pl->merge_threads,
+                                            (size_t) pl->merge_smem, stream, M);
+        if (le) return (int) le;
+        if (pl->nsplit > 0) {
+            long long grid = ((long long) pl->nsplit * 32 + 255) / 256;
+            const long long cap = (long long) acgb200_num_sms() * 8;
+            if (grid > cap) grid = cap;
+            /* reads the control word the merge kernel read (ctrl_in is only rewritten by the iteration's last kernel) */
+            spmv_merge_fix_kernel<<<(int) grid, 256, 0, stream>>>(pl->nsplit, pl->d_msplit, pl->d_mpart, a->x, a->y, a->b, a->acc,
+                                                                 a->dotrows, a->mode, a->ctrl_in, a->st);
+            const cudaError_t fe = cudaGetLastError();
+            if (fe) return (int) fe;
+        }
+    }
     if (pl->nslices > 0) {
         /* first: the tile kernel's last CTA publishes the fused dot, which these rows add into */
         SliceParams S;
@@ -1247,7 +1518,7 @@ extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t strea
         S.patid = pl->d_spatid; S.spatoff = pl->d_spatoff; S.npat = pl->slice_npat; S.lpad = pl->slice_lpad;
         S.x = a->x; S.y = a->y; S.b = a->b; S.acc = a->acc; S.dotrows = a->dotrows; S.mode = a->mode;
         S.ctrl_in = a->ctrl_in; S.ctrl_out = slices_forward ? a->ctrl_out : NULL; S.st = a->st; S.housekeeping = a->housekeeping;
-        const cudaError_t le = launch_chain(slice_variant(pl->slice_ub, pl->slice_threads, pl->slice_pf), pl->slice_grid, pl->slice_threads,
+        const cudaError_t le = launch_chain(slice_variant(pl->slice_ub, pl->slice_threads, pl->slice_pf, pl->slice_minb), pl->slice_grid, pl->slice_threads,
                                             (size_t) pl->slice_smem, stream, S);
         if (le) return (int) le;
     }

@@ -17,6 +17,7 @@
 
 struct record {                       /* what every rank tells every other rank */
     cudaIpcMemHandle_t handle;
+    int valid;                        /* 0: this rank could not set up its window -- nobody uses the exchange */
     int recvsize;
     int rdispl_for[ACGB200_MAXR];     /* offset of sender q's segment in my ghost buffer, -1: not a neighbour */
 };
@@ -76,41 +77,52 @@ int acgb200_p2p_init(struct acgb200_p2p *p, const struct acghalo *halo, int bord
     int err = acgcomm_size(comm, &nranks); if (err) return err;
     err = acgcomm_rank(comm, &rank); if (err) return err;
     if (nranks < 2 || nranks > ACGB200_MAXR || comm->type != acgcomm_nccl) return ACG_ERR_NOT_SUPPORTED;
-    if (halo->nrecipients > ACGB200_MAXR || halo->nsenders > ACGB200_MAXR) return ACG_ERR_NOT_SUPPORTED;
+    /* (every rank sees the same communicator, so the returns above are taken by all ranks or by none) */
     p->nranks = nranks; p->rank = rank;
 
-#define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { if (errcode) *errcode = (int) e_; return ACG_ERR_CUDA; } } while (0)
-    p->window_bytes = off_ghost() + 2 * ghost_stride(halo->recvsize);
-    CUP(cudaMalloc(&p->window, p->window_bytes));
-    CUP(cudaMemset(p->window, 0, p->window_bytes));
-
-    /* all-gather the records */
-    struct record mine, *all = malloc((size_t) nranks * sizeof(*all));
-    if (!all) return ACG_ERR_ERRNO;
+    /* One error path: everything allocated here is released at `done` unless the set-up succeeds.  The
+     * all-gather is executed by every rank, also by one whose local part failed (its record says so): a
+     * rank that skipped the collective would leave its peers inside it and mismatch the communicator's
+     * next collective. */
+#define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { if (errcode) *errcode = (int) e_; err = ACG_ERR_CUDA; goto done; } } while (0)
+    struct record mine, *all = NULL;
+    void *d_mine = NULL, *d_all = NULL;
+    int *bptr = NULL, *bq = NULL, *bdst = NULL, *d_bptr = NULL, *d_bq = NULL, *d_bdst = NULL;
+    struct acgb200_p2pdev *d = &p->h_desc;
     memset(&mine, 0, sizeof(mine));
-    CUP(cudaIpcGetMemHandle(&mine.handle, p->window));
+    mine.valid = 0;
+    if (halo->nrecipients <= ACGB200_MAXR && halo->nsenders <= ACGB200_MAXR) {
+        p->window_bytes = off_ghost() + 2 * ghost_stride(halo->recvsize);
+        cudaError_t e = cudaMalloc(&p->window, p->window_bytes);
+        if (!e) e = cudaMemset(p->window, 0, p->window_bytes);
+        if (!e) e = cudaIpcGetMemHandle(&mine.handle, p->window);
+        if (!e) mine.valid = 1;
+        else { if (errcode) *errcode = (int) e; (void) cudaGetLastError(); }
+    }
     mine.recvsize = halo->recvsize;
     for (int q = 0; q < ACGB200_MAXR; q++) mine.rdispl_for[q] = -1;
-    for (int j = 0; j < halo->nsenders; j++) mine.rdispl_for[halo->senders[j]] = halo->rdispls[j];
-    void *d_mine = NULL, *d_all = NULL;
+    if (mine.valid) for (int j = 0; j < halo->nsenders; j++) mine.rdispl_for[halo->senders[j]] = halo->rdispls[j];
+    all = malloc((size_t) nranks * sizeof(*all));
+    if (!all) { err = ACG_ERR_ERRNO; goto done; }      /* (host malloc of a few KiB: not a case worth a collective) */
     CUP(cudaMalloc(&d_mine, sizeof(mine)));
     CUP(cudaMalloc(&d_all, (size_t) nranks * sizeof(mine)));
     CUP(cudaMemcpyAsync(d_mine, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream));
-    ncclResult_t nr = ncclAllGather(d_mine, d_all, sizeof(mine), ncclChar, comm->ncclcomm, stream);
-    if (nr != ncclSuccess) { if (errcode) *errcode = (int) nr; free(all); return ACG_ERR_NCCL; }
+    {
+        ncclResult_t nr = ncclAllGather(d_mine, d_all, sizeof(mine), ncclChar, comm->ncclcomm, stream);
+        if (nr != ncclSuccess) { if (errcode) *errcode = (int) nr; err = ACG_ERR_NCCL; goto done; }
+    }
     CUP(cudaMemcpyAsync(all, d_all, (size_t) nranks * sizeof(mine), cudaMemcpyDeviceToHost, stream));
     CUP(cudaStreamSynchronize(stream));
-    cudaFree(d_mine); cudaFree(d_all);
+    for (int r = 0; r < nranks; r++)
+        if (!all[r].valid) { err = mine.valid ? ACG_ERR_NOT_SUPPORTED : ACG_ERR_CUDA; goto done; }   /* same verdict on every rank */
 
     /* map every peer's window */
     for (int r = 0; r < nranks; r++) {
         if (r == rank) { p->peer_base[r] = p->window; continue; }
-        cudaError_t e = cudaIpcOpenMemHandle(&p->peer_base[r], all[r].handle, cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) { if (errcode) *errcode = (int) e; free(all); return ACG_ERR_CUDA; }
+        CUP(cudaIpcOpenMemHandle(&p->peer_base[r], all[r].handle, cudaIpcMemLazyEnablePeerAccess));
     }
 
     /* device descriptor */
-    struct acgb200_p2pdev *d = &p->h_desc;
     memset(d, 0, sizeof(*d));
     d->nranks = nranks; d->rank = rank;
     d->nrecip = halo->nrecipients; d->sendsize = halo->sendsize;
@@ -118,7 +130,7 @@ int acgb200_p2p_init(struct acgb200_p2p *p, const struct acghalo *halo, int bord
         const int q = halo->recipients[i];
         d->sdispls[i] = halo->sdispls[i];
         d->peer_rdispl[i] = all[q].rdispl_for[rank];
-        if (d->peer_rdispl[i] < 0) { free(all); return ACG_ERR_INVALID_VALUE; }   /* asymmetric pattern */
+        if (d->peer_rdispl[i] < 0) { err = ACG_ERR_INVALID_VALUE; goto done; }   /* asymmetric pattern */
         char *base = p->peer_base[q];
         d->peer_ghost[i][0] = (double *) (base + off_ghost());
         d->peer_ghost[i][1] = (double *) (base + off_ghost() + ghost_stride(all[q].recvsize));
@@ -127,17 +139,19 @@ int acgb200_p2p_init(struct acgb200_p2p *p, const struct acghalo *halo, int bord
     d->sdispls[halo->nrecipients] = halo->sendsize;
     d->nsenders = halo->nsenders;
     for (int j = 0; j < halo->nsenders; j++) d->senders[j] = halo->senders[j];
-    char *me = p->window;
-    d->my_hflag = (unsigned long long *) (me + off_hflag());
-    d->my_ghost[0] = (double *) (me + off_ghost());
-    d->my_ghost[1] = (double *) (me + off_ghost() + ghost_stride(halo->recvsize));
-    for (int r = 0; r < nranks; r++) {
-        char *base = p->peer_base[r];
-        d->peer_red[r] = (double *) (base + off_red());
-        d->peer_rflag[r] = (unsigned long long *) (base + off_rflag());
+    {
+        char *me = p->window;
+        d->my_hflag = (unsigned long long *) (me + off_hflag());
+        d->my_ghost[0] = (double *) (me + off_ghost());
+        d->my_ghost[1] = (double *) (me + off_ghost() + ghost_stride(halo->recvsize));
+        for (int r = 0; r < nranks; r++) {
+            char *base = p->peer_base[r];
+            d->peer_red[r] = (double *) (base + off_red());
+            d->peer_rflag[r] = (unsigned long long *) (base + off_rflag());
+        }
+        d->my_red = (double *) (me + off_red());
+        d->my_rflag = (unsigned long long *) (me + off_rflag());
     }
-    d->my_red = (double *) (me + off_red());
-    d->my_rflag = (unsigned long long *) (me + off_rflag());
     d->hbase = d->rbase = 1;
     {
         /* watchdog of the device-side waits (kernels.cu, p2p_spin): generous, its
@@ -151,28 +165,40 @@ int acgb200_p2p_init(struct acgb200_p2p *p, const struct acghalo *halo, int bord
     d->borderoff = borderoff; d->nborder = nborder;
     {
         const size_t ne = (size_t) (halo->sendsize > 0 ? halo->sendsize : 1);
-        int *bptr = malloc(((size_t) nborder + 1) * sizeof(int));
-        int *bq = malloc(ne * sizeof(int));
-        int *bdst = malloc(ne * sizeof(int));
-        if (!bptr || !bq || !bdst) { free(bptr); free(bq); free(bdst); free(all); return ACG_ERR_ERRNO; }
+        bptr = malloc(((size_t) nborder + 1) * sizeof(int));
+        bq = malloc(ne * sizeof(int));
+        bdst = malloc(ne * sizeof(int));
+        if (!bptr || !bq || !bdst) { err = ACG_ERR_ERRNO; goto done; }
         err = acgb200_p2p_inverse_map(halo, borderoff, nborder, d->peer_rdispl, bptr, bq, bdst);
-        if (err) { free(bptr); free(bq); free(bdst); free(all); return err; }
-        int *d_bptr = NULL, *d_bq = NULL, *d_bdst = NULL;
+        if (err) goto done;
         CUP(cudaMalloc((void **) &d_bptr, ((size_t) nborder + 1) * sizeof(int)));
         CUP(cudaMalloc((void **) &d_bq, ne * sizeof(int)));
         CUP(cudaMalloc((void **) &d_bdst, ne * sizeof(int)));
         CUP(cudaMemcpy(d_bptr, bptr, ((size_t) nborder + 1) * sizeof(int), cudaMemcpyHostToDevice));
         CUP(cudaMemcpy(d_bq, bq, (size_t) halo->sendsize * sizeof(int), cudaMemcpyHostToDevice));
         CUP(cudaMemcpy(d_bdst, bdst, (size_t) halo->sendsize * sizeof(int), cudaMemcpyHostToDevice));
-        d->bptr = d_bptr; d->bq = d_bq; d->bdst = d_bdst;
-        free(bptr); free(bq); free(bdst);
     }
-    free(all);
     CUP(cudaMalloc((void **) &p->d_desc, sizeof(*d)));
+    d->bptr = d_bptr; d->bq = d_bq; d->bdst = d_bdst;
     CUP(cudaMemcpy(p->d_desc, d, sizeof(*d), cudaMemcpyHostToDevice));
+    d_bptr = d_bq = d_bdst = NULL;             /* owned by the descriptor from here on (acgb200_p2p_free) */
     p->seq = 1;
     p->enabled = 1;
-    return ACG_SUCCESS;
+    err = ACG_SUCCESS;
+done:
+    free(all); free(bptr); free(bq); free(bdst);
+    cudaFree(d_mine); cudaFree(d_all);
+    cudaFree(d_bptr); cudaFree(d_bq); cudaFree(d_bdst);
+    if (err) {
+        /* the caller's agreement step (min-allreduce over the ranks' outcomes, cgcuda.c) follows on all ranks;
+         * the window stays allocated until acgsolvercuda_free, after a barrier: a peer may have mapped it */
+        for (int r = 0; r < nranks; r++)
+            if (r != rank && p->peer_base[r]) { cudaIpcCloseMemHandle(p->peer_base[r]); p->peer_base[r] = NULL; }
+        cudaFree(p->d_desc); p->d_desc = NULL;
+        memset(&p->h_desc, 0, sizeof(p->h_desc));
+        p->enabled = 0;
+    }
+    return err;
 #undef CUP
 }
 

@@ -368,9 +368,12 @@ int acgsymcsrmatrix_partition(
     const int64_t *rp = A->rowptr;
     const acgidx_t *cj = A->colidx;
     int err = ACG_ERR_ERRNO;
+    int64_t **cur = NULL;           /* scratch of pass 2, released on every path */
+    size_t **gseg = NULL;
     if (A->nzrows || A->nghostrows) return ACG_ERR_NOT_SUPPORTED;   /* partition whole matrices only */
     for (acgidx_t i = 0; i < n; i++)
         if (rowparts[i] < 0 || rowparts[i] >= nparts) return ACG_ERR_INDEX_OUT_OF_BOUNDS;
+    memset(sub, 0, (size_t) nparts * sizeof(*sub));      /* the failure path looks at every part */
 
     /* pass 1: cut edges -> (node, other part) pairs for both ends */
     size_t *ncut = calloc((size_t) nparts + 1, sizeof(*ncut));
@@ -482,14 +485,14 @@ int acgsymcsrmatrix_partition(
         }
     }
     {
-        int64_t **cur = calloc((size_t) nparts, sizeof(*cur));
-        size_t **gseg = calloc((size_t) nparts, sizeof(*gseg));   /* start of each owner's ghost segment */
-        if (!cur || !gseg) { free(cur); free(gseg); goto fail; }
+        cur = calloc((size_t) nparts, sizeof(*cur));
+        gseg = calloc((size_t) nparts, sizeof(*gseg));   /* start of each owner's ghost segment */
+        if (!cur || !gseg) goto fail;
         for (int p = 0; p < nparts; p++) {
             struct acggraph *g = sub[p].graph;
             cur[p] = malloc((size_t) (g->npnodes > 0 ? g->npnodes : 1) * sizeof(int64_t));
             gseg[p] = calloc((size_t) nparts + 1, sizeof(size_t));
-            if (!cur[p] || !gseg[p]) goto fail;   /* (leaks the scratch on this cold path) */
+            if (!cur[p] || !gseg[p]) goto fail;
             memcpy(cur[p], g->srcnodeptr, (size_t) g->npnodes * sizeof(int64_t));
             for (size_t i = 0; i < nghostp[p]; i++) gseg[p][ghosts[p][i].part + 1]++;
             for (int q = 0; q < nparts; q++) gseg[p][q + 1] += gseg[p][q];
@@ -553,11 +556,14 @@ int acgsymcsrmatrix_partition(
             }
             matrix_view_graph(&sub[p]);
             free(cur[p]); free(gseg[p]);
+            cur[p] = NULL; gseg[p] = NULL;
         }
-        free(cur); free(gseg);
     }
     err = ACG_SUCCESS;
 fail:
+    if (cur) for (int p = 0; p < nparts; p++) free(cur[p]);
+    if (gseg) for (int p = 0; p < nparts; p++) free(gseg[p]);
+    free(cur); free(gseg);
     if (ghosts) for (int p = 0; p < nparts; p++) free(ghosts[p]);
     if (borders) for (int p = 0; p < nparts; p++) free(borders[p]);
     free(ghosts); free(borders); free(nghostp); free(nborderp);

@@ -18,7 +18,9 @@ extern "C" {
  * "spmv_nnz_cap", "spmv_rows_cap", "spmv_stages", "spmv_threads", "spmv_unroll",
  * "spmv_max_ctas" (SpMV tile plan overrides, read at acgsolvercuda_init), "spmv_slices"
  * (0/1, default 1: index-free slice-major storage of the rows that repeat a pattern, slices.c; shape
- * overrides "slice_ub", "slice_threads", "slice_pf", "slice_max_ctas"), "spmv_medium", "graph"
+ * overrides "slice_ub", "slice_threads", "slice_pf", "slice_max_ctas", "slice_minb"), "spmv_merge" (-1/0/1,
+ * default -1: merge-path tiles when the row lengths are irregular, mergeplan.c; "merge_items", "merge_threads",
+ * "merge_max_ctas"), "spmv_medium", "graph"
  * (0/1: replay iteration pairs as CUDA graphs), "redstream" (0/1: pipelined
  * allreduce on its own stream and communicator; read at acgsolvercuda_init).  Environment variables ACGB200_<KEY> set the
  * same values at first use. */
@@ -58,6 +60,9 @@ struct acgb200_info {
     int spmv_slices;            /* 32-row pattern slices multiplied by spmv_slices_kernel (option "spmv_slices", slices.c) */
     int spmv_slice_rows;        /* rows they cover; the other rows are in tiles */
     int spmv_slice_ub, spmv_slice_grid;
+    int spmv_merge_tiles;       /* merge-path tiles (option "spmv_merge", mergeplan.c) ... */
+    int spmv_merge_rows;        /* ... the rows [0, spmv_merge_rows) they cover ... */
+    int spmv_merge_split;       /* ... and the rows cut by tile boundaries (finished by spmv_merge_fix_kernel) */
 };
 ACG_API int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info);
 
@@ -87,6 +92,12 @@ ACG_API int acgb200_slices_host(int nrows, int cover_hi, const int64_t *rowptr, 
  * want to solve need not call either: acgsolvercuda_init expands on the device by itself when the
  * matrix has no full storage (diagonal shift 0), which also halves the matrix upload. */
 ACG_API int acgsymcsrmatrix_dsymv_init_cuda(struct acgsymcsrmatrix *A, double eps, int *cudaerrcode);
+
+/* The merge-path tile plan of rows [0,hi) of a CSR row-pointer array (mergeplan.c), host only: tiles4 gets
+ * {r0, nre, k0, nnz} per tile (at most maxtiles), split3 {row, ta, tb} per row cut by tile boundaries (at
+ * most maxtiles); *ntiles, *nsplit the counts. */
+ACG_API int acgb200_merge_plan_host(int hi, const int64_t *rowptr, int items, int *tiles4, int maxtiles,
+                                    int *split3, int *ntiles, int *nsplit);
 
 /* One part of the block-partitioned 7- or 27-point stencil matrix on an
  * nx*ny*nz box (diag 6 / 26, neighbours -1, lexicographic numbering, px*py*pz

@@ -270,11 +270,102 @@ static void slices_exec(const struct acgb200_spmvargs *a, int forward)
     if (a->acc) *a->acc += dot;
 }
 
+/* warp_sum of kernels.cu on 32 "lanes": xor-shuffle tree, every lane ends with the same value */
+static double warp_tree(double *v)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        double w[32];
+        for (int l = 0; l < 32; l++) w[l] = v[l] + v[l ^ o];
+        memcpy(v, w, sizeof(w));
+    }
+    return v[0];
+}
+
+/* the merge-path kernels (spmv_merge_kernel + spmv_merge_fix_kernel), tile by tile through the slices the
+ * TMA copies stage, with the kernel's summation orders; every finished row is compared with the row's
+ * product through the CSR arrays (rounding-level tolerance: the orders differ for long pieces) */
+static void merge_exec(const struct acgb200_spmvargs *a, int forward)
+{
+    const struct acgb200_spmvplan *pl = a->plan;
+    const struct gate g = gate_read(a->ctrl_in, a->st);
+    if (forward && a->ctrl_in) {
+        *a->ctrl_out = *a->ctrl_in;
+        if (g.active) {
+            const int s = g.iter & 1;
+            if (a->housekeeping == 1) a->st->rr_loc[s ^ 1] = 0.0;
+            if (a->housekeeping == 2) { a->st->gd_loc[s ^ 1][0] = 0.0; a->st->gd_loc[s ^ 1][1] = 0.0; }
+        }
+    }
+    if (!g.active) return;
+    const int sc = (pl->merge_items + 8 + 3) & ~3, rc = (pl->merge_items + 1 + 8 + 3) & ~3;
+    double *vals = malloc((size_t) sc * sizeof(double)), *prod = malloc((size_t) sc * sizeof(double));
+    int *cols = malloc((size_t) sc * sizeof(int)), *rps = malloc((size_t) rc * sizeof(int));
+    unsigned char *done = calloc((size_t) pl->merge_rows + 1, 1);
+    double dot = 0.0;
+    int bad = 0;
+    for (int t = 0; t < pl->nmtiles && !bad; t++) {
+        const struct acgb200_mtile tl = pl->d_mtiles[t];
+        const int k_al = tl.k0 & ~3, nnz_al = (tl.k0 + tl.nnz - k_al + 3) & ~3;
+        const int row_al = tl.r0 & ~3, nrp = (tl.r0 + tl.nre + 1 - row_al + 3) & ~3;
+        if (nnz_al > sc || nrp > rc || tl.nnz > pl->merge_items || tl.nre > pl->merge_items) { bad = 1; break; }
+        memcpy(vals, a->a + k_al, (size_t) nnz_al * sizeof(double));
+        memcpy(cols, a->colidx + k_al, (size_t) nnz_al * sizeof(int));
+        memcpy(rps, a->rowptr + row_al, (size_t) nrp * sizeof(int));
+        const int koff = tl.k0 & 3;
+        const int *rp = rps + (tl.r0 & 3);
+        for (int kk = 0; kk < tl.nnz; kk++) prod[kk] = vals[koff + kk] * a->x[cols[koff + kk]];
+        const int kend = tl.k0 + tl.nnz;
+        const int head = tl.nre > 0 && rp[0] < tl.k0;
+        if (!head) pl->d_mpart[2 * (size_t) t] = 0.0;
+        for (int j = 0; j <= tl.nre; j++) {
+            const int a0 = (rp[j] > tl.k0 ? rp[j] : tl.k0) - tl.k0;
+            const int b0 = (j < tl.nre ? rp[j + 1] : kend) - tl.k0;
+            if (b0 > tl.nnz || (b0 > a0 && a0 < 0)) { bad = 1; break; }
+            double sum = 0.0;
+            if (b0 - a0 > 32) {
+                double lane[32];
+                for (int l = 0; l < 32; l++) { lane[l] = 0.0; for (int k = a0 + l; k < b0; k += 32) lane[l] += prod[k]; }
+                sum = warp_tree(lane);
+            } else for (int k = a0; k < b0; k++) sum += prod[k];
+            if (j == tl.nre) pl->d_mpart[2 * (size_t) t + 1] = sum;
+            else if (j == 0 && head) pl->d_mpart[2 * (size_t) t] = sum;
+            else {
+                const int row = tl.r0 + j;
+                double direct = 0.0, scale = 0.0;
+                for (int k = a->rowptr[row]; k < a->rowptr[row + 1]; k++) {
+                    direct = fma(a->a[k], a->x[a->colidx[k]], direct); scale += fabs(a->a[k] * a->x[a->colidx[k]]);
+                }
+                if (row >= pl->merge_rows || done[row]++) bad = 1;
+                row_epilogue(a, row, fabs(sum - direct) <= 1e-13 * scale + 1e-300 ? sum : NAN, &dot);
+            }
+        }
+    }
+    /* rows cut by tile boundaries */
+    for (int i = 0; i < pl->nsplit && !bad; i++) {
+        const struct acgb200_msplit sp = pl->d_msplit[i];
+        double lane[32];
+        for (int l = 0; l < 32; l++) { lane[l] = 0.0; for (int t = sp.ta + l; t < sp.tb; t += 32) lane[l] += pl->d_mpart[2 * (size_t) t + 1]; }
+        double sum = warp_tree(lane);
+        sum += pl->d_mpart[2 * (size_t) sp.tb];
+        double direct = 0.0, scale = 0.0;
+        for (int k = a->rowptr[sp.row]; k < a->rowptr[sp.row + 1]; k++) {
+            direct = fma(a->a[k], a->x[a->colidx[k]], direct); scale += fabs(a->a[k] * a->x[a->colidx[k]]);
+        }
+        if (sp.row >= pl->merge_rows || done[sp.row]++) bad = 1;
+        row_epilogue(a, sp.row, fabs(sum - direct) <= 1e-13 * scale + 1e-300 ? sum : NAN, &dot);
+    }
+    for (int r = 0; r < pl->merge_rows; r++) if (done[r] != 1) bad = 1;      /* every row exactly once */
+    if (bad) for (int r = 0; r < pl->merge_rows; r++) a->y[r] = NAN;
+    free(vals); free(prod); free(cols); free(rps); free(done);
+    if (a->acc) *a->acc += dot;
+}
+
 static void spmv_exec(void *p)
 {
     const struct acgb200_spmvargs *a = p;
     const struct acgb200_spmvplan *pl = a->plan;
-    const int slices_forward = pl->nslices > 0 && pl->ntiles == 0 && !a->p2p;
+    const int slices_forward = (pl->nslices > 0 || pl->nmtiles > 0) && pl->ntiles == 0 && !a->p2p;
+    if (pl->nmtiles > 0) merge_exec(a, slices_forward);
     if (pl->nslices > 0) slices_exec(a, slices_forward);
     /* the tile kernel: control word forwarding and housekeeping, then the tiles */
     if (pl->ntiles > 0 || (a->ctrl_in && !slices_forward)) {

@@ -73,7 +73,8 @@ def main():
     cg = ab.SolverCuda(ab.SymCsrMatrix.init_real_double(n, r, c, v) if spec.get("no_full_storage") else A)
     inf = cg.info()
     b = A.vector(); b.x[:] = np.random.default_rng(5).standard_normal(n)
-    out = {"slices": inf["spmv_slices"], "slice_rows": inf["spmv_slice_rows"], "nlong": inf["spmv_nlong"], "nmedium": inf["spmv_nmedium"], "ntiles": inf["spmv_ntiles"], "runs": []}
+    out = {"merge_tiles": inf["spmv_merge_tiles"], "merge_rows": inf["spmv_merge_rows"], "merge_split": inf["spmv_merge_split"],
+           "slices": inf["spmv_slices"], "slice_rows": inf["spmv_slice_rows"], "nlong": inf["spmv_nlong"], "nmedium": inf["spmv_nmedium"], "ntiles": inf["spmv_ntiles"], "runs": []}
     y, _ = cg.spmv(b.x)
     want = O.dsymv(csr, 1.0, b.x, 0.0, np.zeros(n))
     out["spmv_err"] = float(np.abs(y - want).max() / np.abs(want).max())

@@ -46,7 +46,7 @@ def test_spmv_matches_oracle(name, gen, ab, oracle):
     scale = oracle.dsymv((csr[0], csr[1], np.abs(csr[2])), 1.0, np.abs(x), 0.0, np.zeros(n))
     assert np.all(np.abs(y - want) <= SPMV_RTOL * scale + 1e-300)
     if name == "rmat-longrows":
-        assert cg.info()["spmv_nlong"] > 0
+        assert cg.info()["spmv_merge_tiles"] > 0           # power-law rows: merge-path tiles by default
     cg.free()
 
 
@@ -77,7 +77,7 @@ def test_spmv_ragged_rows(ab, oracle):
     scale = oracle.dsymv((csr[0], csr[1], np.abs(csr[2])), 1.0, np.abs(x), 0.0, np.zeros(n))
     assert np.all(np.abs(y - want) <= SPMV_RTOL * scale + 1e-300)
     assert np.all(y[lens == 0] == 0.0)
-    assert cg.info()["spmv_nlong"] >= 1
+    assert cg.info()["spmv_merge_tiles"] > 0 or cg.info()["spmv_nlong"] >= 1
     cg.free()
 
 
@@ -143,7 +143,9 @@ def test_residual_history_fixed_iterations(method, ab, oracle):
         assert cg.c.niterations == k
         # classic: ||r_k||; pipelined reports the last tested iterate, ||r_{k-1}||
         want = hist[k] if method == "solvempi" else hist[k - 1]
-        assert cg.c.rnrm2 == pytest.approx(want, rel=1e-9)
+        # 1e-9 relative while the residual is large; once the solve is down at rounding level (b = 1 on
+        # this box converges to 1e-12 within 40 iterations) only the north-star bound relative to ||r0|| holds
+        assert cg.c.rnrm2 == pytest.approx(want, rel=1e-9, abs=RES_RTOL * hist[0])
     cg.free()
 
 
@@ -285,11 +287,11 @@ def test_power_law_properties(n, edges, ab):
     """BASELINE config 5 (R-MAT power-law SPD; the full 20 M / 200 M size with
     ACGB200_TEST_LARGE=1) through size-independent properties: every row of
     A = D + I - Adj sums to 1, so A*1 = 1 exactly in floating point (sums of small
-    integers); symmetry of the product; the long-row path is in use; and CG on
+    integers); symmetry of the product; the merge-path tiles are in use; and CG on
     b = A*x_true approaches x_true with a true residual equal to the reported one."""
     A = ab.SymCsrMatrix.rmat_spd(n, edges, seed=42).dsymv_init(0.0)
     cg = ab.SolverCuda(A)
-    assert cg.info()["spmv_nlong"] > 0
+    assert cg.info()["spmv_merge_tiles"] > 0 and cg.info()["spmv_merge_rows"] == n
     y1, _ = cg.spmv(np.ones(n))
     assert np.array_equal(y1, np.ones(n))
     rng = np.random.default_rng(3)
@@ -369,15 +371,63 @@ def test_pdl_matches_oracle(method, ab, oracle):
     cg.free()
 
 
+MERGE_CASES = [CASES[5], CASES[4], CASES[3], ("7pt-31", CASES[2][1]), ("hub-100k", lambda: mg.rmat_spd(120000, 1500000, seed=11))]
+
+
+@pytest.mark.parametrize("items,threads", [(1024, 128), (256, 128), (4096, 256), (64, 128)])
+@pytest.mark.parametrize("name,gen", MERGE_CASES, ids=[c[0] for c in MERGE_CASES])
+def test_merge_path_tiles_match_oracle(name, gen, items, threads, ab, oracle):
+    """spmv_merge_kernel + spmv_merge_fix_kernel (mergeplan.c) forced on: power-law rows with hubs that span
+    many tiles, dense rows, banded and stencil rows (every row complete inside a tile), tiny tiles in which
+    most rows are cut -- the product equals the oracle's and the row-aligned tiles' to rounding, the fused
+    dots drive both CG loops to the oracle's iterates."""
+    n, r, c, v = gen()
+    for k, val in (("spmv_merge", 1), ("spmv_slices", 0), ("merge_items", items), ("merge_threads", threads)):
+        ab.set_option(k, val)
+    try:
+        A, cg = _solver(ab, n, r, c, v)
+        ab.set_option("spmv_merge", 0)
+        cg_rows = ab.SolverCuda(A)
+    finally:
+        for k, val in (("spmv_merge", -1), ("spmv_slices", 1), ("merge_items", 0), ("merge_threads", 0)):
+            ab.set_option(k, val)
+    inf = cg.info()
+    if n < 1024:
+        assert inf["spmv_merge_tiles"] == 0           # too small to bother
+    else:
+        assert inf["spmv_merge_tiles"] > 0 and inf["spmv_merge_rows"] == n and inf["spmv_ntiles"] == 0 and inf["spmv_nlong"] == 0
+        if name in ("rmat-longrows", "hub-100k") or items <= 256:
+            assert inf["spmv_merge_split"] > 0
+    csr = (A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy())
+    x = np.random.default_rng(1).standard_normal(n)
+    y, _ = cg.spmv(x)
+    y2, _ = cg_rows.spmv(x)
+    want = oracle.dsymv(csr, 1.0, x, 0.0, np.zeros(n))
+    scale = oracle.dsymv((csr[0], csr[1], np.abs(csr[2])), 1.0, np.abs(x), 0.0, np.zeros(n))
+    assert np.all(np.abs(y - want) <= SPMV_RTOL * scale + 1e-300)
+    assert np.all(np.abs(y - y2) <= SPMV_RTOL * scale + 1e-300)
+    b = A.vector(); b.x[:] = np.random.default_rng(2).standard_normal(n)
+    # hubs of degree 1e4-1e5 make the power-law matrices ill conditioned: rounding differences between summation
+    # orders are amplified from the first iterations on (the hub entry of x moves first)
+    its, xtol = (10, 1e-9) if name not in ("rmat-longrows", "hub-100k") else (10, 1e-7)
+    for method, orc in (("solvempi", oracle.cg), ("solve_pipelined", oracle.cg_pipelined)):
+        ref = orc(csr, b.x, maxits=its, rtol=0.0)
+        xs = A.vector()
+        assert getattr(cg, method)(b, xs, maxits=its) == 0 and cg.c.niterations == its
+        assert np.abs(xs.x - ref["x"]).max() <= xtol * np.abs(ref["x"]).max()
+        assert abs(cg.c.rnrm2 - ref["rnrm2"]) <= xtol * ref["r0nrm2"]
+    cg.free(); cg_rows.free()
+
+
 def test_medium_row_kernel_matches_oracle(ab, oracle):
     """Option spmv_medium (spmv_medium_kernel): same product and same CG iterates on a power-law matrix."""
     n, r, c, v = mg.rmat_spd(30000, 600000, seed=8)
-    ab.set_option("spmv_medium", 96)
+    ab.set_option("spmv_medium", 96); ab.set_option("spmv_merge", 0)      # row-aligned tiles + row lists
     try:
         A, cg = _solver(ab, n, r, c, v)
     finally:
-        ab.set_option("spmv_medium", 0)
-    assert cg.info()["spmv_nmedium"] > 0 and cg.info()["spmv_nlong"] > 0
+        ab.set_option("spmv_medium", 0); ab.set_option("spmv_merge", -1)
+    assert cg.info()["spmv_nmedium"] > 0 and cg.info()["spmv_nlong"] > 0 and cg.info()["spmv_merge_tiles"] == 0
     csr = (A.frowptr.copy(), A.fcolidx.copy(), A.fa.copy())
     x = np.random.default_rng(1).standard_normal(n)
     y, _ = cg.spmv(x)

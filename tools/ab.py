@@ -22,7 +22,7 @@ import numpy as np          # noqa: E402
 
 DEFAULTS = dict(profile=0, spmv_lanes=0, spmv_nnz_cap=0, spmv_rows_cap=0, spmv_stages=0, spmv_threads=0,
                 spmv_unroll=0, spmv_max_ctas=0, graph=1, redstream=1, p2p=1, p2p_fuse=1, blas1_ctas=0, pdl=0,
-                spmv_medium=0, spmv_slices=1, slice_ub=0, slice_threads=0, slice_pf=-1, slice_max_ctas=0)
+                spmv_medium=0, spmv_slices=1, slice_ub=0, slice_threads=0, slice_pf=-1, slice_max_ctas=0, slice_minb=0)
 
 VARIANTS = {
     "base": {},
@@ -47,6 +47,13 @@ VARIANTS = {
     "s5p_t256": {"slice_ub": 5, "slice_pf": 1, "slice_threads": 256},
     "s9p_c4": {"slice_ub": 9, "slice_pf": 1, "slice_max_ctas": 4}, "s9p_c3": {"slice_ub": 9, "slice_pf": 1, "slice_max_ctas": 3},
     "s9_c8": {"slice_ub": 9, "slice_pf": 0, "slice_max_ctas": 8},
+    # register caps: m<CTAs per SM the allocator must leave room for>
+    "s9_m10": {"slice_ub": 9, "slice_pf": 0, "slice_minb": 10}, "s9_m12": {"slice_ub": 9, "slice_pf": 0, "slice_minb": 12},
+    "s7_m10": {"slice_ub": 7, "slice_pf": 0, "slice_minb": 10}, "s7_m12": {"slice_ub": 7, "slice_pf": 0, "slice_minb": 12},
+    "s14_m6": {"slice_ub": 14, "slice_pf": 0, "slice_minb": 6}, "s14_m8": {"slice_ub": 14, "slice_pf": 0, "slice_minb": 8},
+    "s9_t256_m5": {"slice_ub": 9, "slice_pf": 0, "slice_threads": 256, "slice_minb": 5},
+    "s9_t64": {"slice_ub": 9, "slice_pf": 0, "slice_threads": 64}, "s9_t64_m20": {"slice_ub": 9, "slice_pf": 0, "slice_threads": 64, "slice_minb": 20},
+    "s7_t64": {"slice_ub": 7, "slice_pf": 0, "slice_threads": 64},
 }
 
 
