@@ -41,6 +41,8 @@
 /* tunables                                                                  */
 /* ------------------------------------------------------------------------ */
 
+#define SPMV_MAX_STAGES_HOST 8      /* SPMV_MAX_STAGES of kernels.cu */
+
 static struct {
     int profile;        /* record CUDA events around each kernel class */
     int check_every;    /* iterations between convergence polls */
@@ -51,11 +53,12 @@ static struct {
     int redstream;      /* pipelined CG: allreduce on its own stream + communicator */
     int p2p;            /* halo + reductions through peer memory (CUDA IPC) instead of NCCL */
     int p2p_fuse;       /* 1: border x ghost block inside the SpMV, pushes inside the update kernels */
+    int blas1_unroll;   /* rows per thread and loop trip of the pipelined update kernel (1 or 2) */
     int blas1_ctas;     /* CTAs per SM of the fused BLAS-1 kernels (0 = one full wave, from the occupancy) */
     int pdl;            /* 1: programmatic dependent launch along the iteration chain (opt-in) */
     int spmv_medium;    /* > 0: rows longer than this (and shorter than a tile) get a warp each (opt-in) */
     int spmv_merge;     /* merge-path tiles for irregular rows (mergeplan.c): -1 decide from the row lengths, 0 off, 1 on */
-    int merge_items, merge_threads, merge_max_ctas;   /* their shape (0 = default) */
+    int merge_items, merge_threads, merge_max_ctas, merge_stages;   /* their shape (0 = default) */
     int spmv_slices;    /* 1: pattern slices (slices.c) -- index-free slice-major storage of the rows that repeat a pattern */
     int slice_ub, slice_threads, slice_pf, slice_max_ctas, slice_minb;   /* slice kernel shape overrides (0 / -1 = default) */
     int loaded;
@@ -80,6 +83,7 @@ static void cfg_load(void)
     if ((s = getenv("ACGB200_P2P"))) cfg.p2p = atoi(s);
     if ((s = getenv("ACGB200_P2P_FUSE"))) cfg.p2p_fuse = atoi(s);
     if ((s = getenv("ACGB200_BLAS1_CTAS"))) cfg.blas1_ctas = atoi(s);
+    if ((s = getenv("ACGB200_BLAS1_UNROLL"))) cfg.blas1_unroll = atoi(s);
     if (cfg.check_every < 1) cfg.check_every = 1;
     if ((s = getenv("ACGB200_PDL"))) cfg.pdl = atoi(s);
     if ((s = getenv("ACGB200_SPMV_MEDIUM"))) cfg.spmv_medium = atoi(s);
@@ -87,6 +91,7 @@ static void cfg_load(void)
     if ((s = getenv("ACGB200_MERGE_ITEMS"))) cfg.merge_items = atoi(s);
     if ((s = getenv("ACGB200_MERGE_THREADS"))) cfg.merge_threads = atoi(s);
     if ((s = getenv("ACGB200_MERGE_MAX_CTAS"))) cfg.merge_max_ctas = atoi(s);
+    if ((s = getenv("ACGB200_MERGE_STAGES"))) cfg.merge_stages = atoi(s);
     if ((s = getenv("ACGB200_SPMV_SLICES"))) cfg.spmv_slices = atoi(s);
     if ((s = getenv("ACGB200_SLICE_UB"))) cfg.slice_ub = atoi(s);
     if ((s = getenv("ACGB200_SLICE_THREADS"))) cfg.slice_threads = atoi(s);
@@ -94,6 +99,7 @@ static void cfg_load(void)
     if ((s = getenv("ACGB200_SLICE_MAX_CTAS"))) cfg.slice_max_ctas = atoi(s);
     if ((s = getenv("ACGB200_SLICE_MINB"))) cfg.slice_minb = atoi(s);
     acgb200_blas1_set_ctas_per_sm(cfg.blas1_ctas);
+    acgb200_blas1_set_unroll(cfg.blas1_unroll);
     acgb200_set_pdl(cfg.pdl);
 }
 
@@ -114,12 +120,14 @@ int acgb200_set_option(const char *key, int value)
     else if (!strcmp(key, "p2p")) cfg.p2p = value;
     else if (!strcmp(key, "p2p_fuse")) cfg.p2p_fuse = value;
     else if (!strcmp(key, "blas1_ctas")) { cfg.blas1_ctas = value; acgb200_blas1_set_ctas_per_sm(value); }
+    else if (!strcmp(key, "blas1_unroll")) { cfg.blas1_unroll = value; acgb200_blas1_set_unroll(value); }
     else if (!strcmp(key, "pdl")) { cfg.pdl = value; acgb200_set_pdl(value); }
     else if (!strcmp(key, "spmv_medium")) cfg.spmv_medium = value < 0 ? 0 : value;
     else if (!strcmp(key, "spmv_merge")) cfg.spmv_merge = value;
     else if (!strcmp(key, "merge_items")) cfg.merge_items = value;
     else if (!strcmp(key, "merge_threads")) cfg.merge_threads = value;
     else if (!strcmp(key, "merge_max_ctas")) cfg.merge_max_ctas = value;
+    else if (!strcmp(key, "merge_stages")) cfg.merge_stages = value;
     else if (!strcmp(key, "spmv_slices")) cfg.spmv_slices = value;
     else if (!strcmp(key, "slice_ub")) cfg.slice_ub = value;
     else if (!strcmp(key, "slice_threads")) cfg.slice_threads = value;
@@ -718,12 +726,14 @@ static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, 
             int64_t mx = 0;
             for (int i = 0; i < hi; i++) if (frp[i + 1] - frp[i] > mx) mx = frp[i + 1] - frp[i];
             if (hi >= 1024 && (cfg.spmv_merge > 0 || (double) mx > 8.0 * avg + 64.0))
-                err = acgb200_merge_plan(hi, frp, cfg.merge_items > 0 ? cfg.merge_items : 1024, &mp);
+                /* 2048 merged items per tile: measured on R-MAT 20 M (profiles/r02/c_ab_rmat20m.log), 4.32 ms against
+                 * 6.33 ms with 1024 and 4.74 ms with 4096 */
+                err = acgb200_merge_plan(hi, frp, cfg.merge_items > 0 ? cfg.merge_items : 2048, &mp);
         }
         if (!err) err = build_tiles(&pv->plan, frp, &sp, pat.patid, &mp, errcode);
         if (!err && pv->plan.nmtiles > 0) {
             pv->plan.merge_threads = cfg.merge_threads > 0 ? cfg.merge_threads : 128;
-            pv->plan.merge_stages = 2;
+            pv->plan.merge_stages = cfg.merge_stages >= 1 && cfg.merge_stages <= SPMV_MAX_STAGES_HOST ? cfg.merge_stages : 2;
             pv->plan.merge_max_ctas = cfg.merge_max_ctas;
         }
         acgb200_mergeplan_free(&mp);

@@ -24,6 +24,11 @@
 
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#else
+static int omp_get_num_threads(void) { return 1; }
+#endif
 
 struct slot { uint64_t hash; int row; int len; int64_t count; int id; };
 
@@ -65,6 +70,28 @@ void acgb200_patterns_free(struct acgb200_patterns *p)
  * kept, most frequent first.  patid[r] == ACGB200_NOPATTERN marks a row whose
  * pattern was not kept.
  */
+/* count one row's pattern in an open-addressing table of `cap` slots holding at most cap/2 patterns;
+ * returns 0 if the table is full (the pattern is then not tracked) */
+static int table_count(struct slot *tab, size_t cap, size_t *used, const int64_t *rowptr, const int *colidx, int r, int64_t add, int rep)
+{
+    const uint64_t h = row_hash(colidx, rowptr[r], rowptr[r + 1], r);
+    size_t i = (size_t) (h & (cap - 1));
+    for (;;) {
+        if (tab[i].hash == 0) {
+            if (*used >= cap / 2) return 0;
+            tab[i].hash = h; tab[i].row = rep; tab[i].len = (int) (rowptr[r + 1] - rowptr[r]);
+            tab[i].count = add; tab[i].id = -1; (*used)++;
+            return 1;
+        }
+        if (tab[i].hash == h && same_pattern(rowptr, colidx, tab[i].row, r)) {
+            tab[i].count += add;
+            if (rep < tab[i].row) tab[i].row = rep;      /* representative: the pattern's first row, whatever the thread count */
+            return 1;
+        }
+        i = (i + 1) & (cap - 1);
+    }
+}
+
 int acgb200_patterns_build(int nrows, const int64_t *rowptr, const int *colidx, int max_entries,
                            struct acgb200_patterns *out)
 {
@@ -74,21 +101,33 @@ int acgb200_patterns_build(int nrows, const int64_t *rowptr, const int *colidx, 
     out->patid = malloc((size_t) (nrows > 0 ? nrows : 1) * sizeof(*out->patid));
     if (!tab || !out->patid) { free(tab); acgb200_patterns_free(out); return ACG_ERR_ERRNO; }
     size_t used = 0;
-    /* pass 1: count patterns */
-    for (int r = 0; r < nrows; r++) {
-        const uint64_t h = row_hash(colidx, rowptr[r], rowptr[r + 1], r);
-        size_t i = (size_t) (h & (cap - 1));
-        for (;;) {
-            if (tab[i].hash == 0) {
-                if (used >= cap / 2) break;             /* table full: this pattern is not tracked */
-                tab[i].hash = h; tab[i].row = r; tab[i].len = (int) (rowptr[r + 1] - rowptr[r]);
-                tab[i].count = 1; tab[i].id = -1; used++;
-                break;
-            }
-            if (tab[i].hash == h && same_pattern(rowptr, colidx, tab[i].row, r)) { tab[i].count++; break; }
-            i = (i + 1) & (cap - 1);
+    /* pass 1: count patterns -- every thread counts a contiguous block of rows in a table of its own
+     * (2^15 slots), the tables are merged in thread order */
+    int failed = 0;
+#pragma omp parallel
+    {
+        const size_t tcap = 1u << 15;
+        struct slot *mine = calloc(tcap, sizeof(*mine));
+        size_t mused = 0;
+        if (!mine) {
+#pragma omp atomic write
+            failed = 1;
         }
+#pragma omp for schedule(static)
+        for (int r = 0; r < nrows; r++)
+            if (mine) table_count(mine, tcap, &mused, rowptr, colidx, r, 1, r);
+#pragma omp for ordered schedule(static, 1)
+        for (int t = 0; t < omp_get_num_threads(); t++) {
+#pragma omp ordered
+            {
+                if (mine)
+                    for (size_t i = 0; i < tcap; i++)
+                        if (mine[i].hash) table_count(tab, cap, &used, rowptr, colidx, mine[i].row, mine[i].count, mine[i].row);
+            }
+        }
+        free(mine);
     }
+    if (failed) { free(tab); acgb200_patterns_free(out); return ACG_ERR_ERRNO; }
     /* choose the most frequent patterns that fit */
     struct slot *sel = malloc((used ? used : 1) * sizeof(*sel));
     if (!sel) { free(tab); acgb200_patterns_free(out); return ACG_ERR_ERRNO; }
@@ -119,6 +158,7 @@ int acgb200_patterns_build(int nrows, const int64_t *rowptr, const int *colidx, 
     free(sel);
     /* pass 2: ids per row */
     int64_t matched = 0;
+#pragma omp parallel for schedule(static) reduction(+ : matched)
     for (int r = 0; r < nrows; r++) {
         const uint64_t h = row_hash(colidx, rowptr[r], rowptr[r + 1], r);
         size_t i = (size_t) (h & (cap - 1));

@@ -324,6 +324,7 @@ int acgb200_gather(int n, double *dst, const double *src, const int *idx, cudaSt
 int acgb200_scatter(int n, const double *src, double *dst, const int *idx, cudaStream_t stream); /* dst[idx[i]]=src[i] */
 int acgb200_num_sms(void);
 void acgb200_blas1_set_ctas_per_sm(int v);
+void acgb200_blas1_set_unroll(int v);
 void acgb200_set_pdl(int v);
 
 #ifdef __cplusplus

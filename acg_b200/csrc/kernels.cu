@@ -558,26 +558,26 @@ struct SliceParams {
  * is limited by registers only, the loads in flight per SM (warps x UB x 256 B
  * of values) cover the HBM latency.
  */
-/* x entry of slot e+u: the column is formed in 32-bit arithmetic (row + offset), so the address costs one
- * IADD and one IMAD.WIDE instead of a sign extension and a 64-bit add per gather */
+/* xr = x + row.  (Forming the column in 32-bit arithmetic first -- one IADD + IMAD.WIDE instead of the
+ * sign extension and 64-bit add below -- was measured slower: 0.405 against 0.397 ms at C3, profiles/r02.) */
 template <int UB>
-__device__ __forceinline__ void slice_load(double (&vv)[UB], double (&xv)[UB], const double *v, const double *x, int row,
+__device__ __forceinline__ void slice_load(double (&vv)[UB], double (&xv)[UB], const double *v, const double *xr,
                                            const int *offs, int e, uint64_t pol)
 {
 #pragma unroll
     for (int u = 0; u < UB; u++) vv[u] = ld_stream(v + (size_t) (e + u) * 32, pol);
 #pragma unroll
-    for (int u = 0; u < UB; u++) xv[u] = ld_x(x + (row + offs[e + u]));
+    for (int u = 0; u < UB; u++) xv[u] = ld_x(xr + offs[e + u]);
 }
 
 template <int UB>
-__device__ __forceinline__ void slice_load_pred(double (&vv)[UB], double (&xv)[UB], const double *v, const double *x, int row,
+__device__ __forceinline__ void slice_load_pred(double (&vv)[UB], double (&xv)[UB], const double *v, const double *xr,
                                                 const int *offs, int e, int L, uint64_t pol)
 {
 #pragma unroll
     for (int u = 0; u < UB; u++) vv[u] = e + u < L ? ld_stream(v + (size_t) (e + u) * 32, pol) : 0.0;
 #pragma unroll
-    for (int u = 0; u < UB; u++) xv[u] = e + u < L ? ld_x(x + (row + offs[e + u])) : 0.0;
+    for (int u = 0; u < UB; u++) xv[u] = e + u < L ? ld_x(xr + offs[e + u]) : 0.0;
 }
 
 template <int UB>
@@ -623,6 +623,7 @@ spmv_slices_kernel(const SliceParams P)
         const int row = sl.x + lane;
         const int *offs = spat_s + (int) P.patid[row] * P.lpad;
         const double *v = P.sval + ((size_t) sl.w << 5) + lane;
+        const double *xr = P.x + row;
         const int L = sl.z;
         double sum = 0.0;
         int e = 0;
@@ -630,17 +631,17 @@ spmv_slices_kernel(const SliceParams P)
             /* two register sets, straight-line body (predicated loads, no branch between a batch's loads
              * and the previous batch's FMAs); slots past L load nothing and add 0 * 0 */
             double va[UB], xa[UB], vb[UB], xb[UB];
-            slice_load_pred<UB>(va, xa, v, P.x, row, offs, 0, L, pol);
+            slice_load_pred<UB>(va, xa, v, xr, offs, 0, L, pol);
             for (; e < L; e += 2 * UB) {
-                slice_load_pred<UB>(vb, xb, v, P.x, row, offs, e + UB, L, pol);
+                slice_load_pred<UB>(vb, xb, v, xr, offs, e + UB, L, pol);
                 sum = slice_fma<UB>(va, xa, sum);
-                slice_load_pred<UB>(va, xa, v, P.x, row, offs, e + 2 * UB, L, pol);
+                slice_load_pred<UB>(va, xa, v, xr, offs, e + 2 * UB, L, pol);
                 sum = slice_fma<UB>(vb, xb, sum);
             }
         } else {
             for (; e + UB <= L; e += UB) {
                 double vv[UB], xv[UB];
-                slice_load<UB>(vv, xv, v, P.x, row, offs, e, pol);
+                slice_load<UB>(vv, xv, v, xr, offs, e, pol);
                 sum = slice_fma<UB>(vv, xv, sum);
             }
         }
@@ -650,7 +651,7 @@ spmv_slices_kernel(const SliceParams P)
 #pragma unroll
             for (int u = 0; u < UB; u++) vv[u] = e + u < L ? ld_stream(v + (size_t) (e + u) * 32, pol) : 0.0;
 #pragma unroll
-            for (int u = 0; u < UB; u++) xv[u] = e + u < L ? ld_x(P.x + (row + offs[e + u])) : 0.0;
+            for (int u = 0; u < UB; u++) xv[u] = e + u < L ? ld_x(xr + offs[e + u]) : 0.0;
 #pragma unroll
             for (int u = 0; u < UB; u++) if (e + u < L) sum = fma(vv[u], xv[u], sum);
         }
@@ -1187,6 +1188,10 @@ cg_update_xp_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, a
 /* Pipelined CG: z=q+beta z; t=w+beta t; p=r+beta p; x+=alpha p; r-=alpha t;
  * w-=alpha z (acg/cg-kernels-cuda.cu:201-214), plus gamma'=(r,r), delta'=(w,r)
  * of the updated vectors for the next iteration. */
+/* UNR: rows per thread and trip of the grid-stride loop.  2 issues the 14 loads of two rows before the first
+ * store: at one rank's share of the 8-GPU problem (1.4 M rows, 6 rows per thread) the kernel is a chain of
+ * load latencies, not a bandwidth problem, and the chain halves. */
+template <int UNR>
 __global__ void __launch_bounds__(BLAS1_THREADS)
 pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acgb200_p2pdev *P,
                   const double *__restrict__ q, double *__restrict__ z, double *__restrict__ w,
@@ -1233,19 +1238,47 @@ pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acg
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
     for (int pass = 0; pass < 2; pass++) {
         const int lo = pass == 0 ? first : 0, hi = pass == 0 ? n : first;
-        for (int i = lo + gtid; i < hi; i += gstride) {
-            const double zv = fma(beta, z[i], q[i]);
-            const double tv = fma(beta, t[i], w[i]);
-            const double pv = fma(beta, p[i], r[i]);
-            const double rv = fma(-alpha, tv, r[i]);
-            const double wv = fma(-alpha, zv, w[i]);
-            z[i] = zv; t[i] = tv; p[i] = pv;
-            x[i] = fma(alpha, pv, x[i]);
-            r[i] = rv;
-            w[i] = wv;
-            g2 = fma(rv, rv, g2);
-            d2 = fma(wv, rv, d2);
-            if (push && pass == 0) p2p_push_row(P, i, s ^ 1, wv);
+        if (UNR == 1) {
+            /* (the measured kernel of rounds 1 and 2, untouched: 40 registers, three CTAs of 512 threads per SM) */
+            for (int i = lo + gtid; i < hi; i += gstride) {
+                const double zv = fma(beta, z[i], q[i]);
+                const double tv = fma(beta, t[i], w[i]);
+                const double pv = fma(beta, p[i], r[i]);
+                const double rv = fma(-alpha, tv, r[i]);
+                const double wv = fma(-alpha, zv, w[i]);
+                z[i] = zv; t[i] = tv; p[i] = pv;
+                x[i] = fma(alpha, pv, x[i]);
+                r[i] = rv;
+                w[i] = wv;
+                g2 = fma(rv, rv, g2);
+                d2 = fma(wv, rv, d2);
+                if (push && pass == 0) p2p_push_row(P, i, s ^ 1, wv);
+            }
+        } else
+        for (int i0 = lo + gtid; i0 < hi; i0 += UNR * gstride) {
+            double zi[UNR], qi[UNR], ti[UNR], wi[UNR], pi[UNR], ri[UNR], xi[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                const int i = min(i0 + u * gstride, hi - 1);       /* a lane without a row re-reads the last one */
+                zi[u] = z[i]; qi[u] = q[i]; ti[u] = t[i]; wi[u] = w[i]; pi[u] = p[i]; ri[u] = r[i]; xi[u] = x[i];
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                const int i = i0 + u * gstride;
+                if (i >= hi) break;
+                const double zv = fma(beta, zi[u], qi[u]);
+                const double tv = fma(beta, ti[u], wi[u]);
+                const double pv = fma(beta, pi[u], ri[u]);
+                const double rv = fma(-alpha, tv, ri[u]);
+                const double wv = fma(-alpha, zv, wi[u]);
+                z[i] = zv; t[i] = tv; p[i] = pv;
+                x[i] = fma(alpha, pv, xi[u]);
+                r[i] = rv;
+                w[i] = wv;
+                g2 = fma(rv, rv, g2);
+                d2 = fma(wv, rv, d2);
+                if (push && pass == 0) p2p_push_row(P, i, s ^ 1, wv);
+            }
         }
     }
     g2 = block_sum(g2, red);
@@ -1322,6 +1355,10 @@ extern "C" int acgb200_num_sms(void)
 static int g_blas1_ctas_per_sm = 0;
 
 extern "C" void acgb200_blas1_set_ctas_per_sm(int v) { g_blas1_ctas_per_sm = v < 0 ? 0 : v; }
+
+/* rows per thread and loop trip of the pipelined update kernel (1 or 2) */
+static int g_blas1_unroll = 1;
+extern "C" void acgb200_blas1_set_unroll(int v) { g_blas1_unroll = v >= 2 ? 2 : 1; }
 
 /* One wave of grid-stride CTAs: SMs x resident CTAs of that kernel (a grid that
  * is not a multiple of it ends in a partial wave at a fraction of the memory
@@ -1596,8 +1633,11 @@ extern "C" int acgb200_pcg_update(int n, acgb200_devstate *st, int cin, int cout
                                   const double *q, double *z, double *w, double *t, double *p,
                                   double *r, double *x, cudaStream_t stream)
 {
-    static int occ = 0;
-    return (int) launch_chain(pcg_update_kernel, blas1_grid(n, (const void *) pcg_update_kernel, &occ), BLAS1_THREADS, 0, stream,
+    static int occ1 = 0, occ2 = 0;
+    if (g_blas1_unroll >= 2)
+        return (int) launch_chain(pcg_update_kernel<2>, blas1_grid(n, (const void *) pcg_update_kernel<2>, &occ2), BLAS1_THREADS, 0, stream,
+                                  n, st, cin, cout, multi, p2p, q, z, w, t, p, r, x);
+    return (int) launch_chain(pcg_update_kernel<1>, blas1_grid(n, (const void *) pcg_update_kernel<1>, &occ1), BLAS1_THREADS, 0, stream,
                               n, st, cin, cout, multi, p2p, q, z, w, t, p, r, x);
 }
 

@@ -21,13 +21,14 @@ sys.path.insert(0, ROOT)
 import numpy as np          # noqa: E402
 
 DEFAULTS = dict(profile=0, spmv_lanes=0, spmv_nnz_cap=0, spmv_rows_cap=0, spmv_stages=0, spmv_threads=0,
-                spmv_unroll=0, spmv_max_ctas=0, graph=1, redstream=1, p2p=1, p2p_fuse=1, blas1_ctas=0, pdl=0,
-                spmv_medium=0, spmv_slices=1, slice_ub=0, slice_threads=0, slice_pf=-1, slice_max_ctas=0, slice_minb=0)
+                spmv_unroll=0, spmv_max_ctas=0, graph=1, redstream=1, p2p=1, p2p_fuse=1, blas1_ctas=0, blas1_unroll=1, pdl=0,
+                spmv_medium=0, spmv_merge=-1, merge_items=0, merge_threads=0, merge_stages=0, merge_max_ctas=0, spmv_slices=1, slice_ub=0, slice_threads=0, slice_pf=-1, slice_max_ctas=0, slice_minb=0)
 
 VARIANTS = {
     "base": {},
     "noslices": {"spmv_slices": 0},
     "oldgrid": {"blas1_ctas": 4},
+    "unr2": {"blas1_unroll": 2}, "unr2_c2": {"blas1_unroll": 2, "blas1_ctas": 2}, "unr2_pdl": {"blas1_unroll": 2, "pdl": 1},
     "pdl": {"pdl": 1},
     "nograph": {"graph": 0},
     "med128": {"spmv_medium": 128},
