@@ -53,8 +53,10 @@ WORKLOADS = {
     "27pt-64": dict(kind="27pt", N=64, solver="pipelined"),
     "27pt-448": dict(kind="27pt", N=448, solver="pipelined"),      # configs[3]: 8 GPUs only (weak-scaled x8 point)
     # configs[4]: power-law rows (long-row path, gathers without locality); contiguous row blocks or METIS for N>1
-    "rmat-20M": dict(kind="rmat", N=20_000_000, edges=200_000_000, solver="pipelined"),
-    "rmat-2M": dict(kind="rmat", N=2_000_000, edges=20_000_000, solver="pipelined"),
+    # (classic CG: on these ill-conditioned matrices -- hubs of degree 1e5 -- the recurrence residual of pipelined CG
+    # drifts away from the true one within 100 iterations, profiles/r02/d_bench_rmat20m.json)
+    "rmat-20M": dict(kind="rmat", N=20_000_000, edges=200_000_000, solver="classic"),
+    "rmat-2M": dict(kind="rmat", N=2_000_000, edges=20_000_000, solver="classic"),
 }
 
 
@@ -424,8 +426,10 @@ def main():
         nloc = nown
         achieved = 16.0 * nnz_local / t_spmv / 1e9
         # the SpMV of one vector: rows that repeat a pattern through spmv_slices_kernel, the others through spmv_tiles_kernel
-        kernel_name = ("spmv_slices_kernel" if info["spmv_slice_rows"] == nloc else
-                       "spmv_tiles_kernel" if info["spmv_slices"] == 0 else "spmv_slices_kernel + spmv_tiles_kernel")
+        parts = (["spmv_slices_kernel"] if info["spmv_slices"] > 0 else []) + \
+                (["spmv_merge_kernel"] if info["spmv_merge_tiles"] > 0 else []) + \
+                (["spmv_tiles_kernel"] if info["spmv_ntiles"] > 0 else [])
+        kernel_name = " + ".join(parts) or "spmv_tiles_kernel"
         min_bytes = float(info["spmv_min_bytes"])
         prof = os.path.join(ROOT, "profiles", "r02_ncu_spmv.json")
         traffic_source = None
@@ -444,7 +448,8 @@ def main():
                     "note": "whole acgsolvercuda_solve* call with pinned host b, x: H2D of b and x0, set-up, iterations, D2H of x"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": kernel_name,
-                         "slice_rows": info["spmv_slice_rows"], "tile_rows": nloc - info["spmv_slice_rows"],
+                         "slice_rows": info["spmv_slice_rows"], "merge_rows": info["spmv_merge_rows"],
+                         "tile_rows": nloc - info["spmv_slice_rows"] - info["spmv_merge_rows"],
                          "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "traffic_source": traffic_source,
                          "bytes_per_launch": 16 * nnz_local, "ms_per_launch": t_spmv * 1e3, "launches_timed": spmv_n,
