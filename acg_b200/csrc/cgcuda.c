@@ -53,6 +53,7 @@ static struct {
     int redstream;      /* pipelined CG: allreduce on its own stream + communicator */
     int p2p;            /* halo + reductions through peer memory (CUDA IPC) instead of NCCL */
     int p2p_fuse;       /* 1: border x ghost block inside the SpMV, pushes inside the update kernels */
+    int p2p_early_fence; /* 1: pipelined update fences its remote stores right behind the border rows (internal.h) */
     int blas1_unroll;   /* rows per thread and loop trip of the pipelined update kernel (1 or 2) */
     int blas1_ctas;     /* CTAs per SM of the fused BLAS-1 kernels (0 = one full wave, from the occupancy) */
     int pdl;            /* 1: programmatic dependent launch along the iteration chain (opt-in) */
@@ -82,6 +83,7 @@ static void cfg_load(void)
     if ((s = getenv("ACGB200_REDSTREAM"))) cfg.redstream = atoi(s);
     if ((s = getenv("ACGB200_P2P"))) cfg.p2p = atoi(s);
     if ((s = getenv("ACGB200_P2P_FUSE"))) cfg.p2p_fuse = atoi(s);
+    if ((s = getenv("ACGB200_P2P_EARLY_FENCE"))) cfg.p2p_early_fence = atoi(s);
     if ((s = getenv("ACGB200_BLAS1_CTAS"))) cfg.blas1_ctas = atoi(s);
     if ((s = getenv("ACGB200_BLAS1_UNROLL"))) cfg.blas1_unroll = atoi(s);
     if (cfg.check_every < 1) cfg.check_every = 1;
@@ -119,6 +121,7 @@ int acgb200_set_option(const char *key, int value)
     else if (!strcmp(key, "redstream")) cfg.redstream = value;
     else if (!strcmp(key, "p2p")) cfg.p2p = value;
     else if (!strcmp(key, "p2p_fuse")) cfg.p2p_fuse = value;
+    else if (!strcmp(key, "p2p_early_fence")) cfg.p2p_early_fence = value;
     else if (!strcmp(key, "blas1_ctas")) { cfg.blas1_ctas = value; acgb200_blas1_set_ctas_per_sm(value); }
     else if (!strcmp(key, "blas1_unroll")) { cfg.blas1_unroll = value; acgb200_blas1_set_unroll(value); }
     else if (!strcmp(key, "pdl")) { cfg.pdl = value; acgb200_set_pdl(value); }
@@ -626,7 +629,8 @@ static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, 
             CU(ce);
             if (ok) {
                 pv->p2p.h_desc.fuse = cfg.p2p_fuse;
-                CU(cudaMemcpy(&pv->p2p.d_desc->fuse, &pv->p2p.h_desc.fuse, sizeof(int), cudaMemcpyHostToDevice));
+                pv->p2p.h_desc.early_fence = cfg.p2p_early_fence != 0;
+                CU(cudaMemcpy(&pv->p2p.d_desc->fuse, &pv->p2p.h_desc.fuse, 2 * sizeof(int), cudaMemcpyHostToDevice));   /* fuse, early_fence */
             }
             if (!allok) {
                 if (getenv("ACGB200_VERBOSE")) fprintf(stderr, "acgb200: peer-memory exchange unavailable (cuda error %d), using NCCL\n", perr);

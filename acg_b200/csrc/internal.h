@@ -209,6 +209,8 @@ struct acgb200_p2pdev {
     int borderoff, nborder;
     const int *bptr, *bq, *bdst;
     int fuse;                                /* 1: producers push/publish themselves; 0: comm_post_kernel does */
+    int early_fence;                         /* 1: the system-scope fence of a producer kernel sits right behind its
+                                              * border rows (the only remote stores), a device-scope fence at its end */
 };
 
 /* After the producer of a vector / of reduction partials: push them to the

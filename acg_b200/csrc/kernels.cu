@@ -1234,9 +1234,13 @@ pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acg
      * issuing those NVLink stores at the start lets them drain under the
      * interior rows instead of in front of the closing system fence. */
     const bool push = P && P->fuse;
+    const bool early = push && P->early_fence;
     const int first = push ? P->borderoff : 0;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
     for (int pass = 0; pass < 2; pass++) {
+        /* the remote stores are all behind us after the border pass: fence them now, while only a handful of this
+         * thread's stores are outstanding, instead of at the end behind the whole interior pass */
+        if (pass == 1 && early) __threadfence_system();
         const int lo = pass == 0 ? first : 0, hi = pass == 0 ? n : first;
         if (UNR == 1) {
             /* (the measured kernel of rounds 1 and 2, untouched: 40 registers, three CTAs of 512 threads per SM) */
@@ -1290,7 +1294,7 @@ pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acg
     if (P && P->fuse) {
         /* last CTA: this rank's {gamma,delta} of the next iteration to every
          * rank, and the halo sequence number to the neighbours */
-        __threadfence_system();
+        if (early) __threadfence(); else __threadfence_system();
         if (p2p_last_block(P, &last_flag)) {
             const unsigned long long it1 = (unsigned long long) g.iter + 1ull;
             p2p_publish_red(P, 0, s ^ 1, P->rbase + it1, &st->gd_loc[s ^ 1][0], 2);

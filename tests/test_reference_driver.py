@@ -102,7 +102,8 @@ def test_driver_solves_on_several_gpus(solver, method, oracle):
     r0 = float(re.search(r"^\s*initial residual 2-norm: (\S+)", p.stderr, re.M).group(1))
     want = getattr(oracle, method)(csr, np.ones(N), maxits=200, rtol=1e-9)
     assert its == want["niterations"] and r0 == pytest.approx(want["r0nrm2"], rel=1e-12)
-    lines = [ln for ln in p.stdout.splitlines() if ln and not ln.startswith("%")]
+    # (NCCL may print its version banner on stdout: NCCL_DEBUG=VERSION on the GPU boxes)
+    lines = [ln for ln in p.stdout.splitlines() if ln and not ln.startswith("%") and not ln.startswith("NCCL")]
     x = np.array([float(t) for t in lines[1:]])
     assert int(lines[0].split()[0]) == N and np.abs(x - want["x"]).max() <= 1e-9 * np.abs(want["x"]).max()
 

@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 import numpy as np          # noqa: E402
 
 DEFAULTS = dict(profile=0, spmv_lanes=0, spmv_nnz_cap=0, spmv_rows_cap=0, spmv_stages=0, spmv_threads=0,
-                spmv_unroll=0, spmv_max_ctas=0, graph=1, redstream=1, p2p=1, p2p_fuse=1, blas1_ctas=0, blas1_unroll=1, pdl=0,
+                spmv_unroll=0, spmv_max_ctas=0, graph=1, redstream=1, p2p=1, p2p_fuse=1, p2p_early_fence=0, blas1_ctas=0, blas1_unroll=1, pdl=0,
                 spmv_medium=0, spmv_merge=-1, merge_items=0, merge_threads=0, merge_stages=0, merge_max_ctas=0, spmv_slices=1, slice_ub=0, slice_threads=0, slice_pf=-1, slice_max_ctas=0, slice_minb=0)
 
 VARIANTS = {
@@ -38,6 +38,7 @@ VARIANTS = {
     "nccl": {"p2p": 0},
     "nccl_graph": {"p2p": 0, "graph": 2},
     "unfused": {"p2p_fuse": 0},
+    "earlyfence": {"p2p_early_fence": 1}, "earlyfence_unr2": {"p2p_early_fence": 1, "blas1_unroll": 2},
     # slice kernel shapes: s<ub>[p][_t<threads>][_c<max ctas>]  (p = prefetch the next batch)
     "s9": {"slice_ub": 9, "slice_pf": 0}, "s9p": {"slice_ub": 9, "slice_pf": 1},
     "s4": {"slice_ub": 4, "slice_pf": 0}, "s4p": {"slice_ub": 4, "slice_pf": 1},
