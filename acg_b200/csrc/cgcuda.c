@@ -53,17 +53,15 @@ static struct {
     int redstream;      /* pipelined CG: allreduce on its own stream + communicator */
     int p2p;            /* halo + reductions through peer memory (CUDA IPC) instead of NCCL */
     int p2p_fuse;       /* 1: border x ghost block inside the SpMV, pushes inside the update kernels */
-    int p2p_early_fence; /* 1: pipelined update fences its remote stores right behind the border rows (internal.h) */
-    int blas1_unroll;   /* rows per thread and loop trip of the pipelined update kernel (1 or 2) */
     int blas1_ctas;     /* CTAs per SM of the fused BLAS-1 kernels (0 = one full wave, from the occupancy) */
     int pdl;            /* 1: programmatic dependent launch along the iteration chain (opt-in) */
     int spmv_medium;    /* > 0: rows longer than this (and shorter than a tile) get a warp each (opt-in) */
     int spmv_merge;     /* merge-path tiles for irregular rows (mergeplan.c): -1 decide from the row lengths, 0 off, 1 on */
     int merge_items, merge_threads, merge_max_ctas, merge_stages;   /* their shape (0 = default) */
     int spmv_slices;    /* 1: pattern slices (slices.c) -- index-free slice-major storage of the rows that repeat a pattern */
-    int slice_ub, slice_threads, slice_pf, slice_max_ctas, slice_minb;   /* slice kernel shape overrides (0 / -1 = default) */
+    int slice_ub, slice_threads, slice_max_ctas;   /* slice kernel shape overrides (0 = default) */
     int loaded;
-} cfg = { .check_every = 8, .graph = 1, .redstream = 1, .p2p = 1, .p2p_fuse = 1, .spmv_slices = 1, .slice_pf = -1, .spmv_merge = -1 };
+} cfg = { .check_every = 8, .graph = 1, .redstream = 1, .p2p = 1, .p2p_fuse = 1, .spmv_slices = 1, .spmv_merge = -1 };
 
 static void cfg_load(void)
 {
@@ -83,9 +81,7 @@ static void cfg_load(void)
     if ((s = getenv("ACGB200_REDSTREAM"))) cfg.redstream = atoi(s);
     if ((s = getenv("ACGB200_P2P"))) cfg.p2p = atoi(s);
     if ((s = getenv("ACGB200_P2P_FUSE"))) cfg.p2p_fuse = atoi(s);
-    if ((s = getenv("ACGB200_P2P_EARLY_FENCE"))) cfg.p2p_early_fence = atoi(s);
     if ((s = getenv("ACGB200_BLAS1_CTAS"))) cfg.blas1_ctas = atoi(s);
-    if ((s = getenv("ACGB200_BLAS1_UNROLL"))) cfg.blas1_unroll = atoi(s);
     if (cfg.check_every < 1) cfg.check_every = 1;
     if ((s = getenv("ACGB200_PDL"))) cfg.pdl = atoi(s);
     if ((s = getenv("ACGB200_SPMV_MEDIUM"))) cfg.spmv_medium = atoi(s);
@@ -97,11 +93,8 @@ static void cfg_load(void)
     if ((s = getenv("ACGB200_SPMV_SLICES"))) cfg.spmv_slices = atoi(s);
     if ((s = getenv("ACGB200_SLICE_UB"))) cfg.slice_ub = atoi(s);
     if ((s = getenv("ACGB200_SLICE_THREADS"))) cfg.slice_threads = atoi(s);
-    if ((s = getenv("ACGB200_SLICE_PF"))) cfg.slice_pf = atoi(s);
     if ((s = getenv("ACGB200_SLICE_MAX_CTAS"))) cfg.slice_max_ctas = atoi(s);
-    if ((s = getenv("ACGB200_SLICE_MINB"))) cfg.slice_minb = atoi(s);
     acgb200_blas1_set_ctas_per_sm(cfg.blas1_ctas);
-    acgb200_blas1_set_unroll(cfg.blas1_unroll);
     acgb200_set_pdl(cfg.pdl);
 }
 
@@ -121,9 +114,7 @@ int acgb200_set_option(const char *key, int value)
     else if (!strcmp(key, "redstream")) cfg.redstream = value;
     else if (!strcmp(key, "p2p")) cfg.p2p = value;
     else if (!strcmp(key, "p2p_fuse")) cfg.p2p_fuse = value;
-    else if (!strcmp(key, "p2p_early_fence")) cfg.p2p_early_fence = value;
     else if (!strcmp(key, "blas1_ctas")) { cfg.blas1_ctas = value; acgb200_blas1_set_ctas_per_sm(value); }
-    else if (!strcmp(key, "blas1_unroll")) { cfg.blas1_unroll = value; acgb200_blas1_set_unroll(value); }
     else if (!strcmp(key, "pdl")) { cfg.pdl = value; acgb200_set_pdl(value); }
     else if (!strcmp(key, "spmv_medium")) cfg.spmv_medium = value < 0 ? 0 : value;
     else if (!strcmp(key, "spmv_merge")) cfg.spmv_merge = value;
@@ -134,9 +125,7 @@ int acgb200_set_option(const char *key, int value)
     else if (!strcmp(key, "spmv_slices")) cfg.spmv_slices = value;
     else if (!strcmp(key, "slice_ub")) cfg.slice_ub = value;
     else if (!strcmp(key, "slice_threads")) cfg.slice_threads = value;
-    else if (!strcmp(key, "slice_pf")) cfg.slice_pf = value;
     else if (!strcmp(key, "slice_max_ctas")) cfg.slice_max_ctas = value;
-    else if (!strcmp(key, "slice_minb")) cfg.slice_minb = value;
     else return ACG_ERR_INVALID_VALUE;
     return ACG_SUCCESS;
 }
@@ -629,8 +618,7 @@ static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, 
             CU(ce);
             if (ok) {
                 pv->p2p.h_desc.fuse = cfg.p2p_fuse;
-                pv->p2p.h_desc.early_fence = cfg.p2p_early_fence != 0;
-                CU(cudaMemcpy(&pv->p2p.d_desc->fuse, &pv->p2p.h_desc.fuse, 2 * sizeof(int), cudaMemcpyHostToDevice));   /* fuse, early_fence */
+                CU(cudaMemcpy(&pv->p2p.d_desc->fuse, &pv->p2p.h_desc.fuse, sizeof(int), cudaMemcpyHostToDevice));
             }
             if (!allok) {
                 if (getenv("ACGB200_VERBOSE")) fprintf(stderr, "acgb200: peer-memory exchange unavailable (cuda error %d), using NCCL\n", perr);
@@ -745,11 +733,7 @@ static int init_impl(struct acgsolvercuda *cg, const struct acgsymcsrmatrix *A, 
             const int d = sp.domlen;
             pv->plan.slice_ub = cfg.slice_ub > 0 ? cfg.slice_ub : (d % 9 == 0 ? 9 : d % 7 == 0 ? 7 : d % 8 == 0 ? 8 : d % 5 == 0 ? 5 : 8);
             pv->plan.slice_threads = cfg.slice_threads > 0 ? cfg.slice_threads : 128;
-            /* measured on the B200 (profiles/r02/b_ab_224.log): without prefetch the kernel needs 48 registers and ten
-             * CTAs of 128 threads share an SM -- 0.397 ms at C3 against 0.450 ms for the prefetching variant */
-            pv->plan.slice_pf = cfg.slice_pf >= 0 ? (cfg.slice_pf != 0) : 0;
             pv->plan.slice_max_ctas = cfg.slice_max_ctas;
-            pv->plan.slice_minb = cfg.slice_minb;
         }
         acgb200_sliceplan_free(&sp);
         acgb200_patterns_free(&pat);

@@ -71,7 +71,7 @@ struct acgb200_spmvplan {
     int slice_npat;
     int *d_spatoff;                  /* [slice_npat * slice_lpad] offsets col - row, zero beyond a pattern's length */
     unsigned short *d_spatid;        /* [nrows] pattern id per row (valid for covered rows) */
-    int slice_ub, slice_threads, slice_pf, slice_minb, slice_grid, slice_smem, slice_max_ctas;
+    int slice_ub, slice_threads, slice_grid, slice_smem, slice_max_ctas;
     /* merge-path tiles (mergeplan.c): rows [0, merge_rows) of an irregular (power-law) matrix, cut into tiles
      * of merge_items merged items (row ends + nonzeros) and multiplied by spmv_merge_kernel; rows cut by tile
      * boundaries are finished by spmv_merge_fix_kernel from the tiles' partial sums */
@@ -209,8 +209,6 @@ struct acgb200_p2pdev {
     int borderoff, nborder;
     const int *bptr, *bq, *bdst;
     int fuse;                                /* 1: producers push/publish themselves; 0: comm_post_kernel does */
-    int early_fence;                         /* 1: the system-scope fence of a producer kernel sits right behind its
-                                              * border rows (the only remote stores), a device-scope fence at its end */
 };
 
 /* After the producer of a vector / of reduction partials: push them to the
@@ -326,7 +324,6 @@ int acgb200_gather(int n, double *dst, const double *src, const int *idx, cudaSt
 int acgb200_scatter(int n, const double *src, double *dst, const int *idx, cudaStream_t stream); /* dst[idx[i]]=src[i] */
 int acgb200_num_sms(void);
 void acgb200_blas1_set_ctas_per_sm(int v);
-void acgb200_blas1_set_unroll(int v);
 void acgb200_set_pdl(int v);
 
 #ifdef __cplusplus

@@ -571,16 +571,6 @@ __device__ __forceinline__ void slice_load(double (&vv)[UB], double (&xv)[UB], c
 }
 
 template <int UB>
-__device__ __forceinline__ void slice_load_pred(double (&vv)[UB], double (&xv)[UB], const double *v, const double *xr,
-                                                const int *offs, int e, int L, uint64_t pol)
-{
-#pragma unroll
-    for (int u = 0; u < UB; u++) vv[u] = e + u < L ? ld_stream(v + (size_t) (e + u) * 32, pol) : 0.0;
-#pragma unroll
-    for (int u = 0; u < UB; u++) xv[u] = e + u < L ? ld_x(xr + offs[e + u]) : 0.0;
-}
-
-template <int UB>
 __device__ __forceinline__ double slice_fma(const double (&vv)[UB], const double (&xv)[UB], double sum)
 {
 #pragma unroll
@@ -588,12 +578,12 @@ __device__ __forceinline__ double slice_fma(const double (&vv)[UB], const double
     return sum;
 }
 
-/* PF: the loads of batch k+1 are issued before the products of batch k are added.  ptxas places a
- * batch's FMAs as early as their operands allow, i.e. between the loads of the same batch, and a warp
- * issues in order: without the prefetch a warp stalls on its first product with ~3 of its 2*UB loads in
- * flight; with it the operands of the FMA it stalls on were requested a whole batch earlier. */
-template <int UB, int T, bool PF, int MB>
-__global__ void __launch_bounds__(T, MB)
+/* Shapes measured and dropped in round 2 (profiles/r02/b_ab_224.log, c_ab_224.log; C3, this shape 0.397 ms):
+ * prefetching the next batch into a second register set (0.450 ms: 64-96 registers cost more warps than the
+ * prefetch buys), register caps of 40 / 32 per thread (spills), 32-bit column arithmetic (0.405), batches of
+ * 14 (0.433), 256- and 64-thread CTAs (0.425 / 0.431), 3-5 wide batches (0.42-0.59). */
+template <int UB, int T>
+__global__ void __launch_bounds__(T)
 spmv_slices_kernel(const SliceParams P)
 {
     extern __shared__ __align__(16) int spat_s[];
@@ -627,23 +617,10 @@ spmv_slices_kernel(const SliceParams P)
         const int L = sl.z;
         double sum = 0.0;
         int e = 0;
-        if (PF) {
-            /* two register sets, straight-line body (predicated loads, no branch between a batch's loads
-             * and the previous batch's FMAs); slots past L load nothing and add 0 * 0 */
-            double va[UB], xa[UB], vb[UB], xb[UB];
-            slice_load_pred<UB>(va, xa, v, xr, offs, 0, L, pol);
-            for (; e < L; e += 2 * UB) {
-                slice_load_pred<UB>(vb, xb, v, xr, offs, e + UB, L, pol);
-                sum = slice_fma<UB>(va, xa, sum);
-                slice_load_pred<UB>(va, xa, v, xr, offs, e + 2 * UB, L, pol);
-                sum = slice_fma<UB>(vb, xb, sum);
-            }
-        } else {
-            for (; e + UB <= L; e += UB) {
-                double vv[UB], xv[UB];
-                slice_load<UB>(vv, xv, v, xr, offs, e, pol);
-                sum = slice_fma<UB>(vv, xv, sum);
-            }
+        for (; e + UB <= L; e += UB) {
+            double vv[UB], xv[UB];
+            slice_load<UB>(vv, xv, v, xr, offs, e, pol);
+            sum = slice_fma<UB>(vv, xv, sum);
         }
         if (e < L) {
             /* last, partial batch: slots past L are neither loaded nor added */
@@ -1188,10 +1165,9 @@ cg_update_xp_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, a
 /* Pipelined CG: z=q+beta z; t=w+beta t; p=r+beta p; x+=alpha p; r-=alpha t;
  * w-=alpha z (acg/cg-kernels-cuda.cu:201-214), plus gamma'=(r,r), delta'=(w,r)
  * of the updated vectors for the next iteration. */
-/* UNR: rows per thread and trip of the grid-stride loop.  2 issues the 14 loads of two rows before the first
- * store: at one rank's share of the 8-GPU problem (1.4 M rows, 6 rows per thread) the kernel is a chain of
- * load latencies, not a bandwidth problem, and the chain halves. */
-template <int UNR>
+/* (Measured and dropped in round 2, profiles/r02/d_ab_112.log, e3_ab_224_n2.log: two rows per thread and trip
+ * -- 8 % faster at one rank's share of the 8-GPU problem, 5 % slower at C3, nothing between two GPUs; the
+ * system fence moved behind the border rows -- no effect.) */
 __global__ void __launch_bounds__(BLAS1_THREADS)
 pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acgb200_p2pdev *P,
                   const double *__restrict__ q, double *__restrict__ z, double *__restrict__ w,
@@ -1234,55 +1210,23 @@ pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acg
      * issuing those NVLink stores at the start lets them drain under the
      * interior rows instead of in front of the closing system fence. */
     const bool push = P && P->fuse;
-    const bool early = push && P->early_fence;
     const int first = push ? P->borderoff : 0;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
     for (int pass = 0; pass < 2; pass++) {
-        /* the remote stores are all behind us after the border pass: fence them now, while only a handful of this
-         * thread's stores are outstanding, instead of at the end behind the whole interior pass */
-        if (pass == 1 && early) __threadfence_system();
         const int lo = pass == 0 ? first : 0, hi = pass == 0 ? n : first;
-        if (UNR == 1) {
-            /* (the measured kernel of rounds 1 and 2, untouched: 40 registers, three CTAs of 512 threads per SM) */
-            for (int i = lo + gtid; i < hi; i += gstride) {
-                const double zv = fma(beta, z[i], q[i]);
-                const double tv = fma(beta, t[i], w[i]);
-                const double pv = fma(beta, p[i], r[i]);
-                const double rv = fma(-alpha, tv, r[i]);
-                const double wv = fma(-alpha, zv, w[i]);
-                z[i] = zv; t[i] = tv; p[i] = pv;
-                x[i] = fma(alpha, pv, x[i]);
-                r[i] = rv;
-                w[i] = wv;
-                g2 = fma(rv, rv, g2);
-                d2 = fma(wv, rv, d2);
-                if (push && pass == 0) p2p_push_row(P, i, s ^ 1, wv);
-            }
-        } else
-        for (int i0 = lo + gtid; i0 < hi; i0 += UNR * gstride) {
-            double zi[UNR], qi[UNR], ti[UNR], wi[UNR], pi[UNR], ri[UNR], xi[UNR];
-#pragma unroll
-            for (int u = 0; u < UNR; u++) {
-                const int i = min(i0 + u * gstride, hi - 1);       /* a lane without a row re-reads the last one */
-                zi[u] = z[i]; qi[u] = q[i]; ti[u] = t[i]; wi[u] = w[i]; pi[u] = p[i]; ri[u] = r[i]; xi[u] = x[i];
-            }
-#pragma unroll
-            for (int u = 0; u < UNR; u++) {
-                const int i = i0 + u * gstride;
-                if (i >= hi) break;
-                const double zv = fma(beta, zi[u], qi[u]);
-                const double tv = fma(beta, ti[u], wi[u]);
-                const double pv = fma(beta, pi[u], ri[u]);
-                const double rv = fma(-alpha, tv, ri[u]);
-                const double wv = fma(-alpha, zv, wi[u]);
-                z[i] = zv; t[i] = tv; p[i] = pv;
-                x[i] = fma(alpha, pv, xi[u]);
-                r[i] = rv;
-                w[i] = wv;
-                g2 = fma(rv, rv, g2);
-                d2 = fma(wv, rv, d2);
-                if (push && pass == 0) p2p_push_row(P, i, s ^ 1, wv);
-            }
+        for (int i = lo + gtid; i < hi; i += gstride) {
+            const double zv = fma(beta, z[i], q[i]);
+            const double tv = fma(beta, t[i], w[i]);
+            const double pv = fma(beta, p[i], r[i]);
+            const double rv = fma(-alpha, tv, r[i]);
+            const double wv = fma(-alpha, zv, w[i]);
+            z[i] = zv; t[i] = tv; p[i] = pv;
+            x[i] = fma(alpha, pv, x[i]);
+            r[i] = rv;
+            w[i] = wv;
+            g2 = fma(rv, rv, g2);
+            d2 = fma(wv, rv, d2);
+            if (push && pass == 0) p2p_push_row(P, i, s ^ 1, wv);
         }
     }
     g2 = block_sum(g2, red);
@@ -1294,7 +1238,7 @@ pcg_update_kernel(int n, acgb200_devstate *st, int cin, int cout, int multi, acg
     if (P && P->fuse) {
         /* last CTA: this rank's {gamma,delta} of the next iteration to every
          * rank, and the halo sequence number to the neighbours */
-        if (early) __threadfence(); else __threadfence_system();
+        __threadfence_system();
         if (p2p_last_block(P, &last_flag)) {
             const unsigned long long it1 = (unsigned long long) g.iter + 1ull;
             p2p_publish_red(P, 0, s ^ 1, P->rbase + it1, &st->gd_loc[s ^ 1][0], 2);
@@ -1360,9 +1304,6 @@ static int g_blas1_ctas_per_sm = 0;
 
 extern "C" void acgb200_blas1_set_ctas_per_sm(int v) { g_blas1_ctas_per_sm = v < 0 ? 0 : v; }
 
-/* rows per thread and loop trip of the pipelined update kernel (1 or 2) */
-static int g_blas1_unroll = 1;
-extern "C" void acgb200_blas1_set_unroll(int v) { g_blas1_unroll = v >= 2 ? 2 : 1; }
 
 /* One wave of grid-stride CTAs: SMs x resident CTAs of that kernel (a grid that
  * is not a multiple of it ends in a partial wave at a fraction of the memory
@@ -1436,15 +1377,10 @@ static inline int stage_bytes(const acgb200_spmvplan *pl)
 typedef void (*slice_fn)(const SliceParams);
 
 /* (values + gathers in flight per lane, threads per CTA) of the slice kernel */
-/* MB: resident CTAs per SM the register allocator must leave room for (0: no constraint) */
-static slice_fn slice_variant(int UB, int T, int PF, int MB)
+static slice_fn slice_variant(int UB, int T)
 {
-#define X(u, t) if (UB == u && T == t && MB == 0) return PF ? spmv_slices_kernel<u, t, true, 0> : spmv_slices_kernel<u, t, false, 0>;
-    X(3, 128) X(4, 128) X(5, 128) X(7, 128) X(8, 128) X(9, 128) X(14, 128) X(4, 256) X(5, 256) X(7, 256) X(8, 256) X(9, 256) X(14, 256)
-    X(7, 64) X(9, 64)
-#undef X
-#define X(u, t, m) if (UB == u && T == t && MB == m && !PF) return spmv_slices_kernel<u, t, false, m>;
-    X(9, 128, 10) X(9, 128, 12) X(7, 128, 10) X(7, 128, 12) X(14, 128, 6) X(14, 128, 8) X(9, 256, 5) X(9, 64, 20)
+#define X(u, t) if (UB == u && T == t) return spmv_slices_kernel<u, t>;
+    X(5, 128) X(7, 128) X(8, 128) X(9, 128) X(7, 256) X(8, 256) X(9, 256)
 #undef X
     return NULL;
 }
@@ -1496,7 +1432,7 @@ extern "C" int acgb200_spmv_configure(acgb200_spmvplan *pl)
         pl->merge_grid = (int) (mgrid < 1 ? 1 : mgrid);
     }
     if (pl->nslices > 0) {
-        slice_fn sfn = slice_variant(pl->slice_ub, pl->slice_threads, pl->slice_pf, pl->slice_minb);
+        slice_fn sfn = slice_variant(pl->slice_ub, pl->slice_threads);
         if (!sfn) return (int) cudaErrorInvalidConfiguration;
         pl->slice_smem = ((pl->slice_npat * pl->slice_lpad + 3) & ~3) * (int) sizeof(int);
         err = cudaFuncSetAttribute((const void *) sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->slice_smem);
@@ -1559,7 +1495,7 @@ extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t strea
         S.patid = pl->d_spatid; S.spatoff = pl->d_spatoff; S.npat = pl->slice_npat; S.lpad = pl->slice_lpad;
         S.x = a->x; S.y = a->y; S.b = a->b; S.acc = a->acc; S.dotrows = a->dotrows; S.mode = a->mode;
         S.ctrl_in = a->ctrl_in; S.ctrl_out = slices_forward ? a->ctrl_out : NULL; S.st = a->st; S.housekeeping = a->housekeeping;
-        const cudaError_t le = launch_chain(slice_variant(pl->slice_ub, pl->slice_threads, pl->slice_pf, pl->slice_minb), pl->slice_grid, pl->slice_threads,
+        const cudaError_t le = launch_chain(slice_variant(pl->slice_ub, pl->slice_threads), pl->slice_grid, pl->slice_threads,
                                             (size_t) pl->slice_smem, stream, S);
         if (le) return (int) le;
     }
@@ -1637,11 +1573,8 @@ extern "C" int acgb200_pcg_update(int n, acgb200_devstate *st, int cin, int cout
                                   const double *q, double *z, double *w, double *t, double *p,
                                   double *r, double *x, cudaStream_t stream)
 {
-    static int occ1 = 0, occ2 = 0;
-    if (g_blas1_unroll >= 2)
-        return (int) launch_chain(pcg_update_kernel<2>, blas1_grid(n, (const void *) pcg_update_kernel<2>, &occ2), BLAS1_THREADS, 0, stream,
-                                  n, st, cin, cout, multi, p2p, q, z, w, t, p, r, x);
-    return (int) launch_chain(pcg_update_kernel<1>, blas1_grid(n, (const void *) pcg_update_kernel<1>, &occ1), BLAS1_THREADS, 0, stream,
+    static int occ = 0;
+    return (int) launch_chain(pcg_update_kernel, blas1_grid(n, (const void *) pcg_update_kernel, &occ), BLAS1_THREADS, 0, stream,
                               n, st, cin, cout, multi, p2p, q, z, w, t, p, r, x);
 }
 

@@ -18,7 +18,7 @@ extern "C" {
  * "spmv_nnz_cap", "spmv_rows_cap", "spmv_stages", "spmv_threads", "spmv_unroll",
  * "spmv_max_ctas" (SpMV tile plan overrides, read at acgsolvercuda_init), "spmv_slices"
  * (0/1, default 1: index-free slice-major storage of the rows that repeat a pattern, slices.c; shape
- * overrides "slice_ub", "slice_threads", "slice_pf", "slice_max_ctas", "slice_minb"), "spmv_merge" (-1/0/1,
+ * overrides "slice_ub", "slice_threads", "slice_max_ctas"), "spmv_merge" (-1/0/1,
  * default -1: merge-path tiles when the row lengths are irregular, mergeplan.c; "merge_items", "merge_threads",
  * "merge_max_ctas"), "spmv_medium", "graph"
  * (0/1: replay iteration pairs as CUDA graphs), "redstream" (0/1: pipelined

@@ -101,7 +101,6 @@ static void p2p_push_row(const struct acgb200_p2pdev *P, int row, int parity, do
 
 int acgb200_num_sms(void) { return 148; }
 void acgb200_blas1_set_ctas_per_sm(int v) { (void) v; }
-void acgb200_blas1_set_unroll(int v) { (void) v; }
 void acgb200_set_pdl(int v) { (void) v; }
 
 int acgb200_spmv_configure(struct acgb200_spmvplan *pl)

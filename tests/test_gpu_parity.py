@@ -314,20 +314,21 @@ def test_power_law_properties(n, edges, ab):
 SLICE_CASES = [CASES[0], CASES[1], CASES[2], CASES[3]]
 
 
-@pytest.mark.parametrize("ub,pf", [(0, 1), (9, 0), (4, 1), (7, 0), (14, 1), (3, 1)])
+@pytest.mark.parametrize("ub,threads", [(0, 0), (9, 128), (7, 256), (8, 128), (5, 128), (9, 256)])
 @pytest.mark.parametrize("name,gen", SLICE_CASES, ids=[c[0] for c in SLICE_CASES])
-def test_pattern_slices_match_oracle(name, gen, ub, pf, ab, oracle):
+def test_pattern_slices_match_oracle(name, gen, ub, threads, ab, oracle):
     """spmv_slices_kernel (slices.c): rows that repeat a pattern are multiplied from slice-major
-    values without indices; every batch width / prefetch variant gives the oracle's product, the
-    fused dots of both CG loops included, and agrees with the tile kernel (option off) to rounding."""
+    values without indices; every batch width / CTA size gives the oracle's product (full batches and
+    the partial last one), the fused dots of both CG loops included, and agrees with the tile kernel
+    (option off) to rounding."""
     n, r, c, v = gen()
-    ab.set_option("slice_ub", ub); ab.set_option("slice_pf", pf)
+    ab.set_option("slice_ub", ub); ab.set_option("slice_threads", threads)
     try:
         A, cg = _solver(ab, n, r, c, v)
         ab.set_option("spmv_slices", 0)
         cg_tiles = ab.SolverCuda(A)
     finally:
-        ab.set_option("spmv_slices", 1); ab.set_option("slice_ub", 0); ab.set_option("slice_pf", -1)
+        ab.set_option("spmv_slices", 1); ab.set_option("slice_ub", 0); ab.set_option("slice_threads", 0)
     inf = cg.info()
     assert inf["spmv_slices"] > 0 and inf["spmv_slice_rows"] == 32 * inf["spmv_slices"]
     assert cg_tiles.info()["spmv_slices"] == 0

@@ -21,14 +21,13 @@ sys.path.insert(0, ROOT)
 import numpy as np          # noqa: E402
 
 DEFAULTS = dict(profile=0, spmv_lanes=0, spmv_nnz_cap=0, spmv_rows_cap=0, spmv_stages=0, spmv_threads=0,
-                spmv_unroll=0, spmv_max_ctas=0, graph=1, redstream=1, p2p=1, p2p_fuse=1, p2p_early_fence=0, blas1_ctas=0, blas1_unroll=1, pdl=0,
-                spmv_medium=0, spmv_merge=-1, merge_items=0, merge_threads=0, merge_stages=0, merge_max_ctas=0, spmv_slices=1, slice_ub=0, slice_threads=0, slice_pf=-1, slice_max_ctas=0, slice_minb=0)
+                spmv_unroll=0, spmv_max_ctas=0, graph=1, redstream=1, p2p=1, p2p_fuse=1, blas1_ctas=0, pdl=0,
+                spmv_medium=0, spmv_merge=-1, merge_items=0, merge_threads=0, merge_stages=0, merge_max_ctas=0, spmv_slices=1, slice_ub=0, slice_threads=0, slice_max_ctas=0)
 
 VARIANTS = {
     "base": {},
     "noslices": {"spmv_slices": 0},
     "oldgrid": {"blas1_ctas": 4},
-    "unr2": {"blas1_unroll": 2}, "unr2_c2": {"blas1_unroll": 2, "blas1_ctas": 2}, "unr2_pdl": {"blas1_unroll": 2, "pdl": 1},
     "pdl": {"pdl": 1},
     "nograph": {"graph": 0},
     "med128": {"spmv_medium": 128},
@@ -38,24 +37,11 @@ VARIANTS = {
     "nccl": {"p2p": 0},
     "nccl_graph": {"p2p": 0, "graph": 2},
     "unfused": {"p2p_fuse": 0},
-    "earlyfence": {"p2p_early_fence": 1}, "earlyfence_unr2": {"p2p_early_fence": 1, "blas1_unroll": 2},
-    # slice kernel shapes: s<ub>[p][_t<threads>][_c<max ctas>]  (p = prefetch the next batch)
-    "s9": {"slice_ub": 9, "slice_pf": 0}, "s9p": {"slice_ub": 9, "slice_pf": 1},
-    "s4": {"slice_ub": 4, "slice_pf": 0}, "s4p": {"slice_ub": 4, "slice_pf": 1},
-    "s3p": {"slice_ub": 3, "slice_pf": 1}, "s5p": {"slice_ub": 5, "slice_pf": 1}, "s5": {"slice_ub": 5, "slice_pf": 0},
-    "s7": {"slice_ub": 7, "slice_pf": 0}, "s7p": {"slice_ub": 7, "slice_pf": 1},
-    "s8p": {"slice_ub": 8, "slice_pf": 1}, "s14": {"slice_ub": 14, "slice_pf": 0}, "s14p": {"slice_ub": 14, "slice_pf": 1},
-    "s9p_t256": {"slice_ub": 9, "slice_pf": 1, "slice_threads": 256}, "s9_t256": {"slice_ub": 9, "slice_pf": 0, "slice_threads": 256},
-    "s5p_t256": {"slice_ub": 5, "slice_pf": 1, "slice_threads": 256},
-    "s9p_c4": {"slice_ub": 9, "slice_pf": 1, "slice_max_ctas": 4}, "s9p_c3": {"slice_ub": 9, "slice_pf": 1, "slice_max_ctas": 3},
-    "s9_c8": {"slice_ub": 9, "slice_pf": 0, "slice_max_ctas": 8},
-    # register caps: m<CTAs per SM the allocator must leave room for>
-    "s9_m10": {"slice_ub": 9, "slice_pf": 0, "slice_minb": 10}, "s9_m12": {"slice_ub": 9, "slice_pf": 0, "slice_minb": 12},
-    "s7_m10": {"slice_ub": 7, "slice_pf": 0, "slice_minb": 10}, "s7_m12": {"slice_ub": 7, "slice_pf": 0, "slice_minb": 12},
-    "s14_m6": {"slice_ub": 14, "slice_pf": 0, "slice_minb": 6}, "s14_m8": {"slice_ub": 14, "slice_pf": 0, "slice_minb": 8},
-    "s9_t256_m5": {"slice_ub": 9, "slice_pf": 0, "slice_threads": 256, "slice_minb": 5},
-    "s9_t64": {"slice_ub": 9, "slice_pf": 0, "slice_threads": 64}, "s9_t64_m20": {"slice_ub": 9, "slice_pf": 0, "slice_threads": 64, "slice_minb": 20},
-    "s7_t64": {"slice_ub": 7, "slice_pf": 0, "slice_threads": 64},
+    # slice kernel shapes: s<ub>[_t<threads>][_c<max ctas>]  (the prefetching / register-capped shapes of calls B and C
+    # were dropped after measurement: profiles/r02/b_ab_224.log, c_ab_224.log)
+    "s9": {"slice_ub": 9}, "s8": {"slice_ub": 8}, "s7": {"slice_ub": 7}, "s5": {"slice_ub": 5},
+    "s9_t256": {"slice_ub": 9, "slice_threads": 256}, "s7_t256": {"slice_ub": 7, "slice_threads": 256},
+    "s9_c8": {"slice_ub": 9, "slice_max_ctas": 8},
 }
 
 
