@@ -431,11 +431,11 @@ def main():
                 (["spmv_tiles_kernel"] if info["spmv_ntiles"] > 0 else [])
         kernel_name = " + ".join(parts) or "spmv_tiles_kernel"
         min_bytes = float(info["spmv_min_bytes"])
-        prof = os.path.join(ROOT, "profiles", "r02_ncu_spmv.json")
+        prof = os.path.join(ROOT, "profiles", "r02", "h_ncu_slices.json")
         traffic_source = None
-        if os.path.exists(prof) and world == 1 and args.workload == "27pt-224":
+        if os.path.exists(prof) and world == 1 and args.workload == "27pt-224" and info["spmv_slice_rows"] == nloc:
             pj = json.load(open(prof))
-            traffic_source = {"file": "profiles/r02_ncu_spmv.json", "kernel": pj.get("kernel"),
+            traffic_source = {"file": "profiles/r02/h_ncu_slices.json", "kernel": pj.get("kernel"),
                               "dram_bytes_per_launch": pj.get("dram_bytes_per_launch"),
                               "note": "ncu --set full capture of the same kernel and workload, committed; not measured in this run"}
         line = {
