@@ -123,7 +123,8 @@ class acgb200_info(C.Structure):
                                                                                   ("spmv_slice_grid", C.c_int),
                                                                                   ("spmv_merge_tiles", C.c_int),
                                                                                   ("spmv_merge_rows", C.c_int),
-                                                                                  ("spmv_merge_split", C.c_int)]
+                                                                                  ("spmv_merge_split", C.c_int),
+                                                                                  ("spmv_slice_exc", C.c_int)]
 
 
 class acgb200_mtxinfo(C.Structure):
@@ -238,7 +239,8 @@ def lib() -> C.CDLL:
     L.acgb200_p2p_inverse_map.argtypes = [P(acghalo), C.c_int, C.c_int, i32p, i32p, i32p, i32p]
     L.acgb200_spmv_plan_host2.argtypes = [C.c_int, i64p, C.c_void_p, P(acgb200_info), i32p, C.c_int, i32p, C.c_int]
     L.acgb200_merge_plan_host.argtypes = [C.c_int, i64p, C.c_int, i32p, C.c_int, i32p, P(C.c_int), P(C.c_int)]
-    L.acgb200_slices_host.argtypes = [C.c_int, C.c_int, i64p, C.c_void_p, i32p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.acgb200_slices_host.argtypes = [C.c_int, C.c_int, i64p, C.c_void_p, i32p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]
     L.acgb200_spmv_plan_host.argtypes = [C.c_int, i64p, P(acgb200_info), i32p, C.c_int, i32p, C.c_int]
     L.acgb200_comm_init_rank.argtypes = [P(acgcomm), C.c_int, C.c_void_p, C.c_int, P(C.c_int)]
     L.acgb200_comm_destroy.argtypes = [P(acgcomm)]
@@ -303,13 +305,16 @@ def slices_host(rowptr, colidx, cover_hi=None) -> dict:
     covered = np.zeros(max(nsl, 1), dtype=np.uint8)
     totals = np.zeros(6, dtype=np.int64)
     spatoff = np.zeros(8192, dtype=np.int32)
+    patid = np.full(max(n, 1), 0xFFFF, dtype=np.uint16)
+    exc2 = np.zeros(2, dtype=np.int64)
     _check(lib().acgb200_slices_host(n, n if cover_hi is None else cover_hi, rowptr, colidx.ctypes.data_as(C.c_void_p),
                                      slices4, nsl, covered.ctypes.data_as(C.c_void_p), totals.ctypes.data_as(C.c_void_p),
-                                     spatoff.ctypes.data_as(C.c_void_p)), "acgb200_slices_host")
+                                     spatoff.ctypes.data_as(C.c_void_p), patid.ctypes.data_as(C.c_void_p),
+                                     exc2.ctypes.data_as(C.c_void_p)), "acgb200_slices_host")
     ns = int(totals[0])
     return dict(nslices=ns, slices=slices4[:4 * ns].reshape(ns, 4).copy(), covered=covered[:nsl].astype(bool),
                 blocks=int(totals[1]), nnz=int(totals[2]), rows=int(totals[3]), lpad=int(totals[4]), npat=int(totals[5]),
-                spatoff=spatoff)
+                spatoff=spatoff, patid=patid[:n], nexc=int(exc2[0]), excnnz=int(exc2[1]))
 
 
 def spmv_plan_host(rowptr, colidx=None) -> dict:

@@ -345,7 +345,8 @@ static int build_tiles(struct acgb200_spmvplan *pl, const int64_t *rowptr,
     pl->nslices = 0;
     if (!e && sp && sp->nslices > 0) {
         pl->nslices = sp->nslices; pl->sval_blocks = sp->blocks; pl->slice_rows = sp->rows; pl->slice_nnz = sp->nnz;
-        pl->slice_lpad = sp->lpad; pl->slice_npat = sp->npat;
+        pl->slice_lpad = sp->lpad; pl->slice_npat = sp->npat; pl->slice_exc = sp->nexc; pl->slice_excnnz = sp->excnnz;
+        patid = sp->patid;          /* ids as the slice kernel sees them (exception rows marked) */
         const size_t tab = (size_t) sp->npat * (size_t) sp->lpad;
         e = cudaMalloc((void **) &pl->d_slices, (size_t) sp->nslices * sizeof(*sp->slices));
         if (!e) e = cudaMemcpy(pl->d_slices, sp->slices, (size_t) sp->nslices * sizeof(*sp->slices), cudaMemcpyHostToDevice);
@@ -410,7 +411,8 @@ int acgb200_merge_plan_host(int hi, const int64_t *rowptr, int items, int *tiles
 
 /* ext.h: the pattern-slice plan of a CSR matrix, host only (slices.c) */
 int acgb200_slices_host(int nrows, int cover_hi, const int64_t *rowptr, const int *colidx,
-                        int *slices4, int maxslices, unsigned char *covered, int64_t *totals6, int *spatoff)
+                        int *slices4, int maxslices, unsigned char *covered, int64_t *totals6, int *spatoff,
+                        unsigned short *patid, int64_t *exc2)
 {
     struct acgb200_patterns pat;
     struct acgb200_sliceplan sp;
@@ -427,6 +429,8 @@ int acgb200_slices_host(int nrows, int cover_hi, const int64_t *rowptr, const in
         totals6[0] = sp.nslices; totals6[1] = sp.blocks; totals6[2] = sp.nnz; totals6[3] = sp.rows;
         totals6[4] = sp.lpad; totals6[5] = sp.npat;
         if (sp.nslices > 0) memcpy(spatoff, sp.spatoff, (size_t) sp.npat * (size_t) sp.lpad * sizeof(int));
+        if (patid && sp.nslices > 0) memcpy(patid, sp.patid, (size_t) nrows * sizeof(*patid));
+        if (exc2) { exc2[0] = sp.nexc; exc2[1] = sp.excnnz; }
     }
     acgb200_sliceplan_free(&sp);
     acgb200_patterns_free(&pat);
@@ -1743,6 +1747,7 @@ int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info
     info->num_sms = acgb200_num_sms();
     info->spmv_merge_tiles = pv->plan.nmtiles; info->spmv_merge_rows = pv->plan.merge_rows; info->spmv_merge_split = pv->plan.nsplit;
     info->spmv_slices = pv->plan.nslices; info->spmv_slice_rows = pv->plan.slice_rows;
+    info->spmv_slice_exc = (int) pv->plan.slice_exc;
     info->spmv_slice_ub = pv->plan.slice_ub; info->spmv_slice_grid = pv->plan.slice_grid;
     info->spmv_nmedium = pv->plan.nmed;
     info->spmv_min_bytes = acgb200_spmv_min_bytes(&pv->plan);

@@ -72,6 +72,7 @@ struct acgb200_spmvplan {
     int *d_spatoff;                  /* [slice_npat * slice_lpad] offsets col - row, zero beyond a pattern's length */
     unsigned short *d_spatid;        /* [nrows] pattern id per row (valid for covered rows) */
     int slice_ub, slice_threads, slice_grid, slice_smem, slice_max_ctas;
+    int64_t slice_exc, slice_excnnz; /* exception rows inside slices (columns from the CSR index array) and their nonzeros */
     /* merge-path tiles (mergeplan.c): rows [0, merge_rows) of an irregular (power-law) matrix, cut into tiles
      * of merge_items merged items (row ends + nonzeros) and multiplied by spmv_merge_kernel; rows cut by tile
      * boundaries are finished by spmv_merge_fix_kernel from the tiles' partial sums */
@@ -110,6 +111,9 @@ struct acgb200_sliceplan {
     int64_t blocks, nnz;
     int rows, lpad, npat, domlen;    /* domlen: most frequent row length among covered rows */
     int *spatoff;                    /* [npat * lpad] */
+    unsigned short *patid;           /* [nrows] pattern id as the slice kernel sees it: < npat, or ACGB200_NOPATTERN =
+                                      * exception row (columns from the index array) */
+    int64_t nexc, excnnz;            /* exception rows inside covered slices, their nonzeros */
 };
 int acgb200_slices_plan(int nrows, int cover_hi, const int64_t *rowptr, const struct acgb200_patterns *pat,
                         struct acgb200_sliceplan *out);

@@ -533,9 +533,11 @@ struct SliceParams {
     const acgb200_slice *slices;
     int nslices;
     const double *sval;
-    const unsigned short *patid;
+    const unsigned short *patid;   /* pattern id per row; ACGB200_NOPATTERN: exception row (EXC kernels only) */
     const int *spatoff;            /* [npat * lpad], zero beyond a pattern's length */
     int npat, lpad;
+    const int *rowptr;             /* CSR row pointers / column indices: the columns of exception rows */
+    const int *colidx;
     const double *x;
     double *y;
     const double *b;
@@ -581,9 +583,14 @@ __device__ __forceinline__ double slice_fma(const double (&vv)[UB], const double
 /* Shapes measured and dropped in round 2 (profiles/r02/b_ab_224.log, c_ab_224.log; C3, this shape 0.397 ms):
  * prefetching the next batch into a second register set (0.450 ms: 64-96 registers cost more warps than the
  * prefetch buys), register caps of 40 / 32 per thread (spills), 32-bit column arithmetic (0.405), batches of
- * 14 (0.433), 256- and 64-thread CTAs (0.425 / 0.431), 3-5 wide batches (0.42-0.59). */
-template <int UB, int T>
-__global__ void __launch_bounds__(T)
+ * 14 (0.433), 256- and 64-thread CTAs (0.425 / 0.431), 3-5 wide batches (0.42-0.59).
+ *
+ * EXC: the plan has slices with exception rows (rows outside the dictionary, slices.c).  A warp whose 32 rows are
+ * all in the dictionary runs the same loop as the plain kernel; otherwise the exception lanes take each slot's
+ * column from the CSR index array (one extra load per slot for those lanes only), everything else is unchanged.
+ * The plain instantiation is byte for byte the kernel measured in round 2. */
+template <int UB, int T, bool EXC>
+__global__ void __launch_bounds__(T, EXC ? 1280 / T : 0)
 spmv_slices_kernel(const SliceParams P)
 {
     extern __shared__ __align__(16) int spat_s[];
@@ -611,12 +618,33 @@ spmv_slices_kernel(const SliceParams P)
     for (int s = warp; s < P.nslices; s += nwarps) {
         const int4 sl = __ldg(reinterpret_cast<const int4 *>(P.slices) + s);     /* row0, nrows, len, vblk */
         const int row = sl.x + lane;
-        const int *offs = spat_s + (int) P.patid[row] * P.lpad;
+        const int pid = P.patid[row];
+        const bool exc = EXC && pid == (int) ACGB200_NOPATTERN;
+        const int *offs = spat_s + (exc ? 0 : pid) * P.lpad;
         const double *v = P.sval + ((size_t) sl.w << 5) + lane;
         const double *xr = P.x + row;
         const int L = sl.z;
         double sum = 0.0;
         int e = 0;
+        if (EXC && __any_sync(0xffffffffu, exc)) {
+            /* a slice with exception rows: those lanes read their columns from the index array (slots past the
+             * row's end hold the value 0 and gather x[row]) */
+            int kb = 0, len = 0;
+            if (exc) { kb = P.rowptr[row]; len = P.rowptr[row + 1] - kb; }
+            for (; e < L; e += UB) {
+                double vv[UB], xv[UB];
+#pragma unroll
+                for (int u = 0; u < UB; u++) vv[u] = e + u < L ? ld_stream(v + (size_t) (e + u) * 32, pol) : 0.0;
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+                    const int ee = e + u;
+                    int col = row;
+                    if (ee < L) col = exc ? (ee < len ? __ldg(P.colidx + kb + ee) : row) : row + offs[ee];
+                    xv[u] = ee < L ? ld_x(P.x + col) : 0.0;
+                }
+                sum = slice_fma<UB>(vv, xv, sum);
+            }
+        }
         for (; e + UB <= L; e += UB) {
             double vv[UB], xv[UB];
             slice_load<UB>(vv, xv, v, xr, offs, e, pol);
@@ -1377,9 +1405,9 @@ static inline int stage_bytes(const acgb200_spmvplan *pl)
 typedef void (*slice_fn)(const SliceParams);
 
 /* (values + gathers in flight per lane, threads per CTA) of the slice kernel */
-static slice_fn slice_variant(int UB, int T)
+static slice_fn slice_variant(int UB, int T, int EXC)
 {
-#define X(u, t) if (UB == u && T == t) return spmv_slices_kernel<u, t>;
+#define X(u, t) if (UB == u && T == t) return EXC ? spmv_slices_kernel<u, t, true> : spmv_slices_kernel<u, t, false>;
     X(5, 128) X(7, 128) X(8, 128) X(9, 128) X(7, 256) X(8, 256) X(9, 256)
 #undef X
     return NULL;
@@ -1432,7 +1460,7 @@ extern "C" int acgb200_spmv_configure(acgb200_spmvplan *pl)
         pl->merge_grid = (int) (mgrid < 1 ? 1 : mgrid);
     }
     if (pl->nslices > 0) {
-        slice_fn sfn = slice_variant(pl->slice_ub, pl->slice_threads);
+        slice_fn sfn = slice_variant(pl->slice_ub, pl->slice_threads, pl->slice_exc > 0);
         if (!sfn) return (int) cudaErrorInvalidConfiguration;
         pl->slice_smem = ((pl->slice_npat * pl->slice_lpad + 3) & ~3) * (int) sizeof(int);
         err = cudaFuncSetAttribute((const void *) sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->slice_smem);
@@ -1493,9 +1521,10 @@ extern "C" int acgb200_spmv_launch(const acgb200_spmvargs *a, cudaStream_t strea
         SliceParams S;
         S.slices = pl->d_slices; S.nslices = pl->nslices; S.sval = pl->d_sval;
         S.patid = pl->d_spatid; S.spatoff = pl->d_spatoff; S.npat = pl->slice_npat; S.lpad = pl->slice_lpad;
+        S.rowptr = a->rowptr; S.colidx = a->colidx;
         S.x = a->x; S.y = a->y; S.b = a->b; S.acc = a->acc; S.dotrows = a->dotrows; S.mode = a->mode;
         S.ctrl_in = a->ctrl_in; S.ctrl_out = slices_forward ? a->ctrl_out : NULL; S.st = a->st; S.housekeeping = a->housekeeping;
-        const cudaError_t le = launch_chain(slice_variant(pl->slice_ub, pl->slice_threads), pl->slice_grid, pl->slice_threads,
+        const cudaError_t le = launch_chain(slice_variant(pl->slice_ub, pl->slice_threads, pl->slice_exc > 0), pl->slice_grid, pl->slice_threads,
                                             (size_t) pl->slice_smem, stream, S);
         if (le) return (int) le;
     }

@@ -12,7 +12,8 @@ int64_t acgb200_spmv_min_bytes(const struct acgb200_spmvplan *pl)
 {
     /* tiles: values + indices + per row: row pointer, y, x; slices: padded values + per row: pattern id, y, x */
     const int64_t tnnz = pl->nnz - pl->slice_nnz, trows = pl->nrows - pl->slice_rows;
-    return tnnz * 12 + trows * 20 + pl->sval_blocks * 256 + (int64_t) pl->slice_rows * 18;
+    return tnnz * 12 + trows * 20 + pl->sval_blocks * 256 + (int64_t) pl->slice_rows * 18
+           + pl->slice_excnnz * 4 + pl->slice_exc * 8;
 }
 
 /*

@@ -63,6 +63,7 @@ struct acgb200_info {
     int spmv_merge_tiles;       /* merge-path tiles (option "spmv_merge", mergeplan.c) ... */
     int spmv_merge_rows;        /* ... the rows [0, spmv_merge_rows) they cover ... */
     int spmv_merge_split;       /* ... and the rows cut by tile boundaries (finished by spmv_merge_fix_kernel) */
+    int spmv_slice_exc;         /* rows inside slices that are not in the pattern dictionary (columns from the index array) */
 };
 ACG_API int acgsolvercuda_info(const struct acgsolvercuda *cg, struct acgb200_info *info);
 
@@ -80,10 +81,12 @@ ACG_API int acgb200_spmv_plan_host2(int nrows, const int64_t *rowptr, const int 
 /* The pattern-slice plan of a 0-based CSR matrix (slices.c), host only: slices4 gets {row0, nrows,
  * len, vblk} per covered slice (at most maxslices), covered one byte per 32-row slice, totals
  * {nslices, value blocks of 32 doubles, nonzeros covered, rows covered, row stride of the padded
- * offset table, patterns}, spatoff (8192 ints) the zero-padded offset table.  Rows [0,cover_hi) are
- * eligible. */
+ * offset table, patterns in the table}, spatoff (8192 ints) the zero-padded offset table, patid (nrows, may be
+ * NULL) the pattern id per row as the slice kernel sees it (0xFFFF: exception row, columns from the index array),
+ * exc2 (may be NULL) {exception rows inside slices, their nonzeros}.  Rows [0,cover_hi) are eligible. */
 ACG_API int acgb200_slices_host(int nrows, int cover_hi, const int64_t *rowptr, const int *colidx,
-                                int *slices4, int maxslices, unsigned char *covered, int64_t *totals6, int *spatoff);
+                                int *slices4, int maxslices, unsigned char *covered, int64_t *totals6, int *spatoff,
+                                unsigned short *patid, int64_t *exc2);
 
 /* acgsymcsrmatrix_dsymv_init (acg/symcsrmatrix.c:760-851) computed on the current CUDA device
  * (expand.cu): the packed triangle is uploaded, mirrored there into the full local block and the

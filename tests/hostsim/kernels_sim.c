@@ -254,11 +254,13 @@ static void slices_exec(const struct acgb200_spmvargs *a, int forward)
         for (int lane = 0; lane < 32; lane++) {
             const int row = sl.row0 + lane;
             const int id = pl->d_spatid[row];
+            const int exc = id == (int) ACGB200_NOPATTERN;           /* exception row: columns from the index array */
             double sum = 0.0;
-            int bad = id >= pl->slice_npat || sl.nrows != 32;
+            int bad = (!exc && id >= pl->slice_npat) || sl.nrows != 32 || (exc && pl->slice_exc <= 0);
+            const int kb = a->rowptr[row], len = a->rowptr[row + 1] - kb;
             for (int e = 0; e < sl.len && !bad; e++) {
                 const double v = pl->d_sval[((size_t) sl.vblk << 5) + (size_t) e * 32 + lane];
-                const int col = row + pl->d_spatoff[(size_t) id * pl->slice_lpad + e];
+                const int col = exc ? (e < len ? a->colidx[kb + e] : row) : row + pl->d_spatoff[(size_t) id * pl->slice_lpad + e];
                 sum = fma(v, a->x[col], sum);
             }
             /* the same row through the CSR arrays, same order */

@@ -67,6 +67,7 @@ def test_border_ghost_spmv_of_every_part(name, gen, pkind, nparts, dims, ab, ora
     parts = A.partition(nparts, _rowparts(pkind, n, nparts, dims))
     covered = np.zeros(n, bool)
     ghost_nnz = 0
+    exc_rows = 0
     for p, m in enumerate(parts):
         m.dsymv_init(0.0)
         no, nv = m.c.nownedrows, m.c.nprows
@@ -74,6 +75,7 @@ def test_border_ghost_spmv_of_every_part(name, gen, pkind, nparts, dims, ab, ora
         assert m.c.nghostrows > 0 and m.c.onpnzs > 0, "a part without ghosts tests nothing"
         ghost_nnz += int(m.c.onpnzs)
         cg = ab.SolverCuda(m)
+        exc_rows += cg.info()["spmv_slice_exc"]
         xl = xg[gl]
         for path in (0, 1):
             y, dot = cg.spmv_ghost(xl, path)
@@ -84,6 +86,10 @@ def test_border_ghost_spmv_of_every_part(name, gen, pkind, nparts, dims, ab, ora
         covered[gl[:no]] = True
         cg.free()
     assert covered.all() and ghost_nnz > 0
+    if name == "27pt-24-block8":
+        # the interior rows next to a block's border shell are not in the pattern dictionary: they stay in their
+        # slices as exception rows (spmv_slices_kernel<.., EXC>), which this test therefore exercises
+        assert exc_rows > 0
     for m in parts:
         m.free()
     A.free()

@@ -373,10 +373,14 @@ def test_slices_and_tiles_arithmetic_emulated(name, gen, ab, oracle):
     for row0, _, L, vblk in sp["slices"]:
         for lane in range(32):
             row = row0 + lane
-            offs = table[int(pat["patid"][row]) * lpad:][:lpad]
+            pid = int(sp["patid"][row])
+            kb, ln = rowptr[row], rowptr[row + 1] - rowptr[row]
+            offs = table[(0 if pid == 0xFFFF else pid) * lpad:][:lpad]
             acc = 0.0
             for e in range(L):
-                acc += sval[32 * vblk + 32 * e + lane] * x[row + offs[e]]
+                # exception rows (not in the dictionary): the column comes from the index array, padded slots gather x[row]
+                c = (colidx[kb + e] if e < ln else row) if pid == 0xFFFF else row + offs[e]
+                acc += sval[32 * vblk + 32 * e + lane] * x[c]
             y[row] = acc
             count[row] += 1
     for row_begin, nrows, k_al, nnz_al in plan["tiles"]:

@@ -35,13 +35,13 @@ def test_slices_cover_pattern_rows_exactly(name, gen, ab):
         assert L == lens[row0:row0 + 32].max() and L <= lpad
         blocks += L
         for r in range(row0, row0 + 32):
-            pid = int(pat["patid"][r])
-            assert pid != 0xFFFF
+            pid = int(sp["patid"][r])
+            assert pid != 0xFFFF and pid == int(pat["patid"][r])                  # whole stencils: no exception rows
             offs = table[pid * lpad:(pid + 1) * lpad]
             assert np.array_equal(r + offs[:lens[r]], col[rp[r]:rp[r + 1]])      # columns rebuilt from the table
             assert not offs[lens[r]:].any()                                       # padded slots gather x[row]
             nnz += lens[r]
-    assert blocks == sp["blocks"] and nnz == sp["nnz"]
+    assert blocks == sp["blocks"] and nnz == sp["nnz"] and sp["nexc"] == 0
     # slices that are not covered: the ragged end (fewer than 32 rows) or too much padding
     assert sp["covered"].sum() == sp["nslices"]
     assert 8 * 32 * sp["blocks"] <= 11 * sp["nnz"]
@@ -51,6 +51,31 @@ def test_no_slices_for_unstructured_rows(ab):
     n, rp, col, _ = _full(ab, lambda: mg.random_spd(600, 0.05, 3))
     sp = ab.slices_host(rp, col)
     assert sp["nslices"] == 0 and not sp["covered"].any()
+
+
+def test_exception_rows_inside_a_partitions_block(ab):
+    """One block of a 2x2x2 partition: every grid line of the interior has a row next to the border shell whose
+    offsets to the (separately numbered) border rows are unique -- not in the dictionary.  Such rows stay inside
+    their slices as exception rows (columns from the index array): coverage stays near 100 % of the interior
+    instead of losing every slice that holds one."""
+    from acg_b200 import dist as abdist
+    A = abdist.local_stencil_part(27, 48, 48, 48, 0, 8)
+    no, bo = A.c.nownedrows, A.c.borderrowoffset
+    rp = A.frowptr[:no + 1].copy(); col = A.fcolidx[:rp[no]].copy()
+    sp = ab.slices_host(rp, col, cover_hi=bo)
+    assert sp["nexc"] > 0 and sp["rows"] >= 0.95 * (bo - bo % 32)
+    lens = np.diff(rp)
+    nexc = excnnz = 0
+    for row0, _, L, _ in sp["slices"]:
+        ids = sp["patid"][row0:row0 + 32]
+        assert (ids == 0xFFFF).sum() <= 8
+        for r in np.nonzero(ids == 0xFFFF)[0] + row0:
+            nexc += 1; excnnz += lens[r]
+            assert lens[r] <= L
+        for r in np.nonzero(ids != 0xFFFF)[0] + row0:
+            offs = sp["spatoff"][int(sp["patid"][r]) * sp["lpad"]:][:sp["lpad"]]
+            assert np.array_equal(r + offs[:lens[r]], col[rp[r]:rp[r + 1]])
+    assert nexc == sp["nexc"] and excnnz == sp["excnnz"]
 
 
 def test_cover_limit_excludes_border_rows(ab):
