@@ -153,8 +153,7 @@ struct priv {
     struct acgcomm redcomm;             /* private duplicate of the caller's communicator for reductions */
     int have_redcomm;
     double *d_b, *d_x;                  /* right-hand side / solution on the device, kept between solves */
-    cudaGraphExec_t graph[3];           /* [0] classic, [1] pipelined, [2] pipelined as one kernel per iteration:
-                                         * two iterations each (parity 0 then 1) */
+    cudaGraphExec_t graph[3];           /* [0] classic, [1] pipelined ([2] spare): two iterations each (parity 0 then 1) */
     int graph_sig[3];                   /* loop configuration each cached graph was captured with (graph_signature) */
     int graph_launches[3];              /* kernel/NCCL launches inside one replay */
     double last_h2d_ms, last_d2h_ms;    /* host time spent before / after the solve window */

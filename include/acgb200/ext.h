@@ -53,7 +53,7 @@ struct acgb200_info {
     double last_h2d_ms;         /* host time of the b, x0 upload of the last solve */
     double last_d2h_ms;         /* host time of the x download of the last solve */
     double last_blas_ms;        /* device time of the fused vector-update kernels of the last solve (profile=1) */
-    int reserved0;              /* (round 1: compressed tiles, removed) */
+    int reserved0;              /* (was: tiles without column indices, a round-1 variant removed after measurement) */
     int64_t spmv_min_bytes;     /* bytes one SpMV launch must move at least, given the plan */
     int spmv_nmedium;           /* rows handled one warp each (option "spmv_medium") */
     int reserved1;              /* (round 1: loop layout, the variants were removed) */

@@ -149,7 +149,9 @@ def _free_port():
     (2, "27pt", 8, "block", "p2p-fused,p2p-unfused,nccl,nccl-graph,nccl-serial-reduce,tiles-only", []),
     (3, "7pt", 9, "slab", "watchdog,p2p-fused,tiles-only,nccl", []),
     (4, "rmat", 3000, "random", "p2p-fused,nccl", ["--maxits", "12", "--rtol", "0"]),
-], ids=["2-ranks-all-backends", "3-ranks", "4-ranks-power-law"])
+    # 2x2x2 blocks: the interior rows next to a block's border shell are exception rows of their slices (slices.c)
+    (8, "27pt", 24, "block", "p2p-fused,tiles-only", []),
+], ids=["2-ranks-all-backends", "3-ranks", "4-ranks-power-law", "8-ranks-blocks"])
 def test_multi_rank_loops(nproc, matrix, size, partition, backends, extra, simlib):
     """The distributed solver, one process per rank: the library's host code on the stand-in,
     "device" allocations in shared memory so that the CUDA-IPC windows of the peer-memory exchange
