@@ -7,7 +7,7 @@ set -e
 D=tests/hostsim/build_asan
 mkdir -p $D
 FL="-O1 -g -std=gnu11 -fPIC -fopenmp -fsanitize=address,undefined -fno-omit-frame-pointer -Iinclude -Iacg_b200/csrc -Itests/hostsim -I/usr/local/cuda/include"
-for f in error vector symcsrmatrix stencil rmat mtxfile metis_rows comm halo p2p compress plan cgcuda ext; do /usr/bin/gcc $FL -c acg_b200/csrc/$f.c -o $D/$f.o; done
+for f in error vector symcsrmatrix stencil rmat mtxfile metis_rows comm halo p2p compress slices mergeplan plan cgcuda expand_host ext; do /usr/bin/gcc $FL -c acg_b200/csrc/$f.c -o $D/$f.o; done
 for f in cuda_mock nccl_mock kernels_sim; do /usr/bin/gcc $FL -c tests/hostsim/$f.c -o $D/$f.o; done
 /usr/bin/gcc -shared -Wl,-Bsymbolic -fsanitize=address,undefined -o $D/libacgb200_hostsim.so $D/*.o -lgomp -lpthread -lrt -lm
 export LD_PRELOAD="$(/usr/bin/gcc -print-file-name=libasan.so) $(/usr/bin/gcc -print-file-name=libubsan.so)"
@@ -18,9 +18,9 @@ ACGB200_TEST_LIB=$PWD/$D/libacgb200_hostsim.so python -m pytest tests/test_host_
     -k "not metis and not thread_count and not reference and not refuses" -p no:cacheprovider 2>&1 | tail -3
 echo "== solver, 3 ranks, every loop back-end"
 ACGB200_TEST_HOSTSIM=$PWD/$D/libacgb200_hostsim.so python -m torch.distributed.run --nnodes=1 --nproc-per-node=3 \
-    --master-addr 127.0.0.1 --master-port 31114 tests/_dist_worker.py --mode gpu --matrix 27pt --size 8 --partition block \
+    --master-addr 127.0.0.1 --master-port 31114 tests/_dist_worker.py --mode gpu --matrix 27pt --size 16 --partition block \
     --backends p2p-fused,p2p-unfused,tiles-only,nccl,nccl-graph 2>&1 \
     | grep -c " OK$\|FAIL\|runtime error\|AddressSanitizer" 
 echo "== every runtime call of set-up and solves failing in turn (159 at the end of round 1)"
-for k in $(seq 1 165); do ACGB200_TEST_LIB=$PWD/$D/libacgb200_hostsim.so HOSTSIM_FAIL_CALL_AT=$k python tests/hostsim/run_fault.py 2>&1 | grep -i "Sanitizer\|runtime error\|^ok\|^error"; done | sort | uniq -c
+for k in $(seq 1 260); do ACGB200_TEST_LIB=$PWD/$D/libacgb200_hostsim.so HOSTSIM_FAIL_CALL_AT=$k python tests/hostsim/run_fault.py 2>&1 | grep -i "Sanitizer\|runtime error\|^ok\|^error"; done | sort | uniq -c
 rm -f /dev/shm/acgb200nccl_* /dev/shm/acgb200sim_*
