@@ -627,22 +627,31 @@ spmv_slices_kernel(const SliceParams P)
         double sum = 0.0;
         int e = 0;
         if (EXC && __any_sync(0xffffffffu, exc)) {
-            /* a slice with exception rows: those lanes read their columns from the index array (slots past the
-             * row's end hold the value 0 and gather x[row]) */
-            int kb = 0, len = 0;
+            /* a slice with exception rows: those lanes take their columns from the index array (slots past the
+             * row's end hold the value 0 and gather x[row]).  Branch-free: every lane issues the index load --
+             * the lanes that do not need it read colidx[0], one cached sector for the whole warp -- and selects. */
+            int kb = 0, len = 1;
             if (exc) { kb = P.rowptr[row]; len = P.rowptr[row + 1] - kb; }
-            for (; e < L; e += UB) {
+            const int *cbase = P.colidx + kb;
+            const int last = exc ? max(len - 1, 0) : 0;
+            for (; e + UB <= L; e += UB) {
                 double vv[UB], xv[UB];
+                int cc[UB];
 #pragma unroll
-                for (int u = 0; u < UB; u++) vv[u] = e + u < L ? ld_stream(v + (size_t) (e + u) * 32, pol) : 0.0;
+                for (int u = 0; u < UB; u++) vv[u] = ld_stream(v + (size_t) (e + u) * 32, pol);
+#pragma unroll
+                for (int u = 0; u < UB; u++) cc[u] = __ldg(cbase + min(e + u, last));
 #pragma unroll
                 for (int u = 0; u < UB; u++) {
-                    const int ee = e + u;
-                    int col = row;
-                    if (ee < L) col = exc ? (ee < len ? __ldg(P.colidx + kb + ee) : row) : row + offs[ee];
-                    xv[u] = ee < L ? ld_x(P.x + col) : 0.0;
+                    const int col = exc ? (e + u < len ? cc[u] : row) : row + offs[e + u];
+                    xv[u] = ld_x(P.x + col);
                 }
                 sum = slice_fma<UB>(vv, xv, sum);
+            }
+            for (; e < L; e++) {                                   /* the last, partial batch slot by slot */
+                const int c1 = __ldg(cbase + min(e, last));
+                const int col = exc ? (e < len ? c1 : row) : row + offs[e];
+                sum = fma(ld_stream(v + (size_t) e * 32, pol), ld_x(P.x + col), sum);
             }
         }
         for (; e + UB <= L; e += UB) {
