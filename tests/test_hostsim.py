@@ -397,3 +397,18 @@ def test_failing_device_allocations_are_survived(simlib):
         seen.append((k, p.stdout.strip().splitlines()[-1]))
     assert all(out == "error 4" for k, out in seen if k < 150), seen
     assert seen[-1] == (100000, "ok")
+
+
+def test_gpu_test_files_rehearsed_on_the_stand_in(simlib):
+    """The GPU parity files themselves, run against the stand-in instead of the product library
+    (ACGB200_TEST_LIB): expected iteration counts, return codes, plan assertions (slices, merge tiles,
+    exception rows), the byte-identity checks of the device-side expansion (here: expand_host.c around the
+    stand-in's serial fill) -- so that a change of the host logic that would break the hardware run at round
+    end shows up in the CPU suite.  Says nothing about the kernels."""
+    env = dict(os.environ, ACGB200_TEST_LIB=simlib, OMP_NUM_THREADS="2")
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_expand.py"),
+                        os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "not public_blas1 and not full_size and not power_law"],
+                       capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert " passed" in p.stdout and "failed" not in p.stdout
