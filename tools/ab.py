@@ -1,6 +1,6 @@
 """A/B of solver variants in ONE process per GPU (development tool, GPU box only).
 
-    python tools/ab.py --workload 27pt-224 --variants base,compress,onekernel ...
+    python tools/ab.py --workload 27pt-224 --variants base,noslices,s7,pdl ...
     python -m torch.distributed.run --nproc-per-node N ... tools/ab.py --variants ...
 
 bench.py pays matrix generation + full-storage expansion (tens of seconds at C3) for
