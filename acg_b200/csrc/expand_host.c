@@ -112,5 +112,11 @@ int acgsymcsrmatrix_dsymv_init_cuda(struct acgsymcsrmatrix *A, double eps, int *
 done:
     free(t);
     acgb200_expanded_free(&x);
+    if (err) {          /* never leave half-filled full storage behind: the solver would take it for valid */
+        free(A->frowptr); free(A->fcolidx); free(A->fa);
+        free(A->orowptr); free(A->ocolidx); free(A->oa);
+        A->frowptr = NULL; A->fcolidx = NULL; A->fa = NULL; A->orowptr = NULL; A->ocolidx = NULL; A->oa = NULL;
+        A->fnpnzs = 0; A->onpnzs = 0;
+    }
     return err;
 }

@@ -22,6 +22,14 @@ try:
     cg = ab.SolverCuda(ab.SymCsrMatrix.init_real_double(n, r, c, v))      # no full storage: device-side expansion
     cg.solve_pipelined(b, x, maxits=8)
     cg.free()
+    A2 = ab.SymCsrMatrix.init_real_double(n, r, c, v)                      # acgsymcsrmatrix_dsymv_init_cuda
+    try:
+        A2.dsymv_init_cuda(0.0)
+    except ab.AcgError:
+        # a failed expansion leaves no half-filled full storage behind
+        assert not A2.c.frowptr and not A2.c.fcolidx and not A2.c.fa and not A2.c.orowptr and A2.c.fnpnzs == 0
+        raise
+    assert A2.c.fnpnzs == A.c.fnpnzs
     print("ok")
 except ab.AcgError as e:
     print("error", e.code)

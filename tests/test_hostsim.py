@@ -381,21 +381,21 @@ def test_failing_device_allocations_are_survived(simlib):
     this on every allocation)."""
     script = os.path.join(SIM, "run_fault.py")
     seen = []
-    for k in list(range(1, 25, 3)) + [24, 1000]:
+    for k in list(range(1, 25, 3)) + [24, 52, 55, 58, 60, 1000]:     # 52.. : inside acgsymcsrmatrix_dsymv_init_cuda
         p = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=120,
                            env=dict(os.environ, HOSTSIM_FAIL_MALLOC_AT=str(k), OMP_NUM_THREADS="2"))
         assert p.returncode == 0, (k, p.stderr[-2000:])
         seen.append((k, p.stdout.strip().splitlines()[-1]))
-    assert all(out == "error 4" for k, out in seen if k <= 24), seen          # ACG_ERR_CUDA
+    assert all(out == "error 4" for k, out in seen if k <= 60), seen          # ACG_ERR_CUDA
     assert seen[-1] == (1000, "ok")
     # the same for any runtime call (copies, memsets, streams, events, graph capture / instantiate / launch)
     seen = []
-    for k in list(range(2, 160, 13)) + [100000]:
+    for k in list(range(2, 160, 13)) + [200, 220, 235, 100000]:
         p = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=120,
                            env=dict(os.environ, HOSTSIM_FAIL_CALL_AT=str(k), OMP_NUM_THREADS="2"))
         assert p.returncode == 0, (k, p.stderr[-2000:])
         seen.append((k, p.stdout.strip().splitlines()[-1]))
-    assert all(out == "error 4" for k, out in seen if k < 150), seen
+    assert all(out == "error 4" for k, out in seen if k <= 235), seen
     assert seen[-1] == (100000, "ok")
 
 
